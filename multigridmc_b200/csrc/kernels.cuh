@@ -1,0 +1,413 @@
+// Device kernels of the MGMC hot path (sm_100a, fp64, bandwidth-bound stencil work: no tensor cores).
+//
+// Data layout: every level vector is a padded row-major array addressed as v[j * pitch + i] with
+// (i, j) the Euclidean vertex index of the reference's Lattice2d (lattice/lattice2d.hh:96-103),
+// i in [0, nx], j in [0, ny]; the Dirichlet boundary lines i = 0, nx and j = 0, ny and two further
+// ghost lines on every side hold zeros that are never written, so stencils need no boundary
+// branches.  Rows start 128-byte aligned.  Chains are stacked with a fixed stride.
+#pragma once
+#include <cstdint>
+
+#include "philox.cuh"
+
+namespace mgmc {
+
+// radius-1 stencil with constant coefficients (5-point: corners are zero)
+struct Coef9 {
+  double c, w, e, s, n, sw, se, nw, ne;
+};
+
+struct NoiseP {
+  uint64_t seed;
+  uint32_t c1;            // (level << 24) | sweep counter
+  const uint32_t *sample; // device-resident sample index (so that CUDA graphs can be replayed)
+  uint32_t chain0;        // global id of chain 0
+  uint32_t G;             // groups per row = nx / 4 + 1
+};
+
+struct GridP {
+  int nx, ny, pitch;
+  long long stride;  // doubles between chains
+};
+
+// ------------------------------------------------------------------------------------------------
+// y = A_0 x  (LinearOperator::apply sparse part, linear_operator.hh:69) or r = f - A_0 x
+// ------------------------------------------------------------------------------------------------
+template <bool NINE, bool RESIDUAL>
+__global__ void __launch_bounds__(256) apply_kernel(GridP g, Coef9 a, const double *__restrict__ x, const double *__restrict__ f,
+                                                   double *__restrict__ y) {
+  const int i = 1 + blockIdx.x * 64 + threadIdx.x;
+  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  const long long o = (long long)blockIdx.z * g.stride + (long long)j * g.pitch + i;
+  const double *p = x + o;
+  double s = a.c * p[0] + a.w * p[-1] + a.e * p[1] + a.s * p[-g.pitch] + a.n * p[g.pitch];
+  if (NINE) s += a.sw * p[-g.pitch - 1] + a.se * p[-g.pitch + 1] + a.nw * p[g.pitch - 1] + a.ne * p[g.pitch + 1];
+  y[o] = RESIDUAL ? (f[o] - s) : s;
+}
+
+// r = A_0 x - b together with per-block partial sums of r^2 (LoopSolver, loop_solver.cc:26-28)
+template <bool NINE>
+__global__ void __launch_bounds__(256) residual_norm_kernel(GridP g, Coef9 a, const double *__restrict__ x, const double *__restrict__ b,
+                                                           double *__restrict__ r, double *__restrict__ partial) {
+  const int i = 1 + blockIdx.x * 64 + threadIdx.x;
+  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  double v = 0.0;
+  if (i < g.nx && j < g.ny) {
+    const long long o = (long long)j * g.pitch + i;
+    const double *p = x + o;
+    double s = a.c * p[0] + a.w * p[-1] + a.e * p[1] + a.s * p[-g.pitch] + a.n * p[g.pitch];
+    if (NINE) s += a.sw * p[-g.pitch - 1] + a.se * p[-g.pitch + 1] + a.nw * p[g.pitch - 1] + a.ne * p[g.pitch + 1];
+    v = s - b[o];
+    r[o] = v;
+  }
+  v = v * v;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  __shared__ double ws[8];
+  const int t = threadIdx.y * 64 + threadIdx.x;
+  if ((t & 31) == 0) ws[t >> 5] = v;
+  __syncthreads();
+  if (t == 0) {
+    double s = 0.0;
+    for (int k = 0; k < 8; ++k) s += ws[k];
+    partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// deterministic final reduction of the per-block partial sums: out[0] = sum(partial)
+__global__ void __launch_bounds__(1024) reduce_sum_kernel(const double *__restrict__ partial, int n, double *__restrict__ out) {
+  __shared__ double ws[32];
+  double v = 0.0;
+  for (int k = threadIdx.x; k < n; k += 1024) v += partial[k];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = ws[threadIdx.x];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (threadIdx.x == 0) out[0] = v;
+  }
+}
+
+// x -= y on the interior (LoopSolver update x -= Pr, loop_solver.cc:41); or x = 0
+template <int MODE>  // 0: x -= y, 1: x = 0, 2: x = y
+__global__ void __launch_bounds__(256) axpy_kernel(GridP g, double *__restrict__ x, const double *__restrict__ y) {
+  const int i = 1 + blockIdx.x * 64 + threadIdx.x;
+  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  const long long o = (long long)blockIdx.z * g.stride + (long long)j * g.pitch + i;
+  if (MODE == 0) x[o] -= y[o];
+  else if (MODE == 1) x[o] = 0.0;
+  else x[o] = y[o];
+}
+
+// ------------------------------------------------------------------------------------------------
+// One colour of a multicolour SOR / Gibbs sweep (SORSmoother::apply_sparse sor_smoother.cc:56-78
+// with the rows visited colour by colour; SORSampler noise sor_sampler.cc:42-46 generated in
+// registers).  NC = 2: red-black for the 5-point stencil, colour = (i + j) & 1.
+// NC = 4: colour = (i & 1) + 2 (j & 1) for the 9-point Galerkin stencils.
+// Each thread owns one aligned group of 4 columns in one row and updates the (up to) two sites of
+// the colour in it: (i0, i0 + 2) -- they share one Philox call.
+// ------------------------------------------------------------------------------------------------
+template <int NC, bool GIBBS>
+__global__ void __launch_bounds__(256) sweep_colour_kernel(GridP g, Coef9 a, double *__restrict__ x, const double *__restrict__ f, int colour,
+                                                          double omega, double noise_scale, NoiseP nz) {
+  const int p = blockIdx.x * 32 + threadIdx.x;
+  const int jj = blockIdx.y * 8 + threadIdx.y;
+  int j, q;
+  if (NC == 2) {
+    j = 1 + jj;
+    q = (colour ^ j) & 1;
+  } else {
+    j = 2 * jj + ((colour >> 1) ? 1 : 2);
+    q = colour & 1;
+  }
+  const int i0 = 4 * p + q;
+  if (j >= g.ny || i0 >= g.nx) return;
+  const long long o = (long long)blockIdx.z * g.stride + (long long)j * g.pitch + i0;
+  double z0 = 0.0, z1 = 0.0;
+  if (GIBBS) normal_pair(nz.seed, (((uint32_t)j * nz.G + (uint32_t)p) << 1) | (uint32_t)q, nz.c1, *nz.sample, nz.chain0 + blockIdx.z, z0, z1);
+  const double winv = omega / a.c;
+  double *xp = x + o;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = i0 + 2 * k;
+    if (i < 1 || i >= g.nx) continue;
+    double *pc = xp + 2 * k;
+    double s = a.c * pc[0] + a.w * pc[-1] + a.e * pc[1] + a.s * pc[-g.pitch] + a.n * pc[g.pitch];
+    if (NC == 4) s += a.sw * pc[-g.pitch - 1] + a.se * pc[-g.pitch + 1] + a.nw * pc[g.pitch - 1] + a.ne * pc[g.pitch + 1];
+    double b = f[o + 2 * k];
+    if (GIBBS) b += noise_scale * (k ? z1 : z0);
+    pc[0] += winv * (b - s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused residual + restriction: f_c = R (f - A_0 x) with R = {1/2,1,1/2}^(x)2 un-normalised
+// (multigridmc_sampler.cc:118-120, intergrid_operator.hh:74-88, intergrid_operator_linear.cc:13).
+// One thread per coarse vertex (I, J) <-> fine (2I, 2J); the residual is never stored.
+// PLAIN = true: restrict a given fine vector (IntergridOperator::restrict).
+// ------------------------------------------------------------------------------------------------
+template <bool NINE, bool PLAIN>
+__global__ void __launch_bounds__(256) residual_restrict_kernel(GridP g, GridP gc, Coef9 a, const double *__restrict__ x,
+                                                               const double *__restrict__ f, double *__restrict__ fc) {
+  const int I = 1 + blockIdx.x * 64 + threadIdx.x;
+  const int J = 1 + blockIdx.y * 4 + threadIdx.y;
+  if (I >= gc.nx || J >= gc.ny) return;
+  const long long of = (long long)blockIdx.z * g.stride + (long long)(2 * J) * g.pitch + 2 * I;
+  double acc = 0.0;
+#pragma unroll
+  for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+    for (int di = -1; di <= 1; ++di) {
+      const double wgt = ((di == 0) ? 1.0 : 0.5) * ((dj == 0) ? 1.0 : 0.5);
+      const long long o = of + (long long)dj * g.pitch + di;
+      double r;
+      if (PLAIN) {
+        r = f[o];
+      } else {
+        const double *p = x + o;
+        double s = a.c * p[0] + a.w * p[-1] + a.e * p[1] + a.s * p[-g.pitch] + a.n * p[g.pitch];
+        if (NINE) s += a.sw * p[-g.pitch - 1] + a.se * p[-g.pitch + 1] + a.nw * p[g.pitch - 1] + a.ne * p[g.pitch + 1];
+        r = f[o] - s;
+      }
+      acc += wgt * r;
+    }
+  fc[(long long)blockIdx.z * gc.stride + (long long)J * gc.pitch + I] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// x += alpha R^T x_c in gather form (IntergridOperator::prolongate_add, intergrid_operator.hh:106-120):
+// every fine vertex reads its (up to) 4 coarse parents; boundary parents are the zero ghost lines.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prolongate_add_kernel(GridP g, GridP gc, double alpha, const double *__restrict__ xc, double *__restrict__ x) {
+  const int i = 1 + blockIdx.x * 64 + threadIdx.x;
+  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  const double *c = xc + (long long)blockIdx.z * gc.stride;
+  const int I0 = i >> 1, J0 = j >> 1, I1 = (i + 1) >> 1, J1 = (j + 1) >> 1;
+  // even index: I0 == I1 -> weight 1/2 + 1/2 = 1; odd index: the two neighbours with weight 1/2
+  const double v = 0.25 * (c[(long long)J0 * gc.pitch + I0] + c[(long long)J0 * gc.pitch + I1] + c[(long long)J1 * gc.pitch + I0] +
+                           c[(long long)J1 * gc.pitch + I1]);
+  x[(long long)blockIdx.z * g.stride + (long long)j * g.pitch + i] += alpha * v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Low-rank term.  Sparse column storage of a n x m matrix on the device: entries of column k are
+// (site[e], val[e]) for e in [colptr[k], colptr[k+1]); "site" is the offset j * pitch + i.
+// Row-grouped storage ("usites") for deterministic scatter: unique site u has entries
+// (ucol[e], uval[e]) for e in [uptr[u], uptr[u+1]).
+// ------------------------------------------------------------------------------------------------
+struct SparseCols {
+  int m;
+  const int *colptr;
+  const long long *site;
+  const double *val;
+};
+struct SparseRows {
+  int nu;
+  const long long *usite;
+  const int *uptr;
+  const int *ucol;
+  const double *uval;
+};
+
+// y += B Sigma^{-1} B^T x  (linear_operator.hh:71-75).  One block per chain; m <= 1024.
+__global__ void __launch_bounds__(256) lowrank_apply_kernel(SparseCols B, SparseRows Br, const double *__restrict__ sigma_inv, long long stride,
+                                                           const double *__restrict__ x, double *__restrict__ y) {
+  extern __shared__ double sh[];
+  double *t = sh;
+  const double *xc = x + (long long)blockIdx.x * stride;
+  double *yc = y + (long long)blockIdx.x * stride;
+  for (int k = threadIdx.x; k < B.m; k += blockDim.x) {
+    double s = 0.0;
+    for (int e = B.colptr[k]; e < B.colptr[k + 1]; ++e) s += B.val[e] * xc[B.site[e]];
+    t[k] = s * sigma_inv[k];
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < Br.nu; u += blockDim.x) {
+    double s = 0.0;
+    for (int e = Br.uptr[u]; e < Br.uptr[u + 1]; ++e) s += Br.uval[e] * t[Br.ucol[e]];
+    yc[Br.usite[u]] += s;
+  }
+}
+
+// low-rank part of the restricted residual: f_c -= R B Sigma^{-1} B^T x = B_c (Sigma^{-1} B^T x)
+// (R B is exactly the coarse-level B, linear_operator.cc:19), completing multigridmc_sampler.cc:118-120
+__global__ void __launch_bounds__(256) lowrank_restrict_kernel(SparseCols B, SparseRows Bc, const double *__restrict__ sigma_inv, long long stride,
+                                                              long long stride_c, const double *__restrict__ x, double *__restrict__ fc) {
+  extern __shared__ double sh[];
+  double *t = sh;
+  const double *xc = x + (long long)blockIdx.x * stride;
+  double *fcc = fc + (long long)blockIdx.x * stride_c;
+  for (int k = threadIdx.x; k < B.m; k += blockDim.x) {
+    double s = 0.0;
+    for (int e = B.colptr[k]; e < B.colptr[k + 1]; ++e) s += B.val[e] * xc[B.site[e]];
+    t[k] = s * sigma_inv[k];
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < Bc.nu; u += blockDim.x) {
+    double s = 0.0;
+    for (int e = Bc.uptr[u]; e < Bc.uptr[u + 1]; ++e) s += Bc.uval[e] * t[Bc.ucol[e]];
+    fcc[Bc.usite[u]] -= s;
+  }
+}
+
+// Woodbury fix-up after a sweep on A_0 (SORSmoother::apply, sor_smoother.cc:47-51) merged with the
+// low-rank part of the Gibbs noise (sor_sampler.cc:48-56):
+//   y = x + W s,  s = Sigma^{-1/2} xi           (sweep is linear in its rhs: M_0^{-1} B s = W s)
+//   x_new = y - W K B^T y = x + W (s - K (B^T x + G s)),   W = M_0^{-1} B, G = B^T W, K = (Sigma + G)^{-1}
+// where M_0 = D/omega + L in the colour ordering, so W is sparse.
+template <bool GIBBS>
+__global__ void __launch_bounds__(256) lowrank_fix_kernel(SparseCols B, SparseRows W, const double *__restrict__ K, const double *__restrict__ Gm,
+                                                         const double *__restrict__ sigma_inv_sqrt, long long stride, double *__restrict__ x,
+                                                         NoiseP nz) {
+  extern __shared__ double sh[];
+  const int m = B.m;
+  double *t = sh, *s = sh + m, *d = sh + 2 * m;
+  double *xc = x + (long long)blockIdx.x * stride;
+  for (int k = threadIdx.x; k < m; k += blockDim.x) {
+    double acc = 0.0;
+    for (int e = B.colptr[k]; e < B.colptr[k + 1]; ++e) acc += B.val[e] * xc[B.site[e]];
+    t[k] = acc;
+    if (GIBBS) {
+      double z0, z1;
+      normal_pair(nz.seed, 0x80000000u | ((uint32_t)k >> 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.x, z0, z1);
+      s[k] = sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
+    } else {
+      s[k] = 0.0;
+    }
+  }
+  __syncthreads();
+  if (GIBBS) {
+    for (int k = threadIdx.x; k < m; k += blockDim.x) {
+      double acc = t[k];
+      for (int c = 0; c < m; ++c) acc += Gm[k * m + c] * s[c];
+      d[k] = acc;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < m; k += blockDim.x) t[k] = d[k];
+    __syncthreads();
+  }
+  for (int k = threadIdx.x; k < m; k += blockDim.x) {
+    double acc = 0.0;
+    for (int c = 0; c < m; ++c) acc += K[k * m + c] * t[c];
+    d[k] = s[k] - acc;
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < W.nu; u += blockDim.x) {
+    double acc = 0.0;
+    for (int e = W.uptr[u]; e < W.uptr[u + 1]; ++e) acc += W.uval[e] * d[W.ucol[e]];
+    xc[W.usite[u]] += acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Coarsest level: dense lower Cholesky factor L (Np x Np row-major, padded with identity to a
+// multiple of 32) resident on the device plus the inverses of its 32 x 32 diagonal blocks.
+// Blocked substitution, one CTA per chain:
+//   SAMPLE:  x = L^{-T} (xi + L^{-1} f)   (CholeskySampler::apply, cholesky_sampler.hh:50-66)
+//   SOLVE:   x = L^{-T} L^{-1} b          (CholeskySolver::apply, cholesky_solver.cc:30-41; the low-rank
+//            term is folded into the factorised matrix instead of the reference's Woodbury update)
+// ------------------------------------------------------------------------------------------------
+template <bool SAMPLE>
+__global__ void __launch_bounds__(1024) coarse_cholesky_kernel(const double *__restrict__ L, const double *__restrict__ Dinv, int N, int Np, GridP g,
+                                                              const double *__restrict__ f, double *__restrict__ x, NoiseP nz) {
+  extern __shared__ double sh[];
+  double *y = sh;        // Np
+  double *xk = sh + Np;  // 32
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int w = g.nx - 1;
+  const long long base = (long long)blockIdx.x * g.stride;
+  for (int e = tid; e < Np; e += 1024) y[e] = (e < N) ? f[base + (long long)(e / w + 1) * g.pitch + (e % w + 1)] : 0.0;
+  __syncthreads();
+  const int nb = Np / 32;
+  // forward: L y' = y
+  for (int k = 0; k < nb; ++k) {
+    if (warp == 0) {
+      const double *D = Dinv + (long long)k * 1024;
+      double acc = 0.0;
+      for (int c = 0; c <= lane; ++c) acc += D[lane * 32 + c] * y[32 * k + c];
+      xk[lane] = acc;
+    }
+    __syncthreads();
+    if (tid < 32) y[32 * k + tid] = xk[tid];
+    const double xl = xk[lane];
+    for (int r = 32 * (k + 1) + warp; r < Np; r += 32) {
+      double v = L[(long long)r * Np + 32 * k + lane] * xl;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) y[r] -= v;
+    }
+    __syncthreads();
+  }
+  if (SAMPLE) {
+    for (int e2 = tid; 2 * e2 < N; e2 += 1024) {
+      double z0, z1;
+      normal_pair(nz.seed, 0x40000000u | (uint32_t)e2, nz.c1, *nz.sample, nz.chain0 + blockIdx.x, z0, z1);
+      y[2 * e2] += z0;
+      if (2 * e2 + 1 < N) y[2 * e2 + 1] += z1;
+    }
+    __syncthreads();
+  }
+  // backward: L^T x = y
+  for (int k = nb - 1; k >= 0; --k) {
+    if (warp == 0) {
+      const double *D = Dinv + (long long)k * 1024;
+      double acc = 0.0;
+      for (int c = lane; c < 32; ++c) acc += D[c * 32 + lane] * y[32 * k + c];
+      xk[lane] = acc;
+    }
+    __syncthreads();
+    if (tid < 32) y[32 * k + tid] = xk[tid];
+    for (int r = tid; r < 32 * k; r += 1024) {
+      double acc = 0.0;
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) acc += L[(long long)(32 * k + c) * Np + r] * xk[c];
+      y[r] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < N; e += 1024) x[base + (long long)(e / w + 1) * g.pitch + (e % w + 1)] = y[e];
+}
+
+// ------------------------------------------------------------------------------------------------
+// End of an MGMC cycle: z = sample_vector . x for every chain (driver_mgmc.cc:76), stored at
+// series[pos * nchains + chain]; then advance the device-resident sample index and series position.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) end_of_cycle_kernel(int nnz, const long long *__restrict__ qsite, const double *__restrict__ qval,
+                                                          const double *__restrict__ x, long long stride, int nchains, double *__restrict__ series,
+                                                          long long series_cap, uint32_t *sample, unsigned long long *pos) {
+  const unsigned long long p = *pos;
+  if (series != nullptr && nnz > 0 && p < (unsigned long long)series_cap) {
+    for (int c = threadIdx.x >> 5; c < nchains; c += 8) {
+      double v = 0.0;
+      for (int e = threadIdx.x & 31; e < nnz; e += 32) v += qval[e] * x[(long long)c * stride + qsite[e]];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if ((threadIdx.x & 31) == 0) series[p * nchains + c] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *sample = *sample + 1u;
+    *pos = p + 1ull;
+  }
+}
+
+// running mean / second moment fields (posterior_statistics, driver_mgmc.cc:146-151)
+__global__ void __launch_bounds__(256) moments_kernel(GridP g, const double *__restrict__ x, double *__restrict__ mean, double *__restrict__ second,
+                                                     double inv_count) {
+  const int i = 1 + blockIdx.x * 64 + threadIdx.x;
+  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  const long long o = (long long)j * g.pitch + i;
+  const double v = x[o];
+  mean[o] += (v - mean[o]) * inv_count;
+  second[o] += (v * v - second[o]) * inv_count;
+}
+
+}  // namespace mgmc

@@ -1,0 +1,1016 @@
+// C-ABI implementation of the B200 MGMC hot path (include/mgmc_b200.h).
+// Context = operator hierarchy resident in HBM + one CUDA stream; the multigrid recursion of the
+// reference (multigridmc_sampler.cc:103-130, multigrid_preconditioner.cc:74-101) is unrolled on the
+// host into a fixed launch sequence that is captured once into a CUDA graph and replayed per sample.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/mgmc_b200.h"
+#include "kernels.cuh"
+#include "setup.hh"
+
+using namespace mgmc;
+
+static thread_local std::string g_last_error;
+extern "C" const char *mgmc_last_error(void) { return g_last_error.c_str(); }
+
+namespace {
+
+struct MgmcError {
+  int code;
+  std::string msg;
+};
+[[noreturn]] void fail(int code, const std::string &msg) { throw MgmcError{code, msg}; }
+
+#define CUDA_CHECK(expr)                                                                                   \
+  do {                                                                                                     \
+    cudaError_t err__ = (expr);                                                                            \
+    if (err__ != cudaSuccess) fail(MGMC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+  } while (0)
+
+constexpr int GX = 16;  // doubles left of i = 0 (keeps i = 0 128-byte aligned)
+constexpr int GY = 2;   // ghost rows below j = 0 and above j = ny
+
+struct DevSparse {  // device copies of a sparse n x m matrix in both groupings
+  SparseCols cols{0, nullptr, nullptr, nullptr};
+  SparseRows rows{0, nullptr, nullptr, nullptr, nullptr};
+};
+
+struct LowRankDev {
+  DevSparse W[2];  // [0] forward, [1] backward
+  double *K[2] = {nullptr, nullptr};
+  double *G[2] = {nullptr, nullptr};
+};
+
+struct DevLevel {
+  HostLevel h;
+  GridP g;
+  double *x = nullptr, *f = nullptr, *r = nullptr;  // origin pointers (element i = 0, j = 0 of chain 0)
+  Coef9 coef;
+  bool nine = false;
+  DevSparse B;
+  std::map<double, LowRankDev> lowrank;  // keyed by omega
+};
+
+struct ProfSlot {
+  std::string name;
+  double ms = 0.0;
+  int64_t launches = 0;
+};
+
+}  // namespace
+
+struct mgmc_ctx {
+  mgmc_desc d;
+  std::vector<double> Sigma;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<DevLevel> lv;
+  std::vector<void *> allocs;
+  // coarse factor
+  int Nc = 0, Ncp = 0;
+  double *dL = nullptr, *dDinv = nullptr;
+  double *d_sigma_inv = nullptr, *d_sigma_inv_sqrt = nullptr;
+  // noise position
+  uint32_t *d_sample = nullptr;
+  uint32_t h_sample = 0;
+  std::vector<uint32_t> sweep_counter;
+  // QoI / series
+  int qoi_nnz = 0;
+  long long *d_qsite = nullptr;
+  double *d_qval = nullptr;
+  double *d_series = nullptr;
+  long long series_cap = 0;
+  unsigned long long *d_pos = nullptr;
+  // loop solver scratch
+  double *sol_x = nullptr, *sol_b = nullptr, *d_partial = nullptr, *d_norm = nullptr;
+  int npartial = 0;
+  // moments
+  double *d_mean = nullptr, *d_second = nullptr;
+  // graph of one MGMC cycle (+ end-of-cycle kernel)
+  cudaGraphExec_t graph = nullptr;
+  bool use_graph = true;
+  // instrumentation
+  int64_t launch_count = 0;
+  int64_t launches_per_cycle = 0;
+  bool prof_on = false;
+  std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
+
+  template <class T>
+  T *dalloc(size_t n, bool zero = true) {
+    void *p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    allocs.push_back(p);
+    if (zero) CUDA_CHECK(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), stream));
+    return (T *)p;
+  }
+  template <class T>
+  T *dupload(const std::vector<T> &v) {
+    T *p = dalloc<T>(v.size(), false);
+    if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));  // v may be a temporary
+    return p;
+  }
+  void sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
+
+  template <class F>
+  void launch(const char *name, int level, F &&fn) {
+    ++launch_count;
+    if (prof_on) {
+      cudaEvent_t e0, e1;
+      CUDA_CHECK(cudaEventCreate(&e0));
+      CUDA_CHECK(cudaEventCreate(&e1));
+      CUDA_CHECK(cudaEventRecord(e0, stream));
+      fn();
+      CUDA_CHECK(cudaEventRecord(e1, stream));
+      prof_events.push_back({std::string(name) + "/L" + std::to_string(level), {e0, e1}});
+    } else {
+      fn();
+    }
+    CUDA_CHECK(cudaGetLastError());
+  }
+};
+
+namespace {
+
+dim3 grid_sites(const GridP &g, int nch) { return dim3((g.nx - 1 + 63) / 64, (g.ny - 1 + 3) / 4, nch); }
+const dim3 kBlockSites(64, 4, 1);
+
+DevSparse upload_sparse(mgmc_ctx *c, const std::vector<SEntry> &E, int m, int pitch) {
+  DevSparse out;
+  // column grouping
+  std::vector<int> colptr(m + 1, 0);
+  for (const SEntry &e : E) colptr[e.col + 1]++;
+  for (int k = 0; k < m; ++k) colptr[k + 1] += colptr[k];
+  std::vector<long long> site(E.size());
+  std::vector<double> val(E.size());
+  std::vector<int> fill(colptr.begin(), colptr.end() - 1);
+  for (const SEntry &e : E) {
+    const int p = fill[e.col]++;
+    site[p] = (long long)e.j * pitch + e.i;
+    val[p] = e.val;
+  }
+  out.cols.m = m;
+  out.cols.colptr = c->dupload(colptr);
+  out.cols.site = c->dupload(site);
+  out.cols.val = c->dupload(val);
+  // row grouping (unique sites, deterministic scatter)
+  std::map<long long, std::vector<std::pair<int, double>>> bysite;
+  for (const SEntry &e : E) bysite[(long long)e.j * pitch + e.i].push_back({e.col, e.val});
+  std::vector<long long> usite;
+  std::vector<int> uptr(1, 0), ucol;
+  std::vector<double> uval;
+  for (auto &kv : bysite) {
+    usite.push_back(kv.first);
+    for (auto &cv : kv.second) {
+      ucol.push_back(cv.first);
+      uval.push_back(cv.second);
+    }
+    uptr.push_back((int)ucol.size());
+  }
+  out.rows.nu = (int)usite.size();
+  out.rows.usite = c->dupload(usite);
+  out.rows.uptr = c->dupload(uptr);
+  out.rows.ucol = c->dupload(ucol);
+  out.rows.uval = c->dupload(uval);
+  return out;
+}
+
+Coef9 to_coef9(const StencilSet &s) {
+  Coef9 a;
+  a.c = s.at(4, 0, 0);
+  a.w = s.at(4, -1, 0);
+  a.e = s.at(4, 1, 0);
+  a.s = s.at(4, 0, -1);
+  a.n = s.at(4, 0, 1);
+  a.sw = s.at(4, -1, -1);
+  a.se = s.at(4, 1, -1);
+  a.nw = s.at(4, -1, 1);
+  a.ne = s.at(4, 1, 1);
+  return a;
+}
+
+std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
+  if (d.dim != 2) fail(MGMC_ERR_UNSUPPORTED, "only dim = 2 lattices are implemented on the device path");
+  if (d.nx < 2 || d.ny < 2) fail(MGMC_ERR_INVALID, "invalid lattice size");
+  if (d.nlevel < 1) fail(MGMC_ERR_INVALID, "nlevel must be >= 1");
+  if (d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FD && d.pde_model != MGMC_PDE_SQUARED_SHIFTEDLAPLACE_FD) fail(MGMC_ERR_INVALID, "invalid pde_model");
+  if (!(d.Lambda > 0.0)) fail(MGMC_ERR_INVALID, "Lambda must be positive");
+  if (!(d.omega > 0.0 && d.omega < 2.0)) fail(MGMC_ERR_INVALID, "omega must be in (0,2)");
+  if (d.nx >= (1 << 20) || d.ny >= (1 << 20)) fail(MGMC_ERR_INVALID, "lattice too large");
+  std::vector<HostLevel> L(d.nlevel);
+  L[0].nx = d.nx;
+  L[0].ny = d.ny;
+  L[0].st = fine_stencil(d.pde_model, d.nx, d.ny, d.Lambda);
+  const int w = d.nx - 1;
+  for (int64_t e = 0; e < d.B_nnz; ++e) {
+    const int64_t row = d.B_rows[e];
+    if (row < 0 || row >= (int64_t)(d.nx - 1) * (d.ny - 1) || d.B_cols[e] < 0 || d.B_cols[e] >= d.m_lowrank) fail(MGMC_ERR_INVALID, "B entry out of range");
+    L[0].B.push_back({int(row % w) + 1, int(row / w) + 1, d.B_cols[e], d.B_vals[e]});
+  }
+  for (int l = 1; l < d.nlevel; ++l) {
+    const HostLevel &f = L[l - 1];
+    // Lattice2d::get_coarse_lattice (lattice2d.hh:198-213)
+    if ((f.nx % 2) || (f.ny % 2)) fail(MGMC_ERR_INVALID, "cannot coarsen lattice of size " + std::to_string(f.nx) + " x " + std::to_string(f.ny) + " [one of the extents is odd]");
+    if (!(f.nx / 2 > 1 && f.ny / 2 > 1)) fail(MGMC_ERR_INVALID, "cannot coarsen lattice [resulting lattice would have no interior vertices]");
+    L[l].nx = f.nx / 2;
+    L[l].ny = f.ny / 2;
+    L[l].st = coarsen_stencil(f.st, f.nx, f.ny);
+    L[l].B = coarsen_B(f.B, f.nx, f.ny);
+  }
+  return L;
+}
+
+const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega) {
+  DevLevel &L = c->lv[level];
+  auto it = L.lowrank.find(omega);
+  if (it != L.lowrank.end()) return it->second;
+  LowRankDev dev;
+  const int m = c->d.m_lowrank;
+  for (int dir = 0; dir < 2; ++dir) {
+    LowRankDir h = lowrank_setup(L.h, c->Sigma, omega, dir == 0);
+    dev.W[dir] = upload_sparse(c, h.W, m, L.g.pitch);
+    dev.K[dir] = c->dupload(h.K);
+    dev.G[dir] = c->dupload(h.G);
+  }
+  return L.lowrank.emplace(omega, dev).first->second;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host <-> device transfers: lexicographic interior vector <-> padded device layout
+// ---------------------------------------------------------------------------------------------
+void upload_vec(mgmc_ctx *c, int level, double *dev, const double *host) {
+  const DevLevel &L = c->lv[level];
+  const size_t w = L.g.nx - 1, h = L.g.ny - 1;
+  for (int ch = 0; ch < c->d.nchains; ++ch)
+    CUDA_CHECK(cudaMemcpy2DAsync(dev + (size_t)ch * L.g.stride + L.g.pitch + 1, L.g.pitch * sizeof(double), host + (size_t)ch * w * h, w * sizeof(double),
+                                 w * sizeof(double), h, cudaMemcpyHostToDevice, c->stream));
+}
+void download_vec(mgmc_ctx *c, int level, const double *dev, double *host) {
+  const DevLevel &L = c->lv[level];
+  const size_t w = L.g.nx - 1, h = L.g.ny - 1;
+  for (int ch = 0; ch < c->d.nchains; ++ch)
+    CUDA_CHECK(cudaMemcpy2DAsync(host + (size_t)ch * w * h, w * sizeof(double), dev + (size_t)ch * L.g.stride + L.g.pitch + 1, L.g.pitch * sizeof(double),
+                                 w * sizeof(double), h, cudaMemcpyDeviceToHost, c->stream));
+}
+
+NoiseP noise_params(mgmc_ctx *c, int level, bool advance) {
+  NoiseP nz;
+  nz.seed = c->d.seed;
+  nz.c1 = ((uint32_t)level << 24) | (c->sweep_counter[level] & 0xFFFFFFu);
+  if (advance) c->sweep_counter[level]++;
+  nz.sample = c->d_sample;
+  nz.chain0 = (uint32_t)c->d.first_chain;
+  nz.G = (uint32_t)(c->lv[level].g.nx / 4 + 1);
+  return nz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-level building blocks (device vectors)
+// ---------------------------------------------------------------------------------------------
+void dev_zero(mgmc_ctx *c, int level, double *x) {
+  const DevLevel &L = c->lv[level];
+  c->launch("zero", level, [&] { axpy_kernel<1><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, x, nullptr); });
+}
+
+// y = A x (incl. low-rank term)
+void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
+  const DevLevel &L = c->lv[level];
+  c->launch("apply", level, [&] {
+    if (L.nine) apply_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
+    else apply_kernel<false, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
+  });
+  if (c->d.m_lowrank > 0)
+    c->launch("lowrank_apply", level, [&] {
+      lowrank_apply_kernel<<<c->d.nchains, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, L.B.rows, c->d_sigma_inv, L.g.stride, x, y);
+    });
+}
+
+// one directional SOR / Gibbs sweep over all colours + low-rank fix-up
+void dev_sweep(mgmc_ctx *c, int level, bool fwd, bool gibbs, bool fixup, double omega, const double *f, double *x) {
+  DevLevel &L = c->lv[level];
+  const int nc = L.h.st.ncolours;
+  NoiseP nz = noise_params(c, level, gibbs);
+  const double noise_scale = std::sqrt(L.coef.c * (2. - omega) / omega);  // sor_sampler.cc:24-27
+  const int ngroups = L.g.nx / 4 + 1;
+  for (int cc = 0; cc < nc; ++cc) {
+    const int colour = fwd ? cc : nc - 1 - cc;
+    if (nc == 2) {
+      dim3 grid((ngroups + 31) / 32, (L.g.ny - 1 + 7) / 8, c->d.nchains);
+      c->launch(gibbs ? "gibbs_rb" : "sor_rb", level, [&] {
+        if (gibbs) sweep_colour_kernel<2, true><<<grid, dim3(32, 8, 1), 0, c->stream>>>(L.g, L.coef, x, f, colour, omega, noise_scale, nz);
+        else sweep_colour_kernel<2, false><<<grid, dim3(32, 8, 1), 0, c->stream>>>(L.g, L.coef, x, f, colour, omega, noise_scale, nz);
+      });
+    } else {
+      dim3 grid((ngroups + 31) / 32, (L.g.ny / 2 + 7) / 8, c->d.nchains);
+      c->launch(gibbs ? "gibbs_4c" : "sor_4c", level, [&] {
+        if (gibbs) sweep_colour_kernel<4, true><<<grid, dim3(32, 8, 1), 0, c->stream>>>(L.g, L.coef, x, f, colour, omega, noise_scale, nz);
+        else sweep_colour_kernel<4, false><<<grid, dim3(32, 8, 1), 0, c->stream>>>(L.g, L.coef, x, f, colour, omega, noise_scale, nz);
+      });
+    }
+  }
+  if (fixup && c->d.m_lowrank > 0) {
+    const LowRankDev &lr = get_lowrank(c, level, omega);
+    const int dir = fwd ? 0 : 1;
+    const size_t sh = 3 * (size_t)c->d.m_lowrank * sizeof(double);
+    c->launch("lowrank_fix", level, [&] {
+      if (gibbs)
+        lowrank_fix_kernel<true><<<c->d.nchains, 256, sh, c->stream>>>(L.B.cols, lr.W[dir].rows, lr.K[dir], lr.G[dir], c->d_sigma_inv_sqrt, L.g.stride, x, nz);
+      else
+        lowrank_fix_kernel<false><<<c->d.nchains, 256, sh, c->stream>>>(L.B.cols, lr.W[dir].rows, lr.K[dir], lr.G[dir], c->d_sigma_inv_sqrt, L.g.stride, x, nz);
+    });
+  }
+}
+
+// Smoother::apply / Sampler::apply semantics of the reference, including the nsmooth^2 quirk of
+// SORSmoother (sor_smoother.cc:43,64) which the samplers do not have (sor_sampler.cc:28,39)
+void dev_smooth(mgmc_ctx *c, int level, int kind, int direction, double omega, int nsmooth, bool gibbs, const double *f, double *x) {
+  if (kind == MGMC_SMOOTHER_SOR) {
+    const bool fwd = (direction == MGMC_FORWARD);
+    for (int k = 0; k < nsmooth; ++k) {
+      if (gibbs) {
+        dev_sweep(c, level, fwd, true, true, omega, f, x);
+      } else {
+        for (int q = 0; q < nsmooth; ++q) dev_sweep(c, level, fwd, false, q == nsmooth - 1, omega, f, x);
+      }
+    }
+  } else {
+    for (int k = 0; k < nsmooth; ++k) {
+      dev_sweep(c, level, true, gibbs, true, omega, f, x);
+      dev_sweep(c, level, false, gibbs, true, omega, f, x);
+    }
+  }
+}
+
+// f_c = R (f - A x)
+void dev_residual_restrict(mgmc_ctx *c, int level, const double *f, const double *x, double *fc) {
+  const DevLevel &L = c->lv[level], &C = c->lv[level + 1];
+  c->launch("residual_restrict", level, [&] {
+    if (L.nine) residual_restrict_kernel<true, false><<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, L.coef, x, f, fc);
+    else residual_restrict_kernel<false, false><<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, L.coef, x, f, fc);
+  });
+  if (c->d.m_lowrank > 0)
+    c->launch("lowrank_restrict", level, [&] {
+      lowrank_restrict_kernel<<<c->d.nchains, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, C.B.rows, c->d_sigma_inv, L.g.stride, C.g.stride, x, fc);
+    });
+}
+
+void dev_restrict_plain(mgmc_ctx *c, int level, const double *r, double *fc) {
+  const DevLevel &L = c->lv[level], &C = c->lv[level + 1];
+  c->launch("restrict", level, [&] {
+    residual_restrict_kernel<false, true><<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, L.coef, nullptr, r, fc);
+  });
+}
+
+void dev_prolongate_add(mgmc_ctx *c, int level, double alpha, const double *xc, double *x) {
+  const DevLevel &L = c->lv[level], &C = c->lv[level + 1];
+  c->launch("prolongate_add", level, [&] { prolongate_add_kernel<<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, alpha, xc, x); });
+}
+
+void dev_coarse(mgmc_ctx *c, bool sample, const double *f, double *x) {
+  const int lc = c->d.nlevel - 1;
+  const DevLevel &L = c->lv[lc];
+  NoiseP nz = noise_params(c, lc, sample);
+  const size_t sh = (size_t)(c->Ncp + 32) * sizeof(double);
+  c->launch(sample ? "coarse_sample" : "coarse_solve", lc, [&] {
+    if (sample) coarse_cholesky_kernel<true><<<c->d.nchains, 1024, sh, c->stream>>>(c->dL, c->dDinv, c->Nc, c->Ncp, L.g, f, x, nz);
+    else coarse_cholesky_kernel<false><<<c->d.nchains, 1024, sh, c->stream>>>(c->dL, c->dDinv, c->Nc, c->Ncp, L.g, f, x, nz);
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// multilevel recursions
+// ---------------------------------------------------------------------------------------------
+void mgmc_sample_level(mgmc_ctx *c, int level) {  // multigridmc_sampler.cc:103-130
+  const mgmc_desc &d = c->d;
+  DevLevel &L = c->lv[level];
+  if (level == d.nlevel - 1) {
+    if (d.coarse_solver == MGMC_COARSE_CHOLESKY) dev_coarse(c, true, L.f, L.x);
+    else dev_smooth(c, level, MGMC_SMOOTHER_SSOR, MGMC_FORWARD, d.omega, d.ncoarsesmooth, true, L.f, L.x);
+    return;
+  }
+  const int cycle_ = (level > 0) ? d.cycle : 1;
+  for (int j = 0; j < cycle_; ++j) {
+    dev_smooth(c, level, d.smoother, MGMC_FORWARD, d.omega, d.npresmooth, true, L.f, L.x);
+    dev_residual_restrict(c, level, L.f, L.x, c->lv[level + 1].f);
+    dev_zero(c, level + 1, c->lv[level + 1].x);
+    mgmc_sample_level(c, level + 1);
+    dev_prolongate_add(c, level, d.coarse_scaling, c->lv[level + 1].x, L.x);
+    dev_smooth(c, level, d.smoother, MGMC_BACKWARD, d.omega, d.npostsmooth, true, L.f, L.x);
+  }
+}
+
+void mg_solve_level(mgmc_ctx *c, int level) {  // multigrid_preconditioner.cc:74-101
+  const mgmc_desc &d = c->d;
+  DevLevel &L = c->lv[level];
+  if (level == d.nlevel - 1) {
+    dev_coarse(c, false, L.f, L.x);  // writes every interior entry; ghost lines stay zero
+    return;
+  }
+  dev_zero(c, level, L.x);
+  const int cycle_ = (level > 0) ? d.cycle : 1;
+  for (int j = 0; j < cycle_; ++j) {
+    dev_smooth(c, level, d.smoother, MGMC_FORWARD, d.omega, d.npresmooth, false, L.f, L.x);
+    dev_residual_restrict(c, level, L.f, L.x, c->lv[level + 1].f);
+    mg_solve_level(c, level + 1);
+    dev_prolongate_add(c, level, d.coarse_scaling, c->lv[level + 1].x, L.x);
+    dev_smooth(c, level, d.smoother, MGMC_BACKWARD, d.omega, d.npostsmooth, false, L.f, L.x);
+  }
+}
+
+void emit_mgmc_cycle(mgmc_ctx *c) {
+  std::fill(c->sweep_counter.begin(), c->sweep_counter.end(), 0u);
+  mgmc_sample_level(c, 0);
+}
+
+void emit_end_of_cycle(mgmc_ctx *c) {
+  const DevLevel &L = c->lv[0];
+  c->launch("end_of_cycle", 0, [&] {
+    end_of_cycle_kernel<<<1, 256, 0, c->stream>>>(c->qoi_nnz, c->d_qsite, c->d_qval, L.x, L.g.stride, c->d.nchains, c->d_series, c->series_cap, c->d_sample,
+                                                 c->d_pos);
+  });
+  c->h_sample++;
+}
+
+void set_sample_index(mgmc_ctx *c, uint32_t s) {
+  c->h_sample = s;
+  CUDA_CHECK(cudaMemcpyAsync(c->d_sample, &c->h_sample, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  c->sync();
+}
+
+void drop_graph(mgmc_ctx *c) {
+  if (c->graph) {
+    cudaGraphExecDestroy(c->graph);
+    c->graph = nullptr;
+  }
+}
+
+void ensure_series(mgmc_ctx *c, long long n) {
+  if (n > c->series_cap) {
+    drop_graph(c);
+    c->d_series = c->dalloc<double>((size_t)n);
+    c->series_cap = n;
+  }
+}
+
+void run_cycles(mgmc_ctx *c, int64_t nsamples) {
+  const unsigned long long zero = 0ull;
+  CUDA_CHECK(cudaMemcpyAsync(c->d_pos, &zero, sizeof(zero), cudaMemcpyHostToDevice, c->stream));
+  if (c->use_graph && !c->prof_on) {
+    if (!c->graph) {
+      // make sure lazily built low-rank data exists before capture (uploads are not capturable)
+      if (c->d.m_lowrank > 0)
+        for (int l = 0; l < c->d.nlevel; ++l) get_lowrank(c, l, c->d.omega);
+      c->sync();
+      const int64_t count0 = c->launch_count;
+      const uint32_t sample0 = c->h_sample;
+      cudaGraph_t g = nullptr;
+      CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        emit_mgmc_cycle(c);
+        emit_end_of_cycle(c);
+      } catch (...) {
+        cudaStreamEndCapture(c->stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      CUDA_CHECK(cudaStreamEndCapture(c->stream, &g));
+      CUDA_CHECK(cudaGraphInstantiate(&c->graph, g, 0));
+      CUDA_CHECK(cudaGraphDestroy(g));
+      c->launches_per_cycle = c->launch_count - count0;
+      c->launch_count = count0;  // capture itself launched nothing
+      c->h_sample = sample0;
+    }
+  }
+  for (int64_t k = 0; k < nsamples; ++k) {
+    if (c->graph && !c->prof_on) {
+      CUDA_CHECK(cudaGraphLaunch(c->graph, c->stream));
+      c->launch_count += c->launches_per_cycle;
+      c->h_sample++;
+    } else {
+      const int64_t before = c->launch_count;
+      emit_mgmc_cycle(c);
+      emit_end_of_cycle(c);
+      c->launches_per_cycle = c->launch_count - before;
+    }
+  }
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+#define API_BEGIN try {
+#define API_END                                   \
+  }                                               \
+  catch (const MgmcError &e) {                    \
+    g_last_error = e.msg;                         \
+    return e.code;                                \
+  }                                               \
+  catch (const std::exception &e) {               \
+    g_last_error = e.what();                      \
+    return MGMC_ERR_INVALID;                      \
+  }                                               \
+  return MGMC_OK;
+
+static void check_level(const mgmc_ctx *c, int level, bool need_coarser = false) {
+  if (!c) fail(MGMC_ERR_INVALID, "null context");
+  if (level < 0 || level >= c->d.nlevel - (need_coarser ? 1 : 0)) fail(MGMC_ERR_INVALID, "level out of range");
+}
+
+extern "C" {
+
+int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
+  mgmc_ctx *c = nullptr;
+  try {
+    if (!desc || !out) fail(MGMC_ERR_INVALID, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) fail(MGMC_ERR_CUDA, "no CUDA device available: the MGMC path has no CPU fallback");
+    if (desc->device < 0 || desc->device >= ndev) fail(MGMC_ERR_INVALID, "invalid device ordinal");
+    if (desc->nchains < 1) fail(MGMC_ERR_INVALID, "nchains must be >= 1");
+    if (desc->m_lowrank < 0 || desc->m_lowrank > 1024) fail(MGMC_ERR_UNSUPPORTED, "m_lowrank must be in [0, 1024]");
+    if (desc->smoother != MGMC_SMOOTHER_SOR && desc->smoother != MGMC_SMOOTHER_SSOR) fail(MGMC_ERR_INVALID, "invalid smoother");
+    if (desc->coarse_solver != MGMC_COARSE_SSOR && desc->coarse_solver != MGMC_COARSE_CHOLESKY) fail(MGMC_ERR_INVALID, "invalid coarse solver");
+    std::vector<HostLevel> H = build_host_levels(*desc);
+    for (const HostLevel &h : H)
+      if (h.st.radius > 1 || !h.st.uniform) fail(MGMC_ERR_UNSUPPORTED, "squared_shiftedlaplace_fd (13/21-point stencils) is not on the device path yet");
+    const HostLevel &hc = H.back();
+    if (hc.ndof() > 4096) fail(MGMC_ERR_UNSUPPORTED, "coarsest level has more than 4096 unknowns: increase nlevel (dense coarse factor)");
+    c = new mgmc_ctx();
+    c->d = *desc;
+    c->d.B_rows = nullptr;
+    c->d.B_cols = nullptr;
+    c->d.B_vals = nullptr;
+    c->d.Sigma = nullptr;
+    c->Sigma.assign(desc->Sigma, desc->Sigma + desc->m_lowrank);
+    for (double s : c->Sigma)
+      if (!(s > 0.0)) fail(MGMC_ERR_INVALID, "Sigma entries must be positive");
+    c->device = desc->device;
+    CUDA_CHECK(cudaSetDevice(c->device));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->use_graph = (std::getenv("MGMC_NO_GRAPH") == nullptr);
+    c->sweep_counter.assign(desc->nlevel, 0u);
+    c->lv.resize(desc->nlevel);
+    for (int l = 0; l < desc->nlevel; ++l) {
+      DevLevel &L = c->lv[l];
+      L.h = H[l];
+      L.g.nx = L.h.nx;
+      L.g.ny = L.h.ny;
+      L.g.pitch = ((GX + L.h.nx + 1 + 2 + 15) / 16) * 16;
+      const size_t rows = (size_t)L.h.ny + 1 + 2 * GY;
+      L.g.stride = (long long)rows * L.g.pitch;
+      const size_t total = (size_t)L.g.stride * desc->nchains;
+      const size_t origin = (size_t)GY * L.g.pitch + GX;
+      L.x = c->dalloc<double>(total) + origin;
+      L.f = c->dalloc<double>(total) + origin;
+      L.r = c->dalloc<double>(total) + origin;
+      L.coef = to_coef9(L.h.st);
+      L.nine = (L.h.st.ncolours == 4);
+      if (desc->m_lowrank > 0) L.B = upload_sparse(c, L.h.B, desc->m_lowrank, L.g.pitch);
+    }
+    if (desc->m_lowrank > 0) {
+      std::vector<double> si(desc->m_lowrank), sis(desc->m_lowrank);
+      for (int k = 0; k < desc->m_lowrank; ++k) {
+        si[k] = 1.0 / c->Sigma[k];
+        sis[k] = std::sqrt(1.0 / c->Sigma[k]);
+      }
+      c->d_sigma_inv = c->dupload(si);
+      c->d_sigma_inv_sqrt = c->dupload(sis);
+    }
+    {
+      CoarseFactor cf = coarse_factor(hc, c->Sigma);
+      c->Nc = cf.N;
+      c->Ncp = cf.Np;
+      c->dL = c->dupload(cf.L);
+      c->dDinv = c->dupload(cf.Dinv);
+      const size_t sh = (size_t)(cf.Np + 32) * sizeof(double);
+      if (sh > 48 * 1024) {
+        CUDA_CHECK(cudaFuncSetAttribute(coarse_cholesky_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        CUDA_CHECK(cudaFuncSetAttribute(coarse_cholesky_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+      }
+    }
+    c->d_sample = c->dalloc<uint32_t>(1);
+    c->d_pos = c->dalloc<unsigned long long>(1);
+    c->sync();
+    *out = c;
+    return MGMC_OK;
+  } catch (const MgmcError &e) {
+    g_last_error = e.msg;
+    if (c) mgmc_destroy(c);
+    return e.code;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    if (c) mgmc_destroy(c);
+    return MGMC_ERR_INVALID;
+  }
+}
+
+void mgmc_destroy(mgmc_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->graph) cudaGraphExecDestroy(c->graph);
+  for (void *p : c->allocs) cudaFree(p);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int mgmc_level_info(const mgmc_ctx *c, int level, int *nx, int *ny, int64_t *ndof, int *ncolours) {
+  API_BEGIN
+  check_level(c, level);
+  const HostLevel &h = c->lv[level].h;
+  if (nx) *nx = h.nx;
+  if (ny) *ny = h.ny;
+  if (ndof) *ndof = h.ndof();
+  if (ncolours) *ncolours = h.st.ncolours;
+  API_END
+}
+
+int mgmc_get_stencil(const mgmc_ctx *c, int level, double *out225) {
+  API_BEGIN
+  check_level(c, level);
+  std::memcpy(out225, c->lv[level].h.st.a, sizeof(double) * 225);
+  API_END
+}
+
+/* host-only twin of mgmc_get_stencil: runs the setup algebra without a CUDA device (used by the
+ * CPU test-suite to check the Galerkin stencils against the oracle's sparse triple product) */
+int mgmc_host_stencil(const mgmc_desc *desc, int level, double *out225, int *ncolours) {
+  API_BEGIN
+  std::vector<HostLevel> H = build_host_levels(*desc);
+  if (level < 0 || level >= (int)H.size()) fail(MGMC_ERR_INVALID, "level out of range");
+  std::memcpy(out225, H[level].st.a, sizeof(double) * 225);
+  if (ncolours) *ncolours = H[level].st.ncolours;
+  API_END
+}
+
+int mgmc_op_apply(mgmc_ctx *c, int level, const double *x, double *y) {
+  API_BEGIN
+  check_level(c, level);
+  DevLevel &L = c->lv[level];
+  upload_vec(c, level, L.x, x);
+  dev_apply(c, level, L.x, L.r);
+  download_vec(c, level, L.r, y);
+  c->sync();
+  API_END
+}
+
+int mgmc_restrict(mgmc_ctx *c, int level, const double *x_fine, double *x_coarse) {
+  API_BEGIN
+  check_level(c, level, true);
+  upload_vec(c, level, c->lv[level].r, x_fine);
+  dev_restrict_plain(c, level, c->lv[level].r, c->lv[level + 1].f);
+  download_vec(c, level + 1, c->lv[level + 1].f, x_coarse);
+  c->sync();
+  API_END
+}
+
+int mgmc_prolongate_add(mgmc_ctx *c, int level, double alpha, const double *x_coarse, double *x_fine) {
+  API_BEGIN
+  check_level(c, level, true);
+  upload_vec(c, level, c->lv[level].x, x_fine);
+  upload_vec(c, level + 1, c->lv[level + 1].x, x_coarse);
+  dev_prolongate_add(c, level, alpha, c->lv[level + 1].x, c->lv[level].x);
+  download_vec(c, level, c->lv[level].x, x_fine);
+  c->sync();
+  API_END
+}
+
+int mgmc_residual_restrict(mgmc_ctx *c, int level, const double *f, const double *x, double *f_coarse) {
+  API_BEGIN
+  check_level(c, level, true);
+  upload_vec(c, level, c->lv[level].f, f);
+  upload_vec(c, level, c->lv[level].x, x);
+  dev_residual_restrict(c, level, c->lv[level].f, c->lv[level].x, c->lv[level + 1].f);
+  download_vec(c, level + 1, c->lv[level + 1].f, f_coarse);
+  c->sync();
+  API_END
+}
+
+static void check_smoother_args(int kind, int direction, double omega, int nsmooth) {
+  if (kind != MGMC_SMOOTHER_SOR && kind != MGMC_SMOOTHER_SSOR) fail(MGMC_ERR_INVALID, "invalid smoother kind");
+  if (direction != MGMC_FORWARD && direction != MGMC_BACKWARD) fail(MGMC_ERR_INVALID, "invalid direction");
+  if (!(omega > 0.0 && omega < 2.0)) fail(MGMC_ERR_INVALID, "omega must be in (0,2)");
+  if (nsmooth < 0) fail(MGMC_ERR_INVALID, "nsmooth must be >= 0");
+}
+
+int mgmc_smoother_apply(mgmc_ctx *c, int level, int kind, int direction, double omega, int nsmooth, const double *b, double *x) {
+  API_BEGIN
+  check_level(c, level);
+  check_smoother_args(kind, direction, omega, nsmooth);
+  DevLevel &L = c->lv[level];
+  upload_vec(c, level, L.f, b);
+  upload_vec(c, level, L.x, x);
+  dev_smooth(c, level, kind, direction, omega, nsmooth, false, L.f, L.x);
+  download_vec(c, level, L.x, x);
+  c->sync();
+  API_END
+}
+
+int mgmc_sampler_apply(mgmc_ctx *c, int level, int kind, int direction, double omega, int nsmooth, const double *f, double *x) {
+  API_BEGIN
+  check_level(c, level);
+  check_smoother_args(kind, direction, omega, nsmooth);
+  DevLevel &L = c->lv[level];
+  upload_vec(c, level, L.f, f);
+  upload_vec(c, level, L.x, x);
+  dev_smooth(c, level, kind, direction, omega, nsmooth, true, L.f, L.x);
+  download_vec(c, level, L.x, x);
+  c->sync();
+  API_END
+}
+
+int mgmc_coarse_solve(mgmc_ctx *c, const double *b, double *x) {
+  API_BEGIN
+  check_level(c, 0);
+  const int lc = c->d.nlevel - 1;
+  upload_vec(c, lc, c->lv[lc].f, b);
+  dev_coarse(c, false, c->lv[lc].f, c->lv[lc].x);
+  download_vec(c, lc, c->lv[lc].x, x);
+  c->sync();
+  API_END
+}
+
+int mgmc_coarse_sample(mgmc_ctx *c, const double *f, double *x) {
+  API_BEGIN
+  check_level(c, 0);
+  const int lc = c->d.nlevel - 1;
+  upload_vec(c, lc, c->lv[lc].f, f);
+  dev_coarse(c, true, c->lv[lc].f, c->lv[lc].x);
+  download_vec(c, lc, c->lv[lc].x, x);
+  c->sync();
+  API_END
+}
+
+int mgmc_sampler_mgmc_apply(mgmc_ctx *c, const double *f, double *x) {
+  API_BEGIN
+  check_level(c, 0);
+  if (f) upload_vec(c, 0, c->lv[0].f, f);  // f == NULL: right-hand side fixed earlier (Sampler::fix_rhs, sampler.hh:56)
+  upload_vec(c, 0, c->lv[0].x, x);
+  emit_mgmc_cycle(c);
+  download_vec(c, 0, c->lv[0].x, x);
+  set_sample_index(c, c->h_sample + 1);
+  API_END
+}
+
+int mgmc_mgprec_apply(mgmc_ctx *c, const double *b, double *x) {
+  API_BEGIN
+  check_level(c, 0);
+  upload_vec(c, 0, c->lv[0].f, b);
+  mg_solve_level(c, 0);
+  download_vec(c, 0, c->lv[0].x, x);
+  c->sync();
+  API_END
+}
+
+int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double atol, int maxiter, double *history, int *nhist, int *niter,
+                    int *converged) {
+  API_BEGIN
+  check_level(c, 0);
+  if (c->d.nchains != 1) fail(MGMC_ERR_UNSUPPORTED, "mgmc_loop_solve works on a single right-hand side (nchains = 1)");
+  DevLevel &L = c->lv[0];
+  const size_t total = (size_t)L.g.stride;
+  const size_t origin = (size_t)GY * L.g.pitch + GX;
+  if (!c->sol_x) {
+    c->sol_x = c->dalloc<double>(total) + origin;
+    c->sol_b = c->dalloc<double>(total) + origin;
+    dim3 g = grid_sites(L.g, 1);
+    c->npartial = (int)(g.x * g.y);
+    c->d_partial = c->dalloc<double>(c->npartial);
+    c->d_norm = c->dalloc<double>(1);
+  }
+  upload_vec(c, 0, c->sol_b, b);
+  c->launch("zero", 0, [&] { axpy_kernel<1><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, c->sol_x, nullptr); });
+  double r0 = 0.0;
+  const size_t n = (size_t)L.h.ndof();
+  for (size_t k = 0; k < n; ++k) r0 += b[k] * b[k];
+  r0 = std::sqrt(r0);
+  bool conv = false;
+  int it = maxiter, nh = 0;
+  for (int k = 0; k < maxiter; ++k) {
+    // r = A x - b (into f_ell[0], the preconditioner's input) and ||r||
+    c->launch("residual_norm", 0, [&] {
+      if (L.nine) residual_norm_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
+      else residual_norm_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
+    });
+    if (c->d.m_lowrank > 0) {
+      // low-rank part of A x is added to r, then the norm is recomputed from r
+      c->launch("lowrank_apply", 0, [&] {
+        lowrank_apply_kernel<<<1, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, L.B.rows, c->d_sigma_inv, L.g.stride, c->sol_x, L.f);
+      });
+      c->launch("norm", 0, [&] {
+        residual_norm_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, Coef9{0, 0, 0, 0, 0, 0, 0, 0, 0}, c->sol_x, L.f, L.r, c->d_partial);
+      });
+    }
+    c->launch("reduce_sum", 0, [&] { reduce_sum_kernel<<<1, 1024, 0, c->stream>>>(c->d_partial, c->npartial, c->d_norm); });
+    double nrm2 = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(&nrm2, c->d_norm, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    const double r_nrm = std::sqrt(nrm2);
+    if (history) history[nh] = r_nrm;
+    nh++;
+    if ((r_nrm / r0 < rtol) && (r_nrm < atol)) {
+      it = k;
+      conv = true;
+      break;
+    }
+    mg_solve_level(c, 0);  // Pr = x_ell[0]
+    c->launch("axpy", 0, [&] { axpy_kernel<0><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, c->sol_x, L.x); });
+  }
+  download_vec(c, 0, c->sol_x, x);
+  c->sync();
+  if (nhist) *nhist = nh;
+  if (niter) *niter = it;
+  if (converged) *converged = conv ? 1 : 0;
+  API_END
+}
+
+int mgmc_set_philox_position(mgmc_ctx *c, uint32_t sample, uint32_t sweep_counter) {
+  API_BEGIN
+  check_level(c, 0);
+  std::fill(c->sweep_counter.begin(), c->sweep_counter.end(), sweep_counter);
+  set_sample_index(c, sample);
+  API_END
+}
+
+int mgmc_set_rhs(mgmc_ctx *c, const double *f) {
+  API_BEGIN
+  check_level(c, 0);
+  upload_vec(c, 0, c->lv[0].f, f);
+  c->sync();
+  API_END
+}
+int mgmc_set_state(mgmc_ctx *c, const double *x) {
+  API_BEGIN
+  check_level(c, 0);
+  upload_vec(c, 0, c->lv[0].x, x);
+  c->sync();
+  API_END
+}
+int mgmc_get_state(mgmc_ctx *c, double *x) {
+  API_BEGIN
+  check_level(c, 0);
+  download_vec(c, 0, c->lv[0].x, x);
+  c->sync();
+  API_END
+}
+
+int mgmc_set_qoi(mgmc_ctx *c, int64_t nnz, const int64_t *idx, const double *val) {
+  API_BEGIN
+  check_level(c, 0);
+  const DevLevel &L = c->lv[0];
+  const int w = L.g.nx - 1;
+  std::vector<long long> site(nnz);
+  std::vector<double> v(val, val + nnz);
+  for (int64_t e = 0; e < nnz; ++e) {
+    if (idx[e] < 0 || idx[e] >= L.h.ndof()) fail(MGMC_ERR_INVALID, "QoI index out of range");
+    site[e] = (long long)(idx[e] / w + 1) * L.g.pitch + (idx[e] % w + 1);
+  }
+  drop_graph(c);
+  c->d_qsite = c->dupload(site);
+  c->d_qval = c->dupload(v);
+  c->qoi_nnz = (int)nnz;
+  API_END
+}
+
+int mgmc_sample(mgmc_ctx *c, int64_t nsamples, double *qoi_series) {
+  API_BEGIN
+  check_level(c, 0);
+  if (nsamples < 0) fail(MGMC_ERR_INVALID, "nsamples must be >= 0");
+  if (qoi_series) ensure_series(c, nsamples * c->d.nchains);
+  run_cycles(c, nsamples);
+  if (qoi_series && c->qoi_nnz > 0)
+    CUDA_CHECK(cudaMemcpyAsync(qoi_series, c->d_series, sizeof(double) * nsamples * c->d.nchains, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  API_END
+}
+
+int mgmc_sample_timed(mgmc_ctx *c, int64_t nsamples, double *qoi_series, double *elapsed_ms) {
+  API_BEGIN
+  check_level(c, 0);
+  if (nsamples < 0) fail(MGMC_ERR_INVALID, "nsamples must be >= 0");
+  if (qoi_series) ensure_series(c, nsamples * c->d.nchains);
+  if (c->use_graph && !c->graph) run_cycles(c, 0);  // instantiate the graph outside the timed region
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  c->sync();
+  CUDA_CHECK(cudaEventRecord(e0, c->stream));
+  run_cycles(c, nsamples);
+  CUDA_CHECK(cudaEventRecord(e1, c->stream));
+  CUDA_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (elapsed_ms) *elapsed_ms = ms;
+  if (qoi_series && c->qoi_nnz > 0)
+    CUDA_CHECK(cudaMemcpyAsync(qoi_series, c->d_series, sizeof(double) * nsamples * c->d.nchains, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  API_END
+}
+
+int mgmc_sample_moments(mgmc_ctx *c, int64_t nsamples, double *mean_field, double *second_moment_field) {
+  API_BEGIN
+  check_level(c, 0);
+  DevLevel &L = c->lv[0];
+  const size_t origin = (size_t)GY * L.g.pitch + GX;
+  if (!c->d_mean) {
+    c->d_mean = c->dalloc<double>((size_t)L.g.stride) + origin;
+    c->d_second = c->dalloc<double>((size_t)L.g.stride) + origin;
+  }
+  CUDA_CHECK(cudaMemsetAsync(c->d_mean - origin, 0, sizeof(double) * L.g.stride, c->stream));
+  CUDA_CHECK(cudaMemsetAsync(c->d_second - origin, 0, sizeof(double) * L.g.stride, c->stream));
+  for (int64_t k = 0; k < nsamples; ++k) {
+    run_cycles(c, 1);
+    c->launch("moments", 0, [&] { moments_kernel<<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.x, c->d_mean, c->d_second, 1.0 / (k + 1.0)); });
+  }
+  {
+    const size_t w = L.g.nx - 1, h = L.g.ny - 1;
+    CUDA_CHECK(cudaMemcpy2DAsync(mean_field, w * sizeof(double), c->d_mean + L.g.pitch + 1, L.g.pitch * sizeof(double), w * sizeof(double), h,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpy2DAsync(second_moment_field, w * sizeof(double), c->d_second + L.g.pitch + 1, L.g.pitch * sizeof(double), w * sizeof(double), h,
+                                 cudaMemcpyDeviceToHost, c->stream));
+  }
+  c->sync();
+  API_END
+}
+
+int64_t mgmc_launch_count(const mgmc_ctx *c) { return c ? c->launch_count : 0; }
+
+int mgmc_profile_cycle(mgmc_ctx *c, int nsamples, int nslots_max, char *names, double *ms_total, int64_t *launches, int *nslots) {
+  API_BEGIN
+  check_level(c, 0);
+  c->sync();
+  c->prof_on = true;
+  c->prof_events.clear();
+  try {
+    run_cycles(c, nsamples);
+    c->sync();
+  } catch (...) {
+    c->prof_on = false;
+    throw;
+  }
+  c->prof_on = false;
+  std::vector<ProfSlot> slots;
+  std::map<std::string, int> index;
+  for (auto &ev : c->prof_events) {
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ev.second.first, ev.second.second));
+    cudaEventDestroy(ev.second.first);
+    cudaEventDestroy(ev.second.second);
+    auto it = index.find(ev.first);
+    if (it == index.end()) {
+      it = index.emplace(ev.first, (int)slots.size()).first;
+      slots.push_back(ProfSlot{ev.first, 0.0, 0});
+    }
+    slots[it->second].ms += ms;
+    slots[it->second].launches++;
+  }
+  c->prof_events.clear();
+  const int n = std::min<int>((int)slots.size(), nslots_max);
+  for (int k = 0; k < n; ++k) {
+    std::snprintf(names + (size_t)k * 64, 64, "%s", slots[k].name.c_str());
+    ms_total[k] = slots[k].ms;
+    launches[k] = slots[k].launches;
+  }
+  if (nslots) *nslots = n;
+  API_END
+}
+
+int mgmc_cycle_model(const mgmc_ctx *c, double *bytes, double *site_updates) {
+  API_BEGIN
+  check_level(c, 0);
+  // 24 B/site per sweep, 18 B residual+restrict, 18 B prolongate_add, 2 B coarse
+  // zeroing; per level visit.  Level l > 0 is visited cycle^l times.
+  const mgmc_desc &d = c->d;
+  const int per_smooth = (d.smoother == MGMC_SMOOTHER_SSOR) ? 2 : 1;
+  double B = 0.0, U = 0.0, visits = 1.0;  // visits = number of passes through the loop body of a level
+  for (int l = 0; l < d.nlevel - 1; ++l) {
+    if (l > 0) visits *= d.cycle;  // multigridmc_sampler.cc:112
+    const double n = (double)c->lv[l].h.ndof();
+    const double sweeps = per_smooth * (d.npresmooth + d.npostsmooth);
+    B += visits * n * (24.0 * sweeps + 38.0);
+    U += visits * n * sweeps;
+  }
+  const double nc = (double)c->lv[d.nlevel - 1].h.ndof();
+  if (d.coarse_solver == MGMC_COARSE_CHOLESKY) {
+    B += visits * 8.0 * nc * nc;
+    U += visits * nc;
+  } else {
+    B += visits * nc * 24.0 * 2 * d.ncoarsesmooth;
+    U += visits * nc * 2 * d.ncoarsesmooth;
+  }
+  if (bytes) *bytes = B;
+  if (site_updates) *site_updates = U;
+  API_END
+}
+
+}  // extern "C"

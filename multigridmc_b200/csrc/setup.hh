@@ -1,0 +1,354 @@
+// Host-side setup algebra of the B200 MGMC path (no CUDA in this header).
+//
+// The reference builds every coarse operator as an Eigen sparse triple product R A R^T
+// (LinearOperator::coarsen, linear_operator/linear_operator.cc:10-23) and keeps dense n x m
+// matrices for the low-rank smoother correction (SORSmoother ctor, smoother/sor_smoother.cc:17-38).
+// Here the operators stay matrix-free: on a structured lattice with constant kappa the Galerkin
+// product of a stencil with the full-weighting transfer {1/2,1,1/2}^(x)2 is again a stencil, exactly
+//   A_c(I, I+D) = sum_{p,q in {-1,0,1}^2} w(p) w(q) a_{s = 2I+p}(2D + q - p),
+// constant in the interior and (for the squared operator only) different on the first / last
+// interior line.  A level therefore stores 9 position classes x 25 coefficients.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace mgmc {
+
+// position class along one axis: 0 = first interior line, 2 = last interior line, 1 = in between
+inline int pos_class(int i, int n) { return i == 1 ? 0 : (i == n - 1 ? 2 : 1); }
+
+struct StencilSet {
+  double a[9][25];  // a[cx + 3 cy][(dj + 2) * 5 + (di + 2)]
+  int radius = 1;
+  int ncolours = 2;
+  bool uniform = true;  // all classes identical
+  double at(int cls, int di, int dj) const { return a[cls][(dj + 2) * 5 + (di + 2)]; }
+};
+
+inline void classify(StencilSet &s) {
+  s.radius = 0;
+  bool corners = false;
+  s.uniform = true;
+  for (int c = 0; c < 9; ++c) {
+    for (int dj = -2; dj <= 2; ++dj)
+      for (int di = -2; di <= 2; ++di) {
+        const double v = s.at(c, di, dj);
+        if (v != 0.0) {
+          s.radius = std::max(s.radius, std::max(std::abs(di), std::abs(dj)));
+          if (di != 0 && dj != 0) corners = true;
+        }
+      }
+    if (std::memcmp(s.a[c], s.a[4], sizeof(s.a[c])) != 0) s.uniform = false;
+  }
+  s.ncolours = (s.radius >= 2) ? 9 : (corners ? 4 : 2);
+}
+
+// fine-level stencils
+//  pde 0: ShiftedLaplaceFDOperator (shiftedlaplace_fd_operator.cc:33-56): h^d (kappa^2 + sum 2/h_d^2), -h^d/h_d^2
+//  pde 1: SquaredShiftedLaplaceFDOperator (squared_shiftedlaplace_fd_operator.cc:40-93)
+inline StencilSet fine_stencil(int pde, int nx, int ny, double Lambda) {
+  StencilSet s;
+  std::memset(s.a, 0, sizeof(s.a));
+  const double hx = 1.0 / double(nx), hy = 1.0 / double(ny);
+  const double hinv2x = 1.0 / (hx * hx), hinv2y = 1.0 / (hy * hy);
+  const double vol = hx * hy;
+  const double kappa_sq = 1.0 / std::pow(Lambda, 2);
+  for (int cy = 0; cy < 3; ++cy)
+    for (int cx = 0; cx < 3; ++cx) {
+      double *a = s.a[cx + 3 * cy];
+      auto A = [&](int di, int dj) -> double & { return a[(dj + 2) * 5 + (di + 2)]; };
+      if (pde == 0) {
+        double diagonal = vol * kappa_sq;
+        diagonal += 2. * vol * hinv2x;
+        diagonal += 2. * vol * hinv2y;
+        A(0, 0) = diagonal;
+        A(-1, 0) = A(+1, 0) = -vol * hinv2x;
+        A(0, -1) = A(0, +1) = -vol * hinv2y;
+      } else {
+        const double lap00 = -2 * (hinv2x + hinv2y), lap10 = hinv2x, lap01 = hinv2y;
+        double ss[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        ss[0][0] = 6 * (hinv2x * hinv2x + hinv2y * hinv2y) + 8 * hinv2x * hinv2y;
+        ss[1][0] = -4 * hinv2x * (hinv2x + hinv2y);
+        ss[0][1] = -4 * hinv2y * (hinv2x + hinv2y);
+        ss[2][0] = hinv2x * hinv2x;
+        ss[0][2] = hinv2y * hinv2y;
+        ss[1][1] = 2 * hinv2x * hinv2y;
+        double diagonal = (kappa_sq * kappa_sq - 2. * kappa_sq * lap00 + ss[0][0]) * vol;
+        for (int j = -2; j <= 2; ++j)
+          for (int k = -2; k <= 2; ++k) {
+            if ((std::abs(j) + std::abs(k) > 2) || (j == 0 && k == 0)) continue;
+            double e = ss[std::abs(j)][std::abs(k)];
+            if (std::abs(j) + std::abs(k) == 1) e += -2. * kappa_sq * ((j != 0) ? lap10 : lap01);
+            A(j, k) = e * vol;
+          }
+        // missing +-1 neighbour => add the +-2 coefficient to the diagonal (:83-91)
+        if (cx == 0) diagonal += ss[2][0] * vol;
+        if (cx == 2 || nx == 2) diagonal += ss[2][0] * vol;
+        if (cy == 0) diagonal += ss[0][2] * vol;
+        if (cy == 2 || ny == 2) diagonal += ss[0][2] * vol;
+        A(0, 0) = diagonal;
+      }
+    }
+  classify(s);
+  return s;
+}
+
+// Galerkin coarsening of a stencil set (nxf, nyf = fine cells)
+inline StencilSet coarsen_stencil(const StencilSet &f, int nxf, int nyf) {
+  StencilSet c;
+  std::memset(c.a, 0, sizeof(c.a));
+  const int nxc = nxf / 2, nyc = nyf / 2;
+  const double w1[3] = {0.5, 1.0, 0.5};
+  for (int cy = 0; cy < 3; ++cy)
+    for (int cx = 0; cx < 3; ++cx) {
+      double *a = c.a[cx + 3 * cy];
+      for (int Dy = -2; Dy <= 2; ++Dy)
+        for (int Dx = -2; Dx <= 2; ++Dx) {
+          // representative coarse vertex of the class for THIS entry: all interior vertices share one
+          // stencil, so pick one whose target (I + Dx, J + Dy) lies inside the lattice
+          const int I = (cx == 0) ? 1 : (cx == 2 ? nxc - 1 : (Dx < 0 ? nxc - 2 : 2));
+          const int J = (cy == 0) ? 1 : (cy == 2 ? nyc - 1 : (Dy < 0 ? nyc - 2 : 2));
+          if (I < 1 || I > nxc - 1 || J < 1 || J > nyc - 1 || pos_class(I, nxc) != cx || pos_class(J, nyc) != cy) continue;
+          if (I + Dx < 1 || I + Dx > nxc - 1 || J + Dy < 1 || J + Dy > nyc - 1) continue;
+          double acc = 0.0;
+          for (int py = -1; py <= 1; ++py)
+            for (int px = -1; px <= 1; ++px) {
+              const int si = 2 * I + px, sj = 2 * J + py;
+              const int fc = pos_class(si, nxf) + 3 * pos_class(sj, nyf);
+              for (int qy = -1; qy <= 1; ++qy)
+                for (int qx = -1; qx <= 1; ++qx) {
+                  const int ox = 2 * Dx + qx - px, oy = 2 * Dy + qy - py;
+                  if (std::abs(ox) > 2 || std::abs(oy) > 2) continue;
+                  acc += w1[px + 1] * w1[py + 1] * w1[qx + 1] * w1[qy + 1] * f.at(fc, ox, oy);
+                }
+            }
+          a[(Dy + 2) * 5 + (Dx + 2)] = acc;
+        }
+    }
+  // classes without a representative (tiny lattices) copy the interior class / class 0
+  for (int k = 0; k < 9; ++k) {
+    bool zero = true;
+    for (int e = 0; e < 25; ++e) zero = zero && (c.a[k][e] == 0.0);
+    if (zero) std::memcpy(c.a[k], c.a[4][12] != 0.0 ? c.a[4] : c.a[0], sizeof(c.a[k]));
+  }
+  classify(c);
+  return c;
+}
+
+// one entry of the sparse n x m matrix B (or W): Euclidean vertex (i, j), column, value
+struct SEntry {
+  int i, j, col;
+  double val;
+};
+
+// B_c = R B (linear_operator.cc:19)
+inline std::vector<SEntry> coarsen_B(const std::vector<SEntry> &B, int nxf, int nyf) {
+  const int nxc = nxf / 2, nyc = nyf / 2;
+  std::map<std::pair<int, long long>, double> acc;  // (col, J * 2^20 + I)
+  for (const SEntry &e : B) {
+    for (int J = (e.j - 1 + 1) / 2; J <= (e.j + 1) / 2; ++J)
+      for (int I = (e.i - 1 + 1) / 2; I <= (e.i + 1) / 2; ++I) {
+        if (I < 1 || I > nxc - 1 || J < 1 || J > nyc - 1) continue;
+        const int di = std::abs(e.i - 2 * I), dj = std::abs(e.j - 2 * J);
+        if (di > 1 || dj > 1) continue;
+        acc[{e.col, (long long)J * (1ll << 20) + I}] += (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * e.val;
+      }
+  }
+  std::vector<SEntry> out;
+  for (auto &kv : acc) out.push_back({int(kv.first.second % (1ll << 20)), int(kv.first.second >> 20), kv.first.first, kv.second});
+  return out;
+}
+
+inline int site_colour(int nc, int i, int j) {
+  if (nc == 2) return (i + j) & 1;
+  if (nc == 4) return (i & 1) + 2 * (j & 1);
+  return (i % 3) + 3 * (j % 3);
+}
+
+struct HostLevel {
+  int nx = 0, ny = 0;
+  StencilSet st;
+  std::vector<SEntry> B;  // sorted by column
+  long long ndof() const { return (long long)(nx - 1) * (ny - 1); }
+};
+
+// general m x m inverse (Gauss-Jordan, partial pivoting); replaces Eigen's .inverse() (sor_smoother.cc:29,35)
+inline std::vector<double> invert_dense(std::vector<double> A, int n) {
+  std::vector<double> I((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) I[(size_t)i * n + i] = 1.0;
+  for (int c = 0; c < n; ++c) {
+    int p = c;
+    for (int r = c + 1; r < n; ++r)
+      if (std::fabs(A[(size_t)r * n + c]) > std::fabs(A[(size_t)p * n + c])) p = r;
+    if (A[(size_t)p * n + c] == 0.0) throw std::runtime_error("singular low-rank capacitance matrix");
+    if (p != c)
+      for (int k = 0; k < n; ++k) {
+        std::swap(A[(size_t)p * n + k], A[(size_t)c * n + k]);
+        std::swap(I[(size_t)p * n + k], I[(size_t)c * n + k]);
+      }
+    const double inv = 1.0 / A[(size_t)c * n + c];
+    for (int k = 0; k < n; ++k) {
+      A[(size_t)c * n + k] *= inv;
+      I[(size_t)c * n + k] *= inv;
+    }
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      const double f = A[(size_t)r * n + c];
+      if (f == 0.0) continue;
+      for (int k = 0; k < n; ++k) {
+        A[(size_t)r * n + k] -= f * A[(size_t)c * n + k];
+        I[(size_t)r * n + k] -= f * I[(size_t)c * n + k];
+      }
+    }
+  }
+  return I;
+}
+
+// Low-rank smoother data of one level and one sweep direction:
+//   W = M_0^{-1} B with M_0 = D/omega + (strictly earlier part of A_0 in the colour ordering),
+//   G = B^T W, K = (Sigma + G)^{-1}                                  (sor_smoother.cc:17-38)
+// W is computed column by column as one colour sweep from x = 0 on a window around supp(B_k):
+// in the colour ordering information travels at most (ncolours - 1) * radius sites per sweep.
+struct LowRankDir {
+  std::vector<SEntry> W;
+  std::vector<double> G, K;  // m x m row-major
+};
+
+inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &Sigma, double omega, bool forward) {
+  const int m = (int)Sigma.size();
+  LowRankDir out;
+  out.G.assign((size_t)m * m, 0.0);
+  const int nc = L.st.ncolours, reach = (nc - 1) * L.st.radius, rad = L.st.radius;
+  std::vector<std::vector<SEntry>> cols(m);
+  for (const SEntry &e : L.B) cols[e.col].push_back(e);
+  std::vector<std::map<long long, double>> Wmap(m);
+  for (int k = 0; k < m; ++k) {
+    if (cols[k].empty()) continue;
+    int ilo = 1 << 30, ihi = -1, jlo = 1 << 30, jhi = -1;
+    for (const SEntry &e : cols[k]) {
+      ilo = std::min(ilo, e.i);
+      ihi = std::max(ihi, e.i);
+      jlo = std::min(jlo, e.j);
+      jhi = std::max(jhi, e.j);
+    }
+    ilo = std::max(1, ilo - reach);
+    jlo = std::max(1, jlo - reach);
+    ihi = std::min(L.nx - 1, ihi + reach);
+    jhi = std::min(L.ny - 1, jhi + reach);
+    const int wx = ihi - ilo + 1, wy = jhi - jlo + 1;
+    std::vector<double> xw((size_t)wx * wy, 0.0), bw((size_t)wx * wy, 0.0);
+    for (const SEntry &e : cols[k]) bw[(size_t)(e.j - jlo) * wx + (e.i - ilo)] += e.val;
+    for (int cc = 0; cc < nc; ++cc) {
+      const int colour = forward ? cc : nc - 1 - cc;
+      for (int j = jlo; j <= jhi; ++j)
+        for (int i = ilo; i <= ihi; ++i) {
+          if (site_colour(nc, i, j) != colour) continue;
+          const int cls = pos_class(i, L.nx) + 3 * pos_class(j, L.ny);
+          double s = 0.0;
+          for (int dj = -rad; dj <= rad; ++dj)
+            for (int di = -rad; di <= rad; ++di) {
+              const int ii = i + di, jj = j + dj;
+              if (ii < ilo || ii > ihi || jj < jlo || jj > jhi) continue;
+              s += L.st.at(cls, di, dj) * xw[(size_t)(jj - jlo) * wx + (ii - ilo)];
+            }
+          double &xc = xw[(size_t)(j - jlo) * wx + (i - ilo)];
+          xc += omega * (bw[(size_t)(j - jlo) * wx + (i - ilo)] - s) / L.st.at(cls, 0, 0);
+        }
+    }
+    for (int j = jlo; j <= jhi; ++j)
+      for (int i = ilo; i <= ihi; ++i) {
+        const double v = xw[(size_t)(j - jlo) * wx + (i - ilo)];
+        if (v != 0.0) {
+          out.W.push_back({i, j, k, v});
+          Wmap[k][(long long)j * (1ll << 20) + i] = v;
+        }
+      }
+  }
+  std::vector<double> S((size_t)m * m, 0.0);
+  for (int a = 0; a < m; ++a)
+    for (int b = 0; b < m; ++b) {
+      double g = 0.0;
+      for (const SEntry &e : cols[a]) {
+        auto it = Wmap[b].find((long long)e.j * (1ll << 20) + e.i);
+        if (it != Wmap[b].end()) g += e.val * it->second;
+      }
+      out.G[(size_t)a * m + b] = g;
+      S[(size_t)a * m + b] = g + ((a == b) ? Sigma[a] : 0.0);
+    }
+  out.K = invert_dense(S, m);
+  return out;
+}
+
+// dense matrix of the coarsest level, A_0 + B Sigma^{-1} B^T (cholesky_sampler.cc:25-38), its lower
+// Cholesky factor padded with identity to Np = multiple of 32, and the inverses of the diagonal blocks
+struct CoarseFactor {
+  int N = 0, Np = 0;
+  std::vector<double> L;     // Np x Np row-major
+  std::vector<double> Dinv;  // (Np / 32) blocks of 32 x 32 row-major, lower triangular
+};
+
+inline CoarseFactor coarse_factor(const HostLevel &Lv, const std::vector<double> &Sigma) {
+  CoarseFactor cf;
+  const int w = Lv.nx - 1, h = Lv.ny - 1;
+  const int N = w * h, Np = ((N + 31) / 32) * 32;
+  cf.N = N;
+  cf.Np = Np;
+  std::vector<double> &A = cf.L;
+  A.assign((size_t)Np * Np, 0.0);
+  for (int j = 1; j <= h; ++j)
+    for (int i = 1; i <= w; ++i) {
+      const int row = (j - 1) * w + (i - 1);
+      const int cls = pos_class(i, Lv.nx) + 3 * pos_class(j, Lv.ny);
+      for (int dj = -2; dj <= 2; ++dj)
+        for (int di = -2; di <= 2; ++di) {
+          const int ii = i + di, jj = j + dj;
+          if (ii < 1 || ii > w || jj < 1 || jj > h) continue;
+          const double v = Lv.st.at(cls, di, dj);
+          if (v != 0.0) A[(size_t)row * Np + (jj - 1) * w + (ii - 1)] = v;
+        }
+    }
+  const int m = (int)Sigma.size();
+  std::vector<std::vector<SEntry>> cols(m);
+  for (const SEntry &e : Lv.B) cols[e.col].push_back(e);
+  for (int k = 0; k < m; ++k)
+    for (const SEntry &p : cols[k])
+      for (const SEntry &q : cols[k]) A[(size_t)((p.j - 1) * w + (p.i - 1)) * Np + (q.j - 1) * w + (q.i - 1)] += p.val * q.val / Sigma[k];
+  for (int r = N; r < Np; ++r) A[(size_t)r * Np + r] = 1.0;
+  // in-place lower Cholesky
+  for (int j = 0; j < Np; ++j) {
+    double d = A[(size_t)j * Np + j];
+    for (int k = 0; k < j; ++k) d -= A[(size_t)j * Np + k] * A[(size_t)j * Np + k];
+    if (!(d > 0.0)) throw std::runtime_error("coarse matrix is not positive definite");
+    d = std::sqrt(d);
+    A[(size_t)j * Np + j] = d;
+    for (int i = j + 1; i < Np; ++i) {
+      double s = A[(size_t)i * Np + j];
+      const double *ai = &A[(size_t)i * Np], *aj = &A[(size_t)j * Np];
+      for (int k = 0; k < j; ++k) s -= ai[k] * aj[k];
+      A[(size_t)i * Np + j] = s / d;
+    }
+    for (int k = j + 1; k < Np; ++k) A[(size_t)j * Np + k] = 0.0;
+  }
+  // inverses of the 32 x 32 diagonal blocks (lower triangular) by forward substitution
+  const int nb = Np / 32;
+  cf.Dinv.assign((size_t)nb * 1024, 0.0);
+  for (int b = 0; b < nb; ++b) {
+    double *D = &cf.Dinv[(size_t)b * 1024];
+    for (int c = 0; c < 32; ++c) {
+      for (int r = c; r < 32; ++r) {
+        double s = (r == c) ? 1.0 : 0.0;
+        for (int k = c; k < r; ++k) s -= A[(size_t)(32 * b + r) * Np + 32 * b + k] * D[k * 32 + c];
+        D[r * 32 + c] = s / A[(size_t)(32 * b + r) * Np + 32 * b + r];
+      }
+    }
+  }
+  return cf;
+}
+
+}  // namespace mgmc
