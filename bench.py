@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--n", type=int, default=4096)
@@ -128,7 +128,7 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -203,12 +203,12 @@ def run_b200(a):
     ctx.set_philox_position(0)
 
     # ---- device-resident throughput ("value"): inputs already in HBM, CUDA-graph replay ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()  # nvidia-smi needs a few 100 ms to come up: start it before the warm-up
     ctx.sample(a.warmup, series=False)
     launches0 = ctx.launch_count()
-    clocks = ClockSampler(local)
     barrier()
-    if rank == 0:
-        clocks.start()
     ms, series = ctx.sample_timed(a.steps, series=True)
     barrier()
     clk = clocks.stop() if rank == 0 else None
