@@ -1,0 +1,240 @@
+// Fused smoothing kernel: one CTA owns a tile of a level, stages the tile plus a halo of x and f in
+// shared memory once, runs a whole sequence of colour passes (any mix of forward / backward sweeps)
+// on it, and writes the tile back.  Optionally the prolongation of the coarse correction is fused in
+// front (x += alpha R^T x_c while loading) and the residual + restriction behind
+// (f_c = R (f - A_0 x), x_c = 0), so that a V(1,1) level visit of the prior operator is two kernels
+// that move x, f once each way instead of 2 x 4 colour passes + 3 transfer kernels:
+//   reference: SSORSampler::apply + LinearOperator::apply + IntergridOperator::restrict /
+//   prolongate_add (ssor_sampler.cc:9-16, multigridmc_sampler.cc:116-127).
+//
+// Correctness of the overlapped tiles: stage k of S may only update sites whose neighbours held
+// correct values after stage k-1, so the updated region shrinks by the stencil radius (1) per stage
+// from tile +- (S - 1 [+ extra for the residual]) down to the tile; halo sites are recomputed by the
+// neighbouring tiles with IDENTICAL results because the Gibbs noise is a pure function of
+// (seed, chain, sample, level, sweep, site) -- see philox.cuh.  Because tiles overlap the sweep is out
+// of place (x_in -> x_out, ping-pong).
+//
+// Geometry (all index arithmetic is compile-time): a region is always 128 columns = 32 aligned groups
+// of 4 columns wide (one warp lane per group -- the unit that shares a Philox call) and RY rows tall.
+// Shared memory holds row r as 4 planes of 32 doubles, plane k = columns 4p + k: for every neighbour
+// access consecutive lanes read consecutive doubles of one plane (bank-conflict free), and every
+// global access is a 128-bit load / store of an aligned column group.
+// Tiles are group-aligned in x (i_t0 = TX * bx, TX = 128 - HXL - HXR) and start on odd rows in y
+// (j_t0 = 1 + TY * by), which fixes the extra halo the fused residual needs: 2 columns left / 1 right,
+// 1 row below / 2 above.
+#pragma once
+#include "kernels.cuh"
+
+namespace mgmc {
+
+constexpr int kGX = 16;  // allocated doubles left of i = 0
+constexpr int kGY = 2;   // allocated rows below j = 0 / above j = ny
+constexpr int kFusedThreads = 512;
+constexpr int kFusedWarps = kFusedThreads / 32;
+
+struct Stage {
+  int colour;
+  uint32_t c1;  // (level << 24) | sweep counter of the sweep this colour pass belongs to
+};
+
+struct FusedP {
+  GridP g, gc;  // this level, next coarser level
+  Coef9 a;
+  const double *x_in;
+  double *x_out;
+  const double *f;
+  const double *xc_in;  // PROLONG: coarse correction
+  double alpha;
+  double *fc_out;       // RESTRICT: coarse right-hand side
+  double *xc_zero;      // RESTRICT: coarse iterate, set to zero (multigridmc_sampler.cc:122)
+  int nstages;
+  Stage st[8];
+  double omega, noise_scale;
+  NoiseP nz;
+  int HXL, TX, TY, RY, hl;  // region geometry (host-computed, identical for all tiles)
+};
+
+// element at column offset K (-1..4) of group p in a shared-memory row
+template <int K>
+__device__ __forceinline__ double &sat(double *row, int p) {
+  constexpr int plane = (K + 4) & 3;
+  constexpr int dp = (K < 0) ? -1 : ((K >= 4) ? 1 : 0);
+  return row[plane * 32 + p + dp];
+}
+
+// stencil sum  sum_j a_ij x_j  for the site at column offset K of group p
+template <bool NINE, int K>
+__device__ __forceinline__ double stencil_at(const Coef9 &a, double *row, int p) {
+  double s = a.c * sat<K>(row, p) + a.w * sat<K - 1>(row, p) + a.e * sat<K + 1>(row, p) + a.s * sat<K>(row - 128, p) + a.n * sat<K>(row + 128, p);
+  if (NINE)
+    s += a.sw * sat<K - 1>(row - 128, p) + a.se * sat<K + 1>(row - 128, p) + a.nw * sat<K - 1>(row + 128, p) + a.ne * sat<K + 1>(row + 128, p);
+  return s;
+}
+
+// update the two sites (offset Q and Q + 2) of one colour in group p of one row
+template <bool NINE, bool GIBBS, int Q>
+__device__ __forceinline__ void update_pair(const Coef9 &a, double *xrow, const double *frow, int p, bool v0, bool v1, double winv, double nscale, double z0,
+                                            double z1) {
+  if (v0) {
+    const double s = stencil_at<NINE, Q>(a, xrow, p);
+    double b = frow[Q * 32 + p];
+    if (GIBBS) b = fma(nscale, z0, b);
+    sat<Q>(xrow, p) += winv * (b - s);
+  }
+  if (v1) {
+    const double s = stencil_at<NINE, Q + 2>(a, xrow, p);
+    double b = frow[(Q + 2) * 32 + p];
+    if (GIBBS) b = fma(nscale, z1, b);
+    sat<Q + 2>(xrow, p) += winv * (b - s);
+  }
+}
+
+template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT>
+__global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {
+  extern __shared__ double sm[];
+  constexpr bool NINE = (NC == 4);
+  const int RY = P.RY, TX = P.TX, TY = P.TY;
+  double *xs = sm;
+  double *fs = sm + RY * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nx = P.g.nx, ny = P.g.ny, pitch = P.g.pitch;
+  const int i_t0 = TX * blockIdx.x, j_t0 = 1 + TY * blockIdx.y;
+  const int i_r0 = i_t0 - P.HXL, j_r0 = j_t0 - P.hl;
+  const long long cbase = (long long)blockIdx.z * P.g.stride;
+  const double *xg = P.x_in + cbase;
+  double *xo = P.x_out + cbase;
+  const double *fg = P.f + cbase;
+  const int gi0 = i_r0 + 4 * lane;  // first global column of this lane's group
+  const bool cols_alloc = (gi0 >= -kGX) && (gi0 + 3 < pitch - kGX);
+
+  // ---- stage the region: one warp per row, lane p loads its group of 4 columns (2 x 128 bit) ----
+  for (int r = warp; r < RY; r += kFusedWarps) {
+    const int gj = j_r0 + r;
+    double2 xa = make_double2(0.0, 0.0), xb = xa, fa = xa, fb = xa;
+    if (cols_alloc && gj >= -kGY && gj <= ny + kGY) {
+      const long long o = (long long)gj * pitch + gi0;
+      xa = *reinterpret_cast<const double2 *>(xg + o);
+      xb = *reinterpret_cast<const double2 *>(xg + o + 2);
+      fa = *reinterpret_cast<const double2 *>(fg + o);
+      fb = *reinterpret_cast<const double2 *>(fg + o + 2);
+      if (PROLONG) {
+        if (gj >= 1 && gj < ny && gi0 >= -3 && gi0 <= nx) {
+          // x += alpha R^T x_c in gather form: every fine vertex reads its (up to) 4 coarse parents
+          const double *xc = P.xc_in + (long long)blockIdx.z * P.gc.stride;
+          const double *r0 = xc + (long long)(gj >> 1) * P.gc.pitch, *r1 = xc + (long long)((gj + 1) >> 1) * P.gc.pitch;
+          const int I = gi0 >> 1;  // gi0 is a multiple of 4: coarse columns I, I+1, I+2 cover the group
+          const double q0 = 0.5 * (r0[I] + r1[I]), q1 = 0.5 * (r0[I + 1] + r1[I + 1]), q2 = 0.5 * (r0[I + 2] + r1[I + 2]);
+          const double al = P.alpha;
+          if (gi0 >= 1 && gi0 < nx) xa.x += al * q0;
+          if (gi0 + 1 >= 1 && gi0 + 1 < nx) xa.y += al * (0.5 * (q0 + q1));
+          if (gi0 + 2 >= 1 && gi0 + 2 < nx) xb.x += al * q1;
+          if (gi0 + 3 >= 1 && gi0 + 3 < nx) xb.y += al * (0.5 * (q1 + q2));
+        }
+      }
+    }
+    double *xr = xs + r * 128, *fr = fs + r * 128;
+    xr[lane] = xa.x;
+    xr[32 + lane] = xa.y;
+    xr[64 + lane] = xb.x;
+    xr[96 + lane] = xb.y;
+    fr[lane] = fa.x;
+    fr[32 + lane] = fa.y;
+    fr[64 + lane] = fb.x;
+    fr[96 + lane] = fb.y;
+  }
+  __syncthreads();
+
+  // ---- colour passes: one warp per row, lane = group ----
+  const double winv = P.omega / P.a.c;
+  const double nscale = P.noise_scale;
+  const int S = P.nstages;
+  constexpr int EXLX = RESTRICT ? 2 : 0, EXHX = RESTRICT ? 1 : 0, EXLY = RESTRICT ? 1 : 0, EXHY = RESTRICT ? 2 : 0;
+  const uint32_t pg = (uint32_t)((i_r0 >> 2) + lane);
+  for (int s = 0; s < S; ++s) {
+    const int colour = P.st[s].colour;
+    const uint32_t c1 = P.st[s].c1;
+    const int m = S - 1 - s;
+    const int ilo = max(1, i_t0 - m - EXLX), ihi = min(nx - 1, i_t0 + TX - 1 + m + EXHX);
+    int jlo = max(1, j_t0 - m - EXLY);
+    const int jhi = min(ny - 1, j_t0 + TY - 1 + m + EXHY);
+    int step = 1;
+    if (NC == 4) {
+      step = 2;
+      if ((jlo & 1) != (colour >> 1)) ++jlo;
+    }
+    for (int j = jlo + warp * step; j <= jhi; j += kFusedWarps * step) {
+      const int q = (NC == 2) ? ((colour ^ j) & 1) : (colour & 1);
+      const int i0 = gi0 + q;
+      const bool v0 = (i0 >= ilo) && (i0 <= ihi), v1 = (i0 + 2 >= ilo) && (i0 + 2 <= ihi);
+      if (!(v0 || v1)) continue;
+      double z0 = 0.0, z1 = 0.0;
+      if (GIBBS) normal_pair(P.nz.keys, (((uint32_t)j * P.nz.G + pg) << 1) | (uint32_t)q, c1, *P.nz.sample, P.nz.chain0 + blockIdx.z, z0, z1);
+      double *xr = xs + (j - j_r0) * 128;
+      const double *fr = fs + (j - j_r0) * 128;
+      if (q == 0) update_pair<NINE, GIBBS, 0>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
+      else update_pair<NINE, GIBBS, 1>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
+    }
+    __syncthreads();
+  }
+
+  // ---- write the tile to the output buffer (skipped by a pure residual + restrict launch) ----
+  if (PROLONG || S > 0) {
+    const bool mine = (gi0 >= i_t0) && (gi0 < i_t0 + TX) && (gi0 <= nx) && cols_alloc;
+    for (int rr = warp; rr < TY; rr += kFusedWarps) {
+      const int gj = j_t0 + rr;
+      if (mine && gj < ny) {
+        const double *xr = xs + (gj - j_r0) * 128;
+        const long long o = (long long)gj * pitch + gi0;
+        // boundary / pad columns inside the group hold the zeros they were loaded with
+        *reinterpret_cast<double2 *>(xo + o) = make_double2(xr[lane], xr[32 + lane]);
+        *reinterpret_cast<double2 *>(xo + o + 2) = make_double2(xr[64 + lane], xr[96 + lane]);
+      }
+    }
+  }
+
+  // ---- residual on [i_t0 - 1, i_t0 + TX - 1] x [j_t0, j_t0 + TY], then full-weighting restriction ----
+  if (RESTRICT) {
+    for (int rr = warp; rr <= TY; rr += kFusedWarps) {
+      const int gj = j_t0 + rr;
+      double *xr = xs + (gj - j_r0) * 128;
+      double *fr = fs + (gj - j_r0) * 128;
+      double res[4] = {0.0, 0.0, 0.0, 0.0};
+      if (gj < ny) {  // (lanes 0 / 31 read in-bounds garbage for columns that are masked out below)
+        res[0] = fr[lane] - stencil_at<NINE, 0>(P.a, xr, lane);
+        res[1] = fr[32 + lane] - stencil_at<NINE, 1>(P.a, xr, lane);
+        res[2] = fr[64 + lane] - stencil_at<NINE, 2>(P.a, xr, lane);
+        res[3] = fr[96 + lane] - stencil_at<NINE, 3>(P.a, xr, lane);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int gi = gi0 + k;
+        const bool ok = (gi >= max(1, i_t0 - 1)) && (gi <= min(nx - 1, i_t0 + TX - 1)) && (gj < ny);
+        fr[k * 32 + lane] = ok ? res[k] : 0.0;
+      }
+    }
+    __syncthreads();
+    const long long ccb = (long long)blockIdx.z * P.gc.stride;
+    const int I = gi0 >> 1;  // coarse columns I (fine 4p) and I + 1 (fine 4p + 2) of this lane
+    const bool mine = (gi0 >= i_t0) && (gi0 < i_t0 + TX);
+    for (int rr = warp; rr < TY / 2; rr += kFusedWarps) {
+      const int J = (j_t0 + 1) / 2 + rr;
+      if (!mine || J >= P.gc.ny) continue;
+      double *fr = fs + (2 * J - j_r0) * 128;
+      const double a0 = sat<0>(fr, lane) + 0.5 * (sat<-1>(fr, lane) + sat<1>(fr, lane) + sat<0>(fr - 128, lane) + sat<0>(fr + 128, lane)) +
+                        0.25 * (sat<-1>(fr - 128, lane) + sat<1>(fr - 128, lane) + sat<-1>(fr + 128, lane) + sat<1>(fr + 128, lane));
+      const double a1 = sat<2>(fr, lane) + 0.5 * (sat<1>(fr, lane) + sat<3>(fr, lane) + sat<2>(fr - 128, lane) + sat<2>(fr + 128, lane)) +
+                        0.25 * (sat<1>(fr - 128, lane) + sat<3>(fr - 128, lane) + sat<1>(fr + 128, lane) + sat<3>(fr + 128, lane));
+      const long long o = ccb + (long long)J * P.gc.pitch + I;
+      if (I >= 1 && I < P.gc.nx) {
+        P.fc_out[o] = a0;
+        if (P.xc_zero) P.xc_zero[o] = 0.0;
+      }
+      if (I + 1 < P.gc.nx) {
+        P.fc_out[o + 1] = a1;
+        if (P.xc_zero) P.xc_zero[o + 1] = 0.0;
+      }
+    }
+  }
+}
+
+}  // namespace mgmc

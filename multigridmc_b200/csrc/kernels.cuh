@@ -18,7 +18,7 @@ struct Coef9 {
 };
 
 struct NoiseP {
-  uint64_t seed;
+  PhiloxKeys keys;        // round keys of the 64-bit seed
   uint32_t c1;            // (level << 24) | sweep counter
   const uint32_t *sample; // device-resident sample index (so that CUDA graphs can be replayed)
   uint32_t chain0;        // global id of chain 0
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) sweep_colour_kernel(GridP g, Coef9 a, dou
   if (j >= g.ny || i0 >= g.nx) return;
   const long long o = (long long)blockIdx.z * g.stride + (long long)j * g.pitch + i0;
   double z0 = 0.0, z1 = 0.0;
-  if (GIBBS) normal_pair(nz.seed, (((uint32_t)j * nz.G + (uint32_t)p) << 1) | (uint32_t)q, nz.c1, *nz.sample, nz.chain0 + blockIdx.z, z0, z1);
+  if (GIBBS) normal_pair(nz.keys, (((uint32_t)j * nz.G + (uint32_t)p) << 1) | (uint32_t)q, nz.c1, *nz.sample, nz.chain0 + blockIdx.z, z0, z1);
   const double winv = omega / a.c;
   double *xp = x + o;
 #pragma unroll
@@ -259,43 +259,40 @@ __global__ void __launch_bounds__(256) lowrank_restrict_kernel(SparseCols B, Spa
 // Woodbury fix-up after a sweep on A_0 (SORSmoother::apply, sor_smoother.cc:47-51) merged with the
 // low-rank part of the Gibbs noise (sor_sampler.cc:48-56):
 //   y = x + W s,  s = Sigma^{-1/2} xi           (sweep is linear in its rhs: M_0^{-1} B s = W s)
-//   x_new = y - W K B^T y = x + W (s - K (B^T x + G s)),   W = M_0^{-1} B, G = B^T W, K = (Sigma + G)^{-1}
+//   x_new = y - W K B^T y = x + W d,   d = (I - K G) s - K B^T x,   W = M_0^{-1} B, G = B^T W,
+//   K = (Sigma + G)^{-1}
 // where M_0 = D/omega + L in the colour ordering, so W is sparse.
+// Mneg = -K and Ms = I - K G are formed on the host.  One CTA per chain; the two m x m products are
+// warp-cooperative (one warp per row, coalesced row reads, shuffle reduction).
 template <bool GIBBS>
-__global__ void __launch_bounds__(256) lowrank_fix_kernel(SparseCols B, SparseRows W, const double *__restrict__ K, const double *__restrict__ Gm,
+__global__ void __launch_bounds__(256) lowrank_fix_kernel(SparseCols B, SparseRows W, const double *__restrict__ Mneg, const double *__restrict__ Ms,
                                                          const double *__restrict__ sigma_inv_sqrt, long long stride, double *__restrict__ x,
                                                          NoiseP nz) {
   extern __shared__ double sh[];
   const int m = B.m;
   double *t = sh, *s = sh + m, *d = sh + 2 * m;
   double *xc = x + (long long)blockIdx.x * stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k = threadIdx.x; k < m; k += blockDim.x) {
     double acc = 0.0;
     for (int e = B.colptr[k]; e < B.colptr[k + 1]; ++e) acc += B.val[e] * xc[B.site[e]];
     t[k] = acc;
     if (GIBBS) {
       double z0, z1;
-      normal_pair(nz.seed, 0x80000000u | ((uint32_t)k >> 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.x, z0, z1);
+      normal_pair(nz.keys, 0x80000000u | ((uint32_t)k >> 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.x, z0, z1);
       s[k] = sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
-    } else {
-      s[k] = 0.0;
     }
   }
   __syncthreads();
-  if (GIBBS) {
-    for (int k = threadIdx.x; k < m; k += blockDim.x) {
-      double acc = t[k];
-      for (int c = 0; c < m; ++c) acc += Gm[k * m + c] * s[c];
-      d[k] = acc;
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < m; k += blockDim.x) t[k] = d[k];
-    __syncthreads();
-  }
-  for (int k = threadIdx.x; k < m; k += blockDim.x) {
+  for (int k = warp; k < m; k += 8) {
     double acc = 0.0;
-    for (int c = 0; c < m; ++c) acc += K[k * m + c] * t[c];
-    d[k] = s[k] - acc;
+    for (int c = lane; c < m; c += 32) {
+      acc = fma(Mneg[(long long)k * m + c], t[c], acc);
+      if (GIBBS) acc = fma(Ms[(long long)k * m + c], s[c], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) d[k] = acc;
   }
   __syncthreads();
   for (int u = threadIdx.x; u < W.nu; u += blockDim.x) {
@@ -306,72 +303,51 @@ __global__ void __launch_bounds__(256) lowrank_fix_kernel(SparseCols B, SparseRo
 }
 
 // ------------------------------------------------------------------------------------------------
-// Coarsest level: dense lower Cholesky factor L (Np x Np row-major, padded with identity to a
-// multiple of 32) resident on the device plus the inverses of its 32 x 32 diagonal blocks.
-// Blocked substitution, one CTA per chain:
+// Coarsest level: dense lower Cholesky factor of A_0 + B Sigma^{-1} B^T resident on the device.
 //   SAMPLE:  x = L^{-T} (xi + L^{-1} f)   (CholeskySampler::apply, cholesky_sampler.hh:50-66)
 //   SOLVE:   x = L^{-T} L^{-1} b          (CholeskySolver::apply, cholesky_solver.cc:30-41; the low-rank
 //            term is folded into the factorised matrix instead of the reference's Woodbury update)
+// A substitution with N = 961 unknowns is a chain of N dependent steps (or N/32 block steps): latency
+// bound at ~0.6 ms on one SM.  The triangular solves are therefore applied in their fully blocked
+// form -- block size N, i.e. through the triangular inverses T = L^{-1} (row-major lower) and
+// T^T (row-major upper) computed by substitution on the host at setup -- as two triangular
+// matrix-vector products that spread over the whole chip (one warp per row, rows read coalesced from
+// L2).  Vectors are gathered from / scattered to the padded lattice layout through `cidx`.
+//   pass 1: y = T f (+ xi)      pass 2: x = T^T y
 // ------------------------------------------------------------------------------------------------
-template <bool SAMPLE>
-__global__ void __launch_bounds__(1024) coarse_cholesky_kernel(const double *__restrict__ L, const double *__restrict__ Dinv, int N, int Np, GridP g,
-                                                              const double *__restrict__ f, double *__restrict__ x, NoiseP nz) {
-  extern __shared__ double sh[];
-  double *y = sh;        // Np
-  double *xk = sh + Np;  // 32
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int w = g.nx - 1;
-  const long long base = (long long)blockIdx.x * g.stride;
-  for (int e = tid; e < Np; e += 1024) y[e] = (e < N) ? f[base + (long long)(e / w + 1) * g.pitch + (e % w + 1)] : 0.0;
-  __syncthreads();
-  const int nb = Np / 32;
-  // forward: L y' = y
-  for (int k = 0; k < nb; ++k) {
-    if (warp == 0) {
-      const double *D = Dinv + (long long)k * 1024;
-      double acc = 0.0;
-      for (int c = 0; c <= lane; ++c) acc += D[lane * 32 + c] * y[32 * k + c];
-      xk[lane] = acc;
-    }
-    __syncthreads();
-    if (tid < 32) y[32 * k + tid] = xk[tid];
-    const double xl = xk[lane];
-    for (int r = 32 * (k + 1) + warp; r < Np; r += 32) {
-      double v = L[(long long)r * Np + 32 * k + lane] * xl;
+template <bool LOWER, bool NOISE, bool GATHER_IN, bool SCATTER_OUT>
+__global__ void __launch_bounds__(256) trimv_kernel(const double *__restrict__ T, int N, int Np, const int *__restrict__ cidx,
+                                                   const double *__restrict__ in, long long in_stride, double *__restrict__ out, long long out_stride,
+                                                   NoiseP nz) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const double *vin = in + (long long)blockIdx.y * in_stride;
+  const double *Trow = T + (long long)row * Np;
+  const int c_lo = LOWER ? 0 : row, c_hi = LOWER ? row + 1 : N;  // non-zero range of the row
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int c = c_lo + lane;
+  for (; c + 96 < c_hi; c += 128) {
+    const double t0 = Trow[c], t1 = Trow[c + 32], t2 = Trow[c + 64], t3 = Trow[c + 96];
+    const double v0 = vin[GATHER_IN ? cidx[c] : c], v1 = vin[GATHER_IN ? cidx[c + 32] : c + 32];
+    const double v2 = vin[GATHER_IN ? cidx[c + 64] : c + 64], v3 = vin[GATHER_IN ? cidx[c + 96] : c + 96];
+    a0 = fma(t0, v0, a0);
+    a1 = fma(t1, v1, a1);
+    a2 = fma(t2, v2, a2);
+    a3 = fma(t3, v3, a3);
+  }
+  for (; c < c_hi; c += 32) a0 = fma(Trow[c], vin[GATHER_IN ? cidx[c] : c], a0);
+  double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-      if (lane == 0) y[r] -= v;
-    }
-    __syncthreads();
-  }
-  if (SAMPLE) {
-    for (int e2 = tid; 2 * e2 < N; e2 += 1024) {
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (NOISE) {
       double z0, z1;
-      normal_pair(nz.seed, 0x40000000u | (uint32_t)e2, nz.c1, *nz.sample, nz.chain0 + blockIdx.x, z0, z1);
-      y[2 * e2] += z0;
-      if (2 * e2 + 1 < N) y[2 * e2 + 1] += z1;
+      normal_pair(nz.keys, 0x40000000u | ((uint32_t)row >> 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.y, z0, z1);
+      acc += (row & 1) ? z1 : z0;
     }
-    __syncthreads();
+    out[(long long)blockIdx.y * out_stride + (SCATTER_OUT ? cidx[row] : row)] = acc;
   }
-  // backward: L^T x = y
-  for (int k = nb - 1; k >= 0; --k) {
-    if (warp == 0) {
-      const double *D = Dinv + (long long)k * 1024;
-      double acc = 0.0;
-      for (int c = lane; c < 32; ++c) acc += D[c * 32 + lane] * y[32 * k + c];
-      xk[lane] = acc;
-    }
-    __syncthreads();
-    if (tid < 32) y[32 * k + tid] = xk[tid];
-    for (int r = tid; r < 32 * k; r += 1024) {
-      double acc = 0.0;
-#pragma unroll 8
-      for (int c = 0; c < 32; ++c) acc += L[(long long)(32 * k + c) * Np + r] * xk[c];
-      y[r] -= acc;
-    }
-    __syncthreads();
-  }
-  for (int e = tid; e < N; e += 1024) x[base + (long long)(e / w + 1) * g.pitch + (e % w + 1)] = y[e];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/mgmc_b200.h"
+#include "fused.cuh"
 #include "kernels.cuh"
 #include "setup.hh"
 
@@ -44,14 +45,15 @@ struct DevSparse {  // device copies of a sparse n x m matrix in both groupings
 
 struct LowRankDev {
   DevSparse W[2];  // [0] forward, [1] backward
-  double *K[2] = {nullptr, nullptr};
-  double *G[2] = {nullptr, nullptr};
+  double *Mneg[2] = {nullptr, nullptr};  // -K
+  double *Ms[2] = {nullptr, nullptr};    // I - K G
 };
 
 struct DevLevel {
   HostLevel h;
   GridP g;
   double *x = nullptr, *f = nullptr, *r = nullptr;  // origin pointers (element i = 0, j = 0 of chain 0)
+  double *x_alt = nullptr, *x_primary = nullptr;     // ping-pong partner of x / the buffer x must be in between calls
   Coef9 coef;
   bool nine = false;
   DevSparse B;
@@ -75,12 +77,14 @@ struct mgmc_ctx {
   std::vector<void *> allocs;
   // coarse factor
   int Nc = 0, Ncp = 0;
-  double *dL = nullptr, *dDinv = nullptr;
+  double *dT = nullptr, *dTT = nullptr, *d_cy = nullptr;  // L^{-1}, L^{-T}, intermediate vector (Np per chain)
+  int *d_cidx = nullptr;                                  // lexicographic index -> offset in the padded layout
   double *d_sigma_inv = nullptr, *d_sigma_inv_sqrt = nullptr;
   // noise position
   uint32_t *d_sample = nullptr;
   uint32_t h_sample = 0;
   std::vector<uint32_t> sweep_counter;
+  PhiloxKeys keys;
   // QoI / series
   int qoi_nnz = 0;
   long long *d_qsite = nullptr;
@@ -236,8 +240,8 @@ const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega) {
   for (int dir = 0; dir < 2; ++dir) {
     LowRankDir h = lowrank_setup(L.h, c->Sigma, omega, dir == 0);
     dev.W[dir] = upload_sparse(c, h.W, m, L.g.pitch);
-    dev.K[dir] = c->dupload(h.K);
-    dev.G[dir] = c->dupload(h.G);
+    dev.Mneg[dir] = c->dupload(h.Mneg);
+    dev.Ms[dir] = c->dupload(h.Ms);
   }
   return L.lowrank.emplace(omega, dev).first->second;
 }
@@ -260,15 +264,19 @@ void download_vec(mgmc_ctx *c, int level, const double *dev, double *host) {
                                  w * sizeof(double), h, cudaMemcpyDeviceToHost, c->stream));
 }
 
-NoiseP noise_params(mgmc_ctx *c, int level, bool advance) {
+NoiseP noise_params(mgmc_ctx *c, int level, uint32_t c1) {
   NoiseP nz;
-  nz.seed = c->d.seed;
-  nz.c1 = ((uint32_t)level << 24) | (c->sweep_counter[level] & 0xFFFFFFu);
-  if (advance) c->sweep_counter[level]++;
+  nz.keys = c->keys;
+  nz.c1 = c1;
   nz.sample = c->d_sample;
   nz.chain0 = (uint32_t)c->d.first_chain;
   nz.G = (uint32_t)(c->lv[level].g.nx / 4 + 1);
   return nz;
+}
+uint32_t next_c1(mgmc_ctx *c, int level, bool advance) {
+  const uint32_t c1 = ((uint32_t)level << 24) | (c->sweep_counter[level] & 0xFFFFFFu);
+  if (advance) c->sweep_counter[level]++;
+  return c1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -277,6 +285,15 @@ NoiseP noise_params(mgmc_ctx *c, int level, bool advance) {
 void dev_zero(mgmc_ctx *c, int level, double *x) {
   const DevLevel &L = c->lv[level];
   c->launch("zero", level, [&] { axpy_kernel<1><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, x, nullptr); });
+}
+
+// keep the invariant "between API calls / cycles the iterate of a level lives in its primary buffer"
+// (the fused sweeps are out of place and ping-pong between x and x_alt)
+void normalize_x(mgmc_ctx *c, int level) {
+  DevLevel &L = c->lv[level];
+  if (L.x == L.x_primary) return;
+  c->launch("copy_back", level, [&] { axpy_kernel<2><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.x_primary, L.x); });
+  std::swap(L.x, L.x_alt);
 }
 
 // y = A x (incl. low-rank term)
@@ -292,73 +309,148 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
     });
 }
 
-// one directional SOR / Gibbs sweep over all colours + low-rank fix-up
-void dev_sweep(mgmc_ctx *c, int level, bool fwd, bool gibbs, bool fixup, double omega, const double *f, double *x) {
-  DevLevel &L = c->lv[level];
-  const int nc = L.h.st.ncolours;
-  NoiseP nz = noise_params(c, level, gibbs);
-  const double noise_scale = std::sqrt(L.coef.c * (2. - omega) / omega);  // sor_sampler.cc:24-27
-  const int ngroups = L.g.nx / 4 + 1;
-  for (int cc = 0; cc < nc; ++cc) {
-    const int colour = fwd ? cc : nc - 1 - cc;
-    if (nc == 2) {
-      dim3 grid((ngroups + 31) / 32, (L.g.ny - 1 + 7) / 8, c->d.nchains);
-      c->launch(gibbs ? "gibbs_rb" : "sor_rb", level, [&] {
-        if (gibbs) sweep_colour_kernel<2, true><<<grid, dim3(32, 8, 1), 0, c->stream>>>(L.g, L.coef, x, f, colour, omega, noise_scale, nz);
-        else sweep_colour_kernel<2, false><<<grid, dim3(32, 8, 1), 0, c->stream>>>(L.g, L.coef, x, f, colour, omega, noise_scale, nz);
-      });
-    } else {
-      dim3 grid((ngroups + 31) / 32, (L.g.ny / 2 + 7) / 8, c->d.nchains);
-      c->launch(gibbs ? "gibbs_4c" : "sor_4c", level, [&] {
-        if (gibbs) sweep_colour_kernel<4, true><<<grid, dim3(32, 8, 1), 0, c->stream>>>(L.g, L.coef, x, f, colour, omega, noise_scale, nz);
-        else sweep_colour_kernel<4, false><<<grid, dim3(32, 8, 1), 0, c->stream>>>(L.g, L.coef, x, f, colour, omega, noise_scale, nz);
-      });
-    }
+// ---- fused tile kernel dispatch ----
+constexpr int kFusedTY = 32;
+constexpr int kFusedSmemMax = 110 * 1024;
+
+template <int NC, bool G, bool PR, bool RS>
+void launch_fused_t(mgmc_ctx *c, const FusedP &P, dim3 grid, size_t smem) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(fused_smooth_kernel<NC, G, PR, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    attr_set = true;
   }
-  if (fixup && c->d.m_lowrank > 0) {
-    const LowRankDev &lr = get_lowrank(c, level, omega);
-    const int dir = fwd ? 0 : 1;
-    const size_t sh = 3 * (size_t)c->d.m_lowrank * sizeof(double);
-    c->launch("lowrank_fix", level, [&] {
-      if (gibbs)
-        lowrank_fix_kernel<true><<<c->d.nchains, 256, sh, c->stream>>>(L.B.cols, lr.W[dir].rows, lr.K[dir], lr.G[dir], c->d_sigma_inv_sqrt, L.g.stride, x, nz);
-      else
-        lowrank_fix_kernel<false><<<c->d.nchains, 256, sh, c->stream>>>(L.B.cols, lr.W[dir].rows, lr.K[dir], lr.G[dir], c->d_sigma_inv_sqrt, L.g.stride, x, nz);
-    });
-  }
+  fused_smooth_kernel<NC, G, PR, RS><<<grid, kFusedThreads, smem, c->stream>>>(P);
 }
 
-// Smoother::apply / Sampler::apply semantics of the reference, including the nsmooth^2 quirk of
+// one fused launch on `level`: optional prolongation of x_{level+1}, the colour passes in `stages`,
+// optional residual + restriction into f_{level+1} (and x_{level+1} = 0)
+void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, bool gibbs, double omega, bool prolong, double alpha, bool restrict_) {
+  DevLevel &L = c->lv[level];
+  const int nc = L.h.st.ncolours;
+  const int S = (int)stages.size();
+  if (S > 8) fail(MGMC_ERR_INVALID, "internal: more than 8 stages in one fused launch");
+  if (S == 0 && !prolong && !restrict_) return;
+  FusedP P;
+  std::memset(&P, 0, sizeof(P));
+  P.g = L.g;
+  P.a = L.coef;
+  P.x_in = L.x;
+  P.x_out = L.x_alt;
+  P.f = L.f;
+  if (prolong || restrict_) {
+    DevLevel &C = c->lv[level + 1];
+    P.gc = C.g;
+    P.xc_in = C.x;
+    P.alpha = alpha;
+    P.fc_out = C.f;
+    P.xc_zero = C.x;
+  }
+  P.nstages = S;
+  for (int k = 0; k < S; ++k) P.st[k] = stages[k];
+  P.omega = omega;
+  P.noise_scale = std::sqrt(L.coef.c * (2. - omega) / omega);  // sor_sampler.cc:24-27
+  P.nz = noise_params(c, level, 0);
+  auto up4 = [](int v) { return (v + 3) / 4 * 4; };
+  P.HXL = up4(S + (restrict_ ? 2 : 0));
+  const int HXR = up4(S + (restrict_ ? 1 : 0));
+  P.TX = 128 - P.HXL - HXR;
+  P.TY = kFusedTY;
+  P.hl = S + (restrict_ ? 1 : 0);
+  const int hh = S + (restrict_ ? 2 : 0);
+  P.RY = P.TY + P.hl + hh;
+  const size_t smem = (size_t)2 * P.RY * 128 * sizeof(double);
+  if (smem > (size_t)kFusedSmemMax) fail(MGMC_ERR_INVALID, "internal: fused tile does not fit in shared memory");
+  dim3 grid((L.g.nx + P.TX - 1) / P.TX, (L.g.ny - 1 + P.TY - 1) / P.TY, c->d.nchains);
+  std::string name = std::string(gibbs ? "gibbs" : "sor") + (nc == 2 ? "_rb" : "_4c") + std::to_string(S) + (prolong ? "+prolong" : "") + (restrict_ ? "+restrict" : "");
+  c->launch(name.c_str(), level, [&] {
+#define FUSED_CASE(NC_, G_, PR_, RS_) \
+  if (nc == NC_ && gibbs == G_ && prolong == PR_ && restrict_ == RS_) launch_fused_t<NC_, G_, PR_, RS_>(c, P, grid, smem);
+    FUSED_CASE(2, false, false, false) FUSED_CASE(2, false, false, true) FUSED_CASE(2, false, true, false) FUSED_CASE(2, false, true, true)
+    FUSED_CASE(2, true, false, false) FUSED_CASE(2, true, false, true) FUSED_CASE(2, true, true, false) FUSED_CASE(2, true, true, true)
+    FUSED_CASE(4, false, false, false) FUSED_CASE(4, false, false, true) FUSED_CASE(4, false, true, false) FUSED_CASE(4, false, true, true)
+    FUSED_CASE(4, true, false, false) FUSED_CASE(4, true, false, true) FUSED_CASE(4, true, true, false) FUSED_CASE(4, true, true, true)
+#undef FUSED_CASE
+  });
+  if (S > 0 || prolong) std::swap(L.x, L.x_alt);
+}
+
+void dev_lowrank_fix(mgmc_ctx *c, int level, bool fwd, bool gibbs, double omega, uint32_t c1) {
+  DevLevel &L = c->lv[level];
+  const LowRankDev &lr = get_lowrank(c, level, omega);
+  const int dir = fwd ? 0 : 1;
+  const int m = c->d.m_lowrank;
+  const size_t sh = (3 * (size_t)m) * sizeof(double);
+  NoiseP nz = noise_params(c, level, c1);
+  c->launch("lowrank_fix", level, [&] {
+    if (gibbs)
+      lowrank_fix_kernel<true><<<c->d.nchains, 256, sh, c->stream>>>(L.B.cols, lr.W[dir].rows, lr.Mneg[dir], lr.Ms[dir], c->d_sigma_inv_sqrt, L.g.stride, L.x, nz);
+    else
+      lowrank_fix_kernel<false><<<c->d.nchains, 256, sh, c->stream>>>(L.B.cols, lr.W[dir].rows, lr.Mneg[dir], lr.Ms[dir], c->d_sigma_inv_sqrt, L.g.stride, L.x, nz);
+  });
+}
+
+struct SweepSpec {
+  bool fwd;
+  bool fix_after;
+};
+
+// Sweep lists with the reference's semantics, including the nsmooth^2 quirk of the deterministic
 // SORSmoother (sor_smoother.cc:43,64) which the samplers do not have (sor_sampler.cc:28,39)
-void dev_smooth(mgmc_ctx *c, int level, int kind, int direction, double omega, int nsmooth, bool gibbs, const double *f, double *x) {
+std::vector<SweepSpec> sweep_list(int kind, int direction, int nsmooth, bool gibbs) {
+  std::vector<SweepSpec> out;
   if (kind == MGMC_SMOOTHER_SOR) {
     const bool fwd = (direction == MGMC_FORWARD);
     for (int k = 0; k < nsmooth; ++k) {
-      if (gibbs) {
-        dev_sweep(c, level, fwd, true, true, omega, f, x);
-      } else {
-        for (int q = 0; q < nsmooth; ++q) dev_sweep(c, level, fwd, false, q == nsmooth - 1, omega, f, x);
-      }
+      if (gibbs) out.push_back({fwd, true});
+      else
+        for (int q = 0; q < nsmooth; ++q) out.push_back({fwd, q == nsmooth - 1});
     }
   } else {
     for (int k = 0; k < nsmooth; ++k) {
-      dev_sweep(c, level, true, gibbs, true, omega, f, x);
-      dev_sweep(c, level, false, gibbs, true, omega, f, x);
+      out.push_back({true, true});
+      out.push_back({false, true});
     }
   }
+  return out;
 }
 
-// f_c = R (f - A x)
-void dev_residual_restrict(mgmc_ctx *c, int level, const double *f, const double *x, double *fc) {
-  const DevLevel &L = c->lv[level], &C = c->lv[level + 1];
-  c->launch("residual_restrict", level, [&] {
-    if (L.nine) residual_restrict_kernel<true, false><<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, L.coef, x, f, fc);
-    else residual_restrict_kernel<false, false><<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, L.coef, x, f, fc);
-  });
-  if (c->d.m_lowrank > 0)
-    c->launch("lowrank_restrict", level, [&] {
-      lowrank_restrict_kernel<<<c->d.nchains, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, C.B.rows, c->d_sigma_inv, L.g.stride, C.g.stride, x, fc);
-    });
+// A smoothing step of a level: [prolongate_add] sweeps... [residual + restrict].  Without a low-rank
+// term consecutive sweeps are fused into launches of up to 8 colour passes; with it every sweep is one
+// launch followed by the Woodbury fix-up (a grid-wide dependency), and the residual is its own launch.
+void emit_smoothing(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps, bool gibbs, double omega, bool prolong, double alpha, bool restrict_) {
+  DevLevel &L = c->lv[level];
+  const int nc = L.h.st.ncolours;
+  const bool lowrank = c->d.m_lowrank > 0;
+  std::vector<Stage> cur;
+  bool pending_prolong = prolong;
+  auto flush = [&](bool with_restrict) {
+    dev_fused(c, level, cur, gibbs, omega, pending_prolong, alpha, with_restrict);
+    pending_prolong = false;
+    cur.clear();
+  };
+  for (const SweepSpec &sw : sweeps) {
+    const uint32_t c1 = next_c1(c, level, gibbs);
+    const int max_stages = (nc == 2) ? 4 : 8;  // keeps the tile + halo of x and f below ~100 KB (2 CTAs / SM)
+    if (!cur.empty() && ((int)cur.size() + nc > max_stages || lowrank)) flush(false);
+    for (int cc = 0; cc < nc; ++cc) cur.push_back(Stage{sw.fwd ? cc : nc - 1 - cc, c1});
+    if (lowrank) {
+      flush(false);
+      if (sw.fix_after) dev_lowrank_fix(c, level, sw.fwd, gibbs, omega, c1);
+    }
+  }
+  if (!lowrank) {
+    flush(restrict_);
+  } else {
+    if (pending_prolong) flush(false);
+    if (restrict_) {
+      flush(true);
+      DevLevel &C = c->lv[level + 1];
+      c->launch("lowrank_restrict", level, [&] {
+        lowrank_restrict_kernel<<<c->d.nchains, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, C.B.rows, c->d_sigma_inv, L.g.stride, C.g.stride, L.x, C.f);
+      });
+    }
+  }
 }
 
 void dev_restrict_plain(mgmc_ctx *c, int level, const double *r, double *fc) {
@@ -368,19 +460,18 @@ void dev_restrict_plain(mgmc_ctx *c, int level, const double *r, double *fc) {
   });
 }
 
-void dev_prolongate_add(mgmc_ctx *c, int level, double alpha, const double *xc, double *x) {
-  const DevLevel &L = c->lv[level], &C = c->lv[level + 1];
-  c->launch("prolongate_add", level, [&] { prolongate_add_kernel<<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, alpha, xc, x); });
-}
-
 void dev_coarse(mgmc_ctx *c, bool sample, const double *f, double *x) {
   const int lc = c->d.nlevel - 1;
   const DevLevel &L = c->lv[lc];
-  NoiseP nz = noise_params(c, lc, sample);
-  const size_t sh = (size_t)(c->Ncp + 32) * sizeof(double);
-  c->launch(sample ? "coarse_sample" : "coarse_solve", lc, [&] {
-    if (sample) coarse_cholesky_kernel<true><<<c->d.nchains, 1024, sh, c->stream>>>(c->dL, c->dDinv, c->Nc, c->Ncp, L.g, f, x, nz);
-    else coarse_cholesky_kernel<false><<<c->d.nchains, 1024, sh, c->stream>>>(c->dL, c->dDinv, c->Nc, c->Ncp, L.g, f, x, nz);
+  NoiseP nz = noise_params(c, lc, next_c1(c, lc, sample));
+  dim3 grid((c->Nc + 7) / 8, c->d.nchains);
+  // pass 1: y = L^{-1} f (+ xi);  pass 2: x = L^{-T} y
+  c->launch(sample ? "coarse_sample_fwd" : "coarse_solve_fwd", lc, [&] {
+    if (sample) trimv_kernel<true, true, true, false><<<grid, 256, 0, c->stream>>>(c->dT, c->Nc, c->Ncp, c->d_cidx, f, L.g.stride, c->d_cy, c->Ncp, nz);
+    else trimv_kernel<true, false, true, false><<<grid, 256, 0, c->stream>>>(c->dT, c->Nc, c->Ncp, c->d_cidx, f, L.g.stride, c->d_cy, c->Ncp, nz);
+  });
+  c->launch(sample ? "coarse_sample_bwd" : "coarse_solve_bwd", lc, [&] {
+    trimv_kernel<false, false, false, true><<<grid, 256, 0, c->stream>>>(c->dTT, c->Nc, c->Ncp, c->d_cidx, c->d_cy, c->Ncp, x, L.g.stride, nz);
   });
 }
 
@@ -389,20 +480,24 @@ void dev_coarse(mgmc_ctx *c, bool sample, const double *f, double *x) {
 // ---------------------------------------------------------------------------------------------
 void mgmc_sample_level(mgmc_ctx *c, int level) {  // multigridmc_sampler.cc:103-130
   const mgmc_desc &d = c->d;
-  DevLevel &L = c->lv[level];
   if (level == d.nlevel - 1) {
-    if (d.coarse_solver == MGMC_COARSE_CHOLESKY) dev_coarse(c, true, L.f, L.x);
-    else dev_smooth(c, level, MGMC_SMOOTHER_SSOR, MGMC_FORWARD, d.omega, d.ncoarsesmooth, true, L.f, L.x);
+    DevLevel &L = c->lv[level];
+    if (d.coarse_solver == MGMC_COARSE_CHOLESKY) {
+      dev_coarse(c, true, L.f, L.x);
+    } else {
+      emit_smoothing(c, level, sweep_list(MGMC_SMOOTHER_SSOR, MGMC_FORWARD, d.ncoarsesmooth, true), true, d.omega, false, 0.0, false);
+      normalize_x(c, level);
+    }
     return;
   }
   const int cycle_ = (level > 0) ? d.cycle : 1;
   for (int j = 0; j < cycle_; ++j) {
-    dev_smooth(c, level, d.smoother, MGMC_FORWARD, d.omega, d.npresmooth, true, L.f, L.x);
-    dev_residual_restrict(c, level, L.f, L.x, c->lv[level + 1].f);
-    dev_zero(c, level + 1, c->lv[level + 1].x);
+    // presampler + residual + restrict (+ x_{l+1} = 0)
+    emit_smoothing(c, level, sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true), true, d.omega, false, 0.0, true);
     mgmc_sample_level(c, level + 1);
-    dev_prolongate_add(c, level, d.coarse_scaling, c->lv[level + 1].x, L.x);
-    dev_smooth(c, level, d.smoother, MGMC_BACKWARD, d.omega, d.npostsmooth, true, L.f, L.x);
+    // prolongate_add + postsampler
+    emit_smoothing(c, level, sweep_list(d.smoother, MGMC_BACKWARD, d.npostsmooth, true), true, d.omega, true, d.coarse_scaling, false);
+    normalize_x(c, level);
   }
 }
 
@@ -413,14 +508,13 @@ void mg_solve_level(mgmc_ctx *c, int level) {  // multigrid_preconditioner.cc:74
     dev_coarse(c, false, L.f, L.x);  // writes every interior entry; ghost lines stay zero
     return;
   }
-  dev_zero(c, level, L.x);
+  if (level == 0) dev_zero(c, level, L.x);  // deeper levels are zeroed by the restriction that feeds them
   const int cycle_ = (level > 0) ? d.cycle : 1;
   for (int j = 0; j < cycle_; ++j) {
-    dev_smooth(c, level, d.smoother, MGMC_FORWARD, d.omega, d.npresmooth, false, L.f, L.x);
-    dev_residual_restrict(c, level, L.f, L.x, c->lv[level + 1].f);
+    emit_smoothing(c, level, sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, false), false, d.omega, false, 0.0, true);
     mg_solve_level(c, level + 1);
-    dev_prolongate_add(c, level, d.coarse_scaling, c->lv[level + 1].x, L.x);
-    dev_smooth(c, level, d.smoother, MGMC_BACKWARD, d.omega, d.npostsmooth, false, L.f, L.x);
+    emit_smoothing(c, level, sweep_list(d.smoother, MGMC_BACKWARD, d.npostsmooth, false), false, d.omega, true, d.coarse_scaling, false);
+    normalize_x(c, level);
   }
 }
 
@@ -557,6 +651,7 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->use_graph = (std::getenv("MGMC_NO_GRAPH") == nullptr);
     c->sweep_counter.assign(desc->nlevel, 0u);
+    c->keys = philox_round_keys(desc->seed);
     c->lv.resize(desc->nlevel);
     for (int l = 0; l < desc->nlevel; ++l) {
       DevLevel &L = c->lv[l];
@@ -569,6 +664,8 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
       const size_t total = (size_t)L.g.stride * desc->nchains;
       const size_t origin = (size_t)GY * L.g.pitch + GX;
       L.x = c->dalloc<double>(total) + origin;
+      L.x_primary = L.x;
+      L.x_alt = c->dalloc<double>(total) + origin;
       L.f = c->dalloc<double>(total) + origin;
       L.r = c->dalloc<double>(total) + origin;
       L.coef = to_coef9(L.h.st);
@@ -588,13 +685,14 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
       CoarseFactor cf = coarse_factor(hc, c->Sigma);
       c->Nc = cf.N;
       c->Ncp = cf.Np;
-      c->dL = c->dupload(cf.L);
-      c->dDinv = c->dupload(cf.Dinv);
-      const size_t sh = (size_t)(cf.Np + 32) * sizeof(double);
-      if (sh > 48 * 1024) {
-        CUDA_CHECK(cudaFuncSetAttribute(coarse_cholesky_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-        CUDA_CHECK(cudaFuncSetAttribute(coarse_cholesky_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-      }
+      c->dT = c->dupload(cf.T);
+      c->dTT = c->dupload(cf.TT);
+      c->d_cy = c->dalloc<double>((size_t)cf.Np * desc->nchains);
+      std::vector<int> cidx(cf.Np, 0);
+      const DevLevel &LC = c->lv[desc->nlevel - 1];
+      const int w = LC.g.nx - 1;
+      for (int e = 0; e < cf.N; ++e) cidx[e] = (e / w + 1) * LC.g.pitch + (e % w + 1);
+      c->d_cidx = c->dupload(cidx);
     }
     c->d_sample = c->dalloc<uint32_t>(1);
     c->d_pos = c->dalloc<unsigned long long>(1);
@@ -677,7 +775,8 @@ int mgmc_prolongate_add(mgmc_ctx *c, int level, double alpha, const double *x_co
   check_level(c, level, true);
   upload_vec(c, level, c->lv[level].x, x_fine);
   upload_vec(c, level + 1, c->lv[level + 1].x, x_coarse);
-  dev_prolongate_add(c, level, alpha, c->lv[level + 1].x, c->lv[level].x);
+  emit_smoothing(c, level, {}, false, c->d.omega, true, alpha, false);
+  normalize_x(c, level);
   download_vec(c, level, c->lv[level].x, x_fine);
   c->sync();
   API_END
@@ -688,7 +787,7 @@ int mgmc_residual_restrict(mgmc_ctx *c, int level, const double *f, const double
   check_level(c, level, true);
   upload_vec(c, level, c->lv[level].f, f);
   upload_vec(c, level, c->lv[level].x, x);
-  dev_residual_restrict(c, level, c->lv[level].f, c->lv[level].x, c->lv[level + 1].f);
+  emit_smoothing(c, level, {}, false, c->d.omega, false, 0.0, true);
   download_vec(c, level + 1, c->lv[level + 1].f, f_coarse);
   c->sync();
   API_END
@@ -708,7 +807,8 @@ int mgmc_smoother_apply(mgmc_ctx *c, int level, int kind, int direction, double 
   DevLevel &L = c->lv[level];
   upload_vec(c, level, L.f, b);
   upload_vec(c, level, L.x, x);
-  dev_smooth(c, level, kind, direction, omega, nsmooth, false, L.f, L.x);
+  emit_smoothing(c, level, sweep_list(kind, direction, nsmooth, false), false, omega, false, 0.0, false);
+  normalize_x(c, level);
   download_vec(c, level, L.x, x);
   c->sync();
   API_END
@@ -721,7 +821,8 @@ int mgmc_sampler_apply(mgmc_ctx *c, int level, int kind, int direction, double o
   DevLevel &L = c->lv[level];
   upload_vec(c, level, L.f, f);
   upload_vec(c, level, L.x, x);
-  dev_smooth(c, level, kind, direction, omega, nsmooth, true, L.f, L.x);
+  emit_smoothing(c, level, sweep_list(kind, direction, nsmooth, true), true, omega, false, 0.0, false);
+  normalize_x(c, level);
   download_vec(c, level, L.x, x);
   c->sync();
   API_END

@@ -222,7 +222,8 @@ inline std::vector<double> invert_dense(std::vector<double> A, int n) {
 // in the colour ordering information travels at most (ncolours - 1) * radius sites per sweep.
 struct LowRankDir {
   std::vector<SEntry> W;
-  std::vector<double> G, K;  // m x m row-major
+  std::vector<double> G, K;     // m x m row-major
+  std::vector<double> Mneg, Ms;  // -K and I - K G: d = Ms s + Mneg (B^T x)
 };
 
 inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &Sigma, double omega, bool forward) {
@@ -287,6 +288,15 @@ inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &S
       S[(size_t)a * m + b] = g + ((a == b) ? Sigma[a] : 0.0);
     }
   out.K = invert_dense(S, m);
+  out.Mneg.assign((size_t)m * m, 0.0);
+  out.Ms.assign((size_t)m * m, 0.0);
+  for (int a = 0; a < m; ++a)
+    for (int b = 0; b < m; ++b) {
+      double kg = 0.0;
+      for (int c = 0; c < m; ++c) kg += out.K[(size_t)a * m + c] * out.G[(size_t)c * m + b];
+      out.Mneg[(size_t)a * m + b] = -out.K[(size_t)a * m + b];
+      out.Ms[(size_t)a * m + b] = ((a == b) ? 1.0 : 0.0) - kg;
+    }
   return out;
 }
 
@@ -294,8 +304,9 @@ inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &S
 // Cholesky factor padded with identity to Np = multiple of 32, and the inverses of the diagonal blocks
 struct CoarseFactor {
   int N = 0, Np = 0;
-  std::vector<double> L;     // Np x Np row-major
-  std::vector<double> Dinv;  // (Np / 32) blocks of 32 x 32 row-major, lower triangular
+  std::vector<double> L;     // Np x Np row-major lower Cholesky factor (kept for inspection)
+  std::vector<double> T;     // L^{-1}, Np x Np row-major (lower triangular)
+  std::vector<double> TT;    // L^{-T}, Np x Np row-major (upper triangular)
 };
 
 inline CoarseFactor coarse_factor(const HostLevel &Lv, const std::vector<double> &Sigma) {
@@ -340,17 +351,20 @@ inline CoarseFactor coarse_factor(const HostLevel &Lv, const std::vector<double>
     }
     for (int k = j + 1; k < Np; ++k) A[(size_t)j * Np + k] = 0.0;
   }
-  // inverses of the 32 x 32 diagonal blocks (lower triangular) by forward substitution
-  const int nb = Np / 32;
-  cf.Dinv.assign((size_t)nb * 1024, 0.0);
-  for (int b = 0; b < nb; ++b) {
-    double *D = &cf.Dinv[(size_t)b * 1024];
-    for (int c = 0; c < 32; ++c) {
-      for (int r = c; r < 32; ++r) {
-        double s = (r == c) ? 1.0 : 0.0;
-        for (int k = c; k < r; ++k) s -= A[(size_t)(32 * b + r) * Np + 32 * b + k] * D[k * 32 + c];
-        D[r * 32 + c] = s / A[(size_t)(32 * b + r) * Np + 32 * b + r];
-      }
+  // T = L^{-1} column by column (forward substitution); TT = T^T
+  cf.T.assign((size_t)Np * Np, 0.0);
+  cf.TT.assign((size_t)Np * Np, 0.0);
+  std::vector<double> col(Np);
+  for (int c = 0; c < Np; ++c) {
+    for (int r = c; r < Np; ++r) {
+      double s = (r == c) ? 1.0 : 0.0;
+      const double *lr = &A[(size_t)r * Np];
+      for (int k = c; k < r; ++k) s -= lr[k] * col[k];
+      col[r] = s / lr[r];
+    }
+    for (int r = c; r < Np; ++r) {
+      cf.T[(size_t)r * Np + c] = col[r];
+      cf.TT[(size_t)c * Np + r] = col[r];
     }
   }
   return cf;

@@ -665,13 +665,13 @@ struct Philox {
       k1 += 0xBB67AE85u;
     }
   }
-  // two N(0,1) from one counter: Box-Muller on two 53-bit uniforms in (0,1)
+  // two N(0,1) from one counter: Box-Muller on two 52-bit uniforms (k + 1/2) 2^-52 in (0,1)
   static inline void normal_pair(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, double &z0, double &z1) {
     uint32_t c[4] = {c0, c1, c2, c3};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     const uint64_t a = (uint64_t)c[0] | ((uint64_t)c[1] << 32), b = (uint64_t)c[2] | ((uint64_t)c[3] << 32);
-    const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-    const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u1 = ((double)(a >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+    const double u2 = ((double)(b >> 12) + 0.5) * (1.0 / 4503599627370496.0);
     const double r = std::sqrt(-2.0 * std::log(u1));
     const double t = 2.0 * M_PI * u2;
     z0 = r * std::cos(t);
