@@ -107,40 +107,51 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const int gi0 = i_r0 + 4 * lane;  // first global column of this lane's group
   const bool cols_alloc = (gi0 >= -kGX) && (gi0 + 3 < pitch - kGX);
 
-  // ---- stage the region: one warp per row, lane p loads its group of 4 columns (2 x 128 bit) ----
-  for (int r = warp; r < RY; r += kFusedWarps) {
-    const int gj = j_r0 + r;
-    double2 xa = make_double2(0.0, 0.0), xb = xa, fa = xa, fb = xa;
-    if (cols_alloc && gj >= -kGY && gj <= ny + kGY) {
-      const long long o = (long long)gj * pitch + gi0;
-      xa = *reinterpret_cast<const double2 *>(xg + o);
-      xb = *reinterpret_cast<const double2 *>(xg + o + 2);
-      fa = *reinterpret_cast<const double2 *>(fg + o);
-      fb = *reinterpret_cast<const double2 *>(fg + o + 2);
+  // ---- stage the region: one warp per row, lane p loads its group of 4 columns (2 x 128 bit);
+  //      two rows per iteration keep 8 independent 128-bit loads per lane in flight ----
+  for (int r = warp; r < RY; r += 2 * kFusedWarps) {
+    double2 xa[2], xb[2], fa[2], fb[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int gj = j_r0 + r + u * kFusedWarps;
+      xa[u] = xb[u] = fa[u] = fb[u] = make_double2(0.0, 0.0);
+      if (cols_alloc && gj >= -kGY && gj <= ny + kGY && r + u * kFusedWarps < RY) {
+        const long long o = (long long)gj * pitch + gi0;
+        xa[u] = *reinterpret_cast<const double2 *>(xg + o);
+        xb[u] = *reinterpret_cast<const double2 *>(xg + o + 2);
+        fa[u] = *reinterpret_cast<const double2 *>(fg + o);
+        fb[u] = *reinterpret_cast<const double2 *>(fg + o + 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rr = r + u * kFusedWarps;
+      if (rr >= RY) break;
+      const int gj = j_r0 + rr;
       if (PROLONG) {
-        if (gj >= 1 && gj < ny && gi0 >= -3 && gi0 <= nx) {
+        if (cols_alloc && gj >= 1 && gj < ny && gi0 >= -3 && gi0 <= nx) {
           // x += alpha R^T x_c in gather form: every fine vertex reads its (up to) 4 coarse parents
           const double *xc = P.xc_in + (long long)blockIdx.z * P.gc.stride;
           const double *r0 = xc + (long long)(gj >> 1) * P.gc.pitch, *r1 = xc + (long long)((gj + 1) >> 1) * P.gc.pitch;
           const int I = gi0 >> 1;  // gi0 is a multiple of 4: coarse columns I, I+1, I+2 cover the group
           const double q0 = 0.5 * (r0[I] + r1[I]), q1 = 0.5 * (r0[I + 1] + r1[I + 1]), q2 = 0.5 * (r0[I + 2] + r1[I + 2]);
           const double al = P.alpha;
-          if (gi0 >= 1 && gi0 < nx) xa.x += al * q0;
-          if (gi0 + 1 >= 1 && gi0 + 1 < nx) xa.y += al * (0.5 * (q0 + q1));
-          if (gi0 + 2 >= 1 && gi0 + 2 < nx) xb.x += al * q1;
-          if (gi0 + 3 >= 1 && gi0 + 3 < nx) xb.y += al * (0.5 * (q1 + q2));
+          if (gi0 >= 1 && gi0 < nx) xa[u].x += al * q0;
+          if (gi0 + 1 >= 1 && gi0 + 1 < nx) xa[u].y += al * (0.5 * (q0 + q1));
+          if (gi0 + 2 >= 1 && gi0 + 2 < nx) xb[u].x += al * q1;
+          if (gi0 + 3 >= 1 && gi0 + 3 < nx) xb[u].y += al * (0.5 * (q1 + q2));
         }
       }
+      double *xr = xs + rr * 128, *fr = fs + rr * 128;
+      xr[lane] = xa[u].x;
+      xr[32 + lane] = xa[u].y;
+      xr[64 + lane] = xb[u].x;
+      xr[96 + lane] = xb[u].y;
+      fr[lane] = fa[u].x;
+      fr[32 + lane] = fa[u].y;
+      fr[64 + lane] = fb[u].x;
+      fr[96 + lane] = fb[u].y;
     }
-    double *xr = xs + r * 128, *fr = fs + r * 128;
-    xr[lane] = xa.x;
-    xr[32 + lane] = xa.y;
-    xr[64 + lane] = xb.x;
-    xr[96 + lane] = xb.y;
-    fr[lane] = fa.x;
-    fr[32 + lane] = fa.y;
-    fr[64 + lane] = fb.x;
-    fr[96 + lane] = fb.y;
   }
   __syncthreads();
 
@@ -150,6 +161,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const int S = P.nstages;
   constexpr int EXLX = RESTRICT ? 2 : 0, EXHX = RESTRICT ? 1 : 0, EXLY = RESTRICT ? 1 : 0, EXHY = RESTRICT ? 2 : 0;
   const uint32_t pg = (uint32_t)((i_r0 >> 2) + lane);
+  const uint32_t sample = GIBBS ? *P.nz.sample : 0u;
+  const uint32_t chain = P.nz.chain0 + blockIdx.z;
   for (int s = 0; s < S; ++s) {
     const int colour = P.st[s].colour;
     const uint32_t c1 = P.st[s].c1;
@@ -168,7 +181,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       const bool v0 = (i0 >= ilo) && (i0 <= ihi), v1 = (i0 + 2 >= ilo) && (i0 + 2 <= ihi);
       if (!(v0 || v1)) continue;
       double z0 = 0.0, z1 = 0.0;
-      if (GIBBS) normal_pair(P.nz.keys, (((uint32_t)j * P.nz.G + pg) << 1) | (uint32_t)q, c1, *P.nz.sample, P.nz.chain0 + blockIdx.z, z0, z1);
+      if (GIBBS) normal_pair(P.nz.keys, (((uint32_t)j * P.nz.G + pg) << 1) | (uint32_t)q, c1, sample, chain, z0, z1);
       double *xr = xs + (j - j_r0) * 128;
       const double *fr = fs + (j - j_r0) * 128;
       if (q == 0) update_pair<NINE, GIBBS, 0>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);

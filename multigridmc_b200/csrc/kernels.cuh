@@ -262,43 +262,73 @@ __global__ void __launch_bounds__(256) lowrank_restrict_kernel(SparseCols B, Spa
 //   x_new = y - W K B^T y = x + W d,   d = (I - K G) s - K B^T x,   W = M_0^{-1} B, G = B^T W,
 //   K = (Sigma + G)^{-1}
 // where M_0 = D/omega + L in the colour ordering, so W is sparse.
-// Mneg = -K and Ms = I - K G are formed on the host.  One CTA per chain; the two m x m products are
-// warp-cooperative (one warp per row, coalesced row reads, shuffle reduction).
+// Mneg = -K and Ms = I - K G are formed on the host.  One CTA per chain.  The kernel is pure latency
+// (a handful of dependent loads), so B and W are stored padded with a fixed number of entries per
+// column / per touched site: every thread issues all its index loads at once, the two m x m
+// matrices are prefetched into shared memory meanwhile, and only x[site] depends on them.
+struct LowRankFix {
+  int m, EB, nu, EW;
+  const long long *bsite;  // [m * EB]   sites of column k (padded with a repeated site, value 0)
+  const double *bval;      // [m * EB]
+  const long long *usite;  // [nu]       unique sites touched by W
+  const int *wcol;         // [nu * EW]  (padded with column 0, value 0)
+  const double *wval;      // [nu * EW]
+  const double *Mneg, *Ms; // [m * m] row-major
+  const double *sigma_inv_sqrt;
+  int mats_in_smem;
+};
+
 template <bool GIBBS>
-__global__ void __launch_bounds__(256) lowrank_fix_kernel(SparseCols B, SparseRows W, const double *__restrict__ Mneg, const double *__restrict__ Ms,
-                                                         const double *__restrict__ sigma_inv_sqrt, long long stride, double *__restrict__ x,
-                                                         NoiseP nz) {
+__global__ void __launch_bounds__(256) lowrank_fix_kernel(LowRankFix F, long long stride, double *__restrict__ x, NoiseP nz) {
   extern __shared__ double sh[];
-  const int m = B.m;
-  double *t = sh, *s = sh + m, *d = sh + 2 * m;
+  const int m = F.m;
+  double *prod = sh;               // m * EB
+  double *t = prod + m * F.EB;     // m
+  double *s = t + m;               // m
+  double *d = s + m;               // m
+  double *Mn = d + m;              // m * m (if mats_in_smem)
+  double *Mss = Mn + m * m;        // m * m
   double *xc = x + (long long)blockIdx.x * stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = threadIdx.x; k < m; k += blockDim.x) {
-    double acc = 0.0;
-    for (int e = B.colptr[k]; e < B.colptr[k + 1]; ++e) acc += B.val[e] * xc[B.site[e]];
-    t[k] = acc;
-    if (GIBBS) {
+  // independent loads first
+  for (int e = threadIdx.x; e < m * F.EB; e += 256) prod[e] = F.bval[e] * xc[F.bsite[e]];
+  if (F.mats_in_smem) {
+    for (int e = threadIdx.x; e < m * m; e += 256) {
+      Mn[e] = F.Mneg[e];
+      if (GIBBS) Mss[e] = F.Ms[e];
+    }
+  }
+  if (GIBBS) {
+    const uint32_t sample = *nz.sample;
+    for (int k = threadIdx.x; k < m; k += 256) {
       double z0, z1;
-      normal_pair(nz.keys, 0x80000000u | ((uint32_t)k >> 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.x, z0, z1);
-      s[k] = sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
+      normal_pair(nz.keys, 0x80000000u | ((uint32_t)k >> 1), nz.c1, sample, nz.chain0 + blockIdx.x, z0, z1);
+      s[k] = F.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
     }
   }
   __syncthreads();
+  for (int k = threadIdx.x; k < m; k += 256) {
+    double acc = 0.0;
+    for (int e = 0; e < F.EB; ++e) acc += prod[k * F.EB + e];
+    t[k] = acc;
+  }
+  __syncthreads();
+  const double *An = F.mats_in_smem ? Mn : F.Mneg, *As = F.mats_in_smem ? Mss : F.Ms;
   for (int k = warp; k < m; k += 8) {
     double acc = 0.0;
     for (int c = lane; c < m; c += 32) {
-      acc = fma(Mneg[(long long)k * m + c], t[c], acc);
-      if (GIBBS) acc = fma(Ms[(long long)k * m + c], s[c], acc);
+      acc = fma(An[k * m + c], t[c], acc);
+      if (GIBBS) acc = fma(As[k * m + c], s[c], acc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) d[k] = acc;
   }
   __syncthreads();
-  for (int u = threadIdx.x; u < W.nu; u += blockDim.x) {
+  for (int u = threadIdx.x; u < F.nu; u += 256) {
     double acc = 0.0;
-    for (int e = W.uptr[u]; e < W.uptr[u + 1]; ++e) acc += W.uval[e] * d[W.ucol[e]];
-    xc[W.usite[u]] += acc;
+    for (int e = 0; e < F.EW; ++e) acc += F.wval[u * F.EW + e] * d[F.wcol[u * F.EW + e]];
+    xc[F.usite[u]] += acc;
   }
 }
 

@@ -44,9 +44,8 @@ struct DevSparse {  // device copies of a sparse n x m matrix in both groupings
 };
 
 struct LowRankDev {
-  DevSparse W[2];  // [0] forward, [1] backward
-  double *Mneg[2] = {nullptr, nullptr};  // -K
-  double *Ms[2] = {nullptr, nullptr};    // I - K G
+  LowRankFix fix[2];  // [0] forward, [1] backward
+  size_t smem = 0;
 };
 
 struct DevLevel {
@@ -237,12 +236,55 @@ const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega) {
   if (it != L.lowrank.end()) return it->second;
   LowRankDev dev;
   const int m = c->d.m_lowrank;
+  // B padded to EB entries per column
+  std::vector<std::vector<SEntry>> cols(m);
+  for (const SEntry &e : L.h.B) cols[e.col].push_back(e);
+  int EB = 1;
+  for (auto &v : cols) EB = std::max<int>(EB, (int)v.size());
+  std::vector<long long> bsite((size_t)m * EB, 0);
+  std::vector<double> bval((size_t)m * EB, 0.0);
+  for (int k = 0; k < m; ++k)
+    for (int e = 0; e < EB; ++e) {
+      const bool has = e < (int)cols[k].size();
+      const SEntry &src = has ? cols[k][e] : (cols[k].empty() ? SEntry{1, 1, k, 0.0} : cols[k][0]);
+      bsite[(size_t)k * EB + e] = (long long)src.j * L.g.pitch + src.i;
+      bval[(size_t)k * EB + e] = has ? src.val : 0.0;
+    }
+  const long long *d_bsite = c->dupload(bsite);
+  const double *d_bval = c->dupload(bval);
   for (int dir = 0; dir < 2; ++dir) {
     LowRankDir h = lowrank_setup(L.h, c->Sigma, omega, dir == 0);
-    dev.W[dir] = upload_sparse(c, h.W, m, L.g.pitch);
-    dev.Mneg[dir] = c->dupload(h.Mneg);
-    dev.Ms[dir] = c->dupload(h.Ms);
+    std::map<long long, std::vector<std::pair<int, double>>> bysite;
+    for (const SEntry &e : h.W) bysite[(long long)e.j * L.g.pitch + e.i].push_back({e.col, e.val});
+    int EW = 1;
+    for (auto &kv : bysite) EW = std::max<int>(EW, (int)kv.second.size());
+    std::vector<long long> usite;
+    std::vector<int> wcol;
+    std::vector<double> wval;
+    for (auto &kv : bysite) {
+      usite.push_back(kv.first);
+      for (int e = 0; e < EW; ++e) {
+        const bool has = e < (int)kv.second.size();
+        wcol.push_back(has ? kv.second[e].first : 0);
+        wval.push_back(has ? kv.second[e].second : 0.0);
+      }
+    }
+    LowRankFix &F = dev.fix[dir];
+    F.m = m;
+    F.EB = EB;
+    F.nu = (int)usite.size();
+    F.EW = EW;
+    F.bsite = d_bsite;
+    F.bval = d_bval;
+    F.usite = c->dupload(usite);
+    F.wcol = c->dupload(wcol);
+    F.wval = c->dupload(wval);
+    F.Mneg = c->dupload(h.Mneg);
+    F.Ms = c->dupload(h.Ms);
+    F.sigma_inv_sqrt = c->d_sigma_inv_sqrt;
+    F.mats_in_smem = (m <= 48) ? 1 : 0;
   }
+  dev.smem = ((size_t)m * EB + 3 * (size_t)m + (m <= 48 ? 2 * (size_t)m * m : 0)) * sizeof(double);
   return L.lowrank.emplace(omega, dev).first->second;
 }
 
@@ -310,7 +352,9 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
 }
 
 // ---- fused tile kernel dispatch ----
-constexpr int kFusedTY = 32;
+// tile height: 32 rows on the big (bandwidth / issue bound) levels; the small levels are latency bound,
+// there short tiles give every warp at most one row per colour pass and spread over more SMs
+inline int fused_tile_rows(int ny) { return ny > 1024 ? 32 : (ny > 256 ? 16 : 8); }
 constexpr int kFusedSmemMax = 110 * 1024;
 
 template <int NC, bool G, bool PR, bool RS>
@@ -355,7 +399,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, bool gi
   P.HXL = up4(S + (restrict_ ? 2 : 0));
   const int HXR = up4(S + (restrict_ ? 1 : 0));
   P.TX = 128 - P.HXL - HXR;
-  P.TY = kFusedTY;
+  P.TY = fused_tile_rows(L.g.ny);
   P.hl = S + (restrict_ ? 1 : 0);
   const int hh = S + (restrict_ ? 2 : 0);
   P.RY = P.TY + P.hl + hh;
@@ -378,15 +422,11 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, bool gi
 void dev_lowrank_fix(mgmc_ctx *c, int level, bool fwd, bool gibbs, double omega, uint32_t c1) {
   DevLevel &L = c->lv[level];
   const LowRankDev &lr = get_lowrank(c, level, omega);
-  const int dir = fwd ? 0 : 1;
-  const int m = c->d.m_lowrank;
-  const size_t sh = (3 * (size_t)m) * sizeof(double);
+  const LowRankFix &F = lr.fix[fwd ? 0 : 1];
   NoiseP nz = noise_params(c, level, c1);
   c->launch("lowrank_fix", level, [&] {
-    if (gibbs)
-      lowrank_fix_kernel<true><<<c->d.nchains, 256, sh, c->stream>>>(L.B.cols, lr.W[dir].rows, lr.Mneg[dir], lr.Ms[dir], c->d_sigma_inv_sqrt, L.g.stride, L.x, nz);
-    else
-      lowrank_fix_kernel<false><<<c->d.nchains, 256, sh, c->stream>>>(L.B.cols, lr.W[dir].rows, lr.Mneg[dir], lr.Ms[dir], c->d_sigma_inv_sqrt, L.g.stride, L.x, nz);
+    if (gibbs) lowrank_fix_kernel<true><<<c->d.nchains, 256, lr.smem, c->stream>>>(F, L.g.stride, L.x, nz);
+    else lowrank_fix_kernel<false><<<c->d.nchains, 256, lr.smem, c->stream>>>(F, L.g.stride, L.x, nz);
   });
 }
 
