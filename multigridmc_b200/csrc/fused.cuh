@@ -49,7 +49,7 @@ struct FusedP {
   double *xc_zero;      // RESTRICT: coarse iterate, set to zero (multigridmc_sampler.cc:122)
   int nstages;
   Stage st[8];
-  double omega, noise_scale;
+  double winv, noise_scale;  // omega / a_ii, sqrt(a_ii (2 - omega) / omega)
   NoiseP nz;
   int HXL, TX, TY, RY, hl;  // region geometry (host-computed, identical for all tiles)
 };
@@ -107,20 +107,29 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const int gi0 = i_r0 + 4 * lane;  // first global column of this lane's group
   const bool cols_alloc = (gi0 >= -kGX) && (gi0 + 3 < pitch - kGX);
 
-  // ---- stage the region: one warp per row, lane p loads its group of 4 columns (2 x 128 bit);
-  //      two rows per iteration keep 8 independent 128-bit loads per lane in flight ----
+  // ---- stage the region: one warp per row.  Lane l loads the column pairs (2l, 2l+1) and
+  //      (64+2l, 64+2l+1): each 128-bit load instruction covers 512 contiguous bytes (fully coalesced);
+  //      the pair is then scattered into planes 2(l&1), 2(l&1)+1 at index l/2 (+16), conflict free.
+  //      Two rows per iteration keep 8 independent 128-bit loads per lane in flight. ----
+  const int pa = 2 * (lane & 1), ia = lane >> 1;          // plane / index of column 2l; column 64+2l is at index ia + 16
+  const int gia = i_r0 + 2 * lane, gib = gia + 64;        // global columns of the two pairs
+  const bool oka = (gia >= -kGX) && (gia + 1 < pitch - kGX), okb = (gib >= -kGX) && (gib + 1 < pitch - kGX);
   for (int r = warp; r < RY; r += 2 * kFusedWarps) {
     double2 xa[2], xb[2], fa[2], fb[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int gj = j_r0 + r + u * kFusedWarps;
       xa[u] = xb[u] = fa[u] = fb[u] = make_double2(0.0, 0.0);
-      if (cols_alloc && gj >= -kGY && gj <= ny + kGY && r + u * kFusedWarps < RY) {
-        const long long o = (long long)gj * pitch + gi0;
-        xa[u] = *reinterpret_cast<const double2 *>(xg + o);
-        xb[u] = *reinterpret_cast<const double2 *>(xg + o + 2);
-        fa[u] = *reinterpret_cast<const double2 *>(fg + o);
-        fb[u] = *reinterpret_cast<const double2 *>(fg + o + 2);
+      if (gj >= -kGY && gj <= ny + kGY && r + u * kFusedWarps < RY) {
+        const long long o = (long long)gj * pitch;
+        if (oka) {
+          xa[u] = *reinterpret_cast<const double2 *>(xg + o + gia);
+          fa[u] = *reinterpret_cast<const double2 *>(fg + o + gia);
+        }
+        if (okb) {
+          xb[u] = *reinterpret_cast<const double2 *>(xg + o + gib);
+          fb[u] = *reinterpret_cast<const double2 *>(fg + o + gib);
+        }
       }
     }
 #pragma unroll
@@ -129,34 +138,40 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       if (rr >= RY) break;
       const int gj = j_r0 + rr;
       if (PROLONG) {
-        if (cols_alloc && gj >= 1 && gj < ny && gi0 >= -3 && gi0 <= nx) {
+        if (gj >= 1 && gj < ny) {
           // x += alpha R^T x_c in gather form: every fine vertex reads its (up to) 4 coarse parents
           const double *xc = P.xc_in + (long long)blockIdx.z * P.gc.stride;
           const double *r0 = xc + (long long)(gj >> 1) * P.gc.pitch, *r1 = xc + (long long)((gj + 1) >> 1) * P.gc.pitch;
-          const int I = gi0 >> 1;  // gi0 is a multiple of 4: coarse columns I, I+1, I+2 cover the group
-          const double q0 = 0.5 * (r0[I] + r1[I]), q1 = 0.5 * (r0[I + 1] + r1[I + 1]), q2 = 0.5 * (r0[I + 2] + r1[I + 2]);
           const double al = P.alpha;
-          if (gi0 >= 1 && gi0 < nx) xa[u].x += al * q0;
-          if (gi0 + 1 >= 1 && gi0 + 1 < nx) xa[u].y += al * (0.5 * (q0 + q1));
-          if (gi0 + 2 >= 1 && gi0 + 2 < nx) xb[u].x += al * q1;
-          if (gi0 + 3 >= 1 && gi0 + 3 < nx) xb[u].y += al * (0.5 * (q1 + q2));
+          if (oka && gia >= -1 && gia <= nx) {  // gia is even: coarse columns I, I + 1
+            const int I = gia >> 1;
+            const double q0 = 0.5 * (r0[I] + r1[I]), q1 = 0.5 * (r0[I + 1] + r1[I + 1]);
+            if (gia >= 1 && gia < nx) xa[u].x += al * q0;
+            if (gia + 1 >= 1 && gia + 1 < nx) xa[u].y += al * (0.5 * (q0 + q1));
+          }
+          if (okb && gib >= -1 && gib <= nx) {
+            const int I = gib >> 1;
+            const double q0 = 0.5 * (r0[I] + r1[I]), q1 = 0.5 * (r0[I + 1] + r1[I + 1]);
+            if (gib >= 1 && gib < nx) xb[u].x += al * q0;
+            if (gib + 1 >= 1 && gib + 1 < nx) xb[u].y += al * (0.5 * (q0 + q1));
+          }
         }
       }
-      double *xr = xs + rr * 128, *fr = fs + rr * 128;
-      xr[lane] = xa[u].x;
-      xr[32 + lane] = xa[u].y;
-      xr[64 + lane] = xb[u].x;
-      xr[96 + lane] = xb[u].y;
-      fr[lane] = fa[u].x;
-      fr[32 + lane] = fa[u].y;
-      fr[64 + lane] = fb[u].x;
-      fr[96 + lane] = fb[u].y;
+      double *xr = xs + rr * 128 + pa * 32 + ia, *fr = fs + rr * 128 + pa * 32 + ia;
+      xr[0] = xa[u].x;
+      xr[32] = xa[u].y;
+      xr[16] = xb[u].x;
+      xr[48] = xb[u].y;
+      fr[0] = fa[u].x;
+      fr[32] = fa[u].y;
+      fr[16] = fb[u].x;
+      fr[48] = fb[u].y;
     }
   }
   __syncthreads();
 
   // ---- colour passes: one warp per row, lane = group ----
-  const double winv = P.omega / P.a.c;
+  const double winv = P.winv;
   const double nscale = P.noise_scale;
   const int S = P.nstages;
   constexpr int EXLX = RESTRICT ? 2 : 0, EXHX = RESTRICT ? 1 : 0, EXLY = RESTRICT ? 1 : 0, EXHY = RESTRICT ? 2 : 0;
@@ -190,18 +205,19 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     __syncthreads();
   }
 
-  // ---- write the tile to the output buffer (skipped by a pure residual + restrict launch) ----
+  // ---- write the tile to the output buffer (skipped by a pure residual + restrict launch):
+  //      same coalesced column-pair mapping as the load ----
   if (PROLONG || S > 0) {
-    const bool mine = (gi0 >= i_t0) && (gi0 < i_t0 + TX) && (gi0 <= nx) && cols_alloc;
+    const bool minea = (gia >= i_t0) && (gia < i_t0 + TX) && (gia <= nx) && oka;
+    const bool mineb = (gib >= i_t0) && (gib < i_t0 + TX) && (gib <= nx) && okb;
     for (int rr = warp; rr < TY; rr += kFusedWarps) {
       const int gj = j_t0 + rr;
-      if (mine && gj < ny) {
-        const double *xr = xs + (gj - j_r0) * 128;
-        const long long o = (long long)gj * pitch + gi0;
-        // boundary / pad columns inside the group hold the zeros they were loaded with
-        *reinterpret_cast<double2 *>(xo + o) = make_double2(xr[lane], xr[32 + lane]);
-        *reinterpret_cast<double2 *>(xo + o + 2) = make_double2(xr[64 + lane], xr[96 + lane]);
-      }
+      if (gj >= ny) break;
+      const double *xr = xs + (gj - j_r0) * 128 + pa * 32 + ia;
+      const long long o = (long long)gj * pitch;
+      // boundary / pad columns inside a pair hold the zeros they were loaded with
+      if (minea) *reinterpret_cast<double2 *>(xo + o + gia) = make_double2(xr[0], xr[32]);
+      if (mineb) *reinterpret_cast<double2 *>(xo + o + gib) = make_double2(xr[16], xr[48]);
     }
   }
 

@@ -99,6 +99,7 @@ struct mgmc_ctx {
   // graph of one MGMC cycle (+ end-of-cycle kernel)
   cudaGraphExec_t graph = nullptr;
   bool use_graph = true;
+  bool perf_no_noise = false;  // MGMC_PERF_NO_NOISE=1: run the sampling cycle with the deterministic kernels (perf experiments only)
   // instrumentation
   int64_t launch_count = 0;
   int64_t launches_per_cycle = 0;
@@ -392,7 +393,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, bool gi
   }
   P.nstages = S;
   for (int k = 0; k < S; ++k) P.st[k] = stages[k];
-  P.omega = omega;
+  P.winv = omega / L.coef.c;
   P.noise_scale = std::sqrt(L.coef.c * (2. - omega) / omega);  // sor_sampler.cc:24-27
   P.nz = noise_params(c, level, 0);
   auto up4 = [](int v) { return (v + 3) / 4 * 4; };
@@ -533,10 +534,11 @@ void mgmc_sample_level(mgmc_ctx *c, int level) {  // multigridmc_sampler.cc:103-
   const int cycle_ = (level > 0) ? d.cycle : 1;
   for (int j = 0; j < cycle_; ++j) {
     // presampler + residual + restrict (+ x_{l+1} = 0)
-    emit_smoothing(c, level, sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true), true, d.omega, false, 0.0, true);
+    const bool gibbs = !c->perf_no_noise;
+    emit_smoothing(c, level, sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true), gibbs, d.omega, false, 0.0, true);
     mgmc_sample_level(c, level + 1);
     // prolongate_add + postsampler
-    emit_smoothing(c, level, sweep_list(d.smoother, MGMC_BACKWARD, d.npostsmooth, true), true, d.omega, true, d.coarse_scaling, false);
+    emit_smoothing(c, level, sweep_list(d.smoother, MGMC_BACKWARD, d.npostsmooth, true), gibbs, d.omega, true, d.coarse_scaling, false);
     normalize_x(c, level);
   }
 }
@@ -690,6 +692,7 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
     CUDA_CHECK(cudaSetDevice(c->device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->use_graph = (std::getenv("MGMC_NO_GRAPH") == nullptr);
+    c->perf_no_noise = (std::getenv("MGMC_PERF_NO_NOISE") != nullptr);
     c->sweep_counter.assign(desc->nlevel, 0u);
     c->keys = philox_round_keys(desc->seed);
     c->lv.resize(desc->nlevel);
