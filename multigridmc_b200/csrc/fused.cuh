@@ -52,6 +52,7 @@ struct FusedP {
   double winv, noise_scale;  // omega / a_ii, sqrt(a_ii (2 - omega) / omega)
   NoiseP nz;
   int HXL, TX, TY, RY, hl;  // region geometry (host-computed, identical for all tiles)
+  int omega_is_one;
 };
 
 // element at column offset K (-1..4) of group p in a shared-memory row
@@ -71,21 +72,32 @@ __device__ __forceinline__ double stencil_at(const Coef9 &a, double *row, int p)
   return s;
 }
 
-// update the two sites (offset Q and Q + 2) of one colour in group p of one row
-template <bool NINE, bool GIBBS, int Q>
+// off-diagonal part  sum_{j != i} a_ij x_j
+template <bool NINE, int K>
+__device__ __forceinline__ double offdiag_at(const Coef9 &a, double *row, int p) {
+  double s = a.w * sat<K - 1>(row, p) + a.e * sat<K + 1>(row, p) + a.s * sat<K>(row - 128, p) + a.n * sat<K>(row + 128, p);
+  if (NINE)
+    s += a.sw * sat<K - 1>(row - 128, p) + a.se * sat<K + 1>(row - 128, p) + a.nw * sat<K - 1>(row + 128, p) + a.ne * sat<K + 1>(row + 128, p);
+  return s;
+}
+
+// update the two sites (offset Q and Q + 2) of one colour in group p of one row:
+//   x_i += omega (b_i - sum_j a_ij x_j) / a_ii  (sor_smoother.cc:75); for omega = 1 the old value drops
+//   out, x_i = (b_i - sum_{j != i} a_ij x_j) / a_ii, which saves reading it from shared memory
+template <bool NINE, bool GIBBS, bool W1, int Q>
 __device__ __forceinline__ void update_pair(const Coef9 &a, double *xrow, const double *frow, int p, bool v0, bool v1, double winv, double nscale, double z0,
                                             double z1) {
   if (v0) {
-    const double s = stencil_at<NINE, Q>(a, xrow, p);
     double b = frow[Q * 32 + p];
     if (GIBBS) b = fma(nscale, z0, b);
-    sat<Q>(xrow, p) += winv * (b - s);
+    if (W1) sat<Q>(xrow, p) = winv * (b - offdiag_at<NINE, Q>(a, xrow, p));
+    else sat<Q>(xrow, p) += winv * (b - stencil_at<NINE, Q>(a, xrow, p));
   }
   if (v1) {
-    const double s = stencil_at<NINE, Q + 2>(a, xrow, p);
     double b = frow[(Q + 2) * 32 + p];
     if (GIBBS) b = fma(nscale, z1, b);
-    sat<Q + 2>(xrow, p) += winv * (b - s);
+    if (W1) sat<Q + 2>(xrow, p) = winv * (b - offdiag_at<NINE, Q + 2>(a, xrow, p));
+    else sat<Q + 2>(xrow, p) += winv * (b - stencil_at<NINE, Q + 2>(a, xrow, p));
   }
 }
 
@@ -199,8 +211,13 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       if (GIBBS) normal_pair(P.nz.keys, (((uint32_t)j * P.nz.G + pg) << 1) | (uint32_t)q, c1, sample, chain, z0, z1);
       double *xr = xs + (j - j_r0) * 128;
       const double *fr = fs + (j - j_r0) * 128;
-      if (q == 0) update_pair<NINE, GIBBS, 0>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
-      else update_pair<NINE, GIBBS, 1>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
+      if (P.omega_is_one) {
+        if (q == 0) update_pair<NINE, GIBBS, true, 0>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
+        else update_pair<NINE, GIBBS, true, 1>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
+      } else {
+        if (q == 0) update_pair<NINE, GIBBS, false, 0>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
+        else update_pair<NINE, GIBBS, false, 1>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
+      }
     }
     __syncthreads();
   }
@@ -225,8 +242,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   if (RESTRICT) {
     for (int rr = warp; rr <= TY; rr += kFusedWarps) {
       const int gj = j_t0 + rr;
-      double *xr = xs + (gj - j_r0) * 128;
-      double *fr = fs + (gj - j_r0) * 128;
+      double *__restrict__ xr = xs + (gj - j_r0) * 128;
+      double *__restrict__ fr = fs + (gj - j_r0) * 128;
       double res[4] = {0.0, 0.0, 0.0, 0.0};
       if (gj < ny) {  // (lanes 0 / 31 read in-bounds garbage for columns that are masked out below)
         res[0] = fr[lane] - stencil_at<NINE, 0>(P.a, xr, lane);

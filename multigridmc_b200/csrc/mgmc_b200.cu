@@ -394,6 +394,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, bool gi
   P.nstages = S;
   for (int k = 0; k < S; ++k) P.st[k] = stages[k];
   P.winv = omega / L.coef.c;
+  P.omega_is_one = (omega == 1.0) ? 1 : 0;
   P.noise_scale = std::sqrt(L.coef.c * (2. - omega) / omega);  // sor_sampler.cc:24-27
   P.nz = noise_params(c, level, 0);
   auto up4 = [](int v) { return (v + 3) / 4 * 4; };
