@@ -8,7 +8,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-_SO = os.path.join(_CSRC, "libmgmc_b200.so")
+_SO = os.environ.get("MGMC_LIB", os.path.join(_CSRC, "libmgmc_b200.so"))
 _LIB = None
 
 NVCC_FLAGS = [

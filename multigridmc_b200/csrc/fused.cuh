@@ -53,6 +53,7 @@ struct FusedP {
   NoiseP nz;
   int HXL, TX, TY, RY, hl;  // region geometry (host-computed, identical for all tiles)
   int omega_is_one;
+  long long *timing;  // MGMC_TILE_TIMING builds only: 8 clock64 stamps + smid per CTA
 };
 
 // element at column offset K (-1..4) of group p in a shared-memory row
@@ -105,6 +106,14 @@ template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT>
 __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {
   extern __shared__ double sm[];
   constexpr bool NINE = (NC == 4);
+#ifdef MGMC_TILE_TIMING
+  const int cta_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+#define TSTAMP(k) if (threadIdx.x == 0 && P.timing) P.timing[(long long)cta_id * 10 + (k)] = clock64();
+  if (threadIdx.x == 0 && P.timing) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); P.timing[(long long)cta_id * 10 + 9] = smid; }
+#else
+#define TSTAMP(k)
+#endif
+  TSTAMP(0)
   const int RY = P.RY, TX = P.TX, TY = P.TY;
   double *xs = sm;
   double *fs = sm + RY * 128;
@@ -181,6 +190,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     }
   }
   __syncthreads();
+  TSTAMP(1)
 
   // ---- colour passes: one warp per row, lane = group ----
   const double winv = P.winv;
@@ -220,6 +230,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
     }
     __syncthreads();
+    TSTAMP(2 + (s < 4 ? s : 3))
   }
 
   // ---- write the tile to the output buffer (skipped by a pure residual + restrict launch):
@@ -238,6 +249,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     }
   }
 
+  TSTAMP(6)
   // ---- residual on [i_t0 - 1, i_t0 + TX - 1] x [j_t0, j_t0 + TY], then full-weighting restriction ----
   if (RESTRICT) {
     for (int rr = warp; rr <= TY; rr += kFusedWarps) {
@@ -281,6 +293,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
     }
   }
+  TSTAMP(7)
 }
 
 }  // namespace mgmc

@@ -409,6 +409,18 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, bool gi
   if (smem > (size_t)kFusedSmemMax) fail(MGMC_ERR_INVALID, "internal: fused tile does not fit in shared memory");
   dim3 grid((L.g.nx + P.TX - 1) / P.TX, (L.g.ny - 1 + P.TY - 1) / P.TY, c->d.nchains);
   std::string name = std::string(gibbs ? "gibbs" : "sor") + (nc == 2 ? "_rb" : "_4c") + std::to_string(S) + (prolong ? "+prolong" : "") + (restrict_ ? "+restrict" : "");
+#ifdef MGMC_TILE_TIMING
+  // debug build: dump per-CTA phase time stamps of the first level-0 launch of every kernel flavour
+  static std::map<std::string, int> dumped;
+  const char *tfile = std::getenv("MGMC_TIMING_FILE");
+  long long *d_timing = nullptr;
+  const size_t ncta = (size_t)grid.x * grid.y * grid.z;
+  if (tfile && level == 0 && dumped[name]++ == 3) {
+    CUDA_CHECK(cudaMalloc(&d_timing, ncta * 10 * sizeof(long long)));
+    CUDA_CHECK(cudaMemset(d_timing, 0, ncta * 10 * sizeof(long long)));
+    P.timing = d_timing;
+  }
+#endif
   c->launch(name.c_str(), level, [&] {
 #define FUSED_CASE(NC_, G_, PR_, RS_) \
   if (nc == NC_ && gibbs == G_ && prolong == PR_ && restrict_ == RS_) launch_fused_t<NC_, G_, PR_, RS_>(c, P, grid, smem);
@@ -418,6 +430,20 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, bool gi
     FUSED_CASE(4, true, false, false) FUSED_CASE(4, true, false, true) FUSED_CASE(4, true, true, false) FUSED_CASE(4, true, true, true)
 #undef FUSED_CASE
   });
+#ifdef MGMC_TILE_TIMING
+  if (d_timing) {
+    c->sync();
+    std::vector<long long> h(ncta * 10);
+    CUDA_CHECK(cudaMemcpy(h.data(), d_timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_timing);
+    FILE *fp = std::fopen((std::string(tfile) + "." + name + ".txt").c_str(), "w");
+    for (size_t k = 0; k < ncta; ++k) {
+      for (int q = 0; q < 10; ++q) std::fprintf(fp, "%lld ", h[k * 10 + q]);
+      std::fprintf(fp, "\n");
+    }
+    std::fclose(fp);
+  }
+#endif
   if (S > 0 || prolong) std::swap(L.x, L.x_alt);
 }
 
