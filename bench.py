@@ -260,16 +260,17 @@ def run_b200(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-    # algorithmic bytes per launch of the dominant kernel (DESIGN.md "Kernels"): a Gibbs colour pass on
-    # level l updates N_l / ncolours sites at 24 B per site update
-    lvl = int(top[0].split("/L")[1])
-    nl = ctx.ndof(lvl)
-    ncol = ctx.level_info(lvl)[3]
-    per_launch = {"gibbs_rb": 24.0 * nl / 2, "gibbs_4c": 24.0 * nl / 4, "sor_rb": 24.0 * nl / 2, "sor_4c": 24.0 * nl / 4,
-                  "residual_restrict": 18.0 * nl, "prolongate_add": 18.0 * nl, "zero": 8.0 * nl,
-                  "gibbs_fused": None}.get(top[0].split("/")[0])
+    # algorithmic bytes per launch of the dominant kernel: counted by the library itself in the model of
+    # SURVEY.md section 8(d) (24 B per site and sweep, 18 B prolongate_add, 18 + 2 B residual + restrict),
+    # see DESIGN.md "Kernels"; the duration is the CUDA-event average over the launches of that slot
+    per_launch = top[3] / top[2] if top[3] > 0 else None
     avg_ms = top[1] / top[2]
     achieved = (per_launch / (avg_ms * 1e-3) / 1e9) if per_launch else None
+    traffic = None
+    try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top[0])
+    except Exception:
+        pass
     cycle_gbs = byts / (ms_max / a.steps * 1e-3) / 1e9
 
     line = {
@@ -284,10 +285,11 @@ def run_b200(a):
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
                      "kernel_share_of_cycle": top[1] / total_ms if total_ms else None},
-        "kernels": [{"name": p[0], "ms_per_cycle": p[1] / 3.0, "launches_per_cycle": p[2] / 3.0} for p in sorted(prof, key=lambda p: -p[1])[:12]],
+        "kernels": [{"name": p[0], "ms_per_cycle": p[1] / 3.0, "launches_per_cycle": p[2] / 3.0,
+                     "algorithmic_gbs": (p[3] / (p[1] * 1e-3) / 1e9) if p[1] > 0 else None} for p in sorted(prof, key=lambda p: -p[1])[:12]],
         "qoi_mean": float(np.mean(series)),
     }
     if not a.no_cpu_baseline and world == 1:

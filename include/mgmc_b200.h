@@ -133,8 +133,10 @@ int mgmc_sample_timed(mgmc_ctx *, int64_t nsamples, double *qoi_series, double *
 /* number of kernels launched by this context so far */
 int64_t mgmc_launch_count(const mgmc_ctx *);
 /* per-kernel CUDA-event timing of nsamples MGMC cycles: for each distinct (kernel, level) slot of
- * one cycle returns total ms and launch count.  names: caller buffer of nslots_max * 64 chars. */
-int mgmc_profile_cycle(mgmc_ctx *, int nsamples, int nslots_max, char *names, double *ms_total, int64_t *launches, int *nslots);
+ * one cycle returns total ms, launch count and (nullable) the algorithmic bytes of those launches
+ * in the model of mgmc_cycle_model.  names: caller buffer of nslots_max * 64 chars. */
+int mgmc_profile_cycle(mgmc_ctx *, int nsamples, int nslots_max, char *names, double *ms_total, int64_t *launches, double *alg_bytes,
+                       int *nslots);
 /* algorithmic bytes and site updates of one MGMC cycle */
 int mgmc_cycle_model(const mgmc_ctx *, double *bytes, double *site_updates);
 

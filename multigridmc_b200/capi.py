@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
 ]
 SOURCES = ["mgmc_b200.cu"]
-HEADERS = ["kernels.cuh", "philox.cuh", "setup.hh", "../../include/mgmc_b200.h"]
+HEADERS = ["fused.cuh", "kernels.cuh", "philox.cuh", "setup.hh", "../../include/mgmc_b200.h"]
 
 
 def build(force=False, verbose=False):
@@ -92,7 +92,7 @@ def lib():
         "mgmc_sample_moments": (i, [vp, i64, c_dp, c_dp]),
         "mgmc_sample_timed": (i, [vp, i64, c_dp, c_dp]),
         "mgmc_launch_count": (i64, [vp]),
-        "mgmc_profile_cycle": (i, [vp, i, i, C.c_char_p, c_dp, C.POINTER(i64), ip]),
+        "mgmc_profile_cycle": (i, [vp, i, i, C.c_char_p, c_dp, C.POINTER(i64), c_dp, ip]),
         "mgmc_cycle_model": (i, [vp, c_dp, c_dp]),
     }
     for name, (res, args) in sig.items():
@@ -310,11 +310,13 @@ class Context:
         names = C.create_string_buffer(nslots_max * 64)
         ms = np.zeros(nslots_max)
         launches = np.zeros(nslots_max, dtype=np.int64)
+        byts = np.zeros(nslots_max)
         n = C.c_int()
-        _chk(lib().mgmc_profile_cycle(self.h, nsamples, nslots_max, names, ms.ctypes.data_as(c_dp), launches.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n)))
+        _chk(lib().mgmc_profile_cycle(self.h, nsamples, nslots_max, names, ms.ctypes.data_as(c_dp), launches.ctypes.data_as(C.POINTER(C.c_int64)),
+                                      byts.ctypes.data_as(c_dp), C.byref(n)))
         out = []
         for k in range(n.value):
-            out.append((names.raw[k * 64:(k + 1) * 64].split(b"\0")[0].decode(), float(ms[k]), int(launches[k])))
+            out.append((names.raw[k * 64:(k + 1) * 64].split(b"\0")[0].decode(), float(ms[k]), int(launches[k]), float(byts[k])))
         return out
 
     def cycle_model(self):

@@ -37,6 +37,30 @@ struct Stage {
   uint32_t c1;  // (level << 24) | sweep counter of the sweep this colour pass belongs to
 };
 
+// Device-resident data of the low-rank (measurement) term of one level for the in-kernel Woodbury
+// fix-up (see "patch CTAs" below).  Sparse matrices are stored with explicit (i, j) coordinates.
+struct LowRankTile {
+  int m, EB;
+  const int *b_i, *b_j;      // [m * EB]  entries of column k of B, padded by repeating an entry with value 0
+  const double *b_val;       // [m * EB]
+  const int *bbox;           // [m * 4]   i0, i1, j0, j1 of supp(B_k)
+  int nbu;                   // B grouped by unique site (race-free scatter of B u into the residual)
+  const int *bu_i, *bu_j, *bu_ptr, *bu_col;
+  const double *bu_val;
+  int nu[2], EW[2];          // W = M_0^{-1} B per sweep direction, grouped by unique site, EW padded entries each
+  const int *w_i[2], *w_j[2], *w_col[2];
+  const double *w_val[2];
+  const double *Mneg[2], *Ms[2];  // m x m row-major: d = Ms s + Mneg (B^T x)
+  int diag[2];               // Mneg, Ms are diagonal (B^T W is: the measurements do not interact on this level)
+  const int *wbox[2];        // [m * 4]   i0, i1, j0, j1 of supp(W_k)
+  const int *wl_ptr[2], *wl_u[2];  // per measurement k: the unique W sites within 8 sites of supp(B_k)
+  const double *sigma_inv, *sigma_inv_sqrt;
+  double *dbuf;              // [nslots][nchains][m]      fix-up coefficients d (and u = Sigma^{-1} B^T x for the residual)
+  double *tbuf;              // [nslots][nchains][2 m]    t = B^T x and s exchanged between patch CTAs
+  int *flags;                // [nslots][nchains]         1 once dbuf[slot] is complete
+  int *counters;             // [nslots][nchains]         arrival counter of the patch CTAs
+};
+
 struct FusedP {
   GridP g, gc;  // this level, next coarser level
   Coef9 a;
@@ -54,7 +78,246 @@ struct FusedP {
   int HXL, TX, TY, RY, hl;  // region geometry (host-computed, identical for all tiles)
   int omega_is_one;
   long long *timing;  // MGMC_TILE_TIMING builds only: 8 clock64 stamps + smid per CTA
+  int tiles_x;        // the grid is 1-d: npatch patch CTAs followed by tiles_x * tiles_y tile CTAs
+  // low-rank term (LOWRANK kernels): fix-up q follows stage fix_stage[q]
+  const LowRankTile *lr;
+  int npatch, wpw, wcap;  // patch CTAs, windows per warp, doubles per window array
+  int nfix;
+  int fix_stage[2], fix_dir[2];
+  uint32_t fix_c1[2];
+  int lr_slot, nchains;   // first dbuf / flag slot of this launch (nfix fix-ups, then u)
 };
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// Patch CTAs: the Woodbury fix-up after a sweep (sor_smoother.cc:47-51, sor_sampler.cc:48-56),
+//   x += W d,  d = (I - K G) Sigma^{-1/2} xi - K B^T x,
+// needs B^T x of the freshly swept x: a grid-wide dependency in the middle of a fused launch.  But
+// B^T x only involves the few sites of supp(B_k), and their values after `S` colour stages depend on
+// the input x within distance S of them.  The first `npatch` CTAs of the grid therefore re-run the
+// launch on small windows (supp(B_k) dilated by S sites) around every measurement -- same input, same
+// Philox noise, same fix-ups -- publish d for every fix-up (and u = Sigma^{-1} B^T x of the final
+// state for the low-rank part of the residual) in global memory and raise a flag; tile CTAs whose
+// region contains a site of W (or B) wait for the flag and apply x += W d between two stages.
+// Patch CTAs have the lowest block indices of the grid, so they are resident before any tile CTA can wait.
+// ------------------------------------------------------------------------------------------------
+template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT>
+__device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id, int chainz) {
+  const LowRankTile &R = *P.lr;
+  const int m = R.m, S = P.nstages, wcap = P.wcap;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nx = P.g.nx, ny = P.g.ny, pitch = P.g.pitch;
+  // shared memory: t, s, d (m each) | per window: x, f, noise of sweep 0, noise of sweep 1 (wcap each) | meta (wcap ints) | geometry
+  double *tsm = sm, *ssm = sm + m, *dsm = sm + 2 * m;
+  double *wins = sm + 3 * m;
+  const int nwin = P.wpw;  // windows of this patch CTA
+  int *meta = reinterpret_cast<int *>(wins + (size_t)nwin * 4 * wcap);
+  int *geo = meta + (size_t)nwin * wcap;  // per window: wi0, wj0, wx, wy
+  const int k0 = patch_id * nwin;
+  const int nloc = min(nwin, m - k0);
+  const long long cbase = (long long)chainz * P.g.stride;
+  const double *xg = P.x_in + cbase, *fg = P.f + cbase;
+  const uint32_t sample = GIBBS ? *P.nz.sample : 0u;
+  const uint32_t chain = P.nz.chain0 + chainz;
+  const Coef9 &a = P.a;
+  const double winv = P.winv, nscale = P.noise_scale;
+
+  for (int k = threadIdx.x; k < 3 * m; k += kFusedThreads) sm[k] = 0.0;  // padded W entries read d[0] with weight 0
+  for (int w = threadIdx.x; w < nloc; w += kFusedThreads) {
+    const int k = k0 + w;
+    const int wi0 = max(0, R.bbox[4 * k] - S), wi1 = min(nx, R.bbox[4 * k + 1] + S);
+    const int wj0 = max(0, R.bbox[4 * k + 2] - S), wj1 = min(ny, R.bbox[4 * k + 3] + S);
+    geo[4 * w] = wi0;
+    geo[4 * w + 1] = wj0;
+    geo[4 * w + 2] = wi1 - wi0 + 1;
+    geo[4 * w + 3] = wj1 - wj0 + 1;
+  }
+  __syncthreads();
+  // ---- load the windows; meta = (stage of the site's colour within a sweep) | (distance to supp(B_k)) << 8,
+  //      -1 for sites that are never updated ----
+  for (int t = threadIdx.x; t < nloc * wcap; t += kFusedThreads) {
+    const int w = t / wcap, idx = t - w * wcap;
+    const int wi0 = geo[4 * w], wj0 = geo[4 * w + 1], wx = geo[4 * w + 2], wy = geo[4 * w + 3];
+    int mt = -1;
+    if (idx < wx * wy) {
+      const int k = k0 + w;
+      const int i = wi0 + idx % wx, j = wj0 + idx / wx;
+      double xv = xg[(long long)j * pitch + i];
+      const double fv = fg[(long long)j * pitch + i];
+      if (PROLONG && i >= 1 && i < nx && j >= 1 && j < ny) {
+        const double *xc = P.xc_in + (long long)chainz * P.gc.stride;
+        const double *r0 = xc + (long long)(j >> 1) * P.gc.pitch, *r1 = xc + (long long)((j + 1) >> 1) * P.gc.pitch;
+        const int I0 = i >> 1, I1 = (i + 1) >> 1;
+        xv += P.alpha * (0.25 * ((r0[I0] + r1[I0]) + (r0[I1] + r1[I1])));
+      }
+      double *xw = wins + (size_t)w * 4 * wcap;
+      xw[idx] = xv;
+      xw[wcap + idx] = fv;
+      // window edges that are not the Dirichlet boundary are never updated
+      const bool inner = (i > wi0) && (i < wi0 + wx - 1) && (j > wj0) && (j < wj0 + wy - 1);
+      if (inner) {
+        const int dist = max(max(R.bbox[4 * k] - i, i - R.bbox[4 * k + 1]), max(max(R.bbox[4 * k + 2] - j, j - R.bbox[4 * k + 3]), 0));
+        const int colour = (NC == 2) ? ((i + j) & 1) : ((i & 1) + 2 * (j & 1));
+        mt = colour | (dist << 8);
+      }
+    }
+    meta[t] = mt;
+  }
+  __syncthreads();
+  // ---- noise of every (sweep, site) that lies in the dependence cone of supp(B_k): the value of a B site
+  //      after stage S - 1 depends on stage s only within distance S - 1 - s ----
+  if (GIBBS) {
+    const int nsweeps = S / NC;
+    for (int t = threadIdx.x; t < nsweeps * nloc * wcap; t += kFusedThreads) {
+      const int sw = t / (nloc * wcap), r = t - sw * (nloc * wcap);
+      const int mt = meta[r];
+      if (mt < 0) continue;
+      const int colour = mt & 255, dist = mt >> 8;
+      int s = sw * NC;
+      while (P.st[s].colour != colour) ++s;
+      if (dist > S - 1 - s) continue;
+      const int w = r / wcap, idx = r - w * wcap;
+      const int i = geo[4 * w] + idx % geo[4 * w + 2], j = geo[4 * w + 1] + idx / geo[4 * w + 2];
+      double z0, z1;
+      normal_pair(P.nz.keys, (((uint32_t)j * P.nz.G + (uint32_t)(i >> 2)) << 1) | (uint32_t)(i & 1), P.st[s].c1, sample, chain, z0, z1);
+      wins[(size_t)w * 4 * wcap + (2 + sw) * wcap + idx] = (i & 2) ? z1 : z0;
+    }
+    __syncthreads();
+  }
+
+  int fixq = 0;
+  for (int s = 0; s <= S; ++s) {
+    if (s < S) {
+      const int colour = P.st[s].colour;
+      const int key_lo = colour, key_hi = colour | ((S - 1 - s) << 8);  // colour matches and dist <= S - 1 - s
+      for (int t = threadIdx.x; t < nloc * wcap; t += kFusedThreads) {
+        const int mt = meta[t];
+        if (mt < 0 || (mt & 255) != key_lo || mt > key_hi) continue;
+        const int w = t / wcap, idx = t - w * wcap;
+        const int wx = geo[4 * w + 2];
+        double *q = wins + (size_t)w * 4 * wcap + idx;
+        double b = q[wcap];
+        if (GIBBS) b = fma(nscale, q[(2 + s / NC) * wcap], b);
+        double off = a.w * q[-1] + a.e * q[1] + a.s * q[-wx] + a.n * q[wx];
+        if (NC == 4) off += a.sw * q[-wx - 1] + a.se * q[-wx + 1] + a.nw * q[wx - 1] + a.ne * q[wx + 1];
+        if (P.omega_is_one) q[0] = winv * (b - off);
+        else q[0] += winv * (b - (a.c * q[0] + off));
+      }
+      __syncthreads();
+    }
+    const bool fix_here = (s < S) && (fixq < P.nfix) && (P.fix_stage[fixq] == s);
+    const bool u_here = RESTRICT && (s == S);
+    if (!(fix_here || u_here)) continue;
+    // ---- t = B^T x on every window (and the low-rank noise s): one warp per window ----
+    const int slot = P.lr_slot + (fix_here ? fixq : P.nfix);
+    double *tb = R.tbuf + ((size_t)slot * P.nchains + chainz) * 2 * m;
+    double *db = R.dbuf + ((size_t)slot * P.nchains + chainz) * m;
+    const int dir = fix_here ? P.fix_dir[fixq] : 0;
+    const bool diag = fix_here && R.diag[dir];
+    for (int w = warp; w < nloc; w += kFusedWarps) {
+      const int k = k0 + w;
+      const double *xw = wins + (size_t)w * 4 * wcap;
+      const int wi0 = geo[4 * w], wj0 = geo[4 * w + 1], wx = geo[4 * w + 2];
+      double acc = 0.0;
+      for (int e = lane; e < R.EB; e += 32) acc += R.b_val[k * R.EB + e] * xw[(R.b_j[k * R.EB + e] - wj0) * wx + (R.b_i[k * R.EB + e] - wi0)];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        if (u_here) {
+          db[k] = acc * R.sigma_inv[k];  // u_k: low-rank part of the residual, r -= B u
+        } else {
+          double sv = 0.0;
+          if (GIBBS) {
+            double z0, z1;
+            normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[fixq], sample, chain, z0, z1);
+            sv = R.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
+          }
+          if (diag) {
+            // capacitance matrix Sigma + B^T W is diagonal (measurements do not interact on this level)
+            const double dk = fma(R.Ms[dir][(size_t)k * m + k], sv, R.Mneg[dir][(size_t)k * m + k] * acc);
+            dsm[k] = dk;
+            db[k] = dk;
+          } else {
+            tsm[k] = acc;
+            ssm[k] = sv;
+            if (P.npatch > 1) {
+              tb[k] = acc;
+              tb[m + k] = sv;
+            }
+          }
+        }
+      }
+    }
+    int *counter = R.counters + (size_t)slot * P.nchains + chainz;
+    int *flag = R.flags + (size_t)slot * P.nchains + chainz;
+    if (u_here || diag) {
+      // the last patch CTA to arrive publishes u / d
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(counter, 1) == P.npatch - 1) st_release(flag, 1);
+      }
+      if (u_here) continue;
+    } else {
+      if (P.npatch > 1) {
+        // all measurements are coupled through K: exchange t and s between the patch CTAs
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          __threadfence();
+          atomicAdd(counter, 1);
+          while (ld_acquire(counter) < P.npatch) {
+          }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < 2 * m; k += kFusedThreads) tsm[k] = __ldcg(tb + k);  // tsm and ssm are contiguous
+      }
+      __syncthreads();
+      // ---- d = Ms s + Mneg t ----
+      for (int k = warp; k < m; k += kFusedWarps) {
+        double acc = 0.0;
+        for (int c = lane; c < m; c += 32) {
+          acc = fma(R.Mneg[dir][(size_t)k * m + c], tsm[c], acc);
+          if (GIBBS) acc = fma(R.Ms[dir][(size_t)k * m + c], ssm[c], acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+          dsm[k] = acc;
+          if (patch_id == 0) db[k] = acc;
+        }
+      }
+      __syncthreads();
+      if (patch_id == 0 && threadIdx.x == 0) {
+        __threadfence();
+        st_release(flag, 1);
+      }
+    }
+    // ---- x += W d on every window: the W sites near window k are listed per window (with a diagonal
+    //      capacitance matrix these belong to column k alone and only d_k is needed) ----
+    for (int w = warp; w < nloc; w += kFusedWarps) {
+      const int k = k0 + w;
+      double *xw = wins + (size_t)w * 4 * wcap;
+      const int wi0 = geo[4 * w], wj0 = geo[4 * w + 1], wx = geo[4 * w + 2], wy = geo[4 * w + 3];
+      const int EW = R.EW[dir];
+      for (int q = R.wl_ptr[dir][k] + lane; q < R.wl_ptr[dir][k + 1]; q += 32) {
+        const int u = R.wl_u[dir][q];
+        const int i = R.w_i[dir][u] - wi0, j = R.w_j[dir][u] - wj0;
+        if (i < 0 || i >= wx || j < 0 || j >= wy) continue;
+        double acc = 0.0;
+        for (int e = 0; e < EW; ++e) acc += R.w_val[dir][(size_t)u * EW + e] * dsm[R.w_col[dir][(size_t)u * EW + e]];
+        xw[j * wx + i] += acc;
+      }
+    }
+    __syncthreads();  // tsm / ssm / dsm are reused by the next fix-up
+    ++fixq;
+  }
+}
 
 // element at column offset K (-1..4) of group p in a shared-memory row
 template <int K>
@@ -102,12 +365,18 @@ __device__ __forceinline__ void update_pair(const Coef9 &a, double *xrow, const 
   }
 }
 
-template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT>
+template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT, bool LOWRANK>
 __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {
   extern __shared__ double sm[];
   constexpr bool NINE = (NC == 4);
+  if (LOWRANK && (int)blockIdx.x < P.npatch) {
+    patch_cta<NC, GIBBS, PROLONG, RESTRICT>(P, sm, blockIdx.x, blockIdx.z);
+    return;
+  }
+  const int tile_id = (int)blockIdx.x - (LOWRANK ? P.npatch : 0);
+  const int tile_bx = tile_id % P.tiles_x, tile_by = tile_id / P.tiles_x;
 #ifdef MGMC_TILE_TIMING
-  const int cta_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int cta_id = blockIdx.z * gridDim.x + blockIdx.x;
 #define TSTAMP(k) if (threadIdx.x == 0 && P.timing) P.timing[(long long)cta_id * 10 + (k)] = clock64();
   if (threadIdx.x == 0 && P.timing) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); P.timing[(long long)cta_id * 10 + 9] = smid; }
 #else
@@ -119,7 +388,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   double *fs = sm + RY * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nx = P.g.nx, ny = P.g.ny, pitch = P.g.pitch;
-  const int i_t0 = TX * blockIdx.x, j_t0 = 1 + TY * blockIdx.y;
+  const int i_t0 = TX * tile_bx, j_t0 = 1 + TY * tile_by;
   const int i_r0 = i_t0 - P.HXL, j_r0 = j_t0 - P.hl;
   const long long cbase = (long long)blockIdx.z * P.g.stride;
   const double *xg = P.x_in + cbase;
@@ -200,6 +469,20 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const uint32_t pg = (uint32_t)((i_r0 >> 2) + lane);
   const uint32_t sample = GIBBS ? *P.nz.sample : 0u;
   const uint32_t chain = P.nz.chain0 + blockIdx.z;
+  // does the region of this tile contain a site touched by the low-rank fix-ups?
+  bool lr_need[2] = {false, false};
+  int fixq = 0;
+  if (LOWRANK) {
+    const LowRankTile &R = *P.lr;
+    for (int dir = 0; dir < 2; ++dir) {
+      int hit = 0;
+      for (int k = threadIdx.x; k < R.m; k += kFusedThreads) {
+        const int4 bb = reinterpret_cast<const int4 *>(R.wbox[dir])[k];
+        hit |= (bb.y >= i_r0 && bb.x < i_r0 + 128 && bb.w >= j_r0 && bb.z < j_r0 + RY);
+      }
+      lr_need[dir] = __syncthreads_or(hit);
+    }
+  }
   for (int s = 0; s < S; ++s) {
     const int colour = P.st[s].colour;
     const uint32_t c1 = P.st[s].c1;
@@ -230,6 +513,31 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
     }
     __syncthreads();
+    if (LOWRANK && fixq < P.nfix && P.fix_stage[fixq] == s) {
+      // x += W d with d published by the patch CTAs
+      const int dir = P.fix_dir[fixq];
+      if (lr_need[dir]) {
+        const LowRankTile &R = *P.lr;
+        const size_t slot = (size_t)(P.lr_slot + fixq) * P.nchains + blockIdx.z;
+        if (threadIdx.x == 0) {
+          while (ld_acquire(R.flags + slot) == 0) {
+          }
+        }
+        __syncthreads();
+        const double *db = R.dbuf + slot * R.m;
+        const int EW = R.EW[dir];
+        for (int u = threadIdx.x; u < R.nu[dir]; u += kFusedThreads) {
+          const int i = R.w_i[dir][u], j = R.w_j[dir][u];
+          if (!(i >= i_r0 && i < i_r0 + 128 && j >= j_r0 && j < j_r0 + RY)) continue;
+          double acc = 0.0;
+          for (int e = 0; e < EW; ++e) acc += R.w_val[dir][(size_t)u * EW + e] * __ldcg(db + R.w_col[dir][(size_t)u * EW + e]);
+          const int di = i - i_r0;
+          xs[(j - j_r0) * 128 + (di & 3) * 32 + (di >> 2)] += acc;
+        }
+        __syncthreads();
+      }
+      ++fixq;
+    }
     TSTAMP(2 + (s < 4 ? s : 3))
   }
 
@@ -271,6 +579,33 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
     }
     __syncthreads();
+    if (LOWRANK) {
+      // low-rank part of the residual: r -= B u, u = Sigma^{-1} B^T x of the final state (linear_operator.hh:71-75)
+      const LowRankTile &R = *P.lr;
+      int hit = 0;
+      for (int u = threadIdx.x; u < R.nbu; u += kFusedThreads) {
+        const int i = R.bu_i[u], j = R.bu_j[u];
+        hit |= (i >= max(1, i_t0 - 1) && i <= min(nx - 1, i_t0 + TX - 1) && j >= j_t0 && j <= j_t0 + TY && j < ny);
+      }
+      if (__syncthreads_or(hit)) {
+        const size_t slot = (size_t)(P.lr_slot + P.nfix) * P.nchains + blockIdx.z;
+        if (threadIdx.x == 0) {
+          while (ld_acquire(R.flags + slot) == 0) {
+          }
+        }
+        __syncthreads();
+        const double *ub = R.dbuf + slot * R.m;
+        for (int u = threadIdx.x; u < R.nbu; u += kFusedThreads) {
+          const int i = R.bu_i[u], j = R.bu_j[u];
+          if (!(i >= max(1, i_t0 - 1) && i <= min(nx - 1, i_t0 + TX - 1) && j >= j_t0 && j <= j_t0 + TY && j < ny)) continue;
+          double acc = 0.0;
+          for (int e = R.bu_ptr[u]; e < R.bu_ptr[u + 1]; ++e) acc += R.bu_val[e] * __ldcg(ub + R.bu_col[e]);
+          const int di = i - i_r0;
+          fs[(j - j_r0) * 128 + (di & 3) * 32 + (di >> 2)] -= acc;
+        }
+        __syncthreads();
+      }
+    }
     const long long ccb = (long long)blockIdx.z * P.gc.stride;
     const int I = gi0 >> 1;  // coarse columns I (fine 4p) and I + 1 (fine 4p + 2) of this lane
     const bool mine = (gi0 >= i_t0) && (gi0 < i_t0 + TX);

@@ -46,6 +46,9 @@ struct DevSparse {  // device copies of a sparse n x m matrix in both groupings
 struct LowRankDev {
   LowRankFix fix[2];  // [0] forward, [1] backward
   size_t smem = 0;
+  // in-kernel fix-up (patch CTAs of the fused kernel)
+  LowRankTile *d_tile = nullptr;  // device copy of the descriptor
+  int bw = 0, bh = 0;             // largest extent of supp(B_k)
 };
 
 struct DevLevel {
@@ -63,6 +66,13 @@ struct ProfSlot {
   std::string name;
   double ms = 0.0;
   int64_t launches = 0;
+  double bytes = 0.0;  // algorithmic bytes summed over the launches
+};
+
+struct ProfEvent {
+  std::string name;
+  cudaEvent_t e0, e1;
+  double bytes;
 };
 
 }  // namespace
@@ -79,6 +89,12 @@ struct mgmc_ctx {
   double *dT = nullptr, *dTT = nullptr, *d_cy = nullptr;  // L^{-1}, L^{-T}, intermediate vector (Np per chain)
   int *d_cidx = nullptr;                                  // lexicographic index -> offset in the padded layout
   double *d_sigma_inv = nullptr, *d_sigma_inv_sqrt = nullptr;
+  // in-kernel low-rank fix-up: slots of one cycle / API call (d vectors, exchange buffers, flags)
+  static constexpr int kLrSlots = 1024;
+  double *d_lr_dbuf = nullptr, *d_lr_tbuf = nullptr;
+  int *d_lr_flags = nullptr;  // flags [kLrSlots * nchains] followed by counters [kLrSlots * nchains]
+  int lr_slot_next = 0;
+  bool lr_fuse = true;        // MGMC_NO_LR_FUSE=1: separate fix-up launches (fallback path, perf experiments)
   // noise position
   uint32_t *d_sample = nullptr;
   uint32_t h_sample = 0;
@@ -104,7 +120,7 @@ struct mgmc_ctx {
   int64_t launch_count = 0;
   int64_t launches_per_cycle = 0;
   bool prof_on = false;
-  std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
+  std::vector<ProfEvent> prof_events;
 
   template <class T>
   T *dalloc(size_t n, bool zero = true) {
@@ -123,8 +139,9 @@ struct mgmc_ctx {
   }
   void sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
 
+  // alg_bytes: algorithmic bytes of this launch in the model of SURVEY.md section 8(d)
   template <class F>
-  void launch(const char *name, int level, F &&fn) {
+  void launch(const char *name, int level, F &&fn, double alg_bytes = 0.0) {
     ++launch_count;
     if (prof_on) {
       cudaEvent_t e0, e1;
@@ -133,7 +150,7 @@ struct mgmc_ctx {
       CUDA_CHECK(cudaEventRecord(e0, stream));
       fn();
       CUDA_CHECK(cudaEventRecord(e1, stream));
-      prof_events.push_back({std::string(name) + "/L" + std::to_string(level), {e0, e1}});
+      prof_events.push_back({std::string(name) + "/L" + std::to_string(level), e0, e1, alg_bytes});
     } else {
       fn();
     }
@@ -286,6 +303,133 @@ const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega) {
     F.mats_in_smem = (m <= 48) ? 1 : 0;
   }
   dev.smem = ((size_t)m * EB + 3 * (size_t)m + (m <= 48 ? 2 * (size_t)m * m : 0)) * sizeof(double);
+  {
+    // descriptor of the in-kernel fix-up: same matrices with explicit (i, j) coordinates
+    LowRankTile T;
+    std::memset(&T, 0, sizeof(T));
+    T.m = m;
+    T.EB = EB;
+    std::vector<int> bi((size_t)m * EB), bj((size_t)m * EB), bbox((size_t)m * 4);
+    for (int k = 0; k < m; ++k) {
+      int i0 = 1 << 30, i1 = -1, j0 = 1 << 30, j1 = -1;
+      for (int e = 0; e < EB; ++e) {
+        const bool has = e < (int)cols[k].size();
+        const SEntry &src = has ? cols[k][e] : (cols[k].empty() ? SEntry{1, 1, k, 0.0} : cols[k][0]);
+        bi[(size_t)k * EB + e] = src.i;
+        bj[(size_t)k * EB + e] = src.j;
+        i0 = std::min(i0, src.i);
+        i1 = std::max(i1, src.i);
+        j0 = std::min(j0, src.j);
+        j1 = std::max(j1, src.j);
+      }
+      bbox[4 * k] = i0;
+      bbox[4 * k + 1] = i1;
+      bbox[4 * k + 2] = j0;
+      bbox[4 * k + 3] = j1;
+      dev.bw = std::max(dev.bw, i1 - i0 + 1);
+      dev.bh = std::max(dev.bh, j1 - j0 + 1);
+    }
+    T.b_i = c->dupload(bi);
+    T.b_j = c->dupload(bj);
+    T.b_val = d_bval;
+    T.bbox = c->dupload(bbox);
+    {
+      std::map<std::pair<int, int>, std::vector<std::pair<int, double>>> bysite;  // (j, i) -> (col, val)
+      for (const SEntry &e : L.h.B) bysite[{e.j, e.i}].push_back({e.col, e.val});
+      std::vector<int> ui, uj, uptr(1, 0), ucol;
+      std::vector<double> uval;
+      for (auto &kv : bysite) {
+        ui.push_back(kv.first.second);
+        uj.push_back(kv.first.first);
+        for (auto &cv : kv.second) {
+          ucol.push_back(cv.first);
+          uval.push_back(cv.second);
+        }
+        uptr.push_back((int)ucol.size());
+      }
+      T.nbu = (int)ui.size();
+      T.bu_i = c->dupload(ui);
+      T.bu_j = c->dupload(uj);
+      T.bu_ptr = c->dupload(uptr);
+      T.bu_col = c->dupload(ucol);
+      T.bu_val = c->dupload(uval);
+    }
+    for (int dir = 0; dir < 2; ++dir) {
+      const LowRankFix &F = dev.fix[dir];
+      std::vector<long long> usite(F.nu);
+      CUDA_CHECK(cudaMemcpy(usite.data(), F.usite, sizeof(long long) * F.nu, cudaMemcpyDeviceToHost));
+      std::vector<int> wi(F.nu), wj(F.nu);
+      for (int u = 0; u < F.nu; ++u) {
+        wi[u] = (int)(usite[u] % L.g.pitch);
+        wj[u] = (int)(usite[u] / L.g.pitch);
+      }
+      T.nu[dir] = F.nu;
+      T.EW[dir] = F.EW;
+      T.w_i[dir] = c->dupload(wi);
+      T.w_j[dir] = c->dupload(wj);
+      T.w_col[dir] = F.wcol;
+      T.w_val[dir] = F.wval;
+      T.Mneg[dir] = F.Mneg;
+      T.Ms[dir] = F.Ms;
+      // bounding boxes of supp(W_k), W sites near every measurement, diagonality of the capacitance matrix
+      std::vector<int> wcolh((size_t)F.nu * F.EW);
+      std::vector<double> wvalh((size_t)F.nu * F.EW), Mn((size_t)m * m), Msh((size_t)m * m);
+      CUDA_CHECK(cudaMemcpy(wcolh.data(), F.wcol, sizeof(int) * wcolh.size(), cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(wvalh.data(), F.wval, sizeof(double) * wvalh.size(), cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(Mn.data(), F.Mneg, sizeof(double) * Mn.size(), cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(Msh.data(), F.Ms, sizeof(double) * Msh.size(), cudaMemcpyDeviceToHost));
+      std::vector<int> wbox((size_t)m * 4);
+      for (int k = 0; k < m; ++k) {
+        wbox[4 * k] = wbox[4 * k + 2] = 1 << 30;
+        wbox[4 * k + 1] = wbox[4 * k + 3] = -(1 << 30);
+      }
+      for (int u = 0; u < F.nu; ++u)
+        for (int e = 0; e < F.EW; ++e) {
+          if (wvalh[(size_t)u * F.EW + e] == 0.0) continue;
+          const int k = wcolh[(size_t)u * F.EW + e];
+          wbox[4 * k] = std::min(wbox[4 * k], wi[u]);
+          wbox[4 * k + 1] = std::max(wbox[4 * k + 1], wi[u]);
+          wbox[4 * k + 2] = std::min(wbox[4 * k + 2], wj[u]);
+          wbox[4 * k + 3] = std::max(wbox[4 * k + 3], wj[u]);
+        }
+      T.wbox[dir] = c->dupload(wbox);
+      std::vector<int> wl_ptr(1, 0), wl_u;
+      for (int k = 0; k < m; ++k) {
+        for (int u = 0; u < F.nu; ++u)
+          if (wi[u] >= bbox[4 * k] - 8 && wi[u] <= bbox[4 * k + 1] + 8 && wj[u] >= bbox[4 * k + 2] - 8 && wj[u] <= bbox[4 * k + 3] + 8) wl_u.push_back(u);
+        wl_ptr.push_back((int)wl_u.size());
+      }
+      T.wl_ptr[dir] = c->dupload(wl_ptr);
+      T.wl_u[dir] = c->dupload(wl_u);
+      bool diag = true;
+      for (int r = 0; r < m && diag; ++r)
+        for (int q = 0; q < m; ++q)
+          if (r != q && (Mn[(size_t)r * m + q] != 0.0 || Msh[(size_t)r * m + q] != 0.0)) {
+            diag = false;
+            break;
+          }
+      // a diagonal capacitance matrix also needs every W site near window k to belong to column k alone
+      for (int k = 0; k < m && diag; ++k)
+        for (int q = wl_ptr[k]; q < wl_ptr[k + 1] && diag; ++q)
+          for (int e = 0; e < F.EW; ++e)
+            if (wvalh[(size_t)wl_u[q] * F.EW + e] != 0.0 && wcolh[(size_t)wl_u[q] * F.EW + e] != k) diag = false;
+      T.diag[dir] = diag ? 1 : 0;
+    }
+    T.sigma_inv = c->d_sigma_inv;
+    T.sigma_inv_sqrt = c->d_sigma_inv_sqrt;
+    if (!c->d_lr_dbuf) {
+      const size_t n = (size_t)mgmc_ctx::kLrSlots * c->d.nchains;
+      c->d_lr_dbuf = c->dalloc<double>(n * m);
+      c->d_lr_tbuf = c->dalloc<double>(n * 2 * m);
+      c->d_lr_flags = c->dalloc<int>(2 * n);
+    }
+    T.dbuf = c->d_lr_dbuf;
+    T.tbuf = c->d_lr_tbuf;
+    T.flags = c->d_lr_flags;
+    T.counters = c->d_lr_flags + (size_t)mgmc_ctx::kLrSlots * c->d.nchains;
+    std::vector<LowRankTile> tv(1, T);
+    dev.d_tile = c->dupload(tv);
+  }
   return L.lowrank.emplace(omega, dev).first->second;
 }
 
@@ -355,22 +499,60 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
 // ---- fused tile kernel dispatch ----
 // tile height: 32 rows on the big (bandwidth / issue bound) levels; the small levels are latency bound,
 // there short tiles give every warp at most one row per colour pass and spread over more SMs
-inline int fused_tile_rows(int ny) { return ny > 1024 ? 32 : (ny > 256 ? 16 : 8); }
+inline int fused_tile_rows(int ny) {
+  static const char *ov = std::getenv("MGMC_TILE_ROWS");  // perf experiments: tile height of the big levels
+  if (ov && ny > 2048) return std::atoi(ov);
+  // 40 rows on the finest red-black levels: 49 / 47 / 45 / 43 rows per colour pass share 16 warps better than 41..35
+  return ny > 2048 ? 40 : (ny > 1024 ? 32 : (ny > 256 ? 16 : 8));
+}
 constexpr int kFusedSmemMax = 110 * 1024;
 
-template <int NC, bool G, bool PR, bool RS>
+template <int NC, bool G, bool PR, bool RS, bool LR>
 void launch_fused_t(mgmc_ctx *c, const FusedP &P, dim3 grid, size_t smem) {
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(fused_smooth_kernel<NC, G, PR, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    CUDA_CHECK(cudaFuncSetAttribute(fused_smooth_kernel<NC, G, PR, RS, LR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     attr_set = true;
   }
-  fused_smooth_kernel<NC, G, PR, RS><<<grid, kFusedThreads, smem, c->stream>>>(P);
+  fused_smooth_kernel<NC, G, PR, RS, LR><<<grid, kFusedThreads, smem, c->stream>>>(P);
 }
 
-// one fused launch on `level`: optional prolongation of x_{level+1}, the colour passes in `stages`,
-// optional residual + restriction into f_{level+1} (and x_{level+1} = 0)
-void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, bool gibbs, double omega, bool prolong, double alpha, bool restrict_) {
+struct FixSpec {
+  int stage;    // the fix-up follows this stage of the launch
+  int dir;      // 0: forward sweep, 1: backward sweep
+  uint32_t c1;  // Philox word of the sweep (low-rank noise)
+};
+
+// zero the flags / counters of the in-kernel low-rank fix-up: start of every cycle and API call
+void lr_begin_epoch(mgmc_ctx *c) {
+  c->lr_slot_next = 0;
+  if (c->d_lr_flags) CUDA_CHECK(cudaMemsetAsync(c->d_lr_flags, 0, sizeof(int) * 2 * (size_t)mgmc_ctx::kLrSlots * c->d.nchains, c->stream));
+}
+
+// Geometry of the patch CTAs for a launch with S stages on `level`: wpw = windows per patch CTA;
+// false if not even one window fits
+bool lr_patch_geometry(mgmc_ctx *c, const LowRankDev &lr, int S, int &npatch, int &wpw, int &wcap, size_t &smem) {
+  const int m = c->d.m_lowrank;
+  if (!c->lr_fuse || m > 256) return false;
+  wcap = (lr.bw + 2 * S) * (lr.bh + 2 * S);
+  static const char *np_env = std::getenv("MGMC_NPATCH");  // perf experiments
+  const int np0 = np_env ? std::atoi(np_env) : 32;
+  // few windows per patch CTA: the patch CTAs are a serial prefix of the launch, so they are spread wide
+  for (npatch = std::min(m, np0); npatch <= std::min(m, 64); npatch *= 2) {
+    wpw = (m + npatch - 1) / npatch;
+    smem = ((size_t)3 * m + (size_t)wpw * 4 * wcap) * sizeof(double) + ((size_t)wpw * wcap + 4 * (size_t)wpw) * sizeof(int);
+    if (smem <= (size_t)kFusedSmemMax) {
+      npatch = (m + wpw - 1) / wpw;
+      return true;
+    }
+  }
+  return false;
+}
+
+const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega);
+
+void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const std::vector<FixSpec> &fixes, bool use_lr, bool gibbs, double omega, bool prolong,
+               double alpha, bool restrict_) {
   DevLevel &L = c->lv[level];
   const int nc = L.h.st.ncolours;
   const int S = (int)stages.size();
@@ -405,16 +587,39 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, bool gi
   P.hl = S + (restrict_ ? 1 : 0);
   const int hh = S + (restrict_ ? 2 : 0);
   P.RY = P.TY + P.hl + hh;
-  const size_t smem = (size_t)2 * P.RY * 128 * sizeof(double);
+  size_t smem = (size_t)2 * P.RY * 128 * sizeof(double);
   if (smem > (size_t)kFusedSmemMax) fail(MGMC_ERR_INVALID, "internal: fused tile does not fit in shared memory");
-  dim3 grid((L.g.nx + P.TX - 1) / P.TX, (L.g.ny - 1 + P.TY - 1) / P.TY, c->d.nchains);
+  P.tiles_x = (L.g.nx + P.TX - 1) / P.TX;
+  const int tiles_y = (L.g.ny - 1 + P.TY - 1) / P.TY;
+  P.nchains = c->d.nchains;
+  if (use_lr) {
+    const LowRankDev &lr = get_lowrank(c, level, omega);
+    size_t psmem = 0;
+    if (!lr_patch_geometry(c, lr, S, P.npatch, P.wpw, P.wcap, psmem)) fail(MGMC_ERR_INVALID, "internal: low-rank windows do not fit");
+    smem = std::max(smem, psmem);
+    P.lr = lr.d_tile;
+    P.nfix = (int)fixes.size();
+    if (P.nfix > 2) fail(MGMC_ERR_INVALID, "internal: more than 2 fix-ups in one fused launch");
+    for (int q = 0; q < P.nfix; ++q) {
+      P.fix_stage[q] = fixes[q].stage;
+      P.fix_dir[q] = fixes[q].dir;
+      P.fix_c1[q] = fixes[q].c1;
+    }
+    P.lr_slot = c->lr_slot_next;
+    c->lr_slot_next += P.nfix + 1;
+    if (c->lr_slot_next > mgmc_ctx::kLrSlots) fail(MGMC_ERR_UNSUPPORTED, "too many low-rank fix-ups in one cycle (W-cycle too deep)");
+  }
+  dim3 grid(P.npatch + P.tiles_x * tiles_y, 1, c->d.nchains);
+  // algorithmic bytes of this launch: 24 B per site and sweep, 18 B prolongate_add,
+  // 18 + 2 B residual + restrict + coarse zeroing -- fixed by the model, not by what the kernel moves
+  const double alg_bytes = (double)L.h.ndof() * c->d.nchains * (24.0 * S / nc + (prolong ? 18.0 : 0.0) + (restrict_ ? 20.0 : 0.0));
   std::string name = std::string(gibbs ? "gibbs" : "sor") + (nc == 2 ? "_rb" : "_4c") + std::to_string(S) + (prolong ? "+prolong" : "") + (restrict_ ? "+restrict" : "");
 #ifdef MGMC_TILE_TIMING
   // debug build: dump per-CTA phase time stamps of the first level-0 launch of every kernel flavour
   static std::map<std::string, int> dumped;
   const char *tfile = std::getenv("MGMC_TIMING_FILE");
   long long *d_timing = nullptr;
-  const size_t ncta = (size_t)grid.x * grid.y * grid.z;
+  const size_t ncta = (size_t)grid.x * grid.z;
   if (tfile && level == 0 && dumped[name]++ == 3) {
     CUDA_CHECK(cudaMalloc(&d_timing, ncta * 10 * sizeof(long long)));
     CUDA_CHECK(cudaMemset(d_timing, 0, ncta * 10 * sizeof(long long)));
@@ -422,14 +627,17 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, bool gi
   }
 #endif
   c->launch(name.c_str(), level, [&] {
-#define FUSED_CASE(NC_, G_, PR_, RS_) \
-  if (nc == NC_ && gibbs == G_ && prolong == PR_ && restrict_ == RS_) launch_fused_t<NC_, G_, PR_, RS_>(c, P, grid, smem);
+#define FUSED_CASE(NC_, G_, PR_, RS_)                                             \
+  if (nc == NC_ && gibbs == G_ && prolong == PR_ && restrict_ == RS_) {            \
+    if (use_lr) launch_fused_t<NC_, G_, PR_, RS_, true>(c, P, grid, smem);        \
+    else launch_fused_t<NC_, G_, PR_, RS_, false>(c, P, grid, smem);              \
+  }
     FUSED_CASE(2, false, false, false) FUSED_CASE(2, false, false, true) FUSED_CASE(2, false, true, false) FUSED_CASE(2, false, true, true)
     FUSED_CASE(2, true, false, false) FUSED_CASE(2, true, false, true) FUSED_CASE(2, true, true, false) FUSED_CASE(2, true, true, true)
     FUSED_CASE(4, false, false, false) FUSED_CASE(4, false, false, true) FUSED_CASE(4, false, true, false) FUSED_CASE(4, false, true, true)
     FUSED_CASE(4, true, false, false) FUSED_CASE(4, true, false, true) FUSED_CASE(4, true, true, false) FUSED_CASE(4, true, true, true)
 #undef FUSED_CASE
-  });
+  }, alg_bytes);
 #ifdef MGMC_TILE_TIMING
   if (d_timing) {
     c->sync();
@@ -483,31 +691,46 @@ std::vector<SweepSpec> sweep_list(int kind, int direction, int nsmooth, bool gib
   return out;
 }
 
-// A smoothing step of a level: [prolongate_add] sweeps... [residual + restrict].  Without a low-rank
-// term consecutive sweeps are fused into launches of up to 8 colour passes; with it every sweep is one
-// launch followed by the Woodbury fix-up (a grid-wide dependency), and the residual is its own launch.
+// A smoothing step of a level: [prolongate_add] sweeps... [residual + restrict].  Consecutive sweeps are
+// fused into launches of up to 2 sweeps (4 / 8 colour passes).  The Woodbury fix-up of the low-rank
+// term after a sweep is a grid-wide dependency: normally it is resolved inside the launch by the patch
+// CTAs (fused.cuh); if the measurement windows do not fit, every sweep becomes its own launch followed
+// by a fix-up kernel, and the low-rank part of the residual is a separate kernel.
 void emit_smoothing(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps, bool gibbs, double omega, bool prolong, double alpha, bool restrict_) {
   DevLevel &L = c->lv[level];
   const int nc = L.h.st.ncolours;
   const bool lowrank = c->d.m_lowrank > 0;
+  const int max_stages = (nc == 2) ? 4 : 8;  // keeps the tile + halo of x and f below ~100 KB (2 CTAs / SM)
+  bool fusedlr = false;
+  if (lowrank) {
+    int np, wp, wc;
+    size_t sm;
+    fusedlr = lr_patch_geometry(c, get_lowrank(c, level, omega), max_stages, np, wp, wc, sm);
+  }
   std::vector<Stage> cur;
+  std::vector<FixSpec> fixes;
   bool pending_prolong = prolong;
   auto flush = [&](bool with_restrict) {
-    dev_fused(c, level, cur, gibbs, omega, pending_prolong, alpha, with_restrict);
+    const bool use_lr = fusedlr && (!fixes.empty() || with_restrict);
+    dev_fused(c, level, cur, fixes, use_lr, gibbs, omega, pending_prolong, alpha, with_restrict);
     pending_prolong = false;
     cur.clear();
+    fixes.clear();
   };
   for (const SweepSpec &sw : sweeps) {
     const uint32_t c1 = next_c1(c, level, gibbs);
-    const int max_stages = (nc == 2) ? 4 : 8;  // keeps the tile + halo of x and f below ~100 KB (2 CTAs / SM)
-    if (!cur.empty() && ((int)cur.size() + nc > max_stages || lowrank)) flush(false);
+    if (!cur.empty() && ((int)cur.size() + nc > max_stages || (lowrank && !fusedlr))) flush(false);
     for (int cc = 0; cc < nc; ++cc) cur.push_back(Stage{sw.fwd ? cc : nc - 1 - cc, c1});
     if (lowrank) {
-      flush(false);
-      if (sw.fix_after) dev_lowrank_fix(c, level, sw.fwd, gibbs, omega, c1);
+      if (fusedlr) {
+        if (sw.fix_after) fixes.push_back(FixSpec{(int)cur.size() - 1, sw.fwd ? 0 : 1, c1});
+      } else {
+        flush(false);
+        if (sw.fix_after) dev_lowrank_fix(c, level, sw.fwd, gibbs, omega, c1);
+      }
     }
   }
-  if (!lowrank) {
+  if (!lowrank || fusedlr) {
     flush(restrict_);
   } else {
     if (pending_prolong) flush(false);
@@ -537,10 +760,10 @@ void dev_coarse(mgmc_ctx *c, bool sample, const double *f, double *x) {
   c->launch(sample ? "coarse_sample_fwd" : "coarse_solve_fwd", lc, [&] {
     if (sample) trimv_kernel<true, true, true, false><<<grid, 256, 0, c->stream>>>(c->dT, c->Nc, c->Ncp, c->d_cidx, f, L.g.stride, c->d_cy, c->Ncp, nz);
     else trimv_kernel<true, false, true, false><<<grid, 256, 0, c->stream>>>(c->dT, c->Nc, c->Ncp, c->d_cidx, f, L.g.stride, c->d_cy, c->Ncp, nz);
-  });
+  }, 4.0 * c->Nc * c->Nc);
   c->launch(sample ? "coarse_sample_bwd" : "coarse_solve_bwd", lc, [&] {
     trimv_kernel<false, false, false, true><<<grid, 256, 0, c->stream>>>(c->dTT, c->Nc, c->Ncp, c->d_cidx, c->d_cy, c->Ncp, x, L.g.stride, nz);
-  });
+  }, 4.0 * c->Nc * c->Nc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -577,7 +800,10 @@ void mg_solve_level(mgmc_ctx *c, int level) {  // multigrid_preconditioner.cc:74
     dev_coarse(c, false, L.f, L.x);  // writes every interior entry; ghost lines stay zero
     return;
   }
-  if (level == 0) dev_zero(c, level, L.x);  // deeper levels are zeroed by the restriction that feeds them
+  if (level == 0) {
+    lr_begin_epoch(c);
+    dev_zero(c, level, L.x);  // deeper levels are zeroed by the restriction that feeds them
+  }
   const int cycle_ = (level > 0) ? d.cycle : 1;
   for (int j = 0; j < cycle_; ++j) {
     emit_smoothing(c, level, sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, false), false, d.omega, false, 0.0, true);
@@ -588,6 +814,7 @@ void mg_solve_level(mgmc_ctx *c, int level) {  // multigrid_preconditioner.cc:74
 }
 
 void emit_mgmc_cycle(mgmc_ctx *c) {
+  lr_begin_epoch(c);
   std::fill(c->sweep_counter.begin(), c->sweep_counter.end(), 0u);
   mgmc_sample_level(c, 0);
 }
@@ -720,6 +947,7 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->use_graph = (std::getenv("MGMC_NO_GRAPH") == nullptr);
     c->perf_no_noise = (std::getenv("MGMC_PERF_NO_NOISE") != nullptr);
+    c->lr_fuse = (std::getenv("MGMC_NO_LR_FUSE") == nullptr);
     c->sweep_counter.assign(desc->nlevel, 0u);
     c->keys = philox_round_keys(desc->seed);
     c->lv.resize(desc->nlevel);
@@ -845,6 +1073,7 @@ int mgmc_prolongate_add(mgmc_ctx *c, int level, double alpha, const double *x_co
   check_level(c, level, true);
   upload_vec(c, level, c->lv[level].x, x_fine);
   upload_vec(c, level + 1, c->lv[level + 1].x, x_coarse);
+  lr_begin_epoch(c);
   emit_smoothing(c, level, {}, false, c->d.omega, true, alpha, false);
   normalize_x(c, level);
   download_vec(c, level, c->lv[level].x, x_fine);
@@ -857,6 +1086,7 @@ int mgmc_residual_restrict(mgmc_ctx *c, int level, const double *f, const double
   check_level(c, level, true);
   upload_vec(c, level, c->lv[level].f, f);
   upload_vec(c, level, c->lv[level].x, x);
+  lr_begin_epoch(c);
   emit_smoothing(c, level, {}, false, c->d.omega, false, 0.0, true);
   download_vec(c, level + 1, c->lv[level + 1].f, f_coarse);
   c->sync();
@@ -877,6 +1107,7 @@ int mgmc_smoother_apply(mgmc_ctx *c, int level, int kind, int direction, double 
   DevLevel &L = c->lv[level];
   upload_vec(c, level, L.f, b);
   upload_vec(c, level, L.x, x);
+  lr_begin_epoch(c);
   emit_smoothing(c, level, sweep_list(kind, direction, nsmooth, false), false, omega, false, 0.0, false);
   normalize_x(c, level);
   download_vec(c, level, L.x, x);
@@ -891,6 +1122,7 @@ int mgmc_sampler_apply(mgmc_ctx *c, int level, int kind, int direction, double o
   DevLevel &L = c->lv[level];
   upload_vec(c, level, L.f, f);
   upload_vec(c, level, L.x, x);
+  lr_begin_epoch(c);
   emit_smoothing(c, level, sweep_list(kind, direction, nsmooth, true), true, omega, false, 0.0, false);
   normalize_x(c, level);
   download_vec(c, level, L.x, x);
@@ -1116,7 +1348,7 @@ int mgmc_sample_moments(mgmc_ctx *c, int64_t nsamples, double *mean_field, doubl
 
 int64_t mgmc_launch_count(const mgmc_ctx *c) { return c ? c->launch_count : 0; }
 
-int mgmc_profile_cycle(mgmc_ctx *c, int nsamples, int nslots_max, char *names, double *ms_total, int64_t *launches, int *nslots) {
+int mgmc_profile_cycle(mgmc_ctx *c, int nsamples, int nslots_max, char *names, double *ms_total, int64_t *launches, double *alg_bytes, int *nslots) {
   API_BEGIN
   check_level(c, 0);
   c->sync();
@@ -1134,16 +1366,17 @@ int mgmc_profile_cycle(mgmc_ctx *c, int nsamples, int nslots_max, char *names, d
   std::map<std::string, int> index;
   for (auto &ev : c->prof_events) {
     float ms = 0.f;
-    CUDA_CHECK(cudaEventElapsedTime(&ms, ev.second.first, ev.second.second));
-    cudaEventDestroy(ev.second.first);
-    cudaEventDestroy(ev.second.second);
-    auto it = index.find(ev.first);
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+    cudaEventDestroy(ev.e0);
+    cudaEventDestroy(ev.e1);
+    auto it = index.find(ev.name);
     if (it == index.end()) {
-      it = index.emplace(ev.first, (int)slots.size()).first;
-      slots.push_back(ProfSlot{ev.first, 0.0, 0});
+      it = index.emplace(ev.name, (int)slots.size()).first;
+      slots.push_back(ProfSlot{ev.name, 0.0, 0, 0.0});
     }
     slots[it->second].ms += ms;
     slots[it->second].launches++;
+    slots[it->second].bytes += ev.bytes;
   }
   c->prof_events.clear();
   const int n = std::min<int>((int)slots.size(), nslots_max);
@@ -1151,6 +1384,7 @@ int mgmc_profile_cycle(mgmc_ctx *c, int nsamples, int nslots_max, char *names, d
     std::snprintf(names + (size_t)k * 64, 64, "%s", slots[k].name.c_str());
     ms_total[k] = slots[k].ms;
     launches[k] = slots[k].launches;
+    if (alg_bytes) alg_bytes[k] = slots[k].bytes;
   }
   if (nslots) *nslots = n;
   API_END
