@@ -37,6 +37,7 @@ struct Setting {
     if (it == members.end()) throw std::runtime_error("setting '" + name + "' not found");
     return *it->second;
   }
+  const Setting &operator[](const char *name) const { return (*this)[std::string(name)]; }
   const Setting &lookup(const std::string &name) const { return (*this)[name]; }
   bool exists(const std::string &name) const { return members.count(name) > 0; }
   operator int() const { return (int)as_int(); }

@@ -499,11 +499,11 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
 // ---- fused tile kernel dispatch ----
 // tile height: 32 rows on the big (bandwidth / issue bound) levels; the small levels are latency bound,
 // there short tiles give every warp at most one row per colour pass and spread over more SMs
-inline int fused_tile_rows(int ny) {
+inline int fused_tile_rows(int ny, int nc) {
   static const char *ov = std::getenv("MGMC_TILE_ROWS");  // perf experiments: tile height of the big levels
-  if (ov && ny > 2048) return std::atoi(ov);
+  if (ov && ny > 2048 && nc == 2) return std::atoi(ov);
   // 40 rows on the finest red-black levels: 49 / 47 / 45 / 43 rows per colour pass share 16 warps better than 41..35
-  return ny > 2048 ? 40 : (ny > 1024 ? 32 : (ny > 256 ? 16 : 8));
+  return (ny > 2048 && nc == 2) ? 40 : (ny > 1024 ? 32 : (ny > 256 ? 16 : 8));
 }
 constexpr int kFusedSmemMax = 110 * 1024;
 
@@ -583,7 +583,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   P.HXL = up4(S + (restrict_ ? 2 : 0));
   const int HXR = up4(S + (restrict_ ? 1 : 0));
   P.TX = 128 - P.HXL - HXR;
-  P.TY = fused_tile_rows(L.g.ny);
+  P.TY = fused_tile_rows(L.g.ny, nc);
   P.hl = S + (restrict_ ? 1 : 0);
   const int hh = S + (restrict_ ? 2 : 0);
   P.RY = P.TY + P.hl + hh;
@@ -751,7 +751,32 @@ void dev_restrict_plain(mgmc_ctx *c, int level, const double *r, double *fc) {
   });
 }
 
+// dense factor of the coarsest level (cholesky_sampler.cc:25-38), built at first use: contexts that only
+// serve single-level operations (apply, smoothers, transfers) never need it
+void ensure_coarse(mgmc_ctx *c) {
+  if (c->dT) return;
+  const DevLevel &LC = c->lv[c->d.nlevel - 1];
+  if (LC.h.ndof() > 4096) fail(MGMC_ERR_UNSUPPORTED, "coarsest level has more than 4096 unknowns: increase nlevel (dense coarse factor)");
+  CoarseFactor cf;
+  try {
+    cf = coarse_factor(LC.h, c->Sigma);
+  } catch (const std::exception &e) {
+    fail(MGMC_ERR_INVALID, e.what());
+  }
+  c->Nc = cf.N;
+  c->Ncp = cf.Np;
+  c->dT = c->dupload(cf.T);
+  c->dTT = c->dupload(cf.TT);
+  c->d_cy = c->dalloc<double>((size_t)cf.Np * c->d.nchains);
+  std::vector<int> cidx(cf.Np, 0);
+  const int w = LC.g.nx - 1;
+  for (int e = 0; e < cf.N; ++e) cidx[e] = (e / w + 1) * LC.g.pitch + (e % w + 1);
+  c->d_cidx = c->dupload(cidx);
+  c->sync();
+}
+
 void dev_coarse(mgmc_ctx *c, bool sample, const double *f, double *x) {
+  ensure_coarse(c);
   const int lc = c->d.nlevel - 1;
   const DevLevel &L = c->lv[lc];
   NoiseP nz = noise_params(c, lc, next_c1(c, lc, sample));
@@ -857,6 +882,7 @@ void run_cycles(mgmc_ctx *c, int64_t nsamples) {
       // make sure lazily built low-rank data exists before capture (uploads are not capturable)
       if (c->d.m_lowrank > 0)
         for (int l = 0; l < c->d.nlevel; ++l) get_lowrank(c, l, c->d.omega);
+      if (c->d.coarse_solver == MGMC_COARSE_CHOLESKY) ensure_coarse(c);
       c->sync();
       const int64_t count0 = c->launch_count;
       const uint32_t sample0 = c->h_sample;
@@ -931,8 +957,6 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
     std::vector<HostLevel> H = build_host_levels(*desc);
     for (const HostLevel &h : H)
       if (h.st.radius > 1 || !h.st.uniform) fail(MGMC_ERR_UNSUPPORTED, "squared_shiftedlaplace_fd (13/21-point stencils) is not on the device path yet");
-    const HostLevel &hc = H.back();
-    if (hc.ndof() > 4096) fail(MGMC_ERR_UNSUPPORTED, "coarsest level has more than 4096 unknowns: increase nlevel (dense coarse factor)");
     c = new mgmc_ctx();
     c->d = *desc;
     c->d.B_rows = nullptr;
@@ -978,19 +1002,6 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
       }
       c->d_sigma_inv = c->dupload(si);
       c->d_sigma_inv_sqrt = c->dupload(sis);
-    }
-    {
-      CoarseFactor cf = coarse_factor(hc, c->Sigma);
-      c->Nc = cf.N;
-      c->Ncp = cf.Np;
-      c->dT = c->dupload(cf.T);
-      c->dTT = c->dupload(cf.TT);
-      c->d_cy = c->dalloc<double>((size_t)cf.Np * desc->nchains);
-      std::vector<int> cidx(cf.Np, 0);
-      const DevLevel &LC = c->lv[desc->nlevel - 1];
-      const int w = LC.g.nx - 1;
-      for (int e = 0; e < cf.N; ++e) cidx[e] = (e / w + 1) * LC.g.pitch + (e % w + 1);
-      c->d_cidx = c->dupload(cidx);
     }
     c->d_sample = c->dalloc<uint32_t>(1);
     c->d_pos = c->dalloc<unsigned long long>(1);

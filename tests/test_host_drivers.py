@@ -1,0 +1,109 @@
+"""Host drop-in layer (host/): the reference's class names, drivers and .cfg formats over the C ABI.
+
+CPU part: the drivers build, the libconfig-subset reader parses the reference's file format, lattice
+known answers (test_lattice.hh:166).  GPU part: driver_mg reproduces the oracle's residual history
+(colour ordering), driver_mgmc reproduces the exact posterior mean / variance of the observation within
+Monte-Carlo error bars and writes the reference's output files."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "host")
+CONFIGS = os.path.join(HOST, "configs")
+
+
+@pytest.fixture(scope="module")
+def built():
+    import multigridmc_b200 as m
+
+    m.build()
+    subprocess.check_call(["make", "-C", HOST], stdout=subprocess.DEVNULL)
+    return HOST
+
+
+def test_drivers_build(built):
+    for exe in ("driver_mg", "driver_mgmc", "test_config"):
+        assert os.access(os.path.join(built, exe), os.X_OK)
+
+
+def test_config_reader_reads_reference_format(built):
+    from multigridmc_b200 import workloads as w
+
+    out = subprocess.check_output([os.path.join(built, "test_config"), "c3_mgmc_4096.cfg"], cwd=CONFIGS, text=True)
+    assert "dim=2 operator=posterior do_ssor=0 do_multigridmc=1" in out
+    assert "lattice=4096,4096,4096" in out
+    assert "multigrid nlevel=8 smoother=SSOR coarse=Cholesky pre=1 post=1 ncoarse=1 cycle=1 scaling=1 omega=1" in out
+    assert "solver rtol=9.9999999999999998e-13 atol=1.0000000000000001e-15 maxiter=100 verbose=2" in out
+    assert "sampling nsamples=1000 nwarmup=100 nsteps=8 nconv=20" in out
+    loc, sample, mean, var = w.measurement_set(32)
+    rows = [l.split() for l in out.splitlines() if l.startswith("meas ")]
+    assert len(rows) == 32
+    got = np.array([[float(v) for v in r[2:]] for r in rows])
+    assert np.array_equal(got[:, :2], loc) and np.array_equal(got[:, 2], mean) and np.array_equal(got[:, 3], var)
+    m = re.search(r"sample=([0-9.e+-]+),([0-9.e+-]+)", out)
+    assert (float(m.group(1)), float(m.group(2))) == (float(sample[0]), float(sample[1]))
+    # test_lattice.hh:166 (2d lattice 4 x 5): fine_vertex_idx(7) == 38
+    assert "lattice2d Nvertex=12 Ncell=20 fine_vertex_idx(7)=38" in out
+
+
+def test_config_reader_errors_like_the_reference(built, tmp_path):
+    """parameters.cc:25-47: message + exit(-1) on a missing file or a missing setting."""
+    r = subprocess.run([os.path.join(built, "test_config"), "does_not_exist.cfg"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 255 and "cannot open configuration file" in r.stderr
+    (tmp_path / "broken.cfg").write_text("general = { dim = 2; }\n")
+    r = subprocess.run([os.path.join(built, "test_config"), "broken.cfg"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 255 and "cannot read configuration" in r.stderr
+
+
+def _write_cfg(path, text_from, **repl):
+    s = open(os.path.join(CONFIGS, text_from)).read()
+    for k, v in repl.items():
+        s, n = re.subn(rf"(\b{k}\s*=\s*)[^;]+;", rf"\g<1>{v};", s, count=1)
+        assert n == 1, k
+    open(path, "w").write(s)
+
+
+@pytest.mark.gpu
+def test_driver_mg_residual_history_matches_oracle(built, oracle, tmp_path):
+    """driver_mg (config C2 at 256^2, 5 levels, V(2,2) SSOR): printed ||r_k|| == oracle LoopSolver in the same ordering."""
+    n, nlevel = 256, 5
+    _write_cfg(tmp_path / "mg.cfg", "c2_mg_1024.cfg", nx=n, ny=n, nlevel=nlevel, maxiter=12, filename=f'"{CONFIGS}/measurements_8.cfg"')
+    out = subprocess.check_output([os.path.join(built, "driver_mg"), "mg.cfg"], cwd=tmp_path, text=True)
+    hist = np.array([float(l.split()[1]) for l in out.splitlines() if re.match(r"^\s*\d+\s+\d\.\d+e[+-]\d+\s", l)])
+    op = oracle.Operator.prior((n, n), "shiftedlaplace_fd", Lambda=0.2)
+    H = oracle.Hierarchy(op, nlevel, oracle.COLOUR)
+    b = oracle.StdRng(1482817).normal(op.ndof)
+    prec = H.preconditioner(npresmooth=2, npostsmooth=2)
+    _, h_ref, _, _ = oracle.loop_solve(op, prec, b, rtol=1e-12, atol=1e-15, maxiter=12)
+    assert len(hist) == len(h_ref) == 12
+    big = h_ref > 1e-9 * h_ref[0]  # entries above the rounding floor; printed with 4 significant digits
+    assert big.sum() >= 9 and np.abs(hist[big] / h_ref[big] - 1).max() < 2e-3
+    assert os.path.exists(tmp_path / "solution.vtk")
+    assert hist[-1] / hist[0] < 1e-8
+
+
+@pytest.mark.gpu
+def test_driver_mgmc_statistics_and_files(built, tmp_path):
+    """driver_mgmc on a 128^2 posterior: sampled mean / variance of the observation agree with the exact
+    values the driver prints (computed by device MG solves, linear_operator.hh:153-174) within error bars."""
+    _write_cfg(tmp_path / "mgmc.cfg", "small_posterior_128.cfg", filename=f'"{CONFIGS}/measurements_8.cfg"')
+    out = subprocess.check_output([os.path.join(built, "driver_mgmc"), "mgmc.cfg"], cwd=tmp_path, text=True)
+    for label, fname in (("MultigridMC", "timeseries_multigridmc.txt"), ("SSOR", "timeseries_ssor.txt")):
+        blk = out[out.index("**** Multigrid MC ****" if label == "MultigridMC" else "**** SSOR ****"):]
+        mean, err = map(float, re.search(rf"{label} mean\s+=\s+(\S+) \+/-\s+(\S+)", blk).groups())
+        mean_exact = float(re.search(r"exact mean\s+=\s+(\S+)", blk).group(1))
+        var = float(re.search(rf"{label} variance =\s+(\S+)", blk).group(1))
+        var_exact = float(re.search(r"exact variance =\s+(\S+)", blk).group(1))
+        tau = float(re.search(rf"{label} tau_int\s+=\s+(\S+)", blk).group(1))
+        series = np.loadtxt(tmp_path / fname)
+        assert len(series) == 4000
+        if label == "MultigridMC":
+            assert abs(mean - mean_exact) < 5 * err * np.sqrt(max(tau, 1.0))
+            assert abs(var / var_exact - 1) < 0.15
+            assert tau < 2.0
+    conv = open(tmp_path / "convergence_multigridmc.txt").read()
+    assert "q_k = |E[z^k] - E[z]|" in conv and "q_k = |Var[z^k] - Var[z]|" in conv
