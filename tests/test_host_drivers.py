@@ -80,8 +80,8 @@ def test_driver_mg_residual_history_matches_oracle(built, oracle, tmp_path):
     prec = H.preconditioner(npresmooth=2, npostsmooth=2)
     _, h_ref, _, _ = oracle.loop_solve(op, prec, b, rtol=1e-12, atol=1e-15, maxiter=12)
     assert len(hist) == len(h_ref) == 12
-    big = h_ref > 1e-9 * h_ref[0]  # entries above the rounding floor; printed with 4 significant digits
-    assert big.sum() >= 9 and np.abs(hist[big] / h_ref[big] - 1).max() < 2e-3
+    big = h_ref > 1e-11 * h_ref[0]  # entries above the rounding floor; printed with 4 significant digits
+    assert big.sum() >= 8 and np.abs(hist[big] / h_ref[big] - 1).max() < 2e-3
     assert os.path.exists(tmp_path / "solution.vtk")
     assert hist[-1] / hist[0] < 1e-8
 
