@@ -146,6 +146,86 @@ __global__ void __launch_bounds__(256) sweep_colour_kernel(GridP g, Coef9 a, dou
 }
 
 // ------------------------------------------------------------------------------------------------
+// Radius-2 operators (SquaredShiftedLaplaceFDOperator, squared_shiftedlaplace_fd_operator.cc:9-96, and
+// its Galerkin coarsenings): 13-point stencil on the finest level, 21-point below, constant in the
+// interior but with different coefficients on the first / last interior line of either direction
+// (SURVEY.md section 7.3 H1).  `st` = 9 position classes x 25 coefficients, class = cx + 3 cy,
+// coefficient (di, dj) at [(dj + 2) * 5 + (di + 2)].  Sweeps use 9 colours, colour = i % 3 + 3 (j % 3).
+// First correct path: one launch per colour, in place (same-colour sites are >= 3 apart).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pos_class_dev(int i, int n) { return i == 1 ? 0 : (i == n - 1 ? 2 : 1); }
+
+__device__ __forceinline__ double stencil25(const double *__restrict__ a, const double *p, int pitch) {
+  double s = 0.0;
+#pragma unroll
+  for (int dj = -2; dj <= 2; ++dj)
+#pragma unroll
+    for (int di = -2; di <= 2; ++di) {
+      if ((di == -2 || di == 2) && (dj == -2 || dj == 2)) continue;  // the corners of the 5 x 5 box are never populated
+      s = fma(a[(dj + 2) * 5 + (di + 2)], p[dj * pitch + di], s);
+    }
+  return s;
+}
+
+// y = A_0 x, or r = f - A_0 x
+template <bool RESIDUAL>
+__global__ void __launch_bounds__(256) apply25_kernel(GridP g, const double *__restrict__ st, const double *__restrict__ x, const double *__restrict__ f,
+                                                     double *__restrict__ y) {
+  const int i = 1 + blockIdx.x * 64 + threadIdx.x;
+  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  const long long o = (long long)blockIdx.z * g.stride + (long long)j * g.pitch + i;
+  const double s = stencil25(st + 25 * (pos_class_dev(i, g.nx) + 3 * pos_class_dev(j, g.ny)), x + o, g.pitch);
+  y[o] = RESIDUAL ? (f[o] - s) : s;
+}
+
+// r = A_0 x - b with per-block partial sums of r^2 (LoopSolver)
+__global__ void __launch_bounds__(256) residual_norm25_kernel(GridP g, const double *__restrict__ st, const double *__restrict__ x, const double *__restrict__ b,
+                                                             double *__restrict__ r, double *__restrict__ partial) {
+  const int i = 1 + blockIdx.x * 64 + threadIdx.x;
+  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  double v = 0.0;
+  if (i < g.nx && j < g.ny) {
+    const long long o = (long long)j * g.pitch + i;
+    v = stencil25(st + 25 * (pos_class_dev(i, g.nx) + 3 * pos_class_dev(j, g.ny)), x + o, g.pitch) - b[o];
+    r[o] = v;
+  }
+  v = v * v;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  __shared__ double ws[8];
+  const int t = threadIdx.y * 64 + threadIdx.x;
+  if ((t & 31) == 0) ws[t >> 5] = v;
+  __syncthreads();
+  if (t == 0) {
+    double s = 0.0;
+    for (int k = 0; k < 8; ++k) s += ws[k];
+    partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// one colour (0..8) of a 9-colour SOR / Gibbs sweep; the noise of a site is the same pure function of the
+// site as in the radius-1 kernels (philox.cuh)
+template <bool GIBBS>
+__global__ void __launch_bounds__(256) sweep_colour25_kernel(GridP g, const double *__restrict__ st, double *__restrict__ x, const double *__restrict__ f, int colour,
+                                                            double omega, NoiseP nz) {
+  const int ci = colour % 3, cj = colour / 3;
+  const int i = ((ci == 0) ? 3 : ci) + 3 * (blockIdx.x * 64 + threadIdx.x);
+  const int j = ((cj == 0) ? 3 : cj) + 3 * (blockIdx.y * 4 + threadIdx.y);
+  if (i >= g.nx || j >= g.ny) return;
+  const long long o = (long long)blockIdx.z * g.stride + (long long)j * g.pitch + i;
+  const double *a = st + 25 * (pos_class_dev(i, g.nx) + 3 * pos_class_dev(j, g.ny));
+  const double diag = a[12];
+  double b = f[o];
+  if (GIBBS) {
+    double z0, z1;
+    normal_pair(nz.keys, (((uint32_t)j * nz.G + (uint32_t)(i >> 2)) << 1) | (uint32_t)(i & 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.z, z0, z1);
+    b = fma(sqrt(diag * (2. - omega) / omega), (i & 2) ? z1 : z0, b);  // sor_sampler.cc:24-27
+  }
+  x[o] += omega * (b - stencil25(a, x + o, g.pitch)) / diag;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused residual + restriction: f_c = R (f - A_0 x) with R = {1/2,1,1/2}^(x)2 un-normalised
 // (multigridmc_sampler.cc:118-120, intergrid_operator.hh:74-88, intergrid_operator_linear.cc:13).
 // One thread per coarse vertex (I, J) <-> fine (2I, 2J); the residual is never stored.

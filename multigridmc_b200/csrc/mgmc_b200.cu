@@ -58,6 +58,8 @@ struct DevLevel {
   double *x_alt = nullptr, *x_primary = nullptr;     // ping-pong partner of x / the buffer x must be in between calls
   Coef9 coef;
   bool nine = false;
+  bool r2 = false;             // radius-2 stencil with position classes: generic kernels, 9 colours
+  double *d_st = nullptr;      // [9][25] stencil classes (radius-2 levels)
   DevSparse B;
   std::map<double, LowRankDev> lowrank;  // keyed by omega
 };
@@ -88,7 +90,7 @@ struct mgmc_ctx {
   int Nc = 0, Ncp = 0;
   double *dT = nullptr, *dTT = nullptr, *d_cy = nullptr;  // L^{-1}, L^{-T}, intermediate vector (Np per chain)
   int *d_cidx = nullptr;                                  // lexicographic index -> offset in the padded layout
-  double *d_sigma_inv = nullptr, *d_sigma_inv_sqrt = nullptr;
+  double *d_sigma_inv = nullptr, *d_sigma_inv_sqrt = nullptr, *d_sigma_inv_neg = nullptr;
   // in-kernel low-rank fix-up: slots of one cycle / API call (d vectors, exchange buffers, flags)
   static constexpr int kLrSlots = 1024;
   double *d_lr_dbuf = nullptr, *d_lr_tbuf = nullptr;
@@ -487,7 +489,8 @@ void normalize_x(mgmc_ctx *c, int level) {
 void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
   const DevLevel &L = c->lv[level];
   c->launch("apply", level, [&] {
-    if (L.nine) apply_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
+    if (L.r2) apply25_kernel<false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.d_st, x, nullptr, y);
+    else if (L.nine) apply_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
     else apply_kernel<false, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
   });
   if (c->d.m_lowrank > 0)
@@ -696,8 +699,11 @@ std::vector<SweepSpec> sweep_list(int kind, int direction, int nsmooth, bool gib
 // term after a sweep is a grid-wide dependency: normally it is resolved inside the launch by the patch
 // CTAs (fused.cuh); if the measurement windows do not fit, every sweep becomes its own launch followed
 // by a fix-up kernel, and the low-rank part of the residual is a separate kernel.
+void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps, bool gibbs, double omega, bool prolong, double alpha, bool restrict_);
+
 void emit_smoothing(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps, bool gibbs, double omega, bool prolong, double alpha, bool restrict_) {
   DevLevel &L = c->lv[level];
+  if (L.r2) return emit_smoothing_r2(c, level, sweeps, gibbs, omega, prolong, alpha, restrict_);
   const int nc = L.h.st.ncolours;
   const bool lowrank = c->d.m_lowrank > 0;
   const int max_stages = (nc == 2) ? 4 : 8;  // keeps the tile + halo of x and f below ~100 KB (2 CTAs / SM)
@@ -741,6 +747,44 @@ void emit_smoothing(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps
         lowrank_restrict_kernel<<<c->d.nchains, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, C.B.rows, c->d_sigma_inv, L.g.stride, C.g.stride, L.x, C.f);
       });
     }
+  }
+}
+
+void dev_restrict_plain(mgmc_ctx *c, int level, const double *r, double *fc);
+
+// Radius-2 levels (squared shifted Laplacian): colour-by-colour launches of the generic kernels, separate
+// transfer kernels -- the first correct path for this operator family, not yet tiled / fused.
+void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps, bool gibbs, double omega, bool prolong, double alpha, bool restrict_) {
+  DevLevel &L = c->lv[level];
+  const int nch = c->d.nchains;
+  const bool lowrank = c->d.m_lowrank > 0;
+  const double n = (double)L.h.ndof() * nch;
+  if (prolong) {
+    DevLevel &C = c->lv[level + 1];
+    c->launch("prolongate_add", level, [&] { prolongate_add_kernel<<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, C.g, alpha, C.x, L.x); }, 18.0 * n);
+  }
+  dim3 grid((L.g.nx / 3 + 1 + 63) / 64, (L.g.ny / 3 + 1 + 3) / 4, nch);
+  for (const SweepSpec &sw : sweeps) {
+    const uint32_t c1 = next_c1(c, level, gibbs);
+    NoiseP nz = noise_params(c, level, c1);
+    for (int cc = 0; cc < 9; ++cc) {
+      const int colour = sw.fwd ? cc : 8 - cc;
+      c->launch(gibbs ? "gibbs_9c1" : "sor_9c1", level, [&] {
+        if (gibbs) sweep_colour25_kernel<true><<<grid, kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, colour, omega, nz);
+        else sweep_colour25_kernel<false><<<grid, kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, colour, omega, nz);
+      }, 24.0 * n / 9.0);
+    }
+    if (lowrank && sw.fix_after) dev_lowrank_fix(c, level, sw.fwd, gibbs, omega, c1);
+  }
+  if (restrict_) {
+    DevLevel &C = c->lv[level + 1];
+    c->launch("residual", level, [&] { apply25_kernel<true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, L.r); }, 16.0 * n);
+    if (lowrank)
+      c->launch("lowrank_residual", level, [&] {
+        lowrank_apply_kernel<<<nch, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, L.B.rows, c->d_sigma_inv_neg, L.g.stride, L.x, L.r);
+      });
+    dev_restrict_plain(c, level, L.r, C.f);
+    dev_zero(c, level + 1, C.x);
   }
 }
 
@@ -956,7 +1000,7 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
     if (desc->coarse_solver != MGMC_COARSE_SSOR && desc->coarse_solver != MGMC_COARSE_CHOLESKY) fail(MGMC_ERR_INVALID, "invalid coarse solver");
     std::vector<HostLevel> H = build_host_levels(*desc);
     for (const HostLevel &h : H)
-      if (h.st.radius > 1 || !h.st.uniform) fail(MGMC_ERR_UNSUPPORTED, "squared_shiftedlaplace_fd (13/21-point stencils) is not on the device path yet");
+      if (h.st.radius <= 1 && !h.st.uniform) fail(MGMC_ERR_UNSUPPORTED, "internal: radius-1 stencil with position classes");
     c = new mgmc_ctx();
     c->d = *desc;
     c->d.B_rows = nullptr;
@@ -992,6 +1036,11 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
       L.r = c->dalloc<double>(total) + origin;
       L.coef = to_coef9(L.h.st);
       L.nine = (L.h.st.ncolours == 4);
+      L.r2 = (L.h.st.radius > 1);
+      if (L.r2) {
+        std::vector<double> st(&L.h.st.a[0][0], &L.h.st.a[0][0] + 225);
+        L.d_st = c->dupload(st);
+      }
       if (desc->m_lowrank > 0) L.B = upload_sparse(c, L.h.B, desc->m_lowrank, L.g.pitch);
     }
     if (desc->m_lowrank > 0) {
@@ -1001,6 +1050,9 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
         sis[k] = std::sqrt(1.0 / c->Sigma[k]);
       }
       c->d_sigma_inv = c->dupload(si);
+      std::vector<double> sin(si);
+      for (double &v : sin) v = -v;
+      c->d_sigma_inv_neg = c->dupload(sin);
       c->d_sigma_inv_sqrt = c->dupload(sis);
     }
     c->d_sample = c->dalloc<uint32_t>(1);
@@ -1211,7 +1263,8 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
   for (int k = 0; k < maxiter; ++k) {
     // r = A x - b (into f_ell[0], the preconditioner's input) and ||r||
     c->launch("residual_norm", 0, [&] {
-      if (L.nine) residual_norm_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
+      if (L.r2) residual_norm25_kernel<<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, c->sol_x, c->sol_b, L.f, c->d_partial);
+      else if (L.nine) residual_norm_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
       else residual_norm_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
     });
     if (c->d.m_lowrank > 0) {

@@ -25,14 +25,14 @@ def _measurements(oracle, prior, n_meas, seed=7, radius=0.0):
     return prior.measured(locs, var, variance_scaling=1e-6, radius=radius)
 
 
-def _setup(oracle, m, n, nlevel, n_meas=0, radius=0.0, **kw):
+def _setup(oracle, m, n, nlevel, n_meas=0, radius=0.0, pde="shiftedlaplace_fd", **kw):
     """oracle hierarchy (colour ordering) + GPU context for the same problem"""
-    op = oracle.Operator.prior(n, "shiftedlaplace_fd", Lambda=0.2)
+    op = oracle.Operator.prior(n, pde, Lambda=0.2)
     if n_meas:
         op = _measurements(oracle, op, n_meas, radius=radius)
     H = oracle.Hierarchy(op, nlevel, oracle.COLOUR)
     B = op.B() if n_meas else None
-    ctx = m.Context(n[0], n[1], nlevel, Lambda=0.2, B=B, **kw)
+    ctx = m.Context(n[0], n[1], nlevel, Lambda=0.2, B=B, pde=pde, **kw)
     return op, H, ctx
 
 
@@ -190,6 +190,71 @@ def test_mgmc_cycle_same_philox_stream(oracle, m, n, nlevel, n_meas, kw):
     xr2, series_ref = sampler.run(f, xr, b_obs, 4)
     assert rel(ctx.get_state(), xr2) < 1e-10
     assert np.abs(series - series_ref).max() < 1e-10 * np.abs(series_ref).max()
+
+
+# ---- squared shifted Laplacian (biharmonic-type prior, BASELINE config 4): 13 / 21-point stencils with
+#      boundary-ring classes, 9-colour sweeps; never exercised inside multigrid by the reference's own tests ----
+SQ = "squared_shiftedlaplace_fd"
+SQ_CASES = [((64, 64), 3, 0), ((64, 32), 2, 0), ((128, 128), 4, 4)]
+
+
+@pytest.mark.parametrize("n,nlevel,n_meas", SQ_CASES)
+def test_squared_operator_single_level_ops(oracle, m, n, nlevel, n_meas):
+    seed = 77
+    op, H, ctx = _setup(oracle, m, n, nlevel, n_meas, pde=SQ, seed=seed)
+    rng = np.random.default_rng(21)
+    for level in range(nlevel):
+        lop = H.level_op(level)
+        nd = lop.ndof
+        assert ctx.ndof(level) == nd and ctx.level_info(level)[3] == H.ncolours(level) == 9
+        x, b = rng.standard_normal(nd), rng.standard_normal(nd)
+        assert rel(ctx.op_apply(level, x), lop.apply(x)) < TOL
+        for kind, direction, nsmooth, omega in (("SOR", 1, 1, 1.0), ("SOR", 2, 1, 0.8), ("SSOR", 1, 2, 0.9)):
+            ref = H.smoother(level, kind, omega, nsmooth, direction).apply(b, x)
+            assert rel(ctx.smoother_apply(level, kind, b, x, omega=omega, nsmooth=nsmooth, direction=direction), ref) < TOL, (level, kind)
+            s = H.sampler(level, kind, omega=omega, nsmooth=nsmooth, direction=direction, rng=None, philox_seed=seed)
+            s.set_philox_position(3, 0, 1)
+            ctx.set_philox_position(3, 1)
+            assert rel(ctx.sampler_apply(level, kind, b, x, omega=omega, nsmooth=nsmooth, direction=direction), s.apply(b, x)) < 1e-11, (level, kind)
+        if level < nlevel - 1:
+            ref = H.restrict(level, b - lop.apply(x))
+            assert rel(ctx.residual_restrict(level, b, x), ref) < 1e-11
+    # SSOR fixed point (test_smoother.hh:90-114) on the squared operator
+    x_exact = rng.standard_normal(op.ndof)
+    assert rel(ctx.smoother_apply(0, "SSOR", op.apply(x_exact), x_exact, omega=0.8), x_exact) < 1e-9
+
+
+@pytest.mark.parametrize("n,nlevel,n_meas,kw", [
+    ((64, 64), 3, 0, {}),
+    ((128, 128), 4, 4, dict(npresmooth=2, npostsmooth=2)),
+])
+def test_squared_operator_multigrid_and_mgmc(oracle, m, n, nlevel, n_meas, kw):
+    seed = 5418513
+    op, H, ctx = _setup(oracle, m, n, nlevel, n_meas, pde=SQ, seed=seed, **kw)
+    b = oracle.StdRng(1482817).normal(op.ndof)
+    prec = H.preconditioner(**kw)
+    assert rel(ctx.mgprec_apply(b), prec.apply(b, np.zeros_like(b))) < 1e-10
+    # the V-cycle of the squared operator contracts slowly (factor ~0.7 with coarse_scaling = 1, in the
+    # lexicographic reference ordering as well): same history, same iteration count as the oracle
+    x_ref, h_ref, it_ref, cv_ref = oracle.loop_solve(op, prec, b, rtol=1e-6, atol=1e300, maxiter=80)
+    x, h, it, cv = ctx.loop_solve(b, rtol=1e-6, atol=1e300, maxiter=80)
+    assert (it, cv) == (it_ref, cv_ref) and cv
+    assert np.abs(h - h_ref).max() < 1e-10 * np.linalg.norm(b)
+    assert rel(x, x_ref) < 1e-9
+    rng = np.random.default_rng(22)
+    f, x0 = rng.standard_normal(op.ndof), rng.standard_normal(op.ndof)
+    sampler = H.mgmc(rng=None, philox_seed=seed, **kw)
+    ctx.set_philox_position(0)
+    xr, xg = x0, x0
+    for k in range(2):
+        xr = sampler.apply(f, xr)
+        xg = ctx.mgmc_apply(f, xg)
+        assert rel(xg, xr) < 1e-9, k
+    ctx.set_rhs(f)
+    ctx.set_state(xg)
+    ctx.sample(2, series=False)  # graph replay continues the chain
+    xr = sampler.apply(f, sampler.apply(f, xr))
+    assert rel(ctx.get_state(), xr) < 1e-9
 
 
 def test_chains_are_independent_and_reproducible(m):
