@@ -36,6 +36,8 @@ def parse():
     p.add_argument("--nlevel", type=int, default=8)
     p.add_argument("--nmeas", type=int, default=32)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--decomp", default="chains", choices=["chains", "strips"],
+                   help="N > 1: independent chains per GPU (weak scaling, default) or ONE chain on row strips of the lattice (strong scaling)")
     p.add_argument("--cpu-n", type=int, default=1024, help="lattice of the bounded CPU sample")
     return p.parse_args()
 
@@ -187,8 +189,17 @@ def run_b200(a):
     n, nlevel = a.n, a.nlevel
     loc, sample_loc, mean, var = w.measurement_set(a.nmeas) if a.nmeas else (None, np.array([0.5, 0.5]), None, None)
     B = w.point_measurement_matrix(n, n, loc, var, 1e-6) if a.nmeas else None
-    ctx = m.Context(n, n, nlevel, Lambda=0.2, B=B, smoother="SSOR", coarse_solver="Cholesky", npresmooth=1, npostsmooth=1,
-                    cycle=1, omega=1.0, seed=5418513, device=local, nchains=1, first_chain=rank)
+    strips_on = world > 1 and a.decomp == "strips"
+    if strips_on:
+        from multigridmc_b200 import strips
+
+        ctx = m.Context(n, n, nlevel, Lambda=0.2, B=B, smoother="SSOR", coarse_solver="Cholesky", npresmooth=1, npostsmooth=1,
+                        cycle=1, omega=1.0, seed=5418513, device=local, nchains=1, first_chain=0, strip_rank=rank, strip_nranks=world)
+        strips.connect(ctx, dist, torch.device("cuda", local))
+    else:
+        ctx = m.Context(n, n, nlevel, Lambda=0.2, B=B, smoother="SSOR", coarse_solver="Cholesky", npresmooth=1, npostsmooth=1,
+                        cycle=1, omega=1.0, seed=5418513, device=local, nchains=1, first_chain=rank)
+    nchains_total = 1 if strips_on else world
     nd = ctx.ndof()
     # synthetic right-hand side f = A u, u = sin(pi x) sin(pi y); pinned host buffers for the e2e path
     xs = np.arange(1, n) / n
@@ -217,7 +228,11 @@ def run_b200(a):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * a.steps / (ms_max * 1e-3)
+    value = nchains_total * a.steps / (ms_max * 1e-3)
+    if strips_on:
+        series = strips.reduce_series(series, dist, torch.device("cuda", local))
+        if ctx.strip_error():
+            raise SystemExit("bench.py: a device-side wait for a neighbour rank timed out")
 
     # ---- end to end through the reference-facing call with HOST buffers ----
     # MultigridMCSampler::apply(f, x) after fix_rhs(f) (driver_mgmc.cc:65,75): per step H2D of the chain
@@ -228,20 +243,22 @@ def run_b200(a):
     xp = x_np.ctypes.data_as(c_dp)
     e2e_steps = max(3, min(a.steps, 20))
     qidx = w.nearest_vertex(n, n, sample_loc)
-    for _ in range(2):
-        assert L.mgmc_sampler_mgmc_apply(ctx.h, None, xp) == 0
-    barrier()
-    t0 = time.perf_counter()
-    acc = 0.0
-    for _ in range(e2e_steps):
-        assert L.mgmc_sampler_mgmc_apply(ctx.h, None, xp) == 0
-        acc += x_np[qidx]
-    barrier()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps / float(t.item())
+    e2e_value = None
+    if not strips_on:  # (row strips: the chain state is distributed; only the device-resident loop below applies)
+        for _ in range(2):
+            assert L.mgmc_sampler_mgmc_apply(ctx.h, None, xp) == 0
+        barrier()
+        t0 = time.perf_counter()
+        acc = 0.0
+        for _ in range(e2e_steps):
+            assert L.mgmc_sampler_mgmc_apply(ctx.h, None, xp) == 0
+            acc += x_np[qidx]
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = nchains_total * e2e_steps / float(t.item())
 
     # ---- the same metric through the device-resident form of the driver's hot loop (Sampler::sample_series,
     #      host/mgmc_host.hh): chain state stays in HBM, only the QoI series crosses PCIe ----
@@ -254,15 +271,21 @@ def run_b200(a):
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_resident = world * a.steps / float(t.item())
+    e2e_resident = nchains_total * a.steps / float(t.item())
 
+    prof = None
+    if strips_on:  # cooperative: every rank has to run the profiled cycles
+        barrier()
+        prof = ctx.profile_cycle(nsamples=3)
+        barrier()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
     # ---- per-kernel CUDA-event timing of the cycle (rank 0): roofline of the dominant kernel ----
-    prof = ctx.profile_cycle(nsamples=3)
+    if prof is None:
+        prof = ctx.profile_cycle(nsamples=3)
     total_ms = sum(p[1] for p in prof)
     top = max(prof, key=lambda p: p[1])
     byts, upd = ctx.cycle_model()
@@ -288,13 +311,17 @@ def run_b200(a):
 
     line = {
         "metric": "mgmc_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(a),
+        "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "strong" if strips_on else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": dict(workload_config(a), multi_gpu=("row strips of one lattice, halo rows stored into the neighbours' memory over NVLink (CUDA IPC), "
+                                                                           "device-side flags, coarse levels replicated" if strips_on else
+                                                                           ("independent chains per GPU, no data-path collective" if world > 1 else "single GPU"))),
         "site_updates_per_sec": value * upd,
-        "cycle_algorithmic_gbs": cycle_gbs, "cycle_roofline_frac": cycle_gbs / peak,
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": 8 * nd, "d2h_bytes_per_step": 8 * nd,
-                "call": "mgmc_sampler_mgmc_apply(ctx, NULL /*rhs fixed by fix_rhs*/, x) with pinned host x, QoI read on the host",
-                "steps": e2e_steps},
+        "cycle_algorithmic_gbs": cycle_gbs, "cycle_roofline_frac": cycle_gbs / peak / (world if strips_on else 1),
+        "e2e": ({"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": 8 * nd, "d2h_bytes_per_step": 8 * nd,
+                 "call": "mgmc_sampler_mgmc_apply(ctx, NULL /*rhs fixed by fix_rhs*/, x) with pinned host x, QoI read on the host",
+                 "steps": e2e_steps} if e2e_value is not None else
+                {"value": e2e_resident, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+                 "call": "mgmc_sample(ctx, K, qoi_host) on every rank + sum of the partial QoI series (state distributed over the ranks)"}),
         "e2e_resident": {"value": e2e_resident, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
                          "call": "mgmc_sample(ctx, K, qoi_host): K cycles + device QoI, one D2H of the K-entry series (wall clock, host buffers)"},
         "gpu_launches": int(launches),

@@ -61,6 +61,10 @@ typedef struct {
   int device;             /* CUDA device ordinal */
   int nchains;            /* independent Markov chains advanced together (>= 1) */
   int first_chain;        /* global id of chain 0 of this context (Philox counter word 3) */
+  /* row-strip domain decomposition of ONE lattice over the GPUs of a node (one process per GPU):
+   * rank strip_rank of strip_nranks owns a contiguous block of rows of every distributed level; the
+   * coarse levels are replicated.  0 / 1 ranks = off.  See mgmc_strip_* below. */
+  int strip_rank, strip_nranks;
 } mgmc_desc;
 
 const char *mgmc_last_error(void);
@@ -128,6 +132,24 @@ int mgmc_sample(mgmc_ctx *, int64_t nsamples, double *qoi_series);
 int mgmc_sample_moments(mgmc_ctx *, int64_t nsamples, double *mean_field, double *second_moment_field);
 /* like mgmc_sample but timed on the device with CUDA events on the launching stream */
 int mgmc_sample_timed(mgmc_ctx *, int64_t nsamples, double *qoi_series, double *elapsed_ms);
+
+/* ---- row-strip decomposition over several GPUs (no reference counterpart: the
+ *      reference is single-threaded) ----
+ * Every rank creates its context with the same desc except device / strip_rank.  The ranks then exchange
+ * the opaque handle blobs (e.g. torch.distributed.all_gather) and connect; afterwards mgmc_sample /
+ * mgmc_sample_timed advance ONE chain cooperatively: per fused launch the boundary rows of the iterate are
+ * stored straight into the neighbours' memory over NVLink (CUDA IPC mappings) and a flag is raised; the
+ * neighbour's next launch waits on the flag on the device.  The chain is bit-identical to the single-GPU
+ * chain (the noise of a site does not depend on the decomposition). */
+/* rows [row_lo, row_hi] of `level` owned by `rank` (host-only, needs no device); *distributed = 0 for
+ * the replicated coarse levels (every rank owns all rows) */
+int mgmc_strip_partition(const mgmc_desc *desc, int level, int rank, int *row_lo, int *row_hi, int *distributed);
+int mgmc_strip_handle_bytes(void);
+int mgmc_strip_export(mgmc_ctx *, void *handle_out);
+/* all_handles: strip_nranks blobs of mgmc_strip_handle_bytes() bytes, ordered by rank */
+int mgmc_strip_connect(mgmc_ctx *, const void *all_handles);
+/* nonzero if a device-side wait for a neighbour timed out since the last call (then the state is invalid) */
+int mgmc_strip_error(mgmc_ctx *);
 
 /* ---- instrumentation ---- */
 /* number of kernels launched by this context so far */

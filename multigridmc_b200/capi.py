@@ -48,6 +48,7 @@ class Desc(C.Structure):
         ("npresmooth", C.c_int), ("npostsmooth", C.c_int), ("ncoarsesmooth", C.c_int),
         ("cycle", C.c_int), ("coarse_scaling", C.c_double), ("omega", C.c_double),
         ("seed", C.c_uint64), ("device", C.c_int), ("nchains", C.c_int), ("first_chain", C.c_int),
+        ("strip_rank", C.c_int), ("strip_nranks", C.c_int),
     ]
 
 
@@ -91,6 +92,11 @@ def lib():
         "mgmc_sample": (i, [vp, i64, c_dp]),
         "mgmc_sample_moments": (i, [vp, i64, c_dp, c_dp]),
         "mgmc_sample_timed": (i, [vp, i64, c_dp, c_dp]),
+        "mgmc_strip_partition": (i, [C.POINTER(Desc), i, i, ip, ip, ip]),
+        "mgmc_strip_handle_bytes": (i, []),
+        "mgmc_strip_export": (i, [vp, vp]),
+        "mgmc_strip_connect": (i, [vp, vp]),
+        "mgmc_strip_error": (i, [vp]),
         "mgmc_launch_count": (i64, [vp]),
         "mgmc_profile_cycle": (i, [vp, i, i, C.c_char_p, c_dp, C.POINTER(i64), c_dp, ip]),
         "mgmc_cycle_model": (i, [vp, c_dp, c_dp]),
@@ -109,7 +115,8 @@ EXPORTS = [
     "mgmc_sampler_apply", "mgmc_coarse_solve", "mgmc_coarse_sample", "mgmc_sampler_mgmc_apply", "mgmc_mgprec_apply",
     "mgmc_loop_solve", "mgmc_set_philox_position", "mgmc_set_rhs", "mgmc_set_state", "mgmc_get_state", "mgmc_set_qoi",
     "mgmc_sample", "mgmc_sample_moments", "mgmc_sample_timed", "mgmc_launch_count", "mgmc_profile_cycle",
-    "mgmc_cycle_model",
+    "mgmc_cycle_model", "mgmc_strip_partition", "mgmc_strip_handle_bytes", "mgmc_strip_export", "mgmc_strip_connect",
+    "mgmc_strip_error",
 ]
 
 
@@ -131,7 +138,7 @@ FORWARD, BACKWARD = 1, 2
 
 def make_desc(nx, ny, nlevel, pde="shiftedlaplace_fd", Lambda=0.2, B=None, smoother="SSOR", coarse_solver="Cholesky",
               npresmooth=1, npostsmooth=1, ncoarsesmooth=1, cycle=1, coarse_scaling=1.0, omega=1.0, seed=5418513,
-              device=0, nchains=1, first_chain=0):
+              device=0, nchains=1, first_chain=0, strip_rank=0, strip_nranks=0):
     """B = (rows, cols, vals, sigma) COO triplets of the measurement matrix (lexicographic rows)."""
     d = Desc()
     d.dim, d.nx, d.ny, d.nz = 2, nx, ny, 1
@@ -152,8 +159,16 @@ def make_desc(nx, ny, nlevel, pde="shiftedlaplace_fd", Lambda=0.2, B=None, smoot
     d.npresmooth, d.npostsmooth, d.ncoarsesmooth = npresmooth, npostsmooth, ncoarsesmooth
     d.cycle, d.coarse_scaling, d.omega = cycle, coarse_scaling, omega
     d.seed, d.device, d.nchains, d.first_chain = seed, device, nchains, first_chain
+    d.strip_rank, d.strip_nranks = strip_rank, strip_nranks
     d._keep = keep
     return d
+
+
+def strip_partition(desc, level, rank):
+    """(row_lo, row_hi, distributed) of `rank` on `level` (host-only)."""
+    lo, hi, dist = C.c_int(), C.c_int(), C.c_int()
+    _chk(lib().mgmc_strip_partition(C.byref(desc), level, rank, C.byref(lo), C.byref(hi), C.byref(dist)))
+    return lo.value, hi.value, bool(dist.value)
 
 
 def host_stencil(desc, level):
@@ -302,6 +317,20 @@ class Context:
         mean, second = np.empty(n), np.empty(n)
         _chk(lib().mgmc_sample_moments(self.h, nsamples, mean.ctypes.data_as(c_dp), second.ctypes.data_as(c_dp)))
         return mean, second
+
+    # ---- row-strip decomposition (one process per GPU) ----
+    def strip_export(self):
+        buf = C.create_string_buffer(lib().mgmc_strip_handle_bytes())
+        _chk(lib().mgmc_strip_export(self.h, buf))
+        return buf.raw
+
+    def strip_connect(self, blobs):
+        """blobs: list of the handle blobs of all ranks, ordered by rank."""
+        data = b"".join(blobs)
+        _chk(lib().mgmc_strip_connect(self.h, C.c_char_p(data)))
+
+    def strip_error(self):
+        return lib().mgmc_strip_error(self.h)
 
     def launch_count(self):
         return lib().mgmc_launch_count(self.h)

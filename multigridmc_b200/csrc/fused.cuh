@@ -79,6 +79,7 @@ struct FusedP {
   int omega_is_one;
   long long *timing;  // MGMC_TILE_TIMING builds only: 8 clock64 stamps + smid per CTA
   int tiles_x;        // the grid is 1-d: npatch patch CTAs followed by tiles_x * tiles_y tile CTAs
+  int by0;            // first tile row of this launch (row-strip decomposition: the rank's own tile rows)
   // low-rank term (LOWRANK kernels): fix-up q follows stage fix_stage[q]
   const LowRankTile *lr;
   int npatch, wpw, wcap;  // patch CTAs, windows per warp, doubles per window array
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     return;
   }
   const int tile_id = (int)blockIdx.x - (LOWRANK ? P.npatch : 0);
-  const int tile_bx = tile_id % P.tiles_x, tile_by = tile_id / P.tiles_x;
+  const int tile_bx = tile_id % P.tiles_x, tile_by = tile_id / P.tiles_x + P.by0;
 #ifdef MGMC_TILE_TIMING
   const int cta_id = blockIdx.z * gridDim.x + blockIdx.x;
 #define TSTAMP(k) if (threadIdx.x == 0 && P.timing) P.timing[(long long)cta_id * 10 + (k)] = clock64();

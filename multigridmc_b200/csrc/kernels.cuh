@@ -461,6 +461,71 @@ __global__ void __launch_bounds__(256) trimv_kernel(const double *__restrict__ T
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row-strip domain decomposition over several GPUs (one process per GPU, peer memory mapped with CUDA
+// IPC).  After a fused launch a rank stores the boundary rows of its output straight into the
+// neighbours' arrays over NVLink and raises their flag; before a fused launch it waits (on the device,
+// no host round trip, CUDA-graph capturable) until both neighbours have delivered the rows of the
+// previous launch.  All ranks run the same launch sequence, so counting launches is the whole protocol.
+// ------------------------------------------------------------------------------------------------
+struct StripSeg {
+  const double *src;
+  double *dst;     // peer memory
+  long long n;     // doubles, multiple of 2 (rows are 128-byte aligned and a multiple of 16 doubles long)
+};
+struct StripPush {
+  StripSeg seg[8];
+  int nseg;
+  int *flag[8];    // peer flags to increment (system scope) once every segment has landed
+  int nflag;
+  unsigned int *ticket;  // local arrival counter of the CTAs of this launch
+};
+
+__global__ void __launch_bounds__(256) strip_push_kernel(const __grid_constant__ StripPush P) {
+  for (int s = 0; s < P.nseg; ++s) {
+    const double2 *src = reinterpret_cast<const double2 *>(P.seg[s].src);
+    double2 *dst = reinterpret_cast<double2 *>(P.seg[s].dst);
+    const long long n2 = P.seg[s].n >> 1;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n2; k += (long long)gridDim.x * blockDim.x) dst[k] = src[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(P.ticket, 1u);
+    if (t == gridDim.x - 1) {  // last CTA: every other CTA has fenced its stores before taking its ticket
+      *P.ticket = 0u;
+      __threadfence_system();
+      for (int f = 0; f < P.nflag; ++f) atomicAdd_system(P.flag[f], 1);
+    }
+  }
+}
+
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// wait until flag[f] >= per_wait[f] * (number of this wait, counted in *waitno) - lag[f]; a time-out
+// (a peer died) raises *err instead of hanging the GPU
+__global__ void strip_wait_kernel(const int *flag0, const int *flag1, int per_wait0, int per_wait1, int lag0, int lag1, int *waitno, int *err) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int k = *waitno + 1;
+  *waitno = k;
+  const long long t0 = clock64();
+  const int *flags[2] = {flag0, flag1};
+  const int target[2] = {per_wait0 * k - lag0, per_wait1 * k - lag1};
+  for (int f = 0; f < 2; ++f) {
+    if (!flags[f]) continue;
+    while (ld_acquire_sys(flags[f]) < target[f]) {
+      if (clock64() - t0 > 6000000000ll) {  // ~3 s
+        *err = 1;
+        return;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // End of an MGMC cycle: z = sample_vector . x for every chain (driver_mgmc.cc:76), stored at
 // series[pos * nchains + chain]; then advance the device-resident sample index and series position.
 // ------------------------------------------------------------------------------------------------

@@ -49,6 +49,8 @@ struct LowRankDev {
   // in-kernel fix-up (patch CTAs of the fused kernel)
   LowRankTile *d_tile = nullptr;  // device copy of the descriptor
   int bw = 0, bh = 0;             // largest extent of supp(B_k)
+  int wreach = 0;                 // largest distance of a site of supp(W_k) from the bounding box of supp(B_k)
+  bool diag[2] = {false, false};  // capacitance matrix diagonal (measurements do not interact on this level)
 };
 
 struct DevLevel {
@@ -62,6 +64,15 @@ struct DevLevel {
   double *d_st = nullptr;      // [9][25] stencil classes (radius-2 levels)
   DevSparse B;
   std::map<double, LowRankDev> lowrank;  // keyed by omega
+};
+
+// Row-strip decomposition plan (same on every rank): rank r owns the rows (J0_r / 2^l, J1_r / 2^l] of the
+// distributed levels l < ndist, J0_r = r * ny_0 / nranks; strips start on tile boundaries so that a
+// rank simply runs its own tile rows.  Levels >= ndist are replicated.
+struct StripPlan {
+  int nranks = 1, rank = 0, ndist = 0;
+  std::vector<int> lo, hi, halo;  // per distributed level: own rows [lo, hi], rows exchanged with a neighbour
+  bool on() const { return nranks > 1; }
 };
 
 struct ProfSlot {
@@ -97,6 +108,14 @@ struct mgmc_ctx {
   int *d_lr_flags = nullptr;  // flags [kLrSlots * nchains] followed by counters [kLrSlots * nchains]
   int lr_slot_next = 0;
   bool lr_fuse = true;        // MGMC_NO_LR_FUSE=1: separate fix-up launches (fallback path, perf experiments)
+  // row-strip decomposition: arena shared with the neighbours through CUDA IPC
+  StripPlan strip;
+  char *arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<char *> peer_arena;  // per rank (nullptr for self / unconnected)
+  bool strip_connected = false;
+  int *d_strip_ctl = nullptr;      // in the arena: [0] flag from below, [1] flag from above, [2] all-gather count,
+                                   // [3] error, [4] waitno (neighbours), [5] waitno (all-gather), [6] push ticket
   // noise position
   uint32_t *d_sample = nullptr;
   uint32_t h_sample = 0;
@@ -217,6 +236,36 @@ Coef9 to_coef9(const StencilSet &s) {
   a.nw = s.at(4, -1, 1);
   a.ne = s.at(4, 1, 1);
   return a;
+}
+
+inline int fused_tile_rows(int ny, int nc, bool strips);
+
+StripPlan make_strip_plan(const mgmc_desc &d, const std::vector<HostLevel> &H) {
+  StripPlan p;
+  p.nranks = std::max(d.strip_nranks, 1);
+  p.rank = d.strip_rank;
+  if (p.nranks == 1) return p;
+  if (p.rank < 0 || p.rank >= p.nranks) fail(MGMC_ERR_INVALID, "strip_rank out of range");
+  if (d.nchains != 1) fail(MGMC_ERR_UNSUPPORTED, "row strips advance one chain (nchains = 1)");
+  static const char *mr = std::getenv("MGMC_STRIP_MIN_ROWS");
+  const int min_rows = mr ? std::atoi(mr) : 64;
+  for (int l = 0; l + 1 < (int)H.size(); ++l) {  // the coarsest level is always replicated
+    const HostLevel &h = H[l];
+    if (h.st.radius > 1) break;  // radius-2 operators: not decomposed yet
+    const int nc = h.st.ncolours;
+    const int ty = fused_tile_rows(h.ny, nc, true);
+    const int rows = h.ny / p.nranks;
+    // rows exchanged with a neighbour: what a launch of 2 sweeps (+ residual) reads beyond the own rows; with a
+    // low-rank term additionally the windows of the measurements near the strip boundary (patch CTAs)
+    const int halo = (d.m_lowrank > 0) ? ((nc == 2) ? 16 : 28) : ((nc == 2) ? 8 : 12);
+    if (h.ny % p.nranks || rows % ty || rows < std::max(min_rows, 2 * halo) || (rows % 2 && l + 2 < (int)H.size())) break;
+    p.lo.push_back(p.rank * rows + 1);
+    p.hi.push_back(std::min((p.rank + 1) * rows, h.ny - 1));
+    p.halo.push_back(halo);
+    p.ndist = l + 1;
+  }
+  if (p.ndist == 0) fail(MGMC_ERR_UNSUPPORTED, "lattice cannot be split into row strips for this number of ranks (rows per rank must be a multiple of the tile height and >= MGMC_STRIP_MIN_ROWS)");
+  return p;
 }
 
 std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
@@ -395,6 +444,10 @@ const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega) {
           wbox[4 * k + 3] = std::max(wbox[4 * k + 3], wj[u]);
         }
       T.wbox[dir] = c->dupload(wbox);
+      for (int k = 0; k < m; ++k)
+        if (wbox[4 * k + 1] >= wbox[4 * k])
+          dev.wreach = std::max(dev.wreach, std::max(std::max(bbox[4 * k] - wbox[4 * k], wbox[4 * k + 1] - bbox[4 * k + 1]),
+                                                     std::max(bbox[4 * k + 2] - wbox[4 * k + 2], wbox[4 * k + 3] - bbox[4 * k + 3])));
       std::vector<int> wl_ptr(1, 0), wl_u;
       for (int k = 0; k < m; ++k) {
         for (int u = 0; u < F.nu; ++u)
@@ -416,6 +469,7 @@ const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega) {
           for (int e = 0; e < F.EW; ++e)
             if (wvalh[(size_t)wl_u[q] * F.EW + e] != 0.0 && wcolh[(size_t)wl_u[q] * F.EW + e] != k) diag = false;
       T.diag[dir] = diag ? 1 : 0;
+      dev.diag[dir] = diag;
     }
     T.sigma_inv = c->d_sigma_inv;
     T.sigma_inv_sqrt = c->d_sigma_inv_sqrt;
@@ -502,7 +556,8 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
 // ---- fused tile kernel dispatch ----
 // tile height: 32 rows on the big (bandwidth / issue bound) levels; the small levels are latency bound,
 // there short tiles give every warp at most one row per colour pass and spread over more SMs
-inline int fused_tile_rows(int ny, int nc) {
+inline int fused_tile_rows(int ny, int nc, bool strips) {
+  if (strips) return ny > 1024 ? 32 : (ny > 256 ? 16 : 8);  // strips must start on tile boundaries: powers of two only
   static const char *ov = std::getenv("MGMC_TILE_ROWS");  // perf experiments: tile height of the big levels
   if (ov && ny > 2048 && nc == 2) return std::atoi(ov);
   // 40 rows on the finest red-black levels: 49 / 47 / 45 / 43 rows per colour pass share 16 warps better than 41..35
@@ -554,6 +609,82 @@ bool lr_patch_geometry(mgmc_ctx *c, const LowRankDev &lr, int S, int &npatch, in
 
 const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega);
 
+// ---- row strips: device-side wait for the neighbours' rows, push of the own boundary rows ----
+template <class T>
+T *peer_ptr(mgmc_ctx *c, int rank, T *mine) {
+  return (T *)(c->peer_arena[rank] + ((char *)mine - c->arena));
+}
+
+void strip_wait_neighbours(mgmc_ctx *c) {
+  const StripPlan &sp = c->strip;
+  int *ctl = c->d_strip_ctl;
+  c->launch("strip_wait", 0, [&] {
+    strip_wait_kernel<<<1, 32, 0, c->stream>>>(sp.rank > 0 ? ctl + 0 : nullptr, sp.rank + 1 < sp.nranks ? ctl + 1 : nullptr, 1, 1, 1, 1, ctl + 4, ctl + 3);
+  });
+}
+
+// rows [j0, j1] of a level array as one contiguous segment (full padded rows)
+StripSeg row_segment(mgmc_ctx *c, const DevLevel &L, double *arr, int j0, int j1, int dst_rank) {
+  StripSeg sg;
+  double *p = arr + (long long)j0 * L.g.pitch - GX;
+  sg.src = p;
+  sg.dst = peer_ptr(c, dst_rank, p);
+  sg.n = (long long)(j1 - j0 + 1) * L.g.pitch;
+  return sg;
+}
+
+// after a fused launch on a distributed level: boundary rows of the new iterate (and of the restricted
+// right-hand side) go to the neighbours; their flags are raised once everything has landed
+void strip_push_neighbours(mgmc_ctx *c, int level, bool restricted) {
+  const StripPlan &sp = c->strip;
+  DevLevel &L = c->lv[level];
+  StripPush P;
+  std::memset(&P, 0, sizeof(P));
+  const bool has_dn = sp.rank > 0, has_up = sp.rank + 1 < sp.nranks;
+  const int H = sp.halo[level];
+  if (has_dn) P.seg[P.nseg++] = row_segment(c, L, L.x, sp.lo[level], sp.lo[level] + H - 1, sp.rank - 1);
+  if (has_up) P.seg[P.nseg++] = row_segment(c, L, L.x, sp.hi[level] - H + 1, sp.hi[level], sp.rank + 1);
+  if (restricted && level + 1 < sp.ndist) {
+    DevLevel &C = c->lv[level + 1];
+    const int Hc = sp.halo[level + 1];
+    if (has_dn) P.seg[P.nseg++] = row_segment(c, C, C.f, sp.lo[level + 1], sp.lo[level + 1] + Hc - 1, sp.rank - 1);
+    if (has_up) P.seg[P.nseg++] = row_segment(c, C, C.f, sp.hi[level + 1] - Hc + 1, sp.hi[level + 1], sp.rank + 1);
+    // the neighbours zero their rows of x_{l+1} themselves: zero my copies of them (before my flag goes up,
+    // i.e. before a neighbour can push rows of x_{l+1} again)
+    const size_t rowb = (size_t)C.g.pitch * sizeof(double);
+    if (has_dn) CUDA_CHECK(cudaMemsetAsync(C.x + (long long)(sp.lo[level + 1] - Hc) * C.g.pitch - GX, 0, rowb * Hc, c->stream));
+    if (has_up) CUDA_CHECK(cudaMemsetAsync(C.x + (long long)(sp.hi[level + 1] + 1) * C.g.pitch - GX, 0, rowb * Hc, c->stream));
+  }
+  if (has_dn) P.flag[P.nflag++] = peer_ptr(c, sp.rank - 1, c->d_strip_ctl + 1);  // I am the neighbour above rank - 1
+  if (has_up) P.flag[P.nflag++] = peer_ptr(c, sp.rank + 1, c->d_strip_ctl + 0);
+  P.ticket = (unsigned int *)(c->d_strip_ctl + 6);
+  c->launch("strip_push", level, [&] { strip_push_kernel<<<16, 256, 0, c->stream>>>(P); });
+}
+
+// restriction into the first replicated level: every rank sends its rows of f to every other rank,
+// zeroes the whole coarse iterate and waits for the rows of the others
+void strip_allgather_rhs(mgmc_ctx *c, int level /* fine, distributed */) {
+  const StripPlan &sp = c->strip;
+  DevLevel &L = c->lv[level];
+  DevLevel &C = c->lv[level + 1];
+  const int clo = (sp.lo[level] - 1) / 2 + 1, chi = std::min(sp.hi[level] / 2, C.g.ny - 1);  // coarse rows my tiles produce
+  int *ctl = c->d_strip_ctl;
+  for (int base = 0; base < sp.nranks; base += 8) {
+    StripPush P;
+    std::memset(&P, 0, sizeof(P));
+    for (int r = base; r < std::min(base + 8, sp.nranks); ++r) {
+      if (r == sp.rank) continue;
+      P.seg[P.nseg++] = row_segment(c, C, C.f, clo, chi, r);
+      P.flag[P.nflag++] = peer_ptr(c, r, ctl + 2);
+    }
+    P.ticket = (unsigned int *)(ctl + 6);
+    if (P.nseg) c->launch("strip_allgather", level, [&] { strip_push_kernel<<<16, 256, 0, c->stream>>>(P); });
+  }
+  (void)L;
+  dev_zero(c, level + 1, C.x);
+  c->launch("strip_wait_all", level, [&] { strip_wait_kernel<<<1, 32, 0, c->stream>>>(ctl + 2, nullptr, sp.nranks - 1, 0, 0, 0, ctl + 5, ctl + 3); });
+}
+
 void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const std::vector<FixSpec> &fixes, bool use_lr, bool gibbs, double omega, bool prolong,
                double alpha, bool restrict_) {
   DevLevel &L = c->lv[level];
@@ -586,14 +717,32 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   P.HXL = up4(S + (restrict_ ? 2 : 0));
   const int HXR = up4(S + (restrict_ ? 1 : 0));
   P.TX = 128 - P.HXL - HXR;
-  P.TY = fused_tile_rows(L.g.ny, nc);
+  P.TY = fused_tile_rows(L.g.ny, nc, c->strip.on());
   P.hl = S + (restrict_ ? 1 : 0);
   const int hh = S + (restrict_ ? 2 : 0);
   P.RY = P.TY + P.hl + hh;
   size_t smem = (size_t)2 * P.RY * 128 * sizeof(double);
   if (smem > (size_t)kFusedSmemMax) fail(MGMC_ERR_INVALID, "internal: fused tile does not fit in shared memory");
   P.tiles_x = (L.g.nx + P.TX - 1) / P.TX;
-  const int tiles_y = (L.g.ny - 1 + P.TY - 1) / P.TY;
+  int tiles_y = (L.g.ny - 1 + P.TY - 1) / P.TY;
+  const bool strip_level = c->strip.on() && c->strip_connected && level < c->strip.ndist;
+  if (strip_level) {
+    // only this rank's tile rows; the halo rows come from the neighbours
+    P.by0 = (c->strip.lo[level] - 1) / P.TY;
+    tiles_y = (c->strip.hi[level] - c->strip.lo[level] + 1 + P.TY - 1) / P.TY;
+    int need = std::max(P.hl, hh) + 1;
+    if (use_lr) {
+      // every rank runs the patch windows redundantly: those of the measurements whose fix-up reaches its
+      // tiles must lie inside own rows + halo, and must not depend on measurements elsewhere
+      const LowRankDev &lr = get_lowrank(c, level, omega);
+      if (!(lr.diag[0] && lr.diag[1])) fail(MGMC_ERR_UNSUPPORTED, "row strips: measurements interact on a distributed level (raise MGMC_STRIP_MIN_ROWS to replicate it)");
+      need += S + lr.wreach + std::max(lr.bw, lr.bh);
+    } else if (c->d.m_lowrank > 0 && (S > 0 || restrict_)) {
+      fail(MGMC_ERR_UNSUPPORTED, "row strips need the in-kernel low-rank fix-up (measurement windows too large)");
+    }
+    if (need > c->strip.halo[level]) fail(MGMC_ERR_INVALID, "internal: strip halo too small");
+    strip_wait_neighbours(c);
+  }
   P.nchains = c->d.nchains;
   if (use_lr) {
     const LowRankDev &lr = get_lowrank(c, level, omega);
@@ -615,7 +764,9 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   dim3 grid(P.npatch + P.tiles_x * tiles_y, 1, c->d.nchains);
   // algorithmic bytes of this launch: 24 B per site and sweep, 18 B prolongate_add,
   // 18 + 2 B residual + restrict + coarse zeroing -- fixed by the model, not by what the kernel moves
-  const double alg_bytes = (double)L.h.ndof() * c->d.nchains * (24.0 * S / nc + (prolong ? 18.0 : 0.0) + (restrict_ ? 20.0 : 0.0));
+  const bool strip_own = c->strip.on() && c->strip_connected && level < c->strip.ndist;
+  const double nsites = strip_own ? (double)(c->strip.hi[level] - c->strip.lo[level] + 1) * (L.g.nx - 1) : (double)L.h.ndof();
+  const double alg_bytes = nsites * c->d.nchains * (24.0 * S / nc + (prolong ? 18.0 : 0.0) + (restrict_ ? 20.0 : 0.0));
   std::string name = std::string(gibbs ? "gibbs" : "sor") + (nc == 2 ? "_rb" : "_4c") + std::to_string(S) + (prolong ? "+prolong" : "") + (restrict_ ? "+restrict" : "");
 #ifdef MGMC_TILE_TIMING
   // debug build: dump per-CTA phase time stamps of the first level-0 launch of every kernel flavour
@@ -656,6 +807,10 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   }
 #endif
   if (S > 0 || prolong) std::swap(L.x, L.x_alt);
+  if (strip_level) {
+    strip_push_neighbours(c, level, restrict_);
+    if (restrict_ && level + 1 == c->strip.ndist) strip_allgather_rhs(c, level);
+  }
 }
 
 void dev_lowrank_fix(mgmc_ctx *c, int level, bool fwd, bool gibbs, double omega, uint32_t c1) {
@@ -1019,6 +1174,26 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
     c->sweep_counter.assign(desc->nlevel, 0u);
     c->keys = philox_round_keys(desc->seed);
     c->lv.resize(desc->nlevel);
+    c->strip = make_strip_plan(*desc, H);
+    size_t arena_off = 4096;  // control words first
+    if (c->strip.on()) {
+      // x, x_alt and f of every level live in ONE allocation with rank-independent offsets: a neighbour's
+      // array is its arena base (one CUDA IPC handle per rank) plus the same offset
+      size_t bytes = arena_off;
+      for (int l = 0; l < desc->nlevel; ++l) {
+        const size_t pitch = ((GX + H[l].nx + 1 + 2 + 15) / 16) * 16;
+        bytes += 3 * (((size_t)H[l].ny + 1 + 2 * GY) * pitch * sizeof(double) + 256);
+      }
+      c->arena_bytes = bytes;
+      c->arena = (char *)c->dalloc<char>(bytes);
+      c->d_strip_ctl = (int *)c->arena;
+      c->peer_arena.assign(c->strip.nranks, nullptr);
+    }
+    auto carve = [&](size_t total) {
+      double *p = (double *)(c->arena + arena_off);
+      arena_off += (total * sizeof(double) + 255) / 256 * 256;
+      return p;
+    };
     for (int l = 0; l < desc->nlevel; ++l) {
       DevLevel &L = c->lv[l];
       L.h = H[l];
@@ -1029,10 +1204,10 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
       L.g.stride = (long long)rows * L.g.pitch;
       const size_t total = (size_t)L.g.stride * desc->nchains;
       const size_t origin = (size_t)GY * L.g.pitch + GX;
-      L.x = c->dalloc<double>(total) + origin;
+      L.x = (c->strip.on() ? carve(total) : c->dalloc<double>(total)) + origin;
       L.x_primary = L.x;
-      L.x_alt = c->dalloc<double>(total) + origin;
-      L.f = c->dalloc<double>(total) + origin;
+      L.x_alt = (c->strip.on() ? carve(total) : c->dalloc<double>(total)) + origin;
+      L.f = (c->strip.on() ? carve(total) : c->dalloc<double>(total)) + origin;
       L.r = c->dalloc<double>(total) + origin;
       L.coef = to_coef9(L.h.st);
       L.nine = (L.h.st.ncolours == 4);
@@ -1076,6 +1251,8 @@ void mgmc_destroy(mgmc_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->graph) cudaGraphExecDestroy(c->graph);
+  for (char *p : c->peer_arena)
+    if (p) cudaIpcCloseMemHandle(p);
   for (void *p : c->allocs) cudaFree(p);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1338,7 +1515,10 @@ int mgmc_set_qoi(mgmc_ctx *c, int64_t nnz, const int64_t *idx, const double *val
   std::vector<double> v(val, val + nnz);
   for (int64_t e = 0; e < nnz; ++e) {
     if (idx[e] < 0 || idx[e] >= L.h.ndof()) fail(MGMC_ERR_INVALID, "QoI index out of range");
-    site[e] = (long long)(idx[e] / w + 1) * L.g.pitch + (idx[e] % w + 1);
+    const int j = (int)(idx[e] / w) + 1;
+    site[e] = (long long)j * L.g.pitch + (idx[e] % w + 1);
+    // row strips: every rank sums the entries it owns; the caller adds the partial series of all ranks
+    if (c->strip.on() && (j < c->strip.lo[0] || j > c->strip.hi[0])) v[e] = 0.0;
   }
   drop_graph(c);
   c->d_qsite = c->dupload(site);
@@ -1408,6 +1588,59 @@ int mgmc_sample_moments(mgmc_ctx *c, int64_t nsamples, double *mean_field, doubl
   }
   c->sync();
   API_END
+}
+
+int mgmc_strip_partition(const mgmc_desc *desc, int level, int rank, int *row_lo, int *row_hi, int *distributed) {
+  API_BEGIN
+  if (!desc) fail(MGMC_ERR_INVALID, "null argument");
+  std::vector<HostLevel> H = build_host_levels(*desc);
+  if (level < 0 || level >= (int)H.size()) fail(MGMC_ERR_INVALID, "level out of range");
+  mgmc_desc d = *desc;
+  d.strip_rank = rank;
+  StripPlan p = make_strip_plan(d, H);
+  const bool dist = p.on() && level < p.ndist;
+  if (row_lo) *row_lo = dist ? p.lo[level] : 1;
+  if (row_hi) *row_hi = dist ? p.hi[level] : H[level].ny - 1;
+  if (distributed) *distributed = dist ? 1 : 0;
+  API_END
+}
+
+int mgmc_strip_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int mgmc_strip_export(mgmc_ctx *c, void *handle_out) {
+  API_BEGIN
+  check_level(c, 0);
+  if (!c->strip.on()) fail(MGMC_ERR_INVALID, "context was not created with strip_nranks > 1");
+  cudaIpcMemHandle_t h;
+  CUDA_CHECK(cudaIpcGetMemHandle(&h, c->arena));
+  std::memcpy(handle_out, &h, sizeof(h));
+  API_END
+}
+
+int mgmc_strip_connect(mgmc_ctx *c, const void *all_handles) {
+  API_BEGIN
+  check_level(c, 0);
+  if (!c->strip.on()) fail(MGMC_ERR_INVALID, "context was not created with strip_nranks > 1");
+  CUDA_CHECK(cudaSetDevice(c->device));
+  for (int r = 0; r < c->strip.nranks; ++r) {
+    if (r == c->strip.rank || c->peer_arena[r]) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char *)all_handles + (size_t)r * sizeof(h), sizeof(h));
+    void *p = nullptr;
+    CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_arena[r] = (char *)p;
+  }
+  c->strip_connected = true;
+  drop_graph(c);
+  API_END
+}
+
+int mgmc_strip_error(mgmc_ctx *c) {
+  if (!c || !c->strip.on()) return 0;
+  int e = 0;
+  if (cudaMemcpy(&e, c->d_strip_ctl + 3, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  if (e) cudaMemset(c->d_strip_ctl + 3, 0, sizeof(int));
+  return e;
 }
 
 int64_t mgmc_launch_count(const mgmc_ctx *c) { return c ? c->launch_count : 0; }
