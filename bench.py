@@ -273,6 +273,33 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_resident = nchains_total * a.steps / float(t.item())
 
+    # ---- N > 1, default mode (independent chains): additionally time ONE chain on row strips of the same lattice
+    #      (strong scaling; halo rows exchanged inside the tile kernel over NVLink peer memory) ----
+    strips_extra = None
+    if world > 1 and not strips_on:
+        from multigridmc_b200 import strips as _strips
+
+        try:
+            sctx = m.Context(n, n, nlevel, Lambda=0.2, B=B, smoother="SSOR", coarse_solver="Cholesky", npresmooth=1, npostsmooth=1,
+                             cycle=1, omega=1.0, seed=5418513, device=local, nchains=1, first_chain=0, strip_rank=rank, strip_nranks=world)
+            _strips.connect(sctx, dist, torch.device("cuda", local))
+            sctx.set_rhs(f_np)
+            sctx.set_state(np.zeros(nd))
+            sctx.set_philox_position(0)
+            barrier()
+            sctx.sample(a.warmup, series=False)
+            barrier()
+            sms, _ = sctx.sample_timed(a.steps, series=False)
+            barrier()
+            t = torch.tensor([sms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            strips_extra = {"value": a.steps / (float(t.item()) * 1e-3), "unit": "samples/s", "ms_per_step": float(t.item()) / a.steps, "scaling": "strong",
+                            "error_flag": int(sctx.strip_error()),
+                            "what": "ONE chain of the same lattice on row strips over all ranks (bit-identical to the single-GPU chain)"}
+            sctx.close()
+        except m.MgmcError as e:
+            strips_extra = {"unavailable": str(e)}
+
     prof = None
     if strips_on:  # cooperative: every rank has to run the profiled cycles
         barrier()
@@ -334,6 +361,8 @@ def run_b200(a):
                      "algorithmic_gbs": (p[3] / (p[1] * 1e-3) / 1e9) if p[1] > 0 else None} for p in sorted(prof, key=lambda p: -p[1])[:12]],
         "qoi_mean": float(np.mean(series)),
     }
+    if strips_extra is not None:
+        line["strips"] = strips_extra
     if not a.no_cpu_baseline and world == 1:
         r = cpu_reference_run(a, 10, 1)
         line["cpu_baseline"] = {"value": r["samples_per_s_equiv"], "unit": "samples/s", "cores": 1, "kind": "port", "sample": r["sample"],

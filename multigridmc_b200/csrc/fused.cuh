@@ -61,6 +61,53 @@ struct LowRankTile {
   int *counters;             // [nslots][nchains]         arrival counter of the patch CTAs
 };
 
+// Row-strip decomposition (one process per GPU): the tile kernel itself exchanges the halo rows.  Tiles
+// whose region reaches beyond the rank's own rows first wait (device-side, system-scope acquire) until
+// the neighbour has delivered the rows of the previous launch; tiles that own rows of the neighbours'
+// halo store them a second time, straight into the neighbour's array over NVLink (CUDA IPC mapping),
+// and the last of those CTAs raises the neighbour's flag.  Every rank runs the same launch sequence, so
+// the flag value a launch has to see is (cycle number) * (launches per cycle) + (its index in the cycle).
+struct StripK {
+  int on;
+  int own_lo, own_hi, tiles_y;     // own rows of this level, own tile rows
+  int halo;                        // rows of x mirrored into a neighbour
+  int clo, chi, chalo;             // RESTRICT: own coarse rows, rows of f_c mirrored into a neighbour
+  double *peer_x_dn, *peer_x_up;   // the neighbours' x_out (same layout); nullptr at the ends of the lattice
+  double *peer_fc_dn, *peer_fc_up; // the neighbours' f of the coarser level (RESTRICT, coarser level distributed)
+  int *peer_flag_dn, *peer_flag_up;          // flags to raise in the neighbours' memory
+  const int *flag_from_dn, *flag_from_up;    // own flags, raised by the neighbours
+  const int *cycle_no;
+  int per_cycle, index;            // flag value to wait for = *cycle_no * per_cycle + index
+  int edge_rows;                   // tile rows at either end of the strip that mirror rows
+  unsigned int *ticket_dn, *ticket_up;
+  int *err;
+};
+
+__device__ __forceinline__ int ld_acquire_sys_i(const int *p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *flag >= target; a time-out (a peer died) raises *err instead of hanging the GPU
+__device__ __forceinline__ void strip_spin(const int *flag, int target, int *err) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys_i(flag) < target) {
+    if (clock64() - t0 > 6000000000ll) {
+      *err = 1;
+      break;
+    }
+  }
+}
+
+// arrival of one CTA that read halo rows and / or mirrored rows into a neighbour; the last one raises the flag
+__device__ __forceinline__ void strip_arrive(unsigned int *ticket, unsigned int n_expected, int *peer_flag) {
+  if (atomicAdd(ticket, 1u) == n_expected - 1) {
+    *ticket = 0u;
+    __threadfence_system();
+    atomicAdd_system(peer_flag, 1);
+  }
+}
+
 struct FusedP {
   GridP g, gc;  // this level, next coarser level
   Coef9 a;
@@ -80,6 +127,7 @@ struct FusedP {
   long long *timing;  // MGMC_TILE_TIMING builds only: 8 clock64 stamps + smid per CTA
   int tiles_x;        // the grid is 1-d: npatch patch CTAs followed by tiles_x * tiles_y tile CTAs
   int by0;            // first tile row of this launch (row-strip decomposition: the rank's own tile rows)
+  StripK sk;
   // low-rank term (LOWRANK kernels): fix-up q follows stage fix_stage[q]
   const LowRankTile *lr;
   int npatch, wpw, wcap;  // patch CTAs, windows per warp, doubles per window array
@@ -171,6 +219,13 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
     meta[t] = mt;
   }
   __syncthreads();
+  if (P.sk.on && threadIdx.x == 0) {
+    // row strips: this CTA has read everything it needs from the halo rows -- it counts as an edge CTA, so
+    // that a neighbour cannot overwrite those rows (next launch) before the windows are loaded
+    const unsigned int n_edge = (unsigned int)(P.sk.edge_rows * P.tiles_x + P.npatch);
+    if (P.sk.peer_flag_dn) strip_arrive(P.sk.ticket_dn, n_edge, P.sk.peer_flag_dn);
+    if (P.sk.peer_flag_up) strip_arrive(P.sk.ticket_up, n_edge, P.sk.peer_flag_up);
+  }
   // ---- noise of every (sweep, site) that lies in the dependence cone of supp(B_k): the value of a B site
   //      after stage S - 1 depends on stage s only within distance S - 1 - s ----
   if (GIBBS) {
@@ -371,11 +426,22 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   extern __shared__ double sm[];
   constexpr bool NINE = (NC == 4);
   if (LOWRANK && (int)blockIdx.x < P.npatch) {
+    if (P.sk.on) {  // the windows near the strip boundaries read halo rows
+      if (threadIdx.x == 0) {
+        const int target = *P.sk.cycle_no * P.sk.per_cycle + P.sk.index;
+        if (P.sk.flag_from_dn) strip_spin(P.sk.flag_from_dn, target, P.sk.err);
+        if (P.sk.flag_from_up) strip_spin(P.sk.flag_from_up, target, P.sk.err);
+      }
+      __syncthreads();
+    }
     patch_cta<NC, GIBBS, PROLONG, RESTRICT>(P, sm, blockIdx.x, blockIdx.z);
     return;
   }
   const int tile_id = (int)blockIdx.x - (LOWRANK ? P.npatch : 0);
-  const int tile_bx = tile_id % P.tiles_x, tile_by = tile_id / P.tiles_x + P.by0;
+  int tile_row = tile_id / P.tiles_x;
+  // row strips: the tile rows at both ends of the strip run first (they feed the neighbours)
+  if (P.sk.on) tile_row = (tile_row & 1) ? (P.sk.tiles_y - 1 - (tile_row >> 1)) : (tile_row >> 1);
+  const int tile_bx = tile_id % P.tiles_x, tile_by = tile_row + P.by0;
 #ifdef MGMC_TILE_TIMING
   const int cta_id = blockIdx.z * gridDim.x + blockIdx.x;
 #define TSTAMP(k) if (threadIdx.x == 0 && P.timing) P.timing[(long long)cta_id * 10 + (k)] = clock64();
@@ -397,6 +463,17 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const double *fg = P.f + cbase;
   const int gi0 = i_r0 + 4 * lane;  // first global column of this lane's group
   const bool cols_alloc = (gi0 >= -kGX) && (gi0 + 3 < pitch - kGX);
+  if (P.sk.on) {
+    const bool wdn = P.sk.flag_from_dn && (j_r0 < P.sk.own_lo), wup = P.sk.flag_from_up && (j_r0 + RY - 1 > P.sk.own_hi);
+    if (wdn || wup) {
+      if (threadIdx.x == 0) {
+        const int target = *P.sk.cycle_no * P.sk.per_cycle + P.sk.index;
+        if (wdn) strip_spin(P.sk.flag_from_dn, target, P.sk.err);
+        if (wup) strip_spin(P.sk.flag_from_up, target, P.sk.err);
+      }
+      __syncthreads();
+    }
+  }
 
   // ---- stage the region: one warp per row.  Lane l loads the column pairs (2l, 2l+1) and
   //      (64+2l, 64+2l+1): each 128-bit load instruction covers 512 contiguous bytes (fully coalesced);
@@ -555,6 +632,19 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       // boundary / pad columns inside a pair hold the zeros they were loaded with
       if (minea) *reinterpret_cast<double2 *>(xo + o + gia) = make_double2(xr[0], xr[32]);
       if (mineb) *reinterpret_cast<double2 *>(xo + o + gib) = make_double2(xr[16], xr[48]);
+      if (P.sk.on) {  // rows of the neighbours' halo: second store into their memory (pad columns of the pair included)
+        double *pd = nullptr;
+        if (P.sk.peer_x_dn && gj < P.sk.own_lo + P.sk.halo) pd = P.sk.peer_x_dn;
+        if (pd) {
+          if (minea) *reinterpret_cast<double2 *>(pd + cbase + o + gia) = make_double2(xr[0], xr[32]);
+          if (mineb) *reinterpret_cast<double2 *>(pd + cbase + o + gib) = make_double2(xr[16], xr[48]);
+        }
+        if (P.sk.peer_x_up && gj > P.sk.own_hi - P.sk.halo) {
+          pd = P.sk.peer_x_up;
+          if (minea) *reinterpret_cast<double2 *>(pd + cbase + o + gia) = make_double2(xr[0], xr[32]);
+          if (mineb) *reinterpret_cast<double2 *>(pd + cbase + o + gib) = make_double2(xr[16], xr[48]);
+        }
+      }
     }
   }
 
@@ -619,13 +709,34 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       const double a1 = sat<2>(fr, lane) + 0.5 * (sat<1>(fr, lane) + sat<3>(fr, lane) + sat<2>(fr - 128, lane) + sat<2>(fr + 128, lane)) +
                         0.25 * (sat<1>(fr - 128, lane) + sat<3>(fr - 128, lane) + sat<1>(fr + 128, lane) + sat<3>(fr + 128, lane));
       const long long o = ccb + (long long)J * P.gc.pitch + I;
+      double *pf = nullptr;
+      if (P.sk.on) {
+        if (P.sk.peer_fc_dn && J < P.sk.clo + P.sk.chalo) pf = P.sk.peer_fc_dn;
+        if (P.sk.peer_fc_up && J > P.sk.chi - P.sk.chalo) pf = P.sk.peer_fc_up;  // (strips are taller than two halos)
+      }
       if (I >= 1 && I < P.gc.nx) {
         P.fc_out[o] = a0;
         if (P.xc_zero) P.xc_zero[o] = 0.0;
+        if (pf) pf[o] = a0;
       }
       if (I + 1 < P.gc.nx) {
         P.fc_out[o + 1] = a1;
         if (P.xc_zero) P.xc_zero[o + 1] = 0.0;
+        if (pf) pf[o + 1] = a1;
+      }
+    }
+  }
+  if (P.sk.on) {
+    // the last CTA of the tile rows that mirror into a neighbour raises that neighbour's flag
+    const int trow = tile_by - P.by0;
+    const bool edge_dn = P.sk.peer_flag_dn && (trow < P.sk.edge_rows), edge_up = P.sk.peer_flag_up && (trow >= P.sk.tiles_y - P.sk.edge_rows);
+    if (edge_dn || edge_up) {
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int n_edge = (unsigned int)(P.sk.edge_rows * P.tiles_x + (LOWRANK ? P.npatch : 0));
+        if (edge_dn) strip_arrive(P.sk.ticket_dn, n_edge, P.sk.peer_flag_dn);
+        if (edge_up) strip_arrive(P.sk.ticket_up, n_edge, P.sk.peer_flag_up);
       }
     }
   }

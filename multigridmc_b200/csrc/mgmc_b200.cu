@@ -115,7 +115,10 @@ struct mgmc_ctx {
   std::vector<char *> peer_arena;  // per rank (nullptr for self / unconnected)
   bool strip_connected = false;
   int *d_strip_ctl = nullptr;      // in the arena: [0] flag from below, [1] flag from above, [2] all-gather count,
-                                   // [3] error, [4] waitno (neighbours), [5] waitno (all-gather), [6] push ticket
+                                   // [3] error, [5] waitno (all-gather), [6] all-gather push ticket, [7] / [8] tickets of
+                                   // the edge CTAs (below / above), [9] cycle number
+  int strip_index = 0;             // distributed fused launches emitted so far in this cycle
+  int strip_per_cycle = 0;         // ... per cycle (counted by a dry run before the first capture)
   // noise position
   uint32_t *d_sample = nullptr;
   uint32_t h_sample = 0;
@@ -249,6 +252,9 @@ StripPlan make_strip_plan(const mgmc_desc &d, const std::vector<HostLevel> &H) {
   if (d.nchains != 1) fail(MGMC_ERR_UNSUPPORTED, "row strips advance one chain (nchains = 1)");
   static const char *mr = std::getenv("MGMC_STRIP_MIN_ROWS");
   const int min_rows = mr ? std::atoi(mr) : 64;
+  // levels below ~1M sites are latency bound on one GPU already: splitting them only adds NVLink round trips
+  static const char *ms = std::getenv("MGMC_STRIP_MIN_SITES");
+  const long long min_sites = ms ? std::atoll(ms) : (1ll << 20);
   for (int l = 0; l + 1 < (int)H.size(); ++l) {  // the coarsest level is always replicated
     const HostLevel &h = H[l];
     if (h.st.radius > 1) break;  // radius-2 operators: not decomposed yet
@@ -258,7 +264,10 @@ StripPlan make_strip_plan(const mgmc_desc &d, const std::vector<HostLevel> &H) {
     // rows exchanged with a neighbour: what a launch of 2 sweeps (+ residual) reads beyond the own rows; with a
     // low-rank term additionally the windows of the measurements near the strip boundary (patch CTAs)
     const int halo = (d.m_lowrank > 0) ? ((nc == 2) ? 16 : 28) : ((nc == 2) ? 8 : 12);
-    if (h.ny % p.nranks || rows % ty || rows < std::max(min_rows, 2 * halo) || (rows % 2 && l + 2 < (int)H.size())) break;
+    if (h.ny % p.nranks || rows % ty || rows < std::max(min_rows, 2 * halo)) break;
+    if (l > 0 && (long long)h.nx * h.ny < min_sites) break;
+    // every rank runs the measurement windows near its strip on its own: only while the measurements do not interact
+    if (d.m_lowrank > 0 && !lowrank_is_diagonal(h, std::vector<double>(d.Sigma, d.Sigma + d.m_lowrank), d.omega)) break;
     p.lo.push_back(p.rank * rows + 1);
     p.hi.push_back(std::min((p.rank + 1) * rows, h.ny - 1));
     p.halo.push_back(halo);
@@ -615,14 +624,6 @@ T *peer_ptr(mgmc_ctx *c, int rank, T *mine) {
   return (T *)(c->peer_arena[rank] + ((char *)mine - c->arena));
 }
 
-void strip_wait_neighbours(mgmc_ctx *c) {
-  const StripPlan &sp = c->strip;
-  int *ctl = c->d_strip_ctl;
-  c->launch("strip_wait", 0, [&] {
-    strip_wait_kernel<<<1, 32, 0, c->stream>>>(sp.rank > 0 ? ctl + 0 : nullptr, sp.rank + 1 < sp.nranks ? ctl + 1 : nullptr, 1, 1, 1, 1, ctl + 4, ctl + 3);
-  });
-}
-
 // rows [j0, j1] of a level array as one contiguous segment (full padded rows)
 StripSeg row_segment(mgmc_ctx *c, const DevLevel &L, double *arr, int j0, int j1, int dst_rank) {
   StripSeg sg;
@@ -631,34 +632,6 @@ StripSeg row_segment(mgmc_ctx *c, const DevLevel &L, double *arr, int j0, int j1
   sg.dst = peer_ptr(c, dst_rank, p);
   sg.n = (long long)(j1 - j0 + 1) * L.g.pitch;
   return sg;
-}
-
-// after a fused launch on a distributed level: boundary rows of the new iterate (and of the restricted
-// right-hand side) go to the neighbours; their flags are raised once everything has landed
-void strip_push_neighbours(mgmc_ctx *c, int level, bool restricted) {
-  const StripPlan &sp = c->strip;
-  DevLevel &L = c->lv[level];
-  StripPush P;
-  std::memset(&P, 0, sizeof(P));
-  const bool has_dn = sp.rank > 0, has_up = sp.rank + 1 < sp.nranks;
-  const int H = sp.halo[level];
-  if (has_dn) P.seg[P.nseg++] = row_segment(c, L, L.x, sp.lo[level], sp.lo[level] + H - 1, sp.rank - 1);
-  if (has_up) P.seg[P.nseg++] = row_segment(c, L, L.x, sp.hi[level] - H + 1, sp.hi[level], sp.rank + 1);
-  if (restricted && level + 1 < sp.ndist) {
-    DevLevel &C = c->lv[level + 1];
-    const int Hc = sp.halo[level + 1];
-    if (has_dn) P.seg[P.nseg++] = row_segment(c, C, C.f, sp.lo[level + 1], sp.lo[level + 1] + Hc - 1, sp.rank - 1);
-    if (has_up) P.seg[P.nseg++] = row_segment(c, C, C.f, sp.hi[level + 1] - Hc + 1, sp.hi[level + 1], sp.rank + 1);
-    // the neighbours zero their rows of x_{l+1} themselves: zero my copies of them (before my flag goes up,
-    // i.e. before a neighbour can push rows of x_{l+1} again)
-    const size_t rowb = (size_t)C.g.pitch * sizeof(double);
-    if (has_dn) CUDA_CHECK(cudaMemsetAsync(C.x + (long long)(sp.lo[level + 1] - Hc) * C.g.pitch - GX, 0, rowb * Hc, c->stream));
-    if (has_up) CUDA_CHECK(cudaMemsetAsync(C.x + (long long)(sp.hi[level + 1] + 1) * C.g.pitch - GX, 0, rowb * Hc, c->stream));
-  }
-  if (has_dn) P.flag[P.nflag++] = peer_ptr(c, sp.rank - 1, c->d_strip_ctl + 1);  // I am the neighbour above rank - 1
-  if (has_up) P.flag[P.nflag++] = peer_ptr(c, sp.rank + 1, c->d_strip_ctl + 0);
-  P.ticket = (unsigned int *)(c->d_strip_ctl + 6);
-  c->launch("strip_push", level, [&] { strip_push_kernel<<<16, 256, 0, c->stream>>>(P); });
 }
 
 // restriction into the first replicated level: every rank sends its rows of f to every other rank,
@@ -741,7 +714,50 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
       fail(MGMC_ERR_UNSUPPORTED, "row strips need the in-kernel low-rank fix-up (measurement windows too large)");
     }
     if (need > c->strip.halo[level]) fail(MGMC_ERR_INVALID, "internal: strip halo too small");
-    strip_wait_neighbours(c);
+    const StripPlan &sp = c->strip;
+    const bool has_dn = sp.rank > 0, has_up = sp.rank + 1 < sp.nranks;
+    StripK &K = P.sk;
+    K.on = 1;
+    K.own_lo = sp.lo[level];
+    K.own_hi = sp.hi[level];
+    K.tiles_y = tiles_y;
+    K.halo = sp.halo[level];
+    int E = K.halo;
+    // the output buffer of this launch is L.x_alt if the launch writes x (it is swapped in below)
+    double *xout = (S > 0 || prolong) ? L.x_alt : L.x;
+    if (has_dn) K.peer_x_dn = peer_ptr(c, sp.rank - 1, xout);
+    if (has_up) K.peer_x_up = peer_ptr(c, sp.rank + 1, xout);
+    if (restrict_ && level + 1 < sp.ndist) {
+      DevLevel &C = c->lv[level + 1];
+      K.clo = sp.lo[level + 1];
+      K.chi = sp.hi[level + 1];
+      K.chalo = sp.halo[level + 1];
+      E = std::max(E, 2 * K.chalo + 2);
+      if (has_dn) K.peer_fc_dn = peer_ptr(c, sp.rank - 1, C.f);
+      if (has_up) K.peer_fc_up = peer_ptr(c, sp.rank + 1, C.f);
+      // the neighbours zero their rows of x_{l+1} themselves: zero my copies of them.  Safe before this launch
+      // (nobody reads x_{l+1} any more) and ordered before my flags go up, i.e. before a neighbour can mirror
+      // rows of x_{l+1} again.
+      const size_t rowb = (size_t)C.g.pitch * sizeof(double);
+      if (has_dn) CUDA_CHECK(cudaMemsetAsync(C.x + (long long)(K.clo - K.chalo) * C.g.pitch - GX, 0, rowb * K.chalo, c->stream));
+      if (has_up) CUDA_CHECK(cudaMemsetAsync(C.x + (long long)(K.chi + 1) * C.g.pitch - GX, 0, rowb * K.chalo, c->stream));
+    }
+    int *ctl = c->d_strip_ctl;
+    if (has_dn) {
+      K.peer_flag_dn = peer_ptr(c, sp.rank - 1, ctl + 1);  // I am the neighbour above rank - 1
+      K.flag_from_dn = ctl + 0;
+    }
+    if (has_up) {
+      K.peer_flag_up = peer_ptr(c, sp.rank + 1, ctl + 0);
+      K.flag_from_up = ctl + 1;
+    }
+    K.cycle_no = ctl + 9;
+    K.per_cycle = c->strip_per_cycle;
+    K.index = c->strip_index++;
+    K.edge_rows = std::min((E + P.TY - 1) / P.TY, tiles_y);
+    K.ticket_dn = (unsigned int *)(ctl + 7);
+    K.ticket_up = (unsigned int *)(ctl + 8);
+    K.err = ctl + 3;
   }
   P.nchains = c->d.nchains;
   if (use_lr) {
@@ -807,10 +823,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   }
 #endif
   if (S > 0 || prolong) std::swap(L.x, L.x_alt);
-  if (strip_level) {
-    strip_push_neighbours(c, level, restrict_);
-    if (restrict_ && level + 1 == c->strip.ndist) strip_allgather_rhs(c, level);
-  }
+  if (strip_level && restrict_ && level + 1 == c->strip.ndist) strip_allgather_rhs(c, level);
 }
 
 void dev_lowrank_fix(mgmc_ctx *c, int level, bool fwd, bool gibbs, double omega, uint32_t c1) {
@@ -1039,6 +1052,7 @@ void mg_solve_level(mgmc_ctx *c, int level) {  // multigrid_preconditioner.cc:74
 
 void emit_mgmc_cycle(mgmc_ctx *c) {
   lr_begin_epoch(c);
+  c->strip_index = 0;
   std::fill(c->sweep_counter.begin(), c->sweep_counter.end(), 0u);
   mgmc_sample_level(c, 0);
 }
@@ -1047,7 +1061,7 @@ void emit_end_of_cycle(mgmc_ctx *c) {
   const DevLevel &L = c->lv[0];
   c->launch("end_of_cycle", 0, [&] {
     end_of_cycle_kernel<<<1, 256, 0, c->stream>>>(c->qoi_nnz, c->d_qsite, c->d_qval, L.x, L.g.stride, c->d.nchains, c->d_series, c->series_cap, c->d_sample,
-                                                 c->d_pos);
+                                                 c->d_pos, (c->strip.on() && c->strip_connected) ? c->d_strip_ctl + 9 : nullptr);
   });
   c->h_sample++;
 }
@@ -1073,7 +1087,38 @@ void ensure_series(mgmc_ctx *c, long long n) {
   }
 }
 
+// row strips: the number of distributed fused launches per cycle enters the flag protocol; count it by
+// capturing (and discarding) one cycle
+void strip_count_launches(mgmc_ctx *c) {
+  if (!(c->strip.on() && c->strip_connected) || c->strip_per_cycle > 0) return;
+  if (c->d.m_lowrank > 0)
+    for (int l = 0; l < c->d.nlevel; ++l) get_lowrank(c, l, c->d.omega);
+  if (c->d.coarse_solver == MGMC_COARSE_CHOLESKY) ensure_coarse(c);
+  c->sync();
+  const int64_t count0 = c->launch_count;
+  const std::vector<uint32_t> sweeps0 = c->sweep_counter;
+  const bool prof0 = c->prof_on;
+  c->prof_on = false;
+  cudaGraph_t g = nullptr;
+  CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  try {
+    emit_mgmc_cycle(c);
+  } catch (...) {
+    cudaStreamEndCapture(c->stream, &g);
+    if (g) cudaGraphDestroy(g);
+    c->prof_on = prof0;
+    throw;
+  }
+  CUDA_CHECK(cudaStreamEndCapture(c->stream, &g));
+  CUDA_CHECK(cudaGraphDestroy(g));
+  c->prof_on = prof0;
+  c->strip_per_cycle = c->strip_index;
+  c->launch_count = count0;
+  c->sweep_counter = sweeps0;
+}
+
 void run_cycles(mgmc_ctx *c, int64_t nsamples) {
+  strip_count_launches(c);
   const unsigned long long zero = 0ull;
   CUDA_CHECK(cudaMemcpyAsync(c->d_pos, &zero, sizeof(zero), cudaMemcpyHostToDevice, c->stream));
   if (c->use_graph && !c->prof_on) {
@@ -1395,6 +1440,7 @@ int mgmc_coarse_sample(mgmc_ctx *c, const double *f, double *x) {
 int mgmc_sampler_mgmc_apply(mgmc_ctx *c, const double *f, double *x) {
   API_BEGIN
   check_level(c, 0);
+  if (c->strip.on() && c->strip_connected) fail(MGMC_ERR_UNSUPPORTED, "row strips: the chain state is distributed; use mgmc_set_state / mgmc_sample / mgmc_get_state");
   if (f) upload_vec(c, 0, c->lv[0].f, f);  // f == NULL: right-hand side fixed earlier (Sampler::fix_rhs, sampler.hh:56)
   upload_vec(c, 0, c->lv[0].x, x);
   emit_mgmc_cycle(c);

@@ -300,6 +300,34 @@ inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &S
   return out;
 }
 
+// true if the measurements do not interact on this level in either sweep direction: B^T W is diagonal and every
+// site of supp(W_j) keeps a distance > `margin` from the bounding box of supp(B_k), k != j.  Then the Woodbury
+// fix-up of measurement k only needs x near supp(B_k) (in-kernel fix-up without exchange, row strips).
+inline bool lowrank_is_diagonal(const HostLevel &L, const std::vector<double> &Sigma, double omega, int margin = 8) {
+  const int m = (int)Sigma.size();
+  std::vector<int> bb((size_t)m * 4);
+  for (int k = 0; k < m; ++k) {
+    bb[4 * k] = bb[4 * k + 2] = 1 << 30;
+    bb[4 * k + 1] = bb[4 * k + 3] = -(1 << 30);
+  }
+  for (const SEntry &e : L.B) {
+    bb[4 * e.col] = std::min(bb[4 * e.col], e.i);
+    bb[4 * e.col + 1] = std::max(bb[4 * e.col + 1], e.i);
+    bb[4 * e.col + 2] = std::min(bb[4 * e.col + 2], e.j);
+    bb[4 * e.col + 3] = std::max(bb[4 * e.col + 3], e.j);
+  }
+  for (int dir = 0; dir < 2; ++dir) {
+    const LowRankDir h = lowrank_setup(L, Sigma, omega, dir == 0);
+    for (int a = 0; a < m; ++a)
+      for (int b = 0; b < m; ++b)
+        if (a != b && (h.Mneg[(size_t)a * m + b] != 0.0 || h.Ms[(size_t)a * m + b] != 0.0)) return false;
+    for (const SEntry &e : h.W)
+      for (int k = 0; k < m; ++k)
+        if (k != e.col && e.i >= bb[4 * k] - margin && e.i <= bb[4 * k + 1] + margin && e.j >= bb[4 * k + 2] - margin && e.j <= bb[4 * k + 3] + margin) return false;
+  }
+  return true;
+}
+
 // dense matrix of the coarsest level, A_0 + B Sigma^{-1} B^T (cholesky_sampler.cc:25-38), its lower
 // Cholesky factor padded with identity to Np = multiple of 32, and the inverses of the diagonal blocks
 struct CoarseFactor {

@@ -18,6 +18,7 @@ def test_partition_covers_every_row_once(n, nlevel, nranks):
     import multigridmc_b200 as m
     from multigridmc_b200 import capi
 
+    os.environ["MGMC_STRIP_MIN_SITES"] = "1"
     desc = capi.make_desc(n, n, nlevel, strip_nranks=nranks)
     ndist = 0
     for level in range(nlevel):
@@ -74,6 +75,7 @@ def test_host_plumbing_gloo_world2():
 
 def _gpu_worker(rank, world, port, q, n, nlevel, nsamples, nmeas):
     sys.path.insert(0, ROOT)
+    os.environ["MGMC_STRIP_MIN_SITES"] = "1"  # small test lattices: distribute as many levels as the strips allow
     import torch
     import torch.distributed as dist
 
