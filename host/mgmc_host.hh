@@ -9,8 +9,8 @@
 //    the next level of the same device hierarchy (matrix-free Galerkin stencil, linear_operator.cc:10-23).
 //  * Samplers take the reference's std::mt19937_64& for signature compatibility and use ONE draw from
 //    it as the Philox key; the chain is not the reference's mt19937 chain (multicolour + Philox).
-//  * Supported on the device path: dim = 2, shiftedlaplace_fd with constant correlation length, sparse
-//    measurement matrices.  Everything else exits with the ABI's "unsupported" message.
+//  * Supported on the device path: dim = 2, shiftedlaplace_fd and squared_shiftedlaplace_fd with constant
+//    correlation length, sparse measurement matrices.  Everything else exits with the ABI's "unsupported" message.
 #ifndef MGMC_HOST_HH
 #define MGMC_HOST_HH
 #include <algorithm>
@@ -279,8 +279,8 @@ class ShiftedLaplaceFDOperator : public LinearOperator {
   }
 };
 
-/** SquaredShiftedLaplaceFDOperator (squared_shiftedlaplace_fd_operator.hh); the host algebra (13/21
- *  point Galerkin stencils) exists, the device kernels do not yet: mgmc_create reports UNSUPPORTED */
+/** SquaredShiftedLaplaceFDOperator (squared_shiftedlaplace_fd_operator.hh): 13 / 21-point stencils with
+ *  boundary-ring classes, 9-colour sweeps on the device */
 class SquaredShiftedLaplaceFDOperator : public LinearOperator {
  public:
   SquaredShiftedLaplaceFDOperator(const std::shared_ptr<Lattice> lattice_, const std::shared_ptr<CorrelationLengthModel> clm, const int verbose = 0) : LinearOperator(lattice_) {
