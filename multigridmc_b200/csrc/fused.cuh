@@ -424,6 +424,7 @@ __device__ __forceinline__ void update_pair(const Coef9 &a, double *xrow, const 
 template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT, bool LOWRANK>
 __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {
   extern __shared__ double sm[];
+  __shared__ int lr_hits;  // LOWRANK: bit 0 / 1: the region meets supp(W) of the forward / backward sweep, bit 2: the tile meets supp(B)
   constexpr bool NINE = (NC == 4);
   if (LOWRANK && (int)blockIdx.x < P.npatch) {
     if (P.sk.on) {  // the windows near the strip boundaries read halo rows
@@ -463,6 +464,24 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const double *fg = P.f + cbase;
   const int gi0 = i_r0 + 4 * lane;  // first global column of this lane's group
   const bool cols_alloc = (gi0 >= -kGX) && (gi0 + 3 < pitch - kGX);
+  if (LOWRANK) {
+    // does this tile meet a site touched by the low-rank fix-ups?  Tested up front (its loads overlap the tile
+    // load, the barrier that ends the load publishes the result)
+    if (threadIdx.x == 0) lr_hits = 0;
+    __syncthreads();
+    const LowRankTile &R = *P.lr;
+    int bits = 0;
+    for (int k = threadIdx.x; k < R.m; k += kFusedThreads) {
+      const int4 b0 = reinterpret_cast<const int4 *>(R.wbox[0])[k], b1 = reinterpret_cast<const int4 *>(R.wbox[1])[k];
+      bits |= (b0.y >= i_r0 && b0.x < i_r0 + 128 && b0.w >= j_r0 && b0.z < j_r0 + RY) ? 1 : 0;
+      bits |= (b1.y >= i_r0 && b1.x < i_r0 + 128 && b1.w >= j_r0 && b1.z < j_r0 + RY) ? 2 : 0;
+      if (RESTRICT) {
+        const int4 bb = reinterpret_cast<const int4 *>(R.bbox)[k];  // i0, i1, j0, j1 of supp(B_k)
+        bits |= (bb.y >= max(1, i_t0 - 1) && bb.x <= min(nx - 1, i_t0 + TX - 1) && bb.w >= j_t0 && bb.z <= min(j_t0 + TY, ny - 1)) ? 4 : 0;
+      }
+    }
+    if (bits) atomicOr(&lr_hits, bits);
+  }
   if (P.sk.on) {
     const bool wdn = P.sk.flag_from_dn && (j_r0 < P.sk.own_lo), wup = P.sk.flag_from_up && (j_r0 + RY - 1 > P.sk.own_hi);
     if (wdn || wup) {
@@ -551,15 +570,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   bool lr_need[2] = {false, false};
   int fixq = 0;
   if (LOWRANK) {
-    const LowRankTile &R = *P.lr;
-    for (int dir = 0; dir < 2; ++dir) {
-      int hit = 0;
-      for (int k = threadIdx.x; k < R.m; k += kFusedThreads) {
-        const int4 bb = reinterpret_cast<const int4 *>(R.wbox[dir])[k];
-        hit |= (bb.y >= i_r0 && bb.x < i_r0 + 128 && bb.w >= j_r0 && bb.z < j_r0 + RY);
-      }
-      lr_need[dir] = __syncthreads_or(hit);
-    }
+    lr_need[0] = (lr_hits & 1) != 0;
+    lr_need[1] = (lr_hits & 2) != 0;
   }
   for (int s = 0; s < S; ++s) {
     const int colour = P.st[s].colour;
@@ -673,12 +685,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     if (LOWRANK) {
       // low-rank part of the residual: r -= B u, u = Sigma^{-1} B^T x of the final state (linear_operator.hh:71-75)
       const LowRankTile &R = *P.lr;
-      int hit = 0;
-      for (int u = threadIdx.x; u < R.nbu; u += kFusedThreads) {
-        const int i = R.bu_i[u], j = R.bu_j[u];
-        hit |= (i >= max(1, i_t0 - 1) && i <= min(nx - 1, i_t0 + TX - 1) && j >= j_t0 && j <= j_t0 + TY && j < ny);
-      }
-      if (__syncthreads_or(hit)) {
+      if (lr_hits & 4) {  // (bounding boxes: a superset of the sites tested below)
         const size_t slot = (size_t)(P.lr_slot + P.nfix) * P.nchains + blockIdx.z;
         if (threadIdx.x == 0) {
           while (ld_acquire(R.flags + slot) == 0) {

@@ -429,35 +429,44 @@ template <bool LOWER, bool NOISE, bool GATHER_IN, bool SCATTER_OUT>
 __global__ void __launch_bounds__(256) trimv_kernel(const double *__restrict__ T, int N, int Np, const int *__restrict__ cidx,
                                                    const double *__restrict__ in, long long in_stride, double *__restrict__ out, long long out_stride,
                                                    NoiseP nz) {
+  // the input vector is staged in shared memory once per CTA (the gather through cidx is two dependent
+  // loads per element otherwise), the noise of the row is computed while the loads are in flight
+  extern __shared__ double vsh[];
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= N) return;
   const double *vin = in + (long long)blockIdx.y * in_stride;
+  const int r_hi = min(blockIdx.x * 8 + 7, N - 1);
+  const int s_lo = LOWER ? 0 : blockIdx.x * 8, s_hi = LOWER ? r_hi + 1 : N;  // columns any row of this CTA touches
+  for (int c = s_lo + threadIdx.x; c < s_hi; c += 256) vsh[c] = vin[GATHER_IN ? cidx[c] : c];
+  double zn = 0.0;
+  if (NOISE && row < N && lane == 0) {
+    double z0, z1;
+    normal_pair(nz.keys, 0x40000000u | ((uint32_t)row >> 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.y, z0, z1);
+    zn = (row & 1) ? z1 : z0;
+  }
+  __syncthreads();
+  if (row >= N) return;
   const double *Trow = T + (long long)row * Np;
   const int c_lo = LOWER ? 0 : row, c_hi = LOWER ? row + 1 : N;  // non-zero range of the row
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int c = c_lo + lane;
-  for (; c + 96 < c_hi; c += 128) {
+  for (; c + 224 < c_hi; c += 256) {  // 8 independent loads in flight per lane
     const double t0 = Trow[c], t1 = Trow[c + 32], t2 = Trow[c + 64], t3 = Trow[c + 96];
-    const double v0 = vin[GATHER_IN ? cidx[c] : c], v1 = vin[GATHER_IN ? cidx[c + 32] : c + 32];
-    const double v2 = vin[GATHER_IN ? cidx[c + 64] : c + 64], v3 = vin[GATHER_IN ? cidx[c + 96] : c + 96];
-    a0 = fma(t0, v0, a0);
-    a1 = fma(t1, v1, a1);
-    a2 = fma(t2, v2, a2);
-    a3 = fma(t3, v3, a3);
+    const double t4 = Trow[c + 128], t5 = Trow[c + 160], t6 = Trow[c + 192], t7 = Trow[c + 224];
+    a0 = fma(t0, vsh[c], a0);
+    a1 = fma(t1, vsh[c + 32], a1);
+    a2 = fma(t2, vsh[c + 64], a2);
+    a3 = fma(t3, vsh[c + 96], a3);
+    a0 = fma(t4, vsh[c + 128], a0);
+    a1 = fma(t5, vsh[c + 160], a1);
+    a2 = fma(t6, vsh[c + 192], a2);
+    a3 = fma(t7, vsh[c + 224], a3);
   }
-  for (; c < c_hi; c += 32) a0 = fma(Trow[c], vin[GATHER_IN ? cidx[c] : c], a0);
+  for (; c < c_hi; c += 32) a0 = fma(Trow[c], vsh[c], a0);
   double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) {
-    if (NOISE) {
-      double z0, z1;
-      normal_pair(nz.keys, 0x40000000u | ((uint32_t)row >> 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.y, z0, z1);
-      acc += (row & 1) ? z1 : z0;
-    }
-    out[(long long)blockIdx.y * out_stride + (SCATTER_OUT ? cidx[row] : row)] = acc;
-  }
+  if (lane == 0) out[(long long)blockIdx.y * out_stride + (SCATTER_OUT ? cidx[row] : row)] = acc + zn;
 }
 
 // ------------------------------------------------------------------------------------------------

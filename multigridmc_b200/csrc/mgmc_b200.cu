@@ -567,10 +567,20 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
 // there short tiles give every warp at most one row per colour pass and spread over more SMs
 inline int fused_tile_rows(int ny, int nc, bool strips) {
   if (strips) return ny > 1024 ? 32 : (ny > 256 ? 16 : 8);  // strips must start on tile boundaries: powers of two only
-  static const char *ov = std::getenv("MGMC_TILE_ROWS");  // perf experiments: tile height of the big levels
-  if (ov && ny > 2048 && nc == 2) return std::atoi(ov);
-  // 40 rows on the finest red-black levels: 49 / 47 / 45 / 43 rows per colour pass share 16 warps better than 41..35
-  return (ny > 2048 && nc == 2) ? 40 : (ny > 1024 ? 32 : (ny > 256 ? 16 : 8));
+  static const char *ov = std::getenv("MGMC_TILE_ROWS");    // perf experiments: "rb_big,4c_big,4c_mid,small"
+  static int t[4] = {40, 32, 16, 8};
+  static bool parsed = false;
+  if (!parsed) {
+    parsed = true;
+    if (ov) std::sscanf(ov, "%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3]);
+  }
+  // The rows of a colour pass are dealt out to 16 warps, so the tile heights are chosen to make the passes come out
+  // at whole rounds: red-black 40 rows -> 49 / 47 / 45 / 43 rows per pass (4, 3, 3, 3 rounds); 4-colour (every other
+  // row per pass) 36 rows -> 28 .. 21 rows (2 rounds each), 14 rows -> 16 .. 9 rows (1 round each).
+  if (ny > 2048 && nc == 2) return t[0];
+  if (ny > 1024) return nc == 2 ? 32 : t[1];
+  if (ny > 256) return nc == 2 ? 16 : t[2];
+  return t[3];
 }
 constexpr int kFusedSmemMax = 110 * 1024;
 
@@ -995,11 +1005,11 @@ void dev_coarse(mgmc_ctx *c, bool sample, const double *f, double *x) {
   dim3 grid((c->Nc + 7) / 8, c->d.nchains);
   // pass 1: y = L^{-1} f (+ xi);  pass 2: x = L^{-T} y
   c->launch(sample ? "coarse_sample_fwd" : "coarse_solve_fwd", lc, [&] {
-    if (sample) trimv_kernel<true, true, true, false><<<grid, 256, 0, c->stream>>>(c->dT, c->Nc, c->Ncp, c->d_cidx, f, L.g.stride, c->d_cy, c->Ncp, nz);
-    else trimv_kernel<true, false, true, false><<<grid, 256, 0, c->stream>>>(c->dT, c->Nc, c->Ncp, c->d_cidx, f, L.g.stride, c->d_cy, c->Ncp, nz);
+    if (sample) trimv_kernel<true, true, true, false><<<grid, 256, c->Ncp * sizeof(double), c->stream>>>(c->dT, c->Nc, c->Ncp, c->d_cidx, f, L.g.stride, c->d_cy, c->Ncp, nz);
+    else trimv_kernel<true, false, true, false><<<grid, 256, c->Ncp * sizeof(double), c->stream>>>(c->dT, c->Nc, c->Ncp, c->d_cidx, f, L.g.stride, c->d_cy, c->Ncp, nz);
   }, 4.0 * c->Nc * c->Nc);
   c->launch(sample ? "coarse_sample_bwd" : "coarse_solve_bwd", lc, [&] {
-    trimv_kernel<false, false, false, true><<<grid, 256, 0, c->stream>>>(c->dTT, c->Nc, c->Ncp, c->d_cidx, c->d_cy, c->Ncp, x, L.g.stride, nz);
+    trimv_kernel<false, false, false, true><<<grid, 256, c->Ncp * sizeof(double), c->stream>>>(c->dTT, c->Nc, c->Ncp, c->d_cidx, c->d_cy, c->Ncp, x, L.g.stride, nz);
   }, 4.0 * c->Nc * c->Nc);
 }
 
