@@ -53,7 +53,9 @@ struct LowRankTile {
   const double *Mneg[2], *Ms[2];  // m x m row-major: d = Ms s + Mneg (B^T x)
   int diag[2];               // Mneg, Ms are diagonal (B^T W is: the measurements do not interact on this level)
   const int *wbox[2];        // [m * 4]   i0, i1, j0, j1 of supp(W_k)
-  const int *wl_ptr[2], *wl_u[2];  // per measurement k: the unique W sites within 8 sites of supp(B_k)
+  // per measurement k: the W sites within 8 sites of supp(B_k), flattened (site coordinates, EW padded entries each)
+  const int *wl_ptr[2], *wl_i[2], *wl_j[2], *wl_col[2];
+  const double *wl_val[2];
   const double *sigma_inv, *sigma_inv_sqrt;
   double *dbuf;              // [nslots][nchains][m]      fix-up coefficients d (and u = Sigma^{-1} B^T x for the residual)
   double *tbuf;              // [nslots][nchains][2 m]    t = B^T x and s exchanged between patch CTAs
@@ -106,6 +108,12 @@ __device__ __forceinline__ void strip_arrive(unsigned int *ticket, unsigned int 
     __threadfence_system();
     atomicAdd_system(peer_flag, 1);
   }
+}
+
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 struct FusedP {
@@ -168,6 +176,7 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
   const int nwin = P.wpw;  // windows of this patch CTA
   int *meta = reinterpret_cast<int *>(wins + (size_t)nwin * 4 * wcap);
   int *geo = meta + (size_t)nwin * wcap;  // per window: wi0, wj0, wx, wy
+  double *lrn = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(geo + 4 * nwin) + 7) & ~uintptr_t(7));  // [2][nwin] low-rank noise of the fix-ups
   const int k0 = patch_id * nwin;
   const int nloc = min(nwin, m - k0);
   const long long cbase = (long long)chainz * P.g.stride;
@@ -176,6 +185,12 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
   const uint32_t chain = P.nz.chain0 + chainz;
   const Coef9 &a = P.a;
   const double winv = P.winv, nscale = P.noise_scale;
+#ifdef MGMC_TILE_TIMING
+#define PSTAMP(k) if (threadIdx.x == 0 && P.timing) P.timing[(long long)(chainz * gridDim.x + patch_id) * 10 + (k)] = gtimer();
+#else
+#define PSTAMP(k)
+#endif
+  PSTAMP(0)
 
   for (int k = threadIdx.x; k < 3 * m; k += kFusedThreads) sm[k] = 0.0;  // padded W entries read d[0] with weight 0
   for (int w = threadIdx.x; w < nloc; w += kFusedThreads) {
@@ -186,6 +201,30 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
     geo[4 * w + 1] = wj0;
     geo[4 * w + 2] = wi1 - wi0 + 1;
     geo[4 * w + 3] = wj1 - wj0 + 1;
+  }
+  // Everything a fix-up needs besides x is fetched now, while the windows load: the entries of B_k (one per lane),
+  // the head of the W list of the window, the diagonal of the capacitance matrices (warp w <-> window w)
+  const int kw = k0 + warp;               // measurement of this warp (windows per CTA <= warps per CTA)
+  const bool has_win = warp < nloc;
+  int pb_i = 0, pb_j = 0;
+  double pb_val = 0.0;
+  if (has_win && lane < R.EB) {
+    pb_i = R.b_i[kw * R.EB + lane];
+    pb_j = R.b_j[kw * R.EB + lane];
+    pb_val = R.b_val[kw * R.EB + lane];
+  }
+  int wl0[2] = {0, 0}, wl1[2] = {0, 0};
+  double dg_ms[2] = {0.0, 0.0}, dg_mn[2] = {0.0, 0.0}, sg_is = 0.0, sg_i = 0.0;
+  if (has_win) {
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      wl0[dir] = R.wl_ptr[dir][kw];
+      wl1[dir] = R.wl_ptr[dir][kw + 1];
+      dg_ms[dir] = R.Ms[dir][(size_t)kw * m + kw];
+      dg_mn[dir] = R.Mneg[dir][(size_t)kw * m + kw];
+    }
+    sg_is = R.sigma_inv_sqrt[kw];
+    sg_i = R.sigma_inv[kw];
   }
   __syncthreads();
   // ---- load the windows; meta = (stage of the site's colour within a sweep) | (distance to supp(B_k)) << 8,
@@ -219,6 +258,7 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
     meta[t] = mt;
   }
   __syncthreads();
+  PSTAMP(1)
   if (P.sk.on && threadIdx.x == 0) {
     // row strips: this CTA has read everything it needs from the halo rows -- it counts as an edge CTA, so
     // that a neighbour cannot overwrite those rows (next launch) before the windows are loaded
@@ -244,8 +284,16 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
       normal_pair(P.nz.keys, (((uint32_t)j * P.nz.G + (uint32_t)(i >> 2)) << 1) | (uint32_t)(i & 1), P.st[s].c1, sample, chain, z0, z1);
       wins[(size_t)w * 4 * wcap + (2 + sw) * wcap + idx] = (i & 2) ? z1 : z0;
     }
+    // low-rank noise of every (fix-up, window): Sigma^{-1/2} xi (sor_sampler.cc:48-56), kept in ssm until the fix-up
+    for (int t = threadIdx.x; t < P.nfix * nloc; t += kFusedThreads) {
+      const int q = t / nloc, k = k0 + t % nloc;
+      double z0, z1;
+      normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[q], sample, chain, z0, z1);
+      lrn[q * nwin + t % nloc] = R.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
+    }
     __syncthreads();
   }
+  PSTAMP(2)
 
   int fixq = 0;
   for (int s = 0; s <= S; ++s) {
@@ -270,6 +318,7 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
     const bool fix_here = (s < S) && (fixq < P.nfix) && (P.fix_stage[fixq] == s);
     const bool u_here = RESTRICT && (s == S);
     if (!(fix_here || u_here)) continue;
+    if (fixq == 0) { PSTAMP(5) }
     // ---- t = B^T x on every window (and the low-rank noise s): one warp per window ----
     const int slot = P.lr_slot + (fix_here ? fixq : P.nfix);
     double *tb = R.tbuf + ((size_t)slot * P.nchains + chainz) * 2 * m;
@@ -281,22 +330,18 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
       const double *xw = wins + (size_t)w * 4 * wcap;
       const int wi0 = geo[4 * w], wj0 = geo[4 * w + 1], wx = geo[4 * w + 2];
       double acc = 0.0;
-      for (int e = lane; e < R.EB; e += 32) acc += R.b_val[k * R.EB + e] * xw[(R.b_j[k * R.EB + e] - wj0) * wx + (R.b_i[k * R.EB + e] - wi0)];
+      if (lane < R.EB) acc = pb_val * xw[(pb_j - wj0) * wx + (pb_i - wi0)];
+      for (int e = lane + 32; e < R.EB; e += 32) acc += R.b_val[k * R.EB + e] * xw[(R.b_j[k * R.EB + e] - wj0) * wx + (R.b_i[k * R.EB + e] - wi0)];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) {
         if (u_here) {
-          db[k] = acc * R.sigma_inv[k];  // u_k: low-rank part of the residual, r -= B u
+          db[k] = acc * sg_i;  // u_k: low-rank part of the residual, r -= B u
         } else {
-          double sv = 0.0;
-          if (GIBBS) {
-            double z0, z1;
-            normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[fixq], sample, chain, z0, z1);
-            sv = R.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
-          }
+          const double sv = GIBBS ? lrn[fixq * nwin + w] : 0.0;
           if (diag) {
             // capacitance matrix Sigma + B^T W is diagonal (measurements do not interact on this level)
-            const double dk = fma(R.Ms[dir][(size_t)k * m + k], sv, R.Mneg[dir][(size_t)k * m + k] * acc);
+            const double dk = fma(dir ? dg_ms[1] : dg_ms[0], sv, (dir ? dg_mn[1] : dg_mn[0]) * acc);
             dsm[k] = dk;
             db[k] = dk;
           } else {
@@ -312,6 +357,7 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
     }
     int *counter = R.counters + (size_t)slot * P.nchains + chainz;
     int *flag = R.flags + (size_t)slot * P.nchains + chainz;
+    if (fixq == 0) { PSTAMP(7) }
     if (u_here || diag) {
       // the last patch CTA to arrive publishes u / d
       __syncthreads();
@@ -334,6 +380,7 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
         for (int k = threadIdx.x; k < 2 * m; k += kFusedThreads) tsm[k] = __ldcg(tb + k);  // tsm and ssm are contiguous
       }
       __syncthreads();
+      if (fixq == 0) { PSTAMP(8) }
       // ---- d = Ms s + Mneg t ----
       for (int k = warp; k < m; k += kFusedWarps) {
         double acc = 0.0;
@@ -353,6 +400,7 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
         __threadfence();
         st_release(flag, 1);
       }
+      if (fixq == 0) { PSTAMP(9) }
     }
     // ---- x += W d on every window: the W sites near window k are listed per window (with a diagonal
     //      capacitance matrix these belong to column k alone and only d_k is needed) ----
@@ -361,18 +409,19 @@ __device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id
       double *xw = wins + (size_t)w * 4 * wcap;
       const int wi0 = geo[4 * w], wj0 = geo[4 * w + 1], wx = geo[4 * w + 2], wy = geo[4 * w + 3];
       const int EW = R.EW[dir];
-      for (int q = R.wl_ptr[dir][k] + lane; q < R.wl_ptr[dir][k + 1]; q += 32) {
-        const int u = R.wl_u[dir][q];
-        const int i = R.w_i[dir][u] - wi0, j = R.w_j[dir][u] - wj0;
-        if (i < 0 || i >= wx || j < 0 || j >= wy) continue;
+      for (int q = (dir ? wl0[1] : wl0[0]) + lane; q < (dir ? wl1[1] : wl1[0]); q += 32) {
+        const int i = R.wl_i[dir][q] - wi0, j = R.wl_j[dir][q] - wj0;
         double acc = 0.0;
-        for (int e = 0; e < EW; ++e) acc += R.w_val[dir][(size_t)u * EW + e] * dsm[R.w_col[dir][(size_t)u * EW + e]];
+        for (int e = 0; e < EW; ++e) acc += R.wl_val[dir][(size_t)q * EW + e] * dsm[R.wl_col[dir][(size_t)q * EW + e]];
+        if (i < 0 || i >= wx || j < 0 || j >= wy) continue;
         xw[j * wx + i] += acc;
       }
     }
     __syncthreads();  // tsm / ssm / dsm are reused by the next fix-up
+    PSTAMP(3 + fixq)
     ++fixq;
   }
+  PSTAMP(6)
 }
 
 // element at column offset K (-1..4) of group p in a shared-memory row
@@ -445,7 +494,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const int tile_bx = tile_id % P.tiles_x, tile_by = tile_row + P.by0;
 #ifdef MGMC_TILE_TIMING
   const int cta_id = blockIdx.z * gridDim.x + blockIdx.x;
-#define TSTAMP(k) if (threadIdx.x == 0 && P.timing) P.timing[(long long)cta_id * 10 + (k)] = clock64();
+#define TSTAMP(k) if (threadIdx.x == 0 && P.timing) P.timing[(long long)cta_id * 10 + (k)] = gtimer();
   if (threadIdx.x == 0 && P.timing) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); P.timing[(long long)cta_id * 10 + 9] = smid; }
 #else
 #define TSTAMP(k)
@@ -609,14 +658,40 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       if (lr_need[dir]) {
         const LowRankTile &R = *P.lr;
         const size_t slot = (size_t)(P.lr_slot + fixq) * P.nchains + blockIdx.z;
+        const double *db = R.dbuf + slot * R.m;
+        const int EW = R.EW[dir], nu = R.nu[dir];
+        // the W entries of this thread are fetched before the flag is polled: afterwards only d is missing
+        int pidx[4], pcol[4];
+        double pval[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int u = threadIdx.x + q * kFusedThreads;
+          pidx[q] = -1;
+          pcol[q] = 0;
+          pval[q] = 0.0;
+          if (u < nu) {
+            const int i = R.w_i[dir][u], j = R.w_j[dir][u];
+            pcol[q] = R.w_col[dir][(size_t)u * EW];
+            pval[q] = R.w_val[dir][(size_t)u * EW];
+            const int di = i - i_r0;
+            if (i >= i_r0 && i < i_r0 + 128 && j >= j_r0 && j < j_r0 + RY) pidx[q] = (j - j_r0) * 128 + (di & 3) * 32 + (di >> 2);
+          }
+        }
         if (threadIdx.x == 0) {
           while (ld_acquire(R.flags + slot) == 0) {
           }
         }
         __syncthreads();
-        const double *db = R.dbuf + slot * R.m;
-        const int EW = R.EW[dir];
-        for (int u = threadIdx.x; u < R.nu[dir]; u += kFusedThreads) {
+        TSTAMP(8)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (pidx[q] < 0) continue;
+          const int u = threadIdx.x + q * kFusedThreads;
+          double acc = pval[q] * __ldcg(db + pcol[q]);
+          for (int e = 1; e < EW; ++e) acc += R.w_val[dir][(size_t)u * EW + e] * __ldcg(db + R.w_col[dir][(size_t)u * EW + e]);
+          xs[pidx[q]] += acc;
+        }
+        for (int u = threadIdx.x + 4 * kFusedThreads; u < nu; u += kFusedThreads) {
           const int i = R.w_i[dir][u], j = R.w_j[dir][u];
           if (!(i >= i_r0 && i < i_r0 + 128 && j >= j_r0 && j < j_r0 + RY)) continue;
           double acc = 0.0;

@@ -464,7 +464,22 @@ const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega) {
         wl_ptr.push_back((int)wl_u.size());
       }
       T.wl_ptr[dir] = c->dupload(wl_ptr);
-      T.wl_u[dir] = c->dupload(wl_u);
+      {
+        std::vector<int> fi(wl_u.size()), fj(wl_u.size()), fcol(wl_u.size() * F.EW);
+        std::vector<double> fval(wl_u.size() * F.EW);
+        for (size_t q = 0; q < wl_u.size(); ++q) {
+          fi[q] = wi[wl_u[q]];
+          fj[q] = wj[wl_u[q]];
+          for (int e = 0; e < F.EW; ++e) {
+            fcol[q * F.EW + e] = wcolh[(size_t)wl_u[q] * F.EW + e];
+            fval[q * F.EW + e] = wvalh[(size_t)wl_u[q] * F.EW + e];
+          }
+        }
+        T.wl_i[dir] = c->dupload(fi);
+        T.wl_j[dir] = c->dupload(fj);
+        T.wl_col[dir] = c->dupload(fcol);
+        T.wl_val[dir] = c->dupload(fval);
+      }
       bool diag = true;
       for (int r = 0; r < m && diag; ++r)
         for (int q = 0; q < m; ++q)
@@ -617,7 +632,8 @@ bool lr_patch_geometry(mgmc_ctx *c, const LowRankDev &lr, int S, int &npatch, in
   // few windows per patch CTA: the patch CTAs are a serial prefix of the launch, so they are spread wide
   for (npatch = std::min(m, np0); npatch <= std::min(m, 64); npatch *= 2) {
     wpw = (m + npatch - 1) / npatch;
-    smem = ((size_t)3 * m + (size_t)wpw * 4 * wcap) * sizeof(double) + ((size_t)wpw * wcap + 4 * (size_t)wpw) * sizeof(int);
+    if (wpw > kFusedWarps) continue;  // one warp per window
+    smem = ((size_t)3 * m + (size_t)wpw * 4 * wcap + 2 * (size_t)wpw + 1) * sizeof(double) + ((size_t)wpw * wcap + 4 * (size_t)wpw) * sizeof(int);
     if (smem <= (size_t)kFusedSmemMax) {
       npatch = (m + wpw - 1) / wpw;
       return true;
@@ -800,7 +816,8 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   const char *tfile = std::getenv("MGMC_TIMING_FILE");
   long long *d_timing = nullptr;
   const size_t ncta = (size_t)grid.x * grid.z;
-  if (tfile && level == 0 && dumped[name]++ == 3) {
+  static const char *tlev = std::getenv("MGMC_TIMING_LEVEL");
+  if (tfile && level == (tlev ? std::atoi(tlev) : 0) && dumped[name]++ == 3) {
     CUDA_CHECK(cudaMalloc(&d_timing, ncta * 10 * sizeof(long long)));
     CUDA_CHECK(cudaMemset(d_timing, 0, ncta * 10 * sizeof(long long)));
     P.timing = d_timing;
