@@ -32,13 +32,15 @@ constexpr int kGY = 2;   // allocated rows below j = 0 / above j = ny
 constexpr int kFusedThreads = 512;
 constexpr int kFusedWarps = kFusedThreads / 32;
 
+struct LrPkt;
+
 struct Stage {
   int colour;
   uint32_t c1;  // (level << 24) | sweep counter of the sweep this colour pass belongs to
 };
 
 // Device-resident data of the low-rank (measurement) term of one level for the in-kernel Woodbury
-// fix-up (see "patch CTAs" below).  Sparse matrices are stored with explicit (i, j) coordinates.
+// fix-up (see "Low-rank term inside the launch" below).  Sparse matrices carry explicit (i, j) coordinates.
 struct LowRankTile {
   int m, EB;
   const int *b_i, *b_j;      // [m * EB]  entries of column k of B, padded by repeating an entry with value 0
@@ -50,17 +52,13 @@ struct LowRankTile {
   int nu[2], EW[2];          // W = M_0^{-1} B per sweep direction, grouped by unique site, EW padded entries each
   const int *w_i[2], *w_j[2], *w_col[2];
   const double *w_val[2];
+  const int *wbox[2];        // [m * 4]   i0, i1, j0, j1 of supp(W_k)
   const double *Mneg[2], *Ms[2];  // m x m row-major: d = Ms s + Mneg (B^T x)
   int diag[2];               // Mneg, Ms are diagonal (B^T W is: the measurements do not interact on this level)
-  const int *wbox[2];        // [m * 4]   i0, i1, j0, j1 of supp(W_k)
-  // per measurement k: the W sites within 8 sites of supp(B_k), flattened (site coordinates, EW padded entries each)
-  const int *wl_ptr[2], *wl_i[2], *wl_j[2], *wl_col[2];
-  const double *wl_val[2];
   const double *sigma_inv, *sigma_inv_sqrt;
-  double *dbuf;              // [nslots][nchains][m]      fix-up coefficients d (and u = Sigma^{-1} B^T x for the residual)
-  double *tbuf;              // [nslots][nchains][2 m]    t = B^T x and s exchanged between patch CTAs
-  int *flags;                // [nslots][nchains]         1 once dbuf[slot] is complete
-  int *counters;             // [nslots][nchains]         arrival counter of the patch CTAs
+  struct LrPkt *vbuf;        // [nslots][nchains][2 m]  published per fix-up: d_k (diagonal case) or t_k = (B^T x)_k and
+                             //                         the noise s_k; for the residual slot: u_k = (Sigma^{-1} B^T x)_k
+  const int *epoch;          // advanced once per cycle / API call: a packet is valid iff it carries the current epoch
 };
 
 // Row-strip decomposition (one process per GPU): the tile kernel itself exchanges the halo rows.  Tiles
@@ -83,6 +81,7 @@ struct StripK {
   int edge_rows;                   // tile rows at either end of the strip that mirror rows
   unsigned int *ticket_dn, *ticket_up;
   int *err;
+  long long lr_peer_dn, lr_peer_up;  // byte offsets from this rank's vbuf / flags to the neighbours' copies (0: none)
 };
 
 __device__ __forceinline__ int ld_acquire_sys_i(const int *p) {
@@ -133,16 +132,16 @@ struct FusedP {
   int HXL, TX, TY, RY, hl;  // region geometry (host-computed, identical for all tiles)
   int omega_is_one;
   long long *timing;  // MGMC_TILE_TIMING builds only: 8 clock64 stamps + smid per CTA
-  int tiles_x;        // the grid is 1-d: npatch patch CTAs followed by tiles_x * tiles_y tile CTAs
+  int tiles_x;        // the grid is 1-d: tiles_x * tiles_y tile CTAs
   int by0;            // first tile row of this launch (row-strip decomposition: the rank's own tile rows)
   StripK sk;
   // low-rank term (LOWRANK kernels): fix-up q follows stage fix_stage[q]
-  const LowRankTile *lr;
-  int npatch, wpw, wcap;  // patch CTAs, windows per warp, doubles per window array
+  LowRankTile lr;         // by value: its pointers sit in the constant bank, no dependent load to reach the tables
+  int lr_mx, lr_my;       // extent of supp(B_k) beyond its lower left corner: extra halo on the high sides
   int nfix;
   int fix_stage[2], fix_dir[2];
   uint32_t fix_c1[2];
-  int lr_slot, nchains;   // first dbuf / flag slot of this launch (nfix fix-ups, then u)
+  int lr_slot, nchains;   // first vbuf / flag slot of this launch (nfix fix-ups, then u)
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -152,278 +151,44 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// ------------------------------------------------------------------------------------------------
-// Patch CTAs: the Woodbury fix-up after a sweep (sor_smoother.cc:47-51, sor_sampler.cc:48-56),
-//   x += W d,  d = (I - K G) Sigma^{-1/2} xi - K B^T x,
-// needs B^T x of the freshly swept x: a grid-wide dependency in the middle of a fused launch.  But
-// B^T x only involves the few sites of supp(B_k), and their values after `S` colour stages depend on
-// the input x within distance S of them.  The first `npatch` CTAs of the grid therefore re-run the
-// launch on small windows (supp(B_k) dilated by S sites) around every measurement -- same input, same
-// Philox noise, same fix-ups -- publish d for every fix-up (and u = Sigma^{-1} B^T x of the final
-// state for the low-rank part of the residual) in global memory and raise a flag; tile CTAs whose
-// region contains a site of W (or B) wait for the flag and apply x += W d between two stages.
-// Patch CTAs have the lowest block indices of the grid, so they are resident before any tile CTA can wait.
-// ------------------------------------------------------------------------------------------------
-template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT>
-__device__ __noinline__ void patch_cta(const FusedP &P, double *sm, int patch_id, int chainz) {
-  const LowRankTile &R = *P.lr;
-  const int m = R.m, S = P.nstages, wcap = P.wcap;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nx = P.g.nx, ny = P.g.ny, pitch = P.g.pitch;
-  // shared memory: t, s, d (m each) | per window: x, f, noise of sweep 0, noise of sweep 1 (wcap each) | meta (wcap ints) | geometry
-  double *tsm = sm, *ssm = sm + m, *dsm = sm + 2 * m;
-  double *wins = sm + 3 * m;
-  const int nwin = P.wpw;  // windows of this patch CTA
-  int *meta = reinterpret_cast<int *>(wins + (size_t)nwin * 4 * wcap);
-  int *geo = meta + (size_t)nwin * wcap;  // per window: wi0, wj0, wx, wy
-  double *lrn = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(geo + 4 * nwin) + 7) & ~uintptr_t(7));  // [2][nwin] low-rank noise of the fix-ups
-  const int k0 = patch_id * nwin;
-  const int nloc = min(nwin, m - k0);
-  const long long cbase = (long long)chainz * P.g.stride;
-  const double *xg = P.x_in + cbase, *fg = P.f + cbase;
-  const uint32_t sample = GIBBS ? *P.nz.sample : 0u;
-  const uint32_t chain = P.nz.chain0 + chainz;
-  const Coef9 &a = P.a;
-  const double winv = P.winv, nscale = P.noise_scale;
-#ifdef MGMC_TILE_TIMING
-#define PSTAMP(k) if (threadIdx.x == 0 && P.timing) P.timing[(long long)(chainz * gridDim.x + patch_id) * 10 + (k)] = gtimer();
-#else
-#define PSTAMP(k)
-#endif
-  PSTAMP(0)
-
-  for (int k = threadIdx.x; k < 3 * m; k += kFusedThreads) sm[k] = 0.0;  // padded W entries read d[0] with weight 0
-  for (int w = threadIdx.x; w < nloc; w += kFusedThreads) {
-    const int k = k0 + w;
-    const int wi0 = max(0, R.bbox[4 * k] - S), wi1 = min(nx, R.bbox[4 * k + 1] + S);
-    const int wj0 = max(0, R.bbox[4 * k + 2] - S), wj1 = min(ny, R.bbox[4 * k + 3] + S);
-    geo[4 * w] = wi0;
-    geo[4 * w + 1] = wj0;
-    geo[4 * w + 2] = wi1 - wi0 + 1;
-    geo[4 * w + 3] = wj1 - wj0 + 1;
-  }
-  // Everything a fix-up needs besides x is fetched now, while the windows load: the entries of B_k (one per lane),
-  // the head of the W list of the window, the diagonal of the capacitance matrices (warp w <-> window w)
-  const int kw = k0 + warp;               // measurement of this warp (windows per CTA <= warps per CTA)
-  const bool has_win = warp < nloc;
-  int pb_i = 0, pb_j = 0;
-  double pb_val = 0.0;
-  if (has_win && lane < R.EB) {
-    pb_i = R.b_i[kw * R.EB + lane];
-    pb_j = R.b_j[kw * R.EB + lane];
-    pb_val = R.b_val[kw * R.EB + lane];
-  }
-  int wl0[2] = {0, 0}, wl1[2] = {0, 0};
-  double dg_ms[2] = {0.0, 0.0}, dg_mn[2] = {0.0, 0.0}, sg_is = 0.0, sg_i = 0.0;
-  if (has_win) {
-#pragma unroll
-    for (int dir = 0; dir < 2; ++dir) {
-      wl0[dir] = R.wl_ptr[dir][kw];
-      wl1[dir] = R.wl_ptr[dir][kw + 1];
-      dg_ms[dir] = R.Ms[dir][(size_t)kw * m + kw];
-      dg_mn[dir] = R.Mneg[dir][(size_t)kw * m + kw];
-    }
-    sg_is = R.sigma_inv_sqrt[kw];
-    sg_i = R.sigma_inv[kw];
-  }
-  __syncthreads();
-  // ---- load the windows; meta = (stage of the site's colour within a sweep) | (distance to supp(B_k)) << 8,
-  //      -1 for sites that are never updated ----
-  for (int t = threadIdx.x; t < nloc * wcap; t += kFusedThreads) {
-    const int w = t / wcap, idx = t - w * wcap;
-    const int wi0 = geo[4 * w], wj0 = geo[4 * w + 1], wx = geo[4 * w + 2], wy = geo[4 * w + 3];
-    int mt = -1;
-    if (idx < wx * wy) {
-      const int k = k0 + w;
-      const int i = wi0 + idx % wx, j = wj0 + idx / wx;
-      double xv = xg[(long long)j * pitch + i];
-      const double fv = fg[(long long)j * pitch + i];
-      if (PROLONG && i >= 1 && i < nx && j >= 1 && j < ny) {
-        const double *xc = P.xc_in + (long long)chainz * P.gc.stride;
-        const double *r0 = xc + (long long)(j >> 1) * P.gc.pitch, *r1 = xc + (long long)((j + 1) >> 1) * P.gc.pitch;
-        const int I0 = i >> 1, I1 = (i + 1) >> 1;
-        xv += P.alpha * (0.25 * ((r0[I0] + r1[I0]) + (r0[I1] + r1[I1])));
-      }
-      double *xw = wins + (size_t)w * 4 * wcap;
-      xw[idx] = xv;
-      xw[wcap + idx] = fv;
-      // window edges that are not the Dirichlet boundary are never updated
-      const bool inner = (i > wi0) && (i < wi0 + wx - 1) && (j > wj0) && (j < wj0 + wy - 1);
-      if (inner) {
-        const int dist = max(max(R.bbox[4 * k] - i, i - R.bbox[4 * k + 1]), max(max(R.bbox[4 * k + 2] - j, j - R.bbox[4 * k + 3]), 0));
-        const int colour = (NC == 2) ? ((i + j) & 1) : ((i & 1) + 2 * (j & 1));
-        mt = colour | (dist << 8);
-      }
-    }
-    meta[t] = mt;
-  }
-  __syncthreads();
-  PSTAMP(1)
-  if (P.sk.on && threadIdx.x == 0) {
-    // row strips: this CTA has read everything it needs from the halo rows -- it counts as an edge CTA, so
-    // that a neighbour cannot overwrite those rows (next launch) before the windows are loaded
-    const unsigned int n_edge = (unsigned int)(P.sk.edge_rows * P.tiles_x + P.npatch);
-    if (P.sk.peer_flag_dn) strip_arrive(P.sk.ticket_dn, n_edge, P.sk.peer_flag_dn);
-    if (P.sk.peer_flag_up) strip_arrive(P.sk.ticket_up, n_edge, P.sk.peer_flag_up);
-  }
-  // ---- noise of every (sweep, site) that lies in the dependence cone of supp(B_k): the value of a B site
-  //      after stage S - 1 depends on stage s only within distance S - 1 - s ----
-  if (GIBBS) {
-    const int nsweeps = S / NC;
-    for (int t = threadIdx.x; t < nsweeps * nloc * wcap; t += kFusedThreads) {
-      const int sw = t / (nloc * wcap), r = t - sw * (nloc * wcap);
-      const int mt = meta[r];
-      if (mt < 0) continue;
-      const int colour = mt & 255, dist = mt >> 8;
-      int s = sw * NC;
-      while (P.st[s].colour != colour) ++s;
-      if (dist > S - 1 - s) continue;
-      const int w = r / wcap, idx = r - w * wcap;
-      const int i = geo[4 * w] + idx % geo[4 * w + 2], j = geo[4 * w + 1] + idx / geo[4 * w + 2];
-      double z0, z1;
-      normal_pair(P.nz.keys, (((uint32_t)j * P.nz.G + (uint32_t)(i >> 2)) << 1) | (uint32_t)(i & 1), P.st[s].c1, sample, chain, z0, z1);
-      wins[(size_t)w * 4 * wcap + (2 + sw) * wcap + idx] = (i & 2) ? z1 : z0;
-    }
-    // low-rank noise of every (fix-up, window): Sigma^{-1/2} xi (sor_sampler.cc:48-56), kept in ssm until the fix-up
-    for (int t = threadIdx.x; t < P.nfix * nloc; t += kFusedThreads) {
-      const int q = t / nloc, k = k0 + t % nloc;
-      double z0, z1;
-      normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[q], sample, chain, z0, z1);
-      lrn[q * nwin + t % nloc] = R.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
-    }
-    __syncthreads();
-  }
-  PSTAMP(2)
-
-  int fixq = 0;
-  for (int s = 0; s <= S; ++s) {
-    if (s < S) {
-      const int colour = P.st[s].colour;
-      const int key_lo = colour, key_hi = colour | ((S - 1 - s) << 8);  // colour matches and dist <= S - 1 - s
-      for (int t = threadIdx.x; t < nloc * wcap; t += kFusedThreads) {
-        const int mt = meta[t];
-        if (mt < 0 || (mt & 255) != key_lo || mt > key_hi) continue;
-        const int w = t / wcap, idx = t - w * wcap;
-        const int wx = geo[4 * w + 2];
-        double *q = wins + (size_t)w * 4 * wcap + idx;
-        double b = q[wcap];
-        if (GIBBS) b = fma(nscale, q[(2 + s / NC) * wcap], b);
-        double off = a.w * q[-1] + a.e * q[1] + a.s * q[-wx] + a.n * q[wx];
-        if (NC == 4) off += a.sw * q[-wx - 1] + a.se * q[-wx + 1] + a.nw * q[wx - 1] + a.ne * q[wx + 1];
-        if (P.omega_is_one) q[0] = winv * (b - off);
-        else q[0] += winv * (b - (a.c * q[0] + off));
-      }
-      __syncthreads();
-    }
-    const bool fix_here = (s < S) && (fixq < P.nfix) && (P.fix_stage[fixq] == s);
-    const bool u_here = RESTRICT && (s == S);
-    if (!(fix_here || u_here)) continue;
-    if (fixq == 0) { PSTAMP(5) }
-    // ---- t = B^T x on every window (and the low-rank noise s): one warp per window ----
-    const int slot = P.lr_slot + (fix_here ? fixq : P.nfix);
-    double *tb = R.tbuf + ((size_t)slot * P.nchains + chainz) * 2 * m;
-    double *db = R.dbuf + ((size_t)slot * P.nchains + chainz) * m;
-    const int dir = fix_here ? P.fix_dir[fixq] : 0;
-    const bool diag = fix_here && R.diag[dir];
-    for (int w = warp; w < nloc; w += kFusedWarps) {
-      const int k = k0 + w;
-      const double *xw = wins + (size_t)w * 4 * wcap;
-      const int wi0 = geo[4 * w], wj0 = geo[4 * w + 1], wx = geo[4 * w + 2];
-      double acc = 0.0;
-      if (lane < R.EB) acc = pb_val * xw[(pb_j - wj0) * wx + (pb_i - wi0)];
-      for (int e = lane + 32; e < R.EB; e += 32) acc += R.b_val[k * R.EB + e] * xw[(R.b_j[k * R.EB + e] - wj0) * wx + (R.b_i[k * R.EB + e] - wi0)];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) {
-        if (u_here) {
-          db[k] = acc * sg_i;  // u_k: low-rank part of the residual, r -= B u
-        } else {
-          const double sv = GIBBS ? lrn[fixq * nwin + w] : 0.0;
-          if (diag) {
-            // capacitance matrix Sigma + B^T W is diagonal (measurements do not interact on this level)
-            const double dk = fma(dir ? dg_ms[1] : dg_ms[0], sv, (dir ? dg_mn[1] : dg_mn[0]) * acc);
-            dsm[k] = dk;
-            db[k] = dk;
-          } else {
-            tsm[k] = acc;
-            ssm[k] = sv;
-            if (P.npatch > 1) {
-              tb[k] = acc;
-              tb[m + k] = sv;
-            }
-          }
-        }
-      }
-    }
-    int *counter = R.counters + (size_t)slot * P.nchains + chainz;
-    int *flag = R.flags + (size_t)slot * P.nchains + chainz;
-    if (fixq == 0) { PSTAMP(7) }
-    if (u_here || diag) {
-      // the last patch CTA to arrive publishes u / d
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(counter, 1) == P.npatch - 1) st_release(flag, 1);
-      }
-      if (u_here) continue;
-    } else {
-      if (P.npatch > 1) {
-        // all measurements are coupled through K: exchange t and s between the patch CTAs
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          __threadfence();
-          atomicAdd(counter, 1);
-          while (ld_acquire(counter) < P.npatch) {
-          }
-        }
-        __syncthreads();
-        for (int k = threadIdx.x; k < 2 * m; k += kFusedThreads) tsm[k] = __ldcg(tb + k);  // tsm and ssm are contiguous
-      }
-      __syncthreads();
-      if (fixq == 0) { PSTAMP(8) }
-      // ---- d = Ms s + Mneg t ----
-      for (int k = warp; k < m; k += kFusedWarps) {
-        double acc = 0.0;
-        for (int c = lane; c < m; c += 32) {
-          acc = fma(R.Mneg[dir][(size_t)k * m + c], tsm[c], acc);
-          if (GIBBS) acc = fma(R.Ms[dir][(size_t)k * m + c], ssm[c], acc);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) {
-          dsm[k] = acc;
-          if (patch_id == 0) db[k] = acc;
-        }
-      }
-      __syncthreads();
-      if (patch_id == 0 && threadIdx.x == 0) {
-        __threadfence();
-        st_release(flag, 1);
-      }
-      if (fixq == 0) { PSTAMP(9) }
-    }
-    // ---- x += W d on every window: the W sites near window k are listed per window (with a diagonal
-    //      capacitance matrix these belong to column k alone and only d_k is needed) ----
-    for (int w = warp; w < nloc; w += kFusedWarps) {
-      const int k = k0 + w;
-      double *xw = wins + (size_t)w * 4 * wcap;
-      const int wi0 = geo[4 * w], wj0 = geo[4 * w + 1], wx = geo[4 * w + 2], wy = geo[4 * w + 3];
-      const int EW = R.EW[dir];
-      for (int q = (dir ? wl0[1] : wl0[0]) + lane; q < (dir ? wl1[1] : wl1[0]); q += 32) {
-        const int i = R.wl_i[dir][q] - wi0, j = R.wl_j[dir][q] - wj0;
-        double acc = 0.0;
-        for (int e = 0; e < EW; ++e) acc += R.wl_val[dir][(size_t)q * EW + e] * dsm[R.wl_col[dir][(size_t)q * EW + e]];
-        if (i < 0 || i >= wx || j < 0 || j >= wy) continue;
-        xw[j * wx + i] += acc;
-      }
-    }
-    __syncthreads();  // tsm / ssm / dsm are reused by the next fix-up
-    PSTAMP(3 + fixq)
-    ++fixq;
-  }
-  PSTAMP(6)
+// What an owner tile publishes: value and epoch travel in ONE aligned 16-byte store, so no fence / release is
+// needed between "value written" and "flag raised" (a naturally aligned 128-bit access is a single transaction,
+// also across NVLink); consumers poll the packet with volatile 128-bit loads (served by L2) until the epoch matches.
+struct __align__(16) LrPkt {
+  double v;
+  int epoch, pad;
+};
+__device__ __forceinline__ void pkt_store(LrPkt *p, double v, int epoch) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"((unsigned)(b >> 32)), "r"(epoch), "r"(0) : "memory");
+}
+// bounded wait: a bug (or a dead peer) must not hang the GPU
+__device__ __forceinline__ double pkt_wait(const LrPkt *p, int epoch) {
+  unsigned lo, hi;
+  int e, pad;
+  const long long t0 = clock64();
+  do {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(e), "=r"(pad) : "l"(p) : "memory");
+  } while (e < epoch && clock64() - t0 < 4000000000ll);
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Low-rank term inside the launch.  The Woodbury fix-up after a sweep (sor_smoother.cc:47-51,
+// sor_sampler.cc:48-56),   x += W d,  d = (I - K G) Sigma^{-1/2} xi - K B^T x,
+// needs t = B^T x of the freshly swept x: a grid-wide dependency between two colour passes of a fused
+// launch.  But t_k only involves the few sites of supp(B_k).  Every measurement has an OWNER tile (the one
+// that contains the lower left corner of supp(B_k); its halo is widened so that all of supp(B_k) is exact
+// in its shared memory at every fix-up).  After the sweep the owner computes t_k from shared memory and
+// publishes it -- d_k itself when the capacitance matrix is diagonal, i.e. the measurements do not
+// interact on this level, else t_k and the noise s_k -- with a release store of the current epoch into
+// flag k; every tile whose region meets supp(W) acquires the flags of the measurements it needs
+// (all of them in the coupled case, where it forms the needed rows of d = Ms s + Mneg t itself) and
+// applies W d in shared memory.  Tiles elsewhere never wait.  u = Sigma^{-1} B^T x of the final state
+// (low-rank part of the residual) is published the same way.  Owners publish before they wait for
+// anything, and only the few tiles next to a measurement wait, so the scheme cannot deadlock as long as
+// waiting tiles do not fill the chip (host: coupled levels must fit on the chip at once).
+// ------------------------------------------------------------------------------------------------
 // element at column offset K (-1..4) of group p in a shared-memory row
 template <int K>
 __device__ __forceinline__ double &sat(double *row, int p) {
@@ -473,21 +238,9 @@ __device__ __forceinline__ void update_pair(const Coef9 &a, double *xrow, const 
 template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT, bool LOWRANK>
 __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {
   extern __shared__ double sm[];
-  __shared__ int lr_hits;  // LOWRANK: bit 0 / 1: the region meets supp(W) of the forward / backward sweep, bit 2: the tile meets supp(B)
+  __shared__ int lr_cnt[4];  // LOWRANK: measurements owned by this tile, needed for the forward / backward fix-up, for the residual
   constexpr bool NINE = (NC == 4);
-  if (LOWRANK && (int)blockIdx.x < P.npatch) {
-    if (P.sk.on) {  // the windows near the strip boundaries read halo rows
-      if (threadIdx.x == 0) {
-        const int target = *P.sk.cycle_no * P.sk.per_cycle + P.sk.index;
-        if (P.sk.flag_from_dn) strip_spin(P.sk.flag_from_dn, target, P.sk.err);
-        if (P.sk.flag_from_up) strip_spin(P.sk.flag_from_up, target, P.sk.err);
-      }
-      __syncthreads();
-    }
-    patch_cta<NC, GIBBS, PROLONG, RESTRICT>(P, sm, blockIdx.x, blockIdx.z);
-    return;
-  }
-  const int tile_id = (int)blockIdx.x - (LOWRANK ? P.npatch : 0);
+  const int tile_id = (int)blockIdx.x;
   int tile_row = tile_id / P.tiles_x;
   // row strips: the tile rows at both ends of the strip run first (they feed the neighbours)
   if (P.sk.on) tile_row = (tile_row & 1) ? (P.sk.tiles_y - 1 - (tile_row >> 1)) : (tile_row >> 1);
@@ -513,23 +266,31 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const double *fg = P.f + cbase;
   const int gi0 = i_r0 + 4 * lane;  // first global column of this lane's group
   const bool cols_alloc = (gi0 >= -kGX) && (gi0 + 3 < pitch - kGX);
+  // shared memory behind the tile: d (or u) of the current fix-up, t and s (coupled case), the low-rank noise and the
+  // diagonal capacitance entries of the owned measurements, then the index lists
+  // (the pointers are re-derived inside every low-rank block instead of being kept live across the colour passes:
+  //  the passes run at the 64-register limit)
+#define MGMC_LR_PTRS                                                                                                  \
+  const int lrm = P.lr.m;                                                                                             \
+  double *darr = sm + 2 * P.RY * 128, *tarr = darr + lrm, *sarr = tarr + lrm;                                         \
+  double *spre = sarr + lrm;    /* [2][m] noise of fix-up q for owned k */                                            \
+  double *cms = spre + 2 * lrm; /* [2][m] Ms_kk per direction (owned k) */                                            \
+  double *cmn = cms + 2 * lrm;  /* [2][m] Mneg_kk */                                                                  \
+  int *own_list = reinterpret_cast<int *>(cmn + 2 * lrm), *need_list = own_list + lrm; /* need_list: [3][m] */        \
+  int *is_own = need_list + 3 * lrm;                                                                                  \
+  const int lr_epoch = *P.lr.epoch;                                                                                   \
+  const bool lr_to_dn = P.sk.on && P.sk.lr_peer_dn != 0 && (tile_by - P.by0 < P.sk.edge_rows);                        \
+  const bool lr_to_up = P.sk.on && P.sk.lr_peer_up != 0 && (tile_by - P.by0 >= P.sk.tiles_y - P.sk.edge_rows);        \
+  (void)darr; (void)tarr; (void)sarr; (void)spre; (void)cms; (void)cmn; (void)own_list; (void)need_list; (void)is_own; \
+  (void)lr_epoch; (void)lr_to_dn; (void)lr_to_up;
   if (LOWRANK) {
-    // does this tile meet a site touched by the low-rank fix-ups?  Tested up front (its loads overlap the tile
-    // load, the barrier that ends the load publishes the result)
-    if (threadIdx.x == 0) lr_hits = 0;
-    __syncthreads();
-    const LowRankTile &R = *P.lr;
-    int bits = 0;
-    for (int k = threadIdx.x; k < R.m; k += kFusedThreads) {
-      const int4 b0 = reinterpret_cast<const int4 *>(R.wbox[0])[k], b1 = reinterpret_cast<const int4 *>(R.wbox[1])[k];
-      bits |= (b0.y >= i_r0 && b0.x < i_r0 + 128 && b0.w >= j_r0 && b0.z < j_r0 + RY) ? 1 : 0;
-      bits |= (b1.y >= i_r0 && b1.x < i_r0 + 128 && b1.w >= j_r0 && b1.z < j_r0 + RY) ? 2 : 0;
-      if (RESTRICT) {
-        const int4 bb = reinterpret_cast<const int4 *>(R.bbox)[k];  // i0, i1, j0, j1 of supp(B_k)
-        bits |= (bb.y >= max(1, i_t0 - 1) && bb.x <= min(nx - 1, i_t0 + TX - 1) && bb.w >= j_t0 && bb.z <= min(j_t0 + TY, ny - 1)) ? 4 : 0;
-      }
+    MGMC_LR_PTRS
+    if (threadIdx.x < 4) lr_cnt[threadIdx.x] = 0;
+    for (int k = threadIdx.x; k < lrm; k += kFusedThreads) {
+      darr[k] = 0.0;
+      is_own[k] = 0;
     }
-    if (bits) atomicOr(&lr_hits, bits);
+    __syncthreads();
   }
   if (P.sk.on) {
     const bool wdn = P.sk.flag_from_dn && (j_r0 < P.sk.own_lo), wup = P.sk.flag_from_up && (j_r0 + RY - 1 > P.sk.own_hi);
@@ -604,6 +365,36 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       fr[48] = fb[u].y;
     }
   }
+  if (LOWRANK && (int)threadIdx.x < P.lr.m) {
+    // Which measurements does this tile own / need?  (after the tile load has been issued; published by its barrier)
+    MGMC_LR_PTRS
+    const LowRankTile &R = P.lr;
+    const int k = threadIdx.x;
+    const int4 bb = reinterpret_cast<const int4 *>(R.bbox)[k];  // i0, i1, j0, j1 of supp(B_k)
+    const int4 b0 = reinterpret_cast<const int4 *>(R.wbox[0])[k], b1 = reinterpret_cast<const int4 *>(R.wbox[1])[k];
+    if (b0.y >= i_r0 && b0.x < i_r0 + 128 && b0.w >= j_r0 && b0.z < j_r0 + RY) need_list[atomicAdd(&lr_cnt[1], 1)] = k;
+    if (b1.y >= i_r0 && b1.x < i_r0 + 128 && b1.w >= j_r0 && b1.z < j_r0 + RY) need_list[lrm + atomicAdd(&lr_cnt[2], 1)] = k;
+    if (RESTRICT && bb.y >= max(1, i_t0 - 1) && bb.x <= min(nx - 1, i_t0 + TX - 1) && bb.w >= j_t0 && bb.z <= min(j_t0 + TY, ny - 1))
+      need_list[2 * lrm + atomicAdd(&lr_cnt[3], 1)] = k;
+    if (bb.x >= i_t0 && bb.x < i_t0 + TX && bb.z >= j_t0 && bb.z < j_t0 + TY) {  // owner: the tile that holds the lower left corner
+      own_list[atomicAdd(&lr_cnt[0], 1)] = k;
+      is_own[k] = 1;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q >= P.nfix) break;
+        const int dir = P.fix_dir[q];
+        cms[q * lrm + k] = R.Ms[dir][(size_t)k * lrm + k];
+        cmn[q * lrm + k] = R.Mneg[dir][(size_t)k * lrm + k];
+        double sv = 0.0;
+        if (GIBBS) {
+          double z0, z1;
+          normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[q], *P.nz.sample, P.nz.chain0 + blockIdx.z, z0, z1);
+          sv = R.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
+        }
+        spre[q * lrm + k] = sv;
+      }
+    }
+  }
   __syncthreads();
   TSTAMP(1)
 
@@ -611,18 +402,18 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const double winv = P.winv;
   const double nscale = P.noise_scale;
   const int S = P.nstages;
-  constexpr int EXLX = RESTRICT ? 2 : 0, EXHX = RESTRICT ? 1 : 0, EXLY = RESTRICT ? 1 : 0, EXHY = RESTRICT ? 2 : 0;
+  constexpr int EXLX = RESTRICT ? 2 : 0, EXLY = RESTRICT ? 1 : 0;
+  // (low-rank term: supp(B_k) must be exact in its owner tile at every fix-up -- it extends lr_mx / lr_my beyond the lower left corner)
+  const int EXHX = (RESTRICT ? 1 : 0) + (LOWRANK ? P.lr_mx : 0), EXHY = (RESTRICT ? 2 : 0) + (LOWRANK ? P.lr_my : 0);
   const uint32_t pg = (uint32_t)((i_r0 >> 2) + lane);
   const uint32_t sample = GIBBS ? *P.nz.sample : 0u;
   const uint32_t chain = P.nz.chain0 + blockIdx.z;
-  // does the region of this tile contain a site touched by the low-rank fix-ups?
-  bool lr_need[2] = {false, false};
-  int fixq = 0;
-  if (LOWRANK) {
-    lr_need[0] = (lr_hits & 1) != 0;
-    lr_need[1] = (lr_hits & 2) != 0;
-  }
-  for (int s = 0; s < S; ++s) {
+  // the colour passes run in segments that end at a low-rank fix-up (or at the last pass): the fix-up code stays out
+  // of the body of the pass loop
+  int s = 0;
+  for (int seg = 0; seg <= (LOWRANK ? P.nfix : 0); ++seg) {
+   const int s_end = (LOWRANK && seg < P.nfix) ? P.fix_stage[seg] + 1 : S;
+   for (; s < s_end; ++s) {
     const int colour = P.st[s].colour;
     const uint32_t c1 = P.st[s].c1;
     const int m = S - 1 - s;
@@ -652,15 +443,52 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
     }
     __syncthreads();
-    if (LOWRANK && fixq < P.nfix && P.fix_stage[fixq] == s) {
-      // x += W d with d published by the patch CTAs
+    TSTAMP(2 + (s < 4 ? s : 3))
+   }
+    if (LOWRANK && seg < P.nfix) {
+      MGMC_LR_PTRS
+      const int fixq = seg;
+      const LowRankTile &R = P.lr;
       const int dir = P.fix_dir[fixq];
-      if (lr_need[dir]) {
-        const LowRankTile &R = *P.lr;
-        const size_t slot = (size_t)(P.lr_slot + fixq) * P.nchains + blockIdx.z;
-        const double *db = R.dbuf + slot * R.m;
+      const bool diag = R.diag[dir] != 0;
+      const size_t slot = (size_t)(P.lr_slot + fixq) * P.nchains + blockIdx.z;
+      LrPkt *vb = R.vbuf + slot * 2 * lrm;
+      // (1) owners: t_k = (B^T x)_k from shared memory, published as d_k (diagonal capacitance matrix) or as (t_k, s_k);
+      //     the tile keeps its own values in shared memory
+      for (int o = warp; o < lr_cnt[0]; o += kFusedWarps) {
+        const int k = own_list[o];
+        double acc = 0.0;
+        for (int e = lane; e < R.EB; e += 32) {
+          const int bi = R.b_i[k * R.EB + e] - i_r0, bj = R.b_j[k * R.EB + e] - j_r0;
+          acc += R.b_val[k * R.EB + e] * xs[bj * 128 + (bi & 3) * 32 + (bi >> 2)];
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+        if (lane == 0) {
+          const double sv = spre[fixq * lrm + k];
+          const double v0 = diag ? fma(cms[fixq * lrm + k], sv, cmn[fixq * lrm + k] * acc) : acc;
+          if (diag) {
+            darr[k] = v0;
+          } else {
+            tarr[k] = v0;
+            sarr[k] = sv;
+          }
+          pkt_store(vb + k, v0, lr_epoch);
+          if (!diag) pkt_store(vb + lrm + k, sv, lr_epoch);
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            if (!(side ? lr_to_up : lr_to_dn)) continue;
+            LrPkt *pvb = reinterpret_cast<LrPkt *>(reinterpret_cast<char *>(vb) + (side ? P.sk.lr_peer_up : P.sk.lr_peer_dn));
+            pkt_store(pvb + k, v0, lr_epoch);
+            if (!diag) pkt_store(pvb + lrm + k, sv, lr_epoch);
+          }
+        }
+      }
+      const int n_need = lr_cnt[1 + dir];
+      const int *nlist = need_list + dir * lrm;
+      if (n_need > 0) {
         const int EW = R.EW[dir], nu = R.nu[dir];
-        // the W entries of this thread are fetched before the flag is polled: afterwards only d is missing
+        // the W entries of this thread are fetched before any flag is polled: afterwards only d is missing
         int pidx[4], pcol[4];
         double pval[4];
 #pragma unroll
@@ -677,33 +505,79 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
             if (i >= i_r0 && i < i_r0 + 128 && j >= j_r0 && j < j_r0 + RY) pidx[q] = (j - j_r0) * 128 + (di & 3) * 32 + (di >> 2);
           }
         }
-        if (threadIdx.x == 0) {
-          while (ld_acquire(R.flags + slot) == 0) {
+        // (2) consumers: acquire what the owners published
+        if (diag) {
+          for (int n = threadIdx.x; n < n_need; n += kFusedThreads) {
+            const int k = nlist[n];
+            if (!is_own[k]) darr[k] = pkt_wait(vb + k, lr_epoch);
+          }
+        } else {
+          // the measurements interact: every needed d_k is a full row of Ms s + Mneg t
+          for (int k = threadIdx.x; k < lrm; k += kFusedThreads) {
+            if (is_own[k]) continue;
+            tarr[k] = pkt_wait(vb + k, lr_epoch);
+            sarr[k] = pkt_wait(vb + lrm + k, lr_epoch);
+          }
+          __syncthreads();
+          for (int n = warp; n < n_need; n += kFusedWarps) {
+            const int k = nlist[n];
+            double acc = 0.0;
+            for (int c = lane; c < lrm; c += 32) {
+              acc = fma(R.Mneg[dir][(size_t)k * lrm + c], tarr[c], acc);
+              if (GIBBS) acc = fma(R.Ms[dir][(size_t)k * lrm + c], sarr[c], acc);
+            }
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+            if (lane == 0) darr[k] = acc;
           }
         }
         __syncthreads();
-        TSTAMP(8)
+        // (3) x += W d  (columns this tile does not need keep d = 0: their W entries lie outside the region or are padding)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (pidx[q] < 0) continue;
           const int u = threadIdx.x + q * kFusedThreads;
-          double acc = pval[q] * __ldcg(db + pcol[q]);
-          for (int e = 1; e < EW; ++e) acc += R.w_val[dir][(size_t)u * EW + e] * __ldcg(db + R.w_col[dir][(size_t)u * EW + e]);
+          double acc = pval[q] * darr[pcol[q]];
+          for (int e = 1; e < EW; ++e) acc += R.w_val[dir][(size_t)u * EW + e] * darr[R.w_col[dir][(size_t)u * EW + e]];
           xs[pidx[q]] += acc;
         }
         for (int u = threadIdx.x + 4 * kFusedThreads; u < nu; u += kFusedThreads) {
           const int i = R.w_i[dir][u], j = R.w_j[dir][u];
           if (!(i >= i_r0 && i < i_r0 + 128 && j >= j_r0 && j < j_r0 + RY)) continue;
           double acc = 0.0;
-          for (int e = 0; e < EW; ++e) acc += R.w_val[dir][(size_t)u * EW + e] * __ldcg(db + R.w_col[dir][(size_t)u * EW + e]);
+          for (int e = 0; e < EW; ++e) acc += R.w_val[dir][(size_t)u * EW + e] * darr[R.w_col[dir][(size_t)u * EW + e]];
           const int di = i - i_r0;
           xs[(j - j_r0) * 128 + (di & 3) * 32 + (di >> 2)] += acc;
         }
         __syncthreads();
+        for (int n = threadIdx.x; n < n_need; n += kFusedThreads) darr[nlist[n]] = 0.0;  // (ordered before the next use by the pass barriers)
       }
-      ++fixq;
     }
-    TSTAMP(2 + (s < 4 ? s : 3))
+  }
+
+  if (LOWRANK && RESTRICT) {
+    // owners: u_k = (Sigma^{-1} B^T x)_k of the final iterate, for the low-rank part of the residual
+    MGMC_LR_PTRS
+    const LowRankTile &R = P.lr;
+    const size_t slot = (size_t)(P.lr_slot + P.nfix) * P.nchains + blockIdx.z;
+    LrPkt *vb = R.vbuf + slot * 2 * lrm;
+    for (int o = warp; o < lr_cnt[0]; o += kFusedWarps) {
+      const int k = own_list[o];
+      double acc = 0.0;
+      for (int e = lane; e < R.EB; e += 32) {
+        const int bi = R.b_i[k * R.EB + e] - i_r0, bj = R.b_j[k * R.EB + e] - j_r0;
+        acc += R.b_val[k * R.EB + e] * xs[bj * 128 + (bi & 3) * 32 + (bi >> 2)];
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+      if (lane == 0) {
+        const double v0 = acc * R.sigma_inv[k];
+        tarr[k] = v0;  // (kept for this tile's own residual)
+        pkt_store(vb + k, v0, lr_epoch);
+        if (lr_to_dn) pkt_store(reinterpret_cast<LrPkt *>(reinterpret_cast<char *>(vb + k) + P.sk.lr_peer_dn), v0, lr_epoch);
+        if (lr_to_up) pkt_store(reinterpret_cast<LrPkt *>(reinterpret_cast<char *>(vb + k) + P.sk.lr_peer_up), v0, lr_epoch);
+      }
+    }
   }
 
   // ---- write the tile to the output buffer (skipped by a pure residual + restrict launch):
@@ -757,27 +631,27 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
     }
     __syncthreads();
-    if (LOWRANK) {
+    if (LOWRANK && lr_cnt[3] > 0) {
       // low-rank part of the residual: r -= B u, u = Sigma^{-1} B^T x of the final state (linear_operator.hh:71-75)
-      const LowRankTile &R = *P.lr;
-      if (lr_hits & 4) {  // (bounding boxes: a superset of the sites tested below)
-        const size_t slot = (size_t)(P.lr_slot + P.nfix) * P.nchains + blockIdx.z;
-        if (threadIdx.x == 0) {
-          while (ld_acquire(R.flags + slot) == 0) {
-          }
-        }
-        __syncthreads();
-        const double *ub = R.dbuf + slot * R.m;
-        for (int u = threadIdx.x; u < R.nbu; u += kFusedThreads) {
-          const int i = R.bu_i[u], j = R.bu_j[u];
-          if (!(i >= max(1, i_t0 - 1) && i <= min(nx - 1, i_t0 + TX - 1) && j >= j_t0 && j <= j_t0 + TY && j < ny)) continue;
-          double acc = 0.0;
-          for (int e = R.bu_ptr[u]; e < R.bu_ptr[u + 1]; ++e) acc += R.bu_val[e] * __ldcg(ub + R.bu_col[e]);
-          const int di = i - i_r0;
-          fs[(j - j_r0) * 128 + (di & 3) * 32 + (di >> 2)] -= acc;
-        }
-        __syncthreads();
+      MGMC_LR_PTRS
+      const LowRankTile &R = P.lr;
+      const size_t slot = (size_t)(P.lr_slot + P.nfix) * P.nchains + blockIdx.z;
+      const LrPkt *vb = R.vbuf + slot * 2 * lrm;
+      const int *nlist = need_list + 2 * lrm;
+      for (int n = threadIdx.x; n < lr_cnt[3]; n += kFusedThreads) {
+        const int k = nlist[n];
+        darr[k] = is_own[k] ? tarr[k] : pkt_wait(vb + k, lr_epoch);
       }
+      __syncthreads();
+      for (int u = threadIdx.x; u < R.nbu; u += kFusedThreads) {
+        const int i = R.bu_i[u], j = R.bu_j[u];
+        if (!(i >= max(1, i_t0 - 1) && i <= min(nx - 1, i_t0 + TX - 1) && j >= j_t0 && j <= j_t0 + TY && j < ny)) continue;
+        double acc = 0.0;
+        for (int e = R.bu_ptr[u]; e < R.bu_ptr[u + 1]; ++e) acc += R.bu_val[e] * darr[R.bu_col[e]];
+        const int di = i - i_r0;
+        fs[(j - j_r0) * 128 + (di & 3) * 32 + (di >> 2)] -= acc;
+      }
+      __syncthreads();
     }
     const long long ccb = (long long)blockIdx.z * P.gc.stride;
     const int I = gi0 >> 1;  // coarse columns I (fine 4p) and I + 1 (fine 4p + 2) of this lane
@@ -816,7 +690,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       __threadfence_system();
       __syncthreads();
       if (threadIdx.x == 0) {
-        const unsigned int n_edge = (unsigned int)(P.sk.edge_rows * P.tiles_x + (LOWRANK ? P.npatch : 0));
+        const unsigned int n_edge = (unsigned int)(P.sk.edge_rows * P.tiles_x);
         if (edge_dn) strip_arrive(P.sk.ticket_dn, n_edge, P.sk.peer_flag_dn);
         if (edge_up) strip_arrive(P.sk.ticket_up, n_edge, P.sk.peer_flag_up);
       }

@@ -559,6 +559,8 @@ __global__ void __launch_bounds__(256) end_of_cycle_kernel(int nnz, const long l
   }
 }
 
+__global__ void bump_kernel(int *counter) { *counter = *counter + 1; }
+
 // running mean / second moment fields (posterior_statistics, driver_mgmc.cc:146-151)
 __global__ void __launch_bounds__(256) moments_kernel(GridP g, const double *__restrict__ x, double *__restrict__ mean, double *__restrict__ second,
                                                      double inv_count) {

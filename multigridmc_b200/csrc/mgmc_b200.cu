@@ -47,7 +47,7 @@ struct LowRankDev {
   LowRankFix fix[2];  // [0] forward, [1] backward
   size_t smem = 0;
   // in-kernel fix-up (patch CTAs of the fused kernel)
-  LowRankTile *d_tile = nullptr;  // device copy of the descriptor
+  LowRankTile tile;               // descriptor of the in-kernel fix-up (passed to the kernel by value)
   int bw = 0, bh = 0;             // largest extent of supp(B_k)
   int wreach = 0;                 // largest distance of a site of supp(W_k) from the bounding box of supp(B_k)
   bool diag[2] = {false, false};  // capacitance matrix diagonal (measurements do not interact on this level)
@@ -104,8 +104,8 @@ struct mgmc_ctx {
   double *d_sigma_inv = nullptr, *d_sigma_inv_sqrt = nullptr, *d_sigma_inv_neg = nullptr;
   // in-kernel low-rank fix-up: slots of one cycle / API call (d vectors, exchange buffers, flags)
   static constexpr int kLrSlots = 1024;
-  double *d_lr_dbuf = nullptr, *d_lr_tbuf = nullptr;
-  int *d_lr_flags = nullptr;  // flags [kLrSlots * nchains] followed by counters [kLrSlots * nchains]
+  LrPkt *d_lr_vbuf = nullptr;   // [kLrSlots][nchains][2 m] (value, epoch) packets published by the owner tiles
+  int *d_lr_epoch = nullptr;    // advanced at the start of every cycle / API call
   int lr_slot_next = 0;
   bool lr_fuse = true;        // MGMC_NO_LR_FUSE=1: separate fix-up launches (fallback path, perf experiments)
   // row-strip decomposition: arena shared with the neighbours through CUDA IPC
@@ -263,7 +263,7 @@ StripPlan make_strip_plan(const mgmc_desc &d, const std::vector<HostLevel> &H) {
     const int rows = h.ny / p.nranks;
     // rows exchanged with a neighbour: what a launch of 2 sweeps (+ residual) reads beyond the own rows; with a
     // low-rank term additionally the windows of the measurements near the strip boundary (patch CTAs)
-    const int halo = (d.m_lowrank > 0) ? ((nc == 2) ? 16 : 28) : ((nc == 2) ? 8 : 12);
+    const int halo = (d.m_lowrank > 0) ? ((nc == 2) ? 12 : 20) : ((nc == 2) ? 8 : 12);
     if (h.ny % p.nranks || rows % ty || rows < std::max(min_rows, 2 * halo)) break;
     if (l > 0 && (long long)h.nx * h.ny < min_sites) break;
     // every rank runs the measurement windows near its strip on its own: only while the measurements do not interact
@@ -457,29 +457,6 @@ const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega) {
         if (wbox[4 * k + 1] >= wbox[4 * k])
           dev.wreach = std::max(dev.wreach, std::max(std::max(bbox[4 * k] - wbox[4 * k], wbox[4 * k + 1] - bbox[4 * k + 1]),
                                                      std::max(bbox[4 * k + 2] - wbox[4 * k + 2], wbox[4 * k + 3] - bbox[4 * k + 3])));
-      std::vector<int> wl_ptr(1, 0), wl_u;
-      for (int k = 0; k < m; ++k) {
-        for (int u = 0; u < F.nu; ++u)
-          if (wi[u] >= bbox[4 * k] - 8 && wi[u] <= bbox[4 * k + 1] + 8 && wj[u] >= bbox[4 * k + 2] - 8 && wj[u] <= bbox[4 * k + 3] + 8) wl_u.push_back(u);
-        wl_ptr.push_back((int)wl_u.size());
-      }
-      T.wl_ptr[dir] = c->dupload(wl_ptr);
-      {
-        std::vector<int> fi(wl_u.size()), fj(wl_u.size()), fcol(wl_u.size() * F.EW);
-        std::vector<double> fval(wl_u.size() * F.EW);
-        for (size_t q = 0; q < wl_u.size(); ++q) {
-          fi[q] = wi[wl_u[q]];
-          fj[q] = wj[wl_u[q]];
-          for (int e = 0; e < F.EW; ++e) {
-            fcol[q * F.EW + e] = wcolh[(size_t)wl_u[q] * F.EW + e];
-            fval[q * F.EW + e] = wvalh[(size_t)wl_u[q] * F.EW + e];
-          }
-        }
-        T.wl_i[dir] = c->dupload(fi);
-        T.wl_j[dir] = c->dupload(fj);
-        T.wl_col[dir] = c->dupload(fcol);
-        T.wl_val[dir] = c->dupload(fval);
-      }
       bool diag = true;
       for (int r = 0; r < m && diag; ++r)
         for (int q = 0; q < m; ++q)
@@ -487,28 +464,15 @@ const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega) {
             diag = false;
             break;
           }
-      // a diagonal capacitance matrix also needs every W site near window k to belong to column k alone
-      for (int k = 0; k < m && diag; ++k)
-        for (int q = wl_ptr[k]; q < wl_ptr[k + 1] && diag; ++q)
-          for (int e = 0; e < F.EW; ++e)
-            if (wvalh[(size_t)wl_u[q] * F.EW + e] != 0.0 && wcolh[(size_t)wl_u[q] * F.EW + e] != k) diag = false;
       T.diag[dir] = diag ? 1 : 0;
       dev.diag[dir] = diag;
     }
     T.sigma_inv = c->d_sigma_inv;
     T.sigma_inv_sqrt = c->d_sigma_inv_sqrt;
-    if (!c->d_lr_dbuf) {
-      const size_t n = (size_t)mgmc_ctx::kLrSlots * c->d.nchains;
-      c->d_lr_dbuf = c->dalloc<double>(n * m);
-      c->d_lr_tbuf = c->dalloc<double>(n * 2 * m);
-      c->d_lr_flags = c->dalloc<int>(2 * n);
-    }
-    T.dbuf = c->d_lr_dbuf;
-    T.tbuf = c->d_lr_tbuf;
-    T.flags = c->d_lr_flags;
-    T.counters = c->d_lr_flags + (size_t)mgmc_ctx::kLrSlots * c->d.nchains;
-    std::vector<LowRankTile> tv(1, T);
-    dev.d_tile = c->dupload(tv);
+    if (!c->d_lr_vbuf) fail(MGMC_ERR_INVALID, "internal: low-rank buffers missing");
+    T.vbuf = c->d_lr_vbuf;
+    T.epoch = c->d_lr_epoch;
+    dev.tile = T;
   }
   return L.lowrank.emplace(omega, dev).first->second;
 }
@@ -597,7 +561,7 @@ inline int fused_tile_rows(int ny, int nc, bool strips) {
   if (ny > 256) return nc == 2 ? 16 : t[2];
   return t[3];
 }
-constexpr int kFusedSmemMax = 110 * 1024;
+constexpr int kFusedSmemMax = 112 * 1024;  // 2 CTAs per SM: 2 x (112 + 1 KB reserved) <= 227 KB
 
 template <int NC, bool G, bool PR, bool RS, bool LR>
 void launch_fused_t(mgmc_ctx *c, const FusedP &P, dim3 grid, size_t smem) {
@@ -615,31 +579,22 @@ struct FixSpec {
   uint32_t c1;  // Philox word of the sweep (low-rank noise)
 };
 
-// zero the flags / counters of the in-kernel low-rank fix-up: start of every cycle and API call
+// start of every cycle and API call: a new epoch invalidates everything the owner tiles published before
 void lr_begin_epoch(mgmc_ctx *c) {
   c->lr_slot_next = 0;
-  if (c->d_lr_flags) CUDA_CHECK(cudaMemsetAsync(c->d_lr_flags, 0, sizeof(int) * 2 * (size_t)mgmc_ctx::kLrSlots * c->d.nchains, c->stream));
+  if (c->d_lr_epoch) c->launch("lr_epoch", 0, [&] { bump_kernel<<<1, 1, 0, c->stream>>>(c->d_lr_epoch); });
 }
 
-// Geometry of the patch CTAs for a launch with S stages on `level`: wpw = windows per patch CTA;
-// false if not even one window fits
-bool lr_patch_geometry(mgmc_ctx *c, const LowRankDev &lr, int S, int &npatch, int &wpw, int &wcap, size_t &smem) {
+// shared memory the low-rank bookkeeping of a tile needs behind the tile itself
+inline size_t lr_tile_smem(int m) { return (size_t)9 * m * sizeof(double) + (size_t)6 * m * sizeof(int); }
+
+// Can the fix-ups of this level run inside the fused launch?  Always when the measurements do not interact;
+// otherwise every tile that needs a fix-up waits for ALL owner tiles, so the whole grid must be resident at once.
+bool lr_fusable(mgmc_ctx *c, const LowRankDev &lr, int ntiles) {
   const int m = c->d.m_lowrank;
-  if (!c->lr_fuse || m > 256) return false;
-  wcap = (lr.bw + 2 * S) * (lr.bh + 2 * S);
-  static const char *np_env = std::getenv("MGMC_NPATCH");  // perf experiments
-  const int np0 = np_env ? std::atoi(np_env) : 32;
-  // few windows per patch CTA: the patch CTAs are a serial prefix of the launch, so they are spread wide
-  for (npatch = std::min(m, np0); npatch <= std::min(m, 64); npatch *= 2) {
-    wpw = (m + npatch - 1) / npatch;
-    if (wpw > kFusedWarps) continue;  // one warp per window
-    smem = ((size_t)3 * m + (size_t)wpw * 4 * wcap + 2 * (size_t)wpw + 1) * sizeof(double) + ((size_t)wpw * wcap + 4 * (size_t)wpw) * sizeof(int);
-    if (smem <= (size_t)kFusedSmemMax) {
-      npatch = (m + wpw - 1) / wpw;
-      return true;
-    }
-  }
-  return false;
+  if (!c->lr_fuse || m > 256 || lr.bw > 16 || lr.bh > 16) return false;
+  if (lr.diag[0] && lr.diag[1]) return true;
+  return (long long)ntiles * c->d.nchains <= 148;
 }
 
 const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega);
@@ -713,14 +668,27 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   P.noise_scale = std::sqrt(L.coef.c * (2. - omega) / omega);  // sor_sampler.cc:24-27
   P.nz = noise_params(c, level, 0);
   auto up4 = [](int v) { return (v + 3) / 4 * 4; };
+  if (use_lr) {
+    // the owner tile of a measurement must hold all of supp(B_k) exactly at every fix-up: it reaches this far
+    // beyond its lower left corner
+    const LowRankDev &lr = get_lowrank(c, level, omega);
+    P.lr_mx = lr.bw - 1;
+    P.lr_my = lr.bh - 1;
+  }
   P.HXL = up4(S + (restrict_ ? 2 : 0));
-  const int HXR = up4(S + (restrict_ ? 1 : 0));
+  const int HXR = up4(S + (restrict_ ? 1 : 0) + P.lr_mx);
   P.TX = 128 - P.HXL - HXR;
   P.TY = fused_tile_rows(L.g.ny, nc, c->strip.on());
   P.hl = S + (restrict_ ? 1 : 0);
-  const int hh = S + (restrict_ ? 2 : 0);
+  const int hh = S + (restrict_ ? 2 : 0) + P.lr_my;
   P.RY = P.TY + P.hl + hh;
-  size_t smem = (size_t)2 * P.RY * 128 * sizeof(double);
+  size_t smem = (size_t)2 * P.RY * 128 * sizeof(double) + (use_lr ? lr_tile_smem(c->d.m_lowrank) : 0);
+  while (smem > (size_t)kFusedSmemMax && P.TY > 8) {  // (many measurements: a lower tile makes room for their bookkeeping)
+    P.TY -= 8;
+    P.RY = P.TY + P.hl + hh;
+    smem = (size_t)2 * P.RY * 128 * sizeof(double) + (use_lr ? lr_tile_smem(c->d.m_lowrank) : 0);
+  }
+  if (c->strip.on() && P.TY != fused_tile_rows(L.g.ny, nc, true)) fail(MGMC_ERR_UNSUPPORTED, "row strips: too many measurements for the tile geometry");
   if (smem > (size_t)kFusedSmemMax) fail(MGMC_ERR_INVALID, "internal: fused tile does not fit in shared memory");
   P.tiles_x = (L.g.nx + P.TX - 1) / P.TX;
   int tiles_y = (L.g.ny - 1 + P.TY - 1) / P.TY;
@@ -729,15 +697,16 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     // only this rank's tile rows; the halo rows come from the neighbours
     P.by0 = (c->strip.lo[level] - 1) / P.TY;
     tiles_y = (c->strip.hi[level] - c->strip.lo[level] + 1 + P.TY - 1) / P.TY;
-    int need = std::max(P.hl, hh) + 1;
+    const int need = std::max(P.hl, hh) + 1;
+    int lr_reach = 0;
     if (use_lr) {
-      // every rank runs the patch windows redundantly: those of the measurements whose fix-up reaches its
-      // tiles must lie inside own rows + halo, and must not depend on measurements elsewhere
+      // owner tiles near the strip boundary publish into the neighbours' buffers as well: every measurement whose
+      // fix-up reaches a neighbour's tile regions must be owned by one of the edge tile rows
       const LowRankDev &lr = get_lowrank(c, level, omega);
       if (!(lr.diag[0] && lr.diag[1])) fail(MGMC_ERR_UNSUPPORTED, "row strips: measurements interact on a distributed level (raise MGMC_STRIP_MIN_ROWS to replicate it)");
-      need += S + lr.wreach + std::max(lr.bw, lr.bh);
+      lr_reach = need + lr.wreach + lr.bh + 1;
     } else if (c->d.m_lowrank > 0 && (S > 0 || restrict_)) {
-      fail(MGMC_ERR_UNSUPPORTED, "row strips need the in-kernel low-rank fix-up (measurement windows too large)");
+      fail(MGMC_ERR_UNSUPPORTED, "row strips need the in-kernel low-rank fix-up");
     }
     if (need > c->strip.halo[level]) fail(MGMC_ERR_INVALID, "internal: strip halo too small");
     const StripPlan &sp = c->strip;
@@ -748,7 +717,11 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     K.own_hi = sp.hi[level];
     K.tiles_y = tiles_y;
     K.halo = sp.halo[level];
-    int E = K.halo;
+    int E = std::max(K.halo, lr_reach);
+    if (use_lr) {
+      if (has_dn) K.lr_peer_dn = (long long)(c->peer_arena[sp.rank - 1] - c->arena);
+      if (has_up) K.lr_peer_up = (long long)(c->peer_arena[sp.rank + 1] - c->arena);
+    }
     // the output buffer of this launch is L.x_alt if the launch writes x (it is swapped in below)
     double *xout = (S > 0 || prolong) ? L.x_alt : L.x;
     if (has_dn) K.peer_x_dn = peer_ptr(c, sp.rank - 1, xout);
@@ -788,10 +761,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   P.nchains = c->d.nchains;
   if (use_lr) {
     const LowRankDev &lr = get_lowrank(c, level, omega);
-    size_t psmem = 0;
-    if (!lr_patch_geometry(c, lr, S, P.npatch, P.wpw, P.wcap, psmem)) fail(MGMC_ERR_INVALID, "internal: low-rank windows do not fit");
-    smem = std::max(smem, psmem);
-    P.lr = lr.d_tile;
+    P.lr = lr.tile;
     P.nfix = (int)fixes.size();
     if (P.nfix > 2) fail(MGMC_ERR_INVALID, "internal: more than 2 fix-ups in one fused launch");
     for (int q = 0; q < P.nfix; ++q) {
@@ -803,7 +773,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     c->lr_slot_next += P.nfix + 1;
     if (c->lr_slot_next > mgmc_ctx::kLrSlots) fail(MGMC_ERR_UNSUPPORTED, "too many low-rank fix-ups in one cycle (W-cycle too deep)");
   }
-  dim3 grid(P.npatch + P.tiles_x * tiles_y, 1, c->d.nchains);
+  dim3 grid(P.tiles_x * tiles_y, 1, c->d.nchains);
   // algorithmic bytes of this launch: 24 B per site and sweep, 18 B prolongate_add,
   // 18 + 2 B residual + restrict + coarse zeroing -- fixed by the model, not by what the kernel moves
   const bool strip_own = c->strip.on() && c->strip_connected && level < c->strip.ndist;
@@ -904,9 +874,9 @@ void emit_smoothing(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps
   const int max_stages = (nc == 2) ? 4 : 8;  // keeps the tile + halo of x and f below ~100 KB (2 CTAs / SM)
   bool fusedlr = false;
   if (lowrank) {
-    int np, wp, wc;
-    size_t sm;
-    fusedlr = lr_patch_geometry(c, get_lowrank(c, level, omega), max_stages, np, wp, wc, sm);
+    // (tile count of the widest launch geometry: an upper bound is all that matters here)
+    const int ntiles = ((L.g.nx + 87) / 88) * ((L.g.ny + 7) / 8);
+    fusedlr = lr_fusable(c, get_lowrank(c, level, omega), ntiles);
   }
   std::vector<Stage> cur;
   std::vector<FixSpec> fixes;
@@ -1256,6 +1226,8 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
         const size_t pitch = ((GX + H[l].nx + 1 + 2 + 15) / 16) * 16;
         bytes += 3 * (((size_t)H[l].ny + 1 + 2 * GY) * pitch * sizeof(double) + 256);
       }
+      // (+ what the owner tiles of the low-rank fix-ups publish: edge tiles write into the neighbours' copies)
+      bytes += (size_t)mgmc_ctx::kLrSlots * desc->nchains * desc->m_lowrank * 2 * sizeof(LrPkt) + 512;
       c->arena_bytes = bytes;
       c->arena = (char *)c->dalloc<char>(bytes);
       c->d_strip_ctl = (int *)c->arena;
@@ -1266,6 +1238,11 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
       arena_off += (total * sizeof(double) + 255) / 256 * 256;
       return p;
     };
+    if (desc->m_lowrank > 0) {
+      const size_t n = (size_t)mgmc_ctx::kLrSlots * desc->nchains * desc->m_lowrank;
+      c->d_lr_vbuf = c->strip.on() ? (LrPkt *)carve(4 * n) : c->dalloc<LrPkt>(2 * n);
+      c->d_lr_epoch = c->dalloc<int>(1);
+    }
     for (int l = 0; l < desc->nlevel; ++l) {
       DevLevel &L = c->lv[l];
       L.h = H[l];
