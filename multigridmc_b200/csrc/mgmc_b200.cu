@@ -138,6 +138,8 @@ struct mgmc_ctx {
   double *d_mean = nullptr, *d_second = nullptr;
   // graph of one MGMC cycle (+ end-of-cycle kernel)
   cudaGraphExec_t graph = nullptr;
+  cudaGraphExec_t mg_graph = nullptr;  // one LoopSolver iteration: V-cycle, x -= Pr, next residual and its norm
+  int64_t mg_graph_launches = 0;
   bool use_graph = true;
   bool perf_no_noise = false;  // MGMC_PERF_NO_NOISE=1: run the sampling cycle with the deterministic kernels (perf experiments only)
   // instrumentation
@@ -1300,6 +1302,7 @@ void mgmc_destroy(mgmc_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->graph) cudaGraphExecDestroy(c->graph);
+  if (c->mg_graph) cudaGraphExecDestroy(c->mg_graph);
   for (char *p : c->peer_arena)
     if (p) cudaIpcCloseMemHandle(p);
   for (void *p : c->allocs) cudaFree(p);
@@ -1487,8 +1490,8 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
   r0 = std::sqrt(r0);
   bool conv = false;
   int it = maxiter, nh = 0;
-  for (int k = 0; k < maxiter; ++k) {
-    // r = A x - b (into f_ell[0], the preconditioner's input) and ||r||
+  // r = A x - b (into f_ell[0], the preconditioner's input) and ||r||^2 (into d_norm)
+  auto emit_residual = [&] {
     c->launch("residual_norm", 0, [&] {
       if (L.r2) residual_norm25_kernel<<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, c->sol_x, c->sol_b, L.f, c->d_partial);
       else if (L.nine) residual_norm_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
@@ -1504,6 +1507,36 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
       });
     }
     c->launch("reduce_sum", 0, [&] { reduce_sum_kernel<<<1, 1024, 0, c->stream>>>(c->d_partial, c->npartial, c->d_norm); });
+  };
+  // one iteration = V-cycle on r, x -= Pr (loop_solver.cc:40-41), residual of the new iterate: captured once, replayed
+  auto emit_iteration = [&] {
+    mg_solve_level(c, 0);  // Pr = x_ell[0]
+    c->launch("axpy", 0, [&] { axpy_kernel<0><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, c->sol_x, L.x); });
+    emit_residual();
+  };
+  if (c->use_graph && !c->mg_graph && !c->prof_on) {
+    if (c->d.m_lowrank > 0)
+      for (int l = 0; l < c->d.nlevel; ++l) get_lowrank(c, l, c->d.omega);
+    ensure_coarse(c);
+    c->sync();
+    const int64_t count0 = c->launch_count;
+    cudaGraph_t g = nullptr;
+    CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      emit_iteration();
+    } catch (...) {
+      cudaStreamEndCapture(c->stream, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    CUDA_CHECK(cudaStreamEndCapture(c->stream, &g));
+    CUDA_CHECK(cudaGraphInstantiate(&c->mg_graph, g, 0));
+    CUDA_CHECK(cudaGraphDestroy(g));
+    c->mg_graph_launches = c->launch_count - count0;
+    c->launch_count = count0;
+  }
+  emit_residual();
+  for (int k = 0; k < maxiter; ++k) {
     double nrm2 = 0.0;
     CUDA_CHECK(cudaMemcpyAsync(&nrm2, c->d_norm, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     c->sync();
@@ -1515,8 +1548,12 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
       conv = true;
       break;
     }
-    mg_solve_level(c, 0);  // Pr = x_ell[0]
-    c->launch("axpy", 0, [&] { axpy_kernel<0><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, c->sol_x, L.x); });
+    if (c->mg_graph && !c->prof_on) {
+      CUDA_CHECK(cudaGraphLaunch(c->mg_graph, c->stream));
+      c->launch_count += c->mg_graph_launches;
+    } else {
+      emit_iteration();
+    }
   }
   download_vec(c, 0, c->sol_x, x);
   c->sync();
