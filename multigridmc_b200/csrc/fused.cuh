@@ -235,10 +235,27 @@ __device__ __forceinline__ void update_pair(const Coef9 &a, double *xrow, const 
   }
 }
 
+// one colour pass over the rows of a warp: xl / fl point at the lane's group (plane 0) in the first row
+template <bool NINE, bool GIBBS, bool W1, int Q>
+__device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, const double *fl, int nrows, int dl, uint32_t c0, uint32_t dc0, uint32_t c1,
+                                          uint32_t sample, uint32_t chain, const double *ntab, bool v0, bool v1) {
+  const double winv = P.winv, nscale = P.noise_scale;
+  for (int n = 0; n < nrows; ++n) {
+    double z0 = 0.0, z1 = 0.0;
+    if (GIBBS) normal_pair(P.nz.keys, c0, c1, sample, chain, P.nz.mc, ntab, z0, z1);
+    update_pair<NINE, GIBBS, W1, Q>(P.a, xl, fl, 0, v0, v1, winv, nscale, z0, z1);
+    xl += dl;
+    fl += dl;
+    c0 += dc0;
+  }
+}
+
 template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT, bool LOWRANK>
 __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {
   extern __shared__ double sm[];
   __shared__ int lr_cnt[4];  // LOWRANK: measurements owned by this tile, needed for the forward / backward fix-up, for the residual
+  __shared__ __align__(16) double ntab[128];  // GIBBS: tables of the normal generator (philox.cuh), published by the barrier of the tile load
+  if (GIBBS && threadIdx.x < 128) ntab[threadIdx.x] = kNormalTabDev[threadIdx.x];
   constexpr bool NINE = (NC == 4);
   const int tile_id = (int)blockIdx.x;
   int tile_row = tile_id / P.tiles_x;
@@ -388,7 +405,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
         double sv = 0.0;
         if (GIBBS) {
           double z0, z1;
-          normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[q], *P.nz.sample, P.nz.chain0 + blockIdx.z, z0, z1);
+          normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[q], *P.nz.sample, P.nz.chain0 + blockIdx.z, P.nz.mc, kNormalTabDev, z0, z1);
           sv = R.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
         }
         spre[q * lrm + k] = sv;
@@ -399,8 +416,6 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   TSTAMP(1)
 
   // ---- colour passes: one warp per row, lane = group ----
-  const double winv = P.winv;
-  const double nscale = P.noise_scale;
   const int S = P.nstages;
   constexpr int EXLX = RESTRICT ? 2 : 0, EXLY = RESTRICT ? 1 : 0;
   // (low-rank term: supp(B_k) must be exact in its owner tile at every fix-up -- it extends lr_mx / lr_my beyond the lower left corner)
@@ -425,21 +440,26 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       step = 2;
       if ((jlo & 1) != (colour >> 1)) ++jlo;
     }
-    for (int j = jlo + warp * step; j <= jhi; j += kFusedWarps * step) {
-      const int q = (NC == 2) ? ((colour ^ j) & 1) : (colour & 1);
+    // the rows of a warp advance by an even number: the column parity q of the colour, the validity of the two sites
+    // of the lane and the stride of every pointer are invariants of the pass
+    const int jw = jlo + warp * step;
+    if (jw <= jhi) {
+      const int q = (NC == 2) ? ((colour ^ jw) & 1) : (colour & 1);
       const int i0 = gi0 + q;
       const bool v0 = (i0 >= ilo) && (i0 <= ihi), v1 = (i0 + 2 >= ilo) && (i0 + 2 <= ihi);
-      if (!(v0 || v1)) continue;
-      double z0 = 0.0, z1 = 0.0;
-      if (GIBBS) normal_pair(P.nz.keys, (((uint32_t)j * P.nz.G + pg) << 1) | (uint32_t)q, c1, sample, chain, z0, z1);
-      double *xr = xs + (j - j_r0) * 128;
-      const double *fr = fs + (j - j_r0) * 128;
-      if (P.omega_is_one) {
-        if (q == 0) update_pair<NINE, GIBBS, true, 0>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
-        else update_pair<NINE, GIBBS, true, 1>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
-      } else {
-        if (q == 0) update_pair<NINE, GIBBS, false, 0>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
-        else update_pair<NINE, GIBBS, false, 1>(P.a, xr, fr, lane, v0, v1, winv, nscale, z0, z1);
+      if (v0 || v1) {
+        const int nrows = (jhi - jw) / (kFusedWarps * step) + 1;
+        double *xl = xs + (jw - j_r0) * 128 + lane;
+        const double *fl = fs + (jw - j_r0) * 128 + lane;
+        const uint32_t c0 = (((uint32_t)jw * P.nz.G + pg) << 1) | (uint32_t)q, dc0 = ((uint32_t)(kFusedWarps * step) * P.nz.G) << 1;
+        const int dl = kFusedWarps * step * 128;
+        if (P.omega_is_one) {
+          if (q == 0) pass_rows<NINE, GIBBS, true, 0>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
+          else pass_rows<NINE, GIBBS, true, 1>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
+        } else {
+          if (q == 0) pass_rows<NINE, GIBBS, false, 0>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
+          else pass_rows<NINE, GIBBS, false, 1>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
+        }
       }
     }
     __syncthreads();

@@ -19,6 +19,7 @@ struct Coef9 {
 
 struct NoiseP {
   PhiloxKeys keys;        // round keys of the 64-bit seed
+  NormalConsts mc;        // full-width constants of the normal generator (philox.cuh)
   uint32_t c1;            // (level << 24) | sweep counter
   const uint32_t *sample; // device-resident sample index (so that CUDA graphs can be replayed)
   uint32_t chain0;        // global id of chain 0
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256) sweep_colour_kernel(GridP g, Coef9 a, dou
   if (j >= g.ny || i0 >= g.nx) return;
   const long long o = (long long)blockIdx.z * g.stride + (long long)j * g.pitch + i0;
   double z0 = 0.0, z1 = 0.0;
-  if (GIBBS) normal_pair(nz.keys, (((uint32_t)j * nz.G + (uint32_t)p) << 1) | (uint32_t)q, nz.c1, *nz.sample, nz.chain0 + blockIdx.z, z0, z1);
+  if (GIBBS) normal_pair(nz.keys, (((uint32_t)j * nz.G + (uint32_t)p) << 1) | (uint32_t)q, nz.c1, *nz.sample, nz.chain0 + blockIdx.z, nz.mc, kNormalTabDev, z0, z1);
   const double winv = omega / a.c;
   double *xp = x + o;
 #pragma unroll
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256) sweep_colour25_kernel(GridP g, const doub
   double b = f[o];
   if (GIBBS) {
     double z0, z1;
-    normal_pair(nz.keys, (((uint32_t)j * nz.G + (uint32_t)(i >> 2)) << 1) | (uint32_t)(i & 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.z, z0, z1);
+    normal_pair(nz.keys, (((uint32_t)j * nz.G + (uint32_t)(i >> 2)) << 1) | (uint32_t)(i & 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.z, nz.mc, kNormalTabDev, z0, z1);
     b = fma(sqrt(diag * (2. - omega) / omega), (i & 2) ? z1 : z0, b);  // sor_sampler.cc:24-27
   }
   x[o] += omega * (b - stencil25(a, x + o, g.pitch)) / diag;
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(256) lowrank_fix_kernel(LowRankFix F, long lon
     const uint32_t sample = *nz.sample;
     for (int k = threadIdx.x; k < m; k += 256) {
       double z0, z1;
-      normal_pair(nz.keys, 0x80000000u | ((uint32_t)k >> 1), nz.c1, sample, nz.chain0 + blockIdx.x, z0, z1);
+      normal_pair(nz.keys, 0x80000000u | ((uint32_t)k >> 1), nz.c1, sample, nz.chain0 + blockIdx.x, nz.mc, kNormalTabDev, z0, z1);
       s[k] = F.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
     }
   }
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(256) trimv_kernel(const double *__restrict__ T
   double zn = 0.0;
   if (NOISE && row < N && lane == 0) {
     double z0, z1;
-    normal_pair(nz.keys, 0x40000000u | ((uint32_t)row >> 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.y, z0, z1);
+    normal_pair(nz.keys, 0x40000000u | ((uint32_t)row >> 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.y, nz.mc, kNormalTabDev, z0, z1);
     zn = (row & 1) ? z1 : z0;
   }
   __syncthreads();

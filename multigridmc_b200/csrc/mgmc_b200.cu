@@ -500,6 +500,7 @@ void download_vec(mgmc_ctx *c, int level, const double *dev, double *host) {
 NoiseP noise_params(mgmc_ctx *c, int level, uint32_t c1) {
   NoiseP nz;
   nz.keys = c->keys;
+  nz.mc = kNormalConstsHost;
   nz.c1 = c1;
   nz.sample = c->d_sample;
   nz.chain0 = (uint32_t)c->d.first_chain;

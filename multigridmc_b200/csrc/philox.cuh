@@ -15,8 +15,8 @@
 // so that a site's noise is a pure function of (seed, chain, sample, level, sweep, site): tiles may
 // recompute halo sites redundantly and any domain decomposition reproduces the same chain.
 //
-// The transcendental part is hand-written (fdlibm-style kernels, ~1 ulp) because the sweeps are
-// otherwise instruction-issue bound: CUDA's log / sincospi / sqrt carry special-case paths that a
+// The transcendental part is hand-written (table-driven kernels, ~1 ulp, see below) because the sweeps
+// are otherwise instruction-issue bound: CUDA's log / sincospi / sqrt carry special-case paths that a
 // uniform in (0,1) never takes.
 #pragma once
 #include <cmath>
@@ -31,25 +31,29 @@
 
 namespace mgmc {
 
-// Polynomial coefficients of the log / sin / cos kernels.  On the device they live in constant memory
-// so that every DFMA reads its coefficient straight from the constant bank (no UMOV pairs per use).
-#define MGMC_MATH_TABLE                                                                                                          \
-  {6.93147180369123816490e-01, 1.90821492927058770002e-10, /* ln2_hi, ln2_lo */                                                 \
-   6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01, /* Lg1..Lg4 */      \
-   1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,                           /* Lg5..Lg7 */      \
-   -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, /* S1..S3 */                           \
-   2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,  /* S4..S6 */                           \
-   4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,  /* C1..C3 */                           \
-   -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11, /* C4..C6 */                           \
-   3.14159265358979311600e+00, 1.22464679914735317723e-16, 6755399441055744.0}           /* pi_hi, pi_lo, 1.5 * 2^52 */
+// ------------------------------------------------------------------------------------------------
+// Normal variates: Box-Muller on two 52-bit uniforms u = (k + 1/2) 2^-52,
+//   z0 = sqrt(-2 ln u1) cos(2 pi u2),  z1 = sqrt(-2 ln u1) sin(2 pi u2),
+// evaluated to ~1 ulp with two 32-entry tables (512 bytes each; the tile kernel stages them in shared memory)
+// instead of the long fdlibm kernels -- the sweeps are instruction-issue bound:
+//   * -2 ln u: u = 2^e m; cell j = top 5 mantissa bits, r = m / c_j - 1 (one FMA with the tabulated 1 / c_j,
+//     |r| <= 2^-6), -2 ln u = e' (-2 ln 2) + T2[j] - 2 log1p(r) with the degree-9 Taylor polynomial (remainder
+//     < 2^-57 relative).  Cells with m > 1.43 use m / 2 and e + 1, and the last cell has c = 2 exactly, so that
+//     u -> 1 (e' = 0, T2 = 0) suffers no cancellation.
+//   * sin / cos(2 pi u): cell k = top 5 bits, tabulated (sin, cos) at the cell centre, angle addition with
+//     |y| <= pi / 32: sin y up to y^9, cos y - 1 up to y^8 (remainders < 2^-55); no quadrant logic.  The offset
+//     from the cell centre is formed exactly from the integer bits.
+//   * sqrt: MUFU.RSQ64H seed + two coupled Goldschmidt steps.
+// Host and device run the same code on the same tables (normal_tables.inc <- tools/gen_normal_tables.py).
+// ------------------------------------------------------------------------------------------------
+// [2 j], [2 j + 1]: 1 / c_j, T2[j];   [64 + 2 k], [64 + 2 k + 1]: sin, cos at the centre of angle cell k
+static const double kNormalTabHost[128] = {
+#include "normal_tables.inc"
+};
 #if defined(__CUDACC__)
-static __constant__ double kMathDev[24] = MGMC_MATH_TABLE;
-#endif
-static const double kMathHost[24] = MGMC_MATH_TABLE;
-#if defined(__CUDA_ARCH__)
-#define MC(i) kMathDev[i]
-#else
-#define MC(i) kMathHost[i]
+static __device__ const double kNormalTabDev[128] = {
+#include "normal_tables.inc"
+};
 #endif
 
 MGMC_HD double bits_to_double(uint64_t b) {
@@ -77,79 +81,86 @@ MGMC_HD double fma_(double a, double b, double c) {
   return std::fma(a, b, c);
 #endif
 }
-// 1/d for d in [1.4, 3.5]: float seed + 2 Newton steps (full double precision)
-MGMC_HD double rcp_(double d) {
-#if defined(__CUDA_ARCH__)
-  float rf;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)d));  // MUFU.RCP, 1 ulp: 2 Newton steps reach fp64
-  double r = (double)rf;
-#else
-  double r = (double)(1.0f / (float)d);
-#endif
-  r = fma_(r, fma_(-d, r, 1.0), r);
-  r = fma_(r, fma_(-d, r, 1.0), r);
-  return r;
-}
-// sqrt(t) for t in (0, 80]: float rsqrt seed + 2 Newton steps on 1/sqrt + 1 correction on sqrt
+// sqrt(t) for t in [2^-52, 80]: 22-bit reciprocal square root seed, two coupled Goldschmidt steps
+// (g -> sqrt t, h -> 1 / (2 sqrt t); the error is squared per step: 2^-22 -> 2^-43 -> rounding)
 MGMC_HD double sqrt_(double t) {
 #if defined(__CUDA_ARCH__)
-  float yf;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)t));  // MUFU.RSQ
-  double y = (double)yf;
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));  // MUFU.RSQ64H
 #else
-  double y = (double)(1.0f / std::sqrt((float)t));
+  const double y = (double)(1.0f / std::sqrt((float)t));
 #endif
-  const double h = 0.5 * t;
-  y = y * fma_(-h * y, y, 1.5);
-  y = y * fma_(-h * y, y, 1.5);
-  double r = t * y;
-  r = fma_(0.5 * y, fma_(-r, r, t), r);
-  return r;
+  double g = t * y, h = 0.5 * y;
+  double rho = fma_(-g, h, 0.5);
+  g = fma_(g, rho, g);
+  h = fma_(h, rho, h);
+  rho = fma_(-g, h, 0.5);
+  return fma_(g, rho, g);
 }
 
-// -2 ln(u) for a double u in (0, 1)  (fdlibm __ieee754_log kernel, error < 1 ulp)
-MGMC_HD double neg2log_(double u) {
-  const double ln2_hi = MC(0), ln2_lo = MC(1);
-  const double Lg1 = MC(2), Lg2 = MC(3), Lg3 = MC(4), Lg4 = MC(5), Lg5 = MC(6), Lg6 = MC(7), Lg7 = MC(8);
-  uint64_t b = double_to_bits(u);
-  int hx = (int)(b >> 32);
-  int k = (hx >> 20) - 1023;
-  hx &= 0x000fffff;
-  const int i = (hx + 0x95f64) & 0x100000;  // 1 if mantissa > sqrt(2)
-  b = (b & 0x000fffffffffffffull) | ((uint64_t)(0x3ff00000 ^ i) << 32);
-  k += (i >> 20);
-  const double f = bits_to_double(b) - 1.0;
-  const double s = f * rcp_(2.0 + f);
-  const double dk = (double)k;
-  const double z = s * s;
-  const double w = z * z;
-  const double t1 = w * fma_(w, fma_(w, Lg6, Lg4), Lg2);
-  const double t2 = z * fma_(w, fma_(w, fma_(w, Lg7, Lg5), Lg3), Lg1);
-  const double R = t2 + t1;
-  const double hfsq = 0.5 * f * f;
-  const double lg = fma_(dk, ln2_hi, -((hfsq - fma_(s, hfsq + R, dk * ln2_lo)) - f));
-  return -2.0 * lg;
+// The constants that need all 64 bits travel in the kernel parameters (one LDCU.64 per use; as literals
+// they would cost two UMOVs each).  Every other coefficient below has zero low 32 bits (high-order
+// coefficients are rounded to that form, which moves the result by < 2^-60) and is an immediate operand.
+struct NormalConsts {
+  double v[11];
+};
+enum { NC_U0 = 0, NC_L3, NC_L5, NC_L6, NC_KLO, NC_ASCALE, NC_S3, NC_S5, NC_S7, NC_C4, NC_C6 };
+#define MGMC_NORMAL_CONSTS                                                                                         \
+  {{1.0 - 1.1102230246251565e-16, /* 1 - 2^-53 */                                                                  \
+    -0.6666666666666666, -0.4, 0.3333333333333333, /* -2/3, -2/5, 1/3 */                                           \
+    3.809308599915536e-09,                         /* -2 ln 2 - K_hi */                                            \
+    6.975736996017264e-16,                         /* 2 pi / 2^53 */                                               \
+    -0.16666666666666666, 0.008333333333333333, -0.0001984126984126984, /* -1/3!, 1/5!, -1/7! */                   \
+    0.041666666666666664, -0.001388888888888889}}  /* 1/4!, -1/6! */
+static const NormalConsts kNormalConstsHost = MGMC_NORMAL_CONSTS;
+
+// -2 ln(u) for u = (k + 1/2) 2^-52, k = top 52 bits of a
+MGMC_HD double neg2log_u52(uint64_t a, const NormalConsts &mc, const double *tab) {
+  // (1 + k 2^-52) - (1 - 2^-53): exact, normalised by the adder
+  const double u = bits_to_double(0x3FF0000000000000ull | (a >> 12)) - mc.v[NC_U0];
+  const uint64_t ub = double_to_bits(u);
+  const uint32_t hx = (uint32_t)(ub >> 32);
+  const uint32_t j = (hx >> 15) & 31u;
+  const int e = (int)(hx >> 20) - 1023 + (int)((j + 18u) >> 5);  // cells j >= 14 use m / 2
+  const double m = bits_to_double((ub & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+  const double r = fma_(m, tab[2 * j], -1.0);
+  const double de = (double)e;
+  // -2 log1p(r) = r (-2 + r - 2/3 r^2 + 1/2 r^3 - 2/5 r^4 + 1/3 r^5 - 2/7 r^6 + 1/4 r^7 - 2/9 r^8)
+#if defined(__CUDA_ARCH__)
+  double p = __dadd_rn(__dmul_rn(r, -0x1.c71c7p-3), 0.25);  // (one immediate per instruction: DMUL + DADD instead of MOV, MOV, DFMA)
+#else
+  double p = r * -0x1.c71c7p-3 + 0.25;
+#endif
+  p = fma_(p, r, -0x1.24925p-2);
+  p = fma_(p, r, mc.v[NC_L6]);
+  p = fma_(p, r, mc.v[NC_L5]);
+  p = fma_(p, r, 0.5);
+  p = fma_(p, r, mc.v[NC_L3]);
+  p = fma_(p, r, 1.0);
+  p = fma_(p, r, -2.0);
+  // -2 ln 2 = K_hi + K_lo, K_hi with 20 significant bits: de * K_hi is exact
+  const double w = fma_(r, p, de * mc.v[NC_KLO]);
+  return fma_(de, -0x1.62e43p+0, tab[2 * j + 1]) + w;
 }
 
-// (sin, cos)(pi x) for x in (0, 2): octant reduction + fdlibm __kernel_sin / __kernel_cos
-MGMC_HD void sincospi_(double x, double &sn, double &cs) {
-  const double S1 = MC(9), S2 = MC(10), S3 = MC(11), S4 = MC(12), S5 = MC(13), S6 = MC(14);
-  const double C1 = MC(15), C2 = MC(16), C3 = MC(17), C4 = MC(18), C5 = MC(19), C6 = MC(20);
-  // n = nearest integer to 2x (0..4), r = x - n/2 in [-1/4, 1/4] exactly
-  const double two52 = MC(23);  // 1.5 * 2^52: adding it rounds to nearest integer
-  const double tn = fma_(2.0, x, two52);
-  const int n = (int)(uint32_t)double_to_bits(tn);
-  const double r = fma_(-0.5, tn - two52, x);
-  const double y = fma_(r, MC(21), r * MC(22));
+// (sin, cos)(2 pi u) for u = (k + 1/2) 2^-52, k = top 52 bits of b
+MGMC_HD void sincos2pi_u52(uint64_t b, const NormalConsts &mc, const double *tab, double &sn, double &cs) {
+  const uint32_t k = (uint32_t)(b >> 59);
+  // 2 F + 1 for the 47 bits F below the cell index, minus 2^47: twice the offset from the cell centre, exact
+  const double d = bits_to_double(0x4330000000000000ull | ((b >> 11) & 0x0000FFFFFFFFFFFFull) | 1ull) - 4644337115725824.0;
+  const double y = d * mc.v[NC_ASCALE];
   const double z = y * y;
-  const double ps = fma_(z, fma_(z, fma_(z, fma_(z, fma_(z, S6, S5), S4), S3), S2), S1);
-  const double s0 = fma_(y * z, ps, y);
-  const double pc = fma_(z, fma_(z, fma_(z, fma_(z, fma_(z, C6, C5), C4), C3), C2), C1);
-  const double c0 = fma_(z * z, pc, fma_(-0.5, z, 1.0));
-  const double a = (n & 1) ? c0 : s0;  // |sin|-branch
-  const double b = (n & 1) ? s0 : c0;  // |cos|-branch
-  sn = (n & 2) ? -a : a;
-  cs = ((n + 1) & 2) ? -b : b;
+  double ps = fma_(z, 0x1.71de4p-19, mc.v[NC_S7]);
+  ps = fma_(ps, z, mc.v[NC_S5]);
+  ps = fma_(ps, z, mc.v[NC_S3]);
+  const double sy = fma_(y * z, ps, y);  // sin y
+  double pc = fma_(z, 0x1.a01ap-16, mc.v[NC_C6]);
+  pc = fma_(pc, z, mc.v[NC_C4]);
+  pc = fma_(pc, z, -0.5);
+  const double cm = z * pc;  // cos y - 1
+  const double S = tab[64 + 2 * k], C = tab[64 + 2 * k + 1];
+  sn = fma_(C, sy, fma_(S, cm, S));
+  cs = fma_(-S, sy, fma_(C, cm, C));
 }
 
 // Round keys of Philox4x32-10 for a 64-bit seed: computed once on the host and passed by value in the
@@ -183,23 +194,20 @@ MGMC_HD void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c
   }
 }
 
-// uniform in (0,1) with 52 random bits: (k + 1/2) 2^-52, k = top 52 bits
-MGMC_HD double uniform52(uint64_t a) { return bits_to_double(0x3FF0000000000000ull | (a >> 12)) - (1.0 - 1.1102230246251565e-16); }
-
 // Box-Muller on two 64-bit words
-MGMC_HD void box_muller(uint64_t a, uint64_t b, double &z0, double &z1) {
-  const double u1 = uniform52(a), u2 = uniform52(b);
-  const double r = sqrt_(neg2log_(u1));
+MGMC_HD void box_muller(uint64_t a, uint64_t b, const NormalConsts &mc, const double *tab, double &z0, double &z1) {
+  const double r = sqrt_(neg2log_u52(a, mc, tab));
   double s, c;
-  sincospi_(2.0 * u2, s, c);
+  sincos2pi_u52(b, mc, tab, s, c);
   z0 = r * c;
   z1 = r * s;
 }
 
-// two independent N(0,1) variates from one counter
-MGMC_HD void normal_pair(const PhiloxKeys &K, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, double &z0, double &z1) {
+// two independent N(0,1) variates from one counter; tab = the 128-entry table above (shared, global or host memory)
+MGMC_HD void normal_pair(const PhiloxKeys &K, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const NormalConsts &mc, const double *tab, double &z0,
+                         double &z1) {
   philox4x32_10(c0, c1, c2, c3, K);
-  box_muller((uint64_t)c0 | ((uint64_t)c1 << 32), (uint64_t)c2 | ((uint64_t)c3 << 32), z0, z1);
+  box_muller((uint64_t)c0 | ((uint64_t)c1 << 32), (uint64_t)c2 | ((uint64_t)c3 << 32), mc, tab, z0, z1);
 }
 
 }  // namespace mgmc
