@@ -34,9 +34,18 @@ constexpr int kFusedWarps = kFusedThreads / 32;
 
 struct LrPkt;
 
+// One colour pass of a fused launch.  The host plans the passes backwards from what the launch must deliver
+// (plan_stages, mgmc_b200.cu): a pass only updates the rectangle tile + (xl, xh, yl, yh) whose values a later
+// pass, the residual or the output can still see.  With omega = 1 a site update does not read the site's own
+// value, so a pass whose colour is updated again before any other colour moves (the last colour of a forward
+// sweep followed by a backward sweep) is dead: it is skipped, or -- if a low-rank fix-up reads x in between --
+// restricted to supp(B_k) of the measurements the tile owns.  The results are bit-identical to running it.
+enum { STAGE_FULL = 0, STAGE_SKIP = 1, STAGE_SPARSE = 2 };
 struct Stage {
   int colour;
   uint32_t c1;  // (level << 24) | sweep counter of the sweep this colour pass belongs to
+  short xl, xh, yl, yh;
+  int mode;
 };
 
 // Device-resident data of the low-rank (measurement) term of one level for the in-kernel Woodbury
@@ -417,9 +426,6 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
 
   // ---- colour passes: one warp per row, lane = group ----
   const int S = P.nstages;
-  constexpr int EXLX = RESTRICT ? 2 : 0, EXLY = RESTRICT ? 1 : 0;
-  // (low-rank term: supp(B_k) must be exact in its owner tile at every fix-up -- it extends lr_mx / lr_my beyond the lower left corner)
-  const int EXHX = (RESTRICT ? 1 : 0) + (LOWRANK ? P.lr_mx : 0), EXHY = (RESTRICT ? 2 : 0) + (LOWRANK ? P.lr_my : 0);
   const uint32_t pg = (uint32_t)((i_r0 >> 2) + lane);
   const uint32_t sample = GIBBS ? *P.nz.sample : 0u;
   const uint32_t chain = P.nz.chain0 + blockIdx.z;
@@ -431,10 +437,32 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
    for (; s < s_end; ++s) {
     const int colour = P.st[s].colour;
     const uint32_t c1 = P.st[s].c1;
-    const int m = S - 1 - s;
-    const int ilo = max(1, i_t0 - m - EXLX), ihi = min(nx - 1, i_t0 + TX - 1 + m + EXHX);
-    int jlo = max(1, j_t0 - m - EXLY);
-    const int jhi = min(ny - 1, j_t0 + TY - 1 + m + EXHY);
+    const int mode = P.st[s].mode;
+    if (mode == STAGE_SKIP) continue;  // (uniform over the launch)
+    if (LOWRANK && mode == STAGE_SPARSE) {
+      // dead pass that a fix-up still looks at: only supp(B_k) of the owned measurements (omega = 1 here)
+      MGMC_LR_PTRS
+      for (int o = warp; o < lr_cnt[0]; o += kFusedWarps) {
+        const int4 bb = reinterpret_cast<const int4 *>(P.lr.bbox)[own_list[o]];  // i0, i1, j0, j1
+        for (int j = bb.z; j <= bb.w; ++j) {
+          if (NC == 4 && (j & 1) != (colour >> 1)) continue;
+          const int q = (NC == 2) ? ((colour ^ j) & 1) : (colour & 1);
+          const int i0 = gi0 + q;
+          const bool v0 = (i0 >= bb.x) && (i0 <= bb.y), v1 = (i0 + 2 >= bb.x) && (i0 + 2 <= bb.y);
+          if (!(v0 || v1)) continue;
+          double *xl = xs + (j - j_r0) * 128 + lane;
+          const double *fl = fs + (j - j_r0) * 128 + lane;
+          const uint32_t c0 = (((uint32_t)j * P.nz.G + pg) << 1) | (uint32_t)q;
+          if (q == 0) pass_rows<NINE, GIBBS, true, 0>(P, xl, fl, 1, 0, c0, 0u, c1, sample, chain, ntab, v0, v1);
+          else pass_rows<NINE, GIBBS, true, 1>(P, xl, fl, 1, 0, c0, 0u, c1, sample, chain, ntab, v0, v1);
+        }
+      }
+      __syncthreads();
+      continue;
+    }
+    const int ilo = max(1, i_t0 - P.st[s].xl), ihi = min(nx - 1, i_t0 + TX - 1 + P.st[s].xh);
+    int jlo = max(1, j_t0 - P.st[s].yl);
+    const int jhi = min(ny - 1, j_t0 + TY - 1 + P.st[s].yh);
     int step = 1;
     if (NC == 4) {
       step = 2;

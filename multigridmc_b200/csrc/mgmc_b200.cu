@@ -642,6 +642,79 @@ void strip_allgather_rhs(mgmc_ctx *c, int level /* fine, distributed */) {
   c->launch("strip_wait_all", level, [&] { strip_wait_kernel<<<1, 32, 0, c->stream>>>(ctl + 2, nullptr, sp.nranks - 1, 0, 0, 0, ctl + 5, ctl + 3); });
 }
 
+// Plans the colour passes of one fused launch backwards from what the launch must deliver (fused.cuh "Stage").
+// A rectangle is the margin (xl, xh, yl, yh) around the tile inside which the sites of a colour must be exact.
+//   end:      every colour on the tile (+ the halo of the fused residual / restriction, + supp(B_k) of the owned
+//             measurements for the low-rank part of the residual)
+//   pass s:   updates its colour where it is needed; for that the neighbouring colours must be exact one site
+//             further out -- only in the directions in which they are neighbours (4-colour ordering: the colour
+//             that differs in the column parity is a neighbour in x only, ...), which keeps the y-halo of an
+//             8-pass launch at 3 rows instead of 7.  With omega = 1 the colour's own old values are not read:
+//             nothing is required of it before the pass, and a pass nobody needs is dead (skipped).
+//   fix-up:   x += W d is pointwise (requirements pass through), but d needs x on supp(B_k) of the owned
+//             measurements: every colour becomes "sparsely" needed there (inside tile + (0, lr_mx, 0, lr_my)).
+// Returns the halo of the input the launch must load.
+struct Margin {
+  bool on = false;
+  int v[4] = {0, 0, 0, 0};
+  void join(const Margin &o) {
+    if (!o.on) return;
+    if (!on) { *this = o; return; }
+    for (int k = 0; k < 4; ++k) v[k] = std::max(v[k], o.v[k]);
+  }
+  Margin grown(int dx, int dy) const {
+    Margin m = *this;
+    m.v[0] += dx; m.v[1] += dx; m.v[2] += dy; m.v[3] += dy;
+    return m;
+  }
+};
+Margin plan_stages(int nc, std::vector<Stage> &st, const std::vector<FixSpec> &fixes, bool use_lr, bool w1, bool restrict_, int lr_mx, int lr_my) {
+  static const bool noskip = std::getenv("MGMC_NO_DEAD_PASS") != nullptr;  // (experiments: run every pass in full)
+  Margin end;
+  end.on = true;
+  if (restrict_) { end.v[0] = 2; end.v[1] = 1; end.v[2] = 1; end.v[3] = 2; }
+  Margin elr;  // where the owned measurements live
+  elr.on = true;
+  elr.v[1] = lr_mx;
+  elr.v[3] = lr_my;
+  if (use_lr && restrict_) end.join(elr);
+  std::vector<Margin> req(nc, end);
+  std::vector<char> sparse(nc, 0);
+  for (int s = (int)st.size() - 1; s >= 0; --s) {
+    if (use_lr)
+      for (const FixSpec &fx : fixes)
+        if (fx.stage == s) std::fill(sparse.begin(), sparse.end(), 1);
+    const int cs = st[s].colour;
+    Margin r = req[cs];
+    const bool sp = sparse[cs] != 0;
+    if (noskip && !r.on) r = end;
+    st[s].mode = r.on ? STAGE_FULL : (sp ? STAGE_SPARSE : STAGE_SKIP);
+    if (r.on && sp) r.join(elr);
+    Margin src = r;
+    if (!r.on && sp) src = elr;
+    st[s].xl = (short)r.v[0]; st[s].xh = (short)r.v[1]; st[s].yl = (short)r.v[2]; st[s].yh = (short)r.v[3];
+    if (src.on) {
+      for (int c2 = 0; c2 < nc; ++c2) {
+        if (c2 == cs) continue;
+        const int dx = (nc == 2) ? 1 : ((c2 ^ cs) & 1), dy = (nc == 2) ? 1 : (((c2 ^ cs) >> 1) & 1);
+        req[c2].join(src.grown(dx, dy));
+      }
+      if (w1) {
+        req[cs] = Margin();
+        sparse[cs] = 0;
+      } else {
+        req[cs].join(src);
+      }
+    }
+  }
+  Margin in;
+  for (int c2 = 0; c2 < nc; ++c2) {
+    in.join(req[c2]);
+    if (sparse[c2]) in.join(elr);
+  }
+  return in;
+}
+
 void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const std::vector<FixSpec> &fixes, bool use_lr, bool gibbs, double omega, bool prolong,
                double alpha, bool restrict_) {
   DevLevel &L = c->lv[level];
@@ -665,7 +738,6 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     P.xc_zero = C.x;
   }
   P.nstages = S;
-  for (int k = 0; k < S; ++k) P.st[k] = stages[k];
   P.winv = omega / L.coef.c;
   P.omega_is_one = (omega == 1.0) ? 1 : 0;
   P.noise_scale = std::sqrt(L.coef.c * (2. - omega) / omega);  // sor_sampler.cc:24-27
@@ -678,12 +750,15 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     P.lr_mx = lr.bw - 1;
     P.lr_my = lr.bh - 1;
   }
-  P.HXL = up4(S + (restrict_ ? 2 : 0));
-  const int HXR = up4(S + (restrict_ ? 1 : 0) + P.lr_mx);
+  std::vector<Stage> plan = stages;
+  const Margin halo = plan_stages(nc, plan, fixes, use_lr, omega == 1.0, restrict_, P.lr_mx, P.lr_my);
+  for (int k = 0; k < S; ++k) P.st[k] = plan[k];
+  P.HXL = up4(halo.v[0]);
+  const int HXR = up4(halo.v[1]);
   P.TX = 128 - P.HXL - HXR;
   P.TY = fused_tile_rows(L.g.ny, nc, c->strip.on());
-  P.hl = S + (restrict_ ? 1 : 0);
-  const int hh = S + (restrict_ ? 2 : 0) + P.lr_my;
+  P.hl = halo.v[2];
+  const int hh = halo.v[3];
   P.RY = P.TY + P.hl + hh;
   size_t smem = (size_t)2 * P.RY * 128 * sizeof(double) + (use_lr ? lr_tile_smem(c->d.m_lowrank) : 0);
   while (smem > (size_t)kFusedSmemMax && P.TY > 8) {  // (many measurements: a lower tile makes room for their bookkeeping)
