@@ -135,6 +135,7 @@ struct FusedP {
   double *fc_out;       // RESTRICT: coarse right-hand side
   double *xc_zero;      // RESTRICT: coarse iterate, set to zero (multigridmc_sampler.cc:122)
   int nstages;
+  int res_stage;  // RESTRICT, omega = 1: index of the last pass (its sites get their residual for free), else -1
   Stage st[8];
   double winv, noise_scale;  // omega / a_ii, sqrt(a_ii (2 - omega) / omega)
   NoiseP nz;
@@ -150,6 +151,7 @@ struct FusedP {
   int nfix;
   int fix_stage[2], fix_dir[2];
   uint32_t fix_c1[2];
+  unsigned char *lr_flags; // [tiles of the launch] see "Per-tile flag" in the kernel
   int lr_slot, nchains;   // first vbuf / flag slot of this launch (nfix fix-ups, then u)
 };
 
@@ -227,32 +229,36 @@ __device__ __forceinline__ double offdiag_at(const Coef9 &a, double *row, int p)
 // update the two sites (offset Q and Q + 2) of one colour in group p of one row:
 //   x_i += omega (b_i - sum_j a_ij x_j) / a_ii  (sor_smoother.cc:75); for omega = 1 the old value drops
 //   out, x_i = (b_i - sum_{j != i} a_ij x_j) / a_ii, which saves reading it from shared memory
-template <bool NINE, bool GIBBS, bool W1, int Q>
-__device__ __forceinline__ void update_pair(const Coef9 &a, double *xrow, const double *frow, int p, bool v0, bool v1, double winv, double nscale, double z0,
+// RES (omega = 1, last pass before a fused residual): the residual of a site that has just been updated is known
+// without a stencil evaluation, f_i - sum_j a_ij x_j = f_i - b_i = -(noise), so the pass leaves it in the slot of f_i
+template <bool NINE, bool GIBBS, bool W1, int Q, bool RES>
+__device__ __forceinline__ void update_pair(const Coef9 &a, double *xrow, double *frow, int p, bool v0, bool v1, double winv, double nscale, double z0,
                                             double z1) {
   if (v0) {
     double b = frow[Q * 32 + p];
     if (GIBBS) b = fma(nscale, z0, b);
     if (W1) sat<Q>(xrow, p) = winv * (b - offdiag_at<NINE, Q>(a, xrow, p));
     else sat<Q>(xrow, p) += winv * (b - stencil_at<NINE, Q>(a, xrow, p));
+    if (RES) frow[Q * 32 + p] = GIBBS ? -(nscale * z0) : 0.0;
   }
   if (v1) {
     double b = frow[(Q + 2) * 32 + p];
     if (GIBBS) b = fma(nscale, z1, b);
     if (W1) sat<Q + 2>(xrow, p) = winv * (b - offdiag_at<NINE, Q + 2>(a, xrow, p));
     else sat<Q + 2>(xrow, p) += winv * (b - stencil_at<NINE, Q + 2>(a, xrow, p));
+    if (RES) frow[(Q + 2) * 32 + p] = GIBBS ? -(nscale * z1) : 0.0;
   }
 }
 
 // one colour pass over the rows of a warp: xl / fl point at the lane's group (plane 0) in the first row
-template <bool NINE, bool GIBBS, bool W1, int Q>
-__device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, const double *fl, int nrows, int dl, uint32_t c0, uint32_t dc0, uint32_t c1,
+template <bool NINE, bool GIBBS, bool W1, int Q, bool RES = false>
+__device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, double *fl, int nrows, int dl, uint32_t c0, uint32_t dc0, uint32_t c1,
                                           uint32_t sample, uint32_t chain, const double *ntab, bool v0, bool v1) {
   const double winv = P.winv, nscale = P.noise_scale;
   for (int n = 0; n < nrows; ++n) {
     double z0 = 0.0, z1 = 0.0;
     if (GIBBS) normal_pair(P.nz.keys, c0, c1, sample, chain, P.nz.mc, ntab, z0, z1);
-    update_pair<NINE, GIBBS, W1, Q>(P.a, xl, fl, 0, v0, v1, winv, nscale, z0, z1);
+    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, xl, fl, 0, v0, v1, winv, nscale, z0, z1);
     xl += dl;
     fl += dl;
     c0 += dc0;
@@ -309,7 +315,11 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const bool lr_to_up = P.sk.on && P.sk.lr_peer_up != 0 && (tile_by - P.by0 >= P.sk.tiles_y - P.sk.edge_rows);        \
   (void)darr; (void)tarr; (void)sarr; (void)spre; (void)cms; (void)cmn; (void)own_list; (void)need_list; (void)is_own; \
   (void)lr_epoch; (void)lr_to_dn; (void)lr_to_up;
-  if (LOWRANK) {
+  // Per-tile flag of this launch geometry (self-initialising: 0xFF = not known yet): 0 = the tile is nowhere near a
+  // measurement and skips every low-rank block -- set-up, tests and their loads included -- on one uniform branch
+  int lr_flag = 0;
+  if (LOWRANK) lr_flag = P.lr_flags ? (int)P.lr_flags[blockIdx.x] : 0xFF;
+  if (LOWRANK && lr_flag) {
     MGMC_LR_PTRS
     if (threadIdx.x < 4) lr_cnt[threadIdx.x] = 0;
     for (int k = threadIdx.x; k < lrm; k += kFusedThreads) {
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       fr[48] = fb[u].y;
     }
   }
-  if (LOWRANK && (int)threadIdx.x < P.lr.m) {
+  if (LOWRANK && lr_flag && (int)threadIdx.x < P.lr.m) {
     // Which measurements does this tile own / need?  (after the tile load has been issued; published by its barrier)
     MGMC_LR_PTRS
     const LowRankTile &R = P.lr;
@@ -423,6 +433,11 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   }
   __syncthreads();
   TSTAMP(1)
+  // most tiles are nowhere near a measurement: they skip every low-rank block below (and its loads) on one uniform test
+  const bool lr_own = LOWRANK && lr_flag && lr_cnt[0] > 0;
+  const bool lr_tile = LOWRANK && lr_flag && (lr_cnt[0] | lr_cnt[1] | lr_cnt[2]) != 0;
+  const bool lr_res = LOWRANK && lr_flag && lr_cnt[3] > 0;
+  if (LOWRANK && lr_flag == 0xFF && P.lr_flags && threadIdx.x == 0) P.lr_flags[blockIdx.x] = (lr_cnt[0] | lr_cnt[1] | lr_cnt[2] | lr_cnt[3]) ? 1 : 0;
 
   // ---- colour passes: one warp per row, lane = group ----
   const int S = P.nstages;
@@ -441,6 +456,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     if (mode == STAGE_SKIP) continue;  // (uniform over the launch)
     if (LOWRANK && mode == STAGE_SPARSE) {
       // dead pass that a fix-up still looks at: only supp(B_k) of the owned measurements (omega = 1 here)
+      if (!lr_own) continue;
       MGMC_LR_PTRS
       for (int o = warp; o < lr_cnt[0]; o += kFusedWarps) {
         const int4 bb = reinterpret_cast<const int4 *>(P.lr.bbox)[own_list[o]];  // i0, i1, j0, j1
@@ -451,7 +467,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
           const bool v0 = (i0 >= bb.x) && (i0 <= bb.y), v1 = (i0 + 2 >= bb.x) && (i0 + 2 <= bb.y);
           if (!(v0 || v1)) continue;
           double *xl = xs + (j - j_r0) * 128 + lane;
-          const double *fl = fs + (j - j_r0) * 128 + lane;
+          double *fl = fs + (j - j_r0) * 128 + lane;
           const uint32_t c0 = (((uint32_t)j * P.nz.G + pg) << 1) | (uint32_t)q;
           if (q == 0) pass_rows<NINE, GIBBS, true, 0>(P, xl, fl, 1, 0, c0, 0u, c1, sample, chain, ntab, v0, v1);
           else pass_rows<NINE, GIBBS, true, 1>(P, xl, fl, 1, 0, c0, 0u, c1, sample, chain, ntab, v0, v1);
@@ -478,10 +494,13 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       if (v0 || v1) {
         const int nrows = (jhi - jw) / (kFusedWarps * step) + 1;
         double *xl = xs + (jw - j_r0) * 128 + lane;
-        const double *fl = fs + (jw - j_r0) * 128 + lane;
+        double *fl = fs + (jw - j_r0) * 128 + lane;
         const uint32_t c0 = (((uint32_t)jw * P.nz.G + pg) << 1) | (uint32_t)q, dc0 = ((uint32_t)(kFusedWarps * step) * P.nz.G) << 1;
         const int dl = kFusedWarps * step * 128;
-        if (P.omega_is_one) {
+        if (RESTRICT && s == P.res_stage && !lr_tile) {  // last pass before the residual (omega = 1): leaves the residual of its sites in fs
+          if (q == 0) pass_rows<NINE, GIBBS, true, 0, true>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
+          else pass_rows<NINE, GIBBS, true, 1, true>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
+        } else if (P.omega_is_one) {
           if (q == 0) pass_rows<NINE, GIBBS, true, 0>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
           else pass_rows<NINE, GIBBS, true, 1>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
         } else {
@@ -493,7 +512,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     __syncthreads();
     TSTAMP(2 + (s < 4 ? s : 3))
    }
-    if (LOWRANK && seg < P.nfix) {
+    if (LOWRANK && seg < P.nfix && lr_tile) {
       MGMC_LR_PTRS
       const int fixq = seg;
       const LowRankTile &R = P.lr;
@@ -603,7 +622,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     }
   }
 
-  if (LOWRANK && RESTRICT) {
+  if (LOWRANK && RESTRICT && lr_own) {
     // owners: u_k = (Sigma^{-1} B^T x)_k of the final iterate, for the low-rank part of the residual
     MGMC_LR_PTRS
     const LowRankTile &R = P.lr;
@@ -664,12 +683,28 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       const int gj = j_t0 + rr;
       double *__restrict__ xr = xs + (gj - j_r0) * 128;
       double *__restrict__ fr = fs + (gj - j_r0) * 128;
+      // sites of the last pass already hold their residual (unless this tile takes part in a low-rank fix-up)
+      const int lastc = (P.res_stage >= 0 && !lr_tile) ? P.st[P.res_stage].colour : -1;
+      int hq = -1;  // column parity of the sites of this row that hold their residual already
+      if (lastc >= 0) {
+        if (NC == 2) hq = (lastc ^ gj) & 1;
+        else if ((gj & 1) == (lastc >> 1)) hq = lastc & 1;
+      }
+      const bool have0 = (hq == 0), have1 = (hq == 1);
       double res[4] = {0.0, 0.0, 0.0, 0.0};
       if (gj < ny) {  // (lanes 0 / 31 read in-bounds garbage for columns that are masked out below)
-        res[0] = fr[lane] - stencil_at<NINE, 0>(P.a, xr, lane);
-        res[1] = fr[32 + lane] - stencil_at<NINE, 1>(P.a, xr, lane);
-        res[2] = fr[64 + lane] - stencil_at<NINE, 2>(P.a, xr, lane);
-        res[3] = fr[96 + lane] - stencil_at<NINE, 3>(P.a, xr, lane);
+        res[0] = fr[lane];
+        res[1] = fr[32 + lane];
+        res[2] = fr[64 + lane];
+        res[3] = fr[96 + lane];
+        if (!have0) {  // (warp-uniform branches: the stencils are really skipped)
+          res[0] -= stencil_at<NINE, 0>(P.a, xr, lane);
+          res[2] -= stencil_at<NINE, 2>(P.a, xr, lane);
+        }
+        if (!have1) {
+          res[1] -= stencil_at<NINE, 1>(P.a, xr, lane);
+          res[3] -= stencil_at<NINE, 3>(P.a, xr, lane);
+        }
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -679,7 +714,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
     }
     __syncthreads();
-    if (LOWRANK && lr_cnt[3] > 0) {
+    if (lr_res) {
       // low-rank part of the residual: r -= B u, u = Sigma^{-1} B^T x of the final state (linear_operator.hh:71-75)
       MGMC_LR_PTRS
       const LowRankTile &R = P.lr;

@@ -138,6 +138,10 @@ struct mgmc_ctx {
   double *d_mean = nullptr, *d_second = nullptr;
   // graph of one MGMC cycle (+ end-of-cycle kernel)
   cudaGraphExec_t graph = nullptr;
+  // per-tile low-rank flags of the fused launches (fused.cuh): a pool allocated with the context, handed out per launch geometry
+  unsigned char *d_lr_flag_pool = nullptr;
+  size_t lr_flag_pool_size = 0, lr_flag_pool_used = 0;
+  std::map<std::string, size_t> lr_flag_slots;
   cudaGraphExec_t mg_graph = nullptr;  // one LoopSolver iteration: V-cycle, x -= Pr, next residual and its norm
   int64_t mg_graph_launches = 0;
   bool use_graph = true;
@@ -243,7 +247,7 @@ Coef9 to_coef9(const StencilSet &s) {
   return a;
 }
 
-inline int fused_tile_rows(int ny, int nc, bool strips);
+inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_);
 
 StripPlan make_strip_plan(const mgmc_desc &d, const std::vector<HostLevel> &H) {
   StripPlan p;
@@ -261,7 +265,7 @@ StripPlan make_strip_plan(const mgmc_desc &d, const std::vector<HostLevel> &H) {
     const HostLevel &h = H[l];
     if (h.st.radius > 1) break;  // radius-2 operators: not decomposed yet
     const int nc = h.st.ncolours;
-    const int ty = fused_tile_rows(h.ny, nc, true);
+    const int ty = fused_tile_rows(h.ny, nc, true, true);
     const int rows = h.ny / p.nranks;
     // rows exchanged with a neighbour: what a launch of 2 sweeps (+ residual) reads beyond the own rows; with a
     // low-rank term additionally the windows of the measurements near the strip boundary (patch CTAs)
@@ -547,19 +551,19 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
 // ---- fused tile kernel dispatch ----
 // tile height: 32 rows on the big (bandwidth / issue bound) levels; the small levels are latency bound,
 // there short tiles give every warp at most one row per colour pass and spread over more SMs
-inline int fused_tile_rows(int ny, int nc, bool strips) {
+inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_) {
   if (strips) return ny > 1024 ? 32 : (ny > 256 ? 16 : 8);  // strips must start on tile boundaries: powers of two only
-  static const char *ov = std::getenv("MGMC_TILE_ROWS");    // perf experiments: "rb_big,4c_big,4c_mid,small"
-  static int t[4] = {40, 32, 16, 8};
+  static const char *ov = std::getenv("MGMC_TILE_ROWS");    // perf experiments: "rb_big,4c_big,4c_mid,small,rb_big_prolong"
+  static int t[5] = {40, 32, 16, 8, 40};
   static bool parsed = false;
   if (!parsed) {
     parsed = true;
-    if (ov) std::sscanf(ov, "%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3]);
+    if (ov) std::sscanf(ov, "%d,%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3], &t[4]);
   }
   // The rows of a colour pass are dealt out to 16 warps, so the tile heights are chosen to make the passes come out
-  // at whole rounds: red-black 40 rows -> 49 / 47 / 45 / 43 rows per pass (4, 3, 3, 3 rounds); 4-colour (every other
-  // row per pass) 36 rows -> 28 .. 21 rows (2 rounds each), 14 rows -> 16 .. 9 rows (1 round each).
-  if (ny > 2048 && nc == 2) return t[0];
+  // at whole rounds (plan_stages: a red-black launch with restriction updates TY + 7 / 5 / 3 rows, without TY + 4 / 2 / 0;
+  // a 4-colour launch every other row of TY + 7 ... TY + 3).
+  if (ny > 2048 && nc == 2) return restrict_ ? t[0] : t[4];
   if (ny > 1024) return nc == 2 ? 32 : t[1];
   if (ny > 256) return nc == 2 ? 16 : t[2];
   return t[3];
@@ -753,10 +757,12 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   std::vector<Stage> plan = stages;
   const Margin halo = plan_stages(nc, plan, fixes, use_lr, omega == 1.0, restrict_, P.lr_mx, P.lr_my);
   for (int k = 0; k < S; ++k) P.st[k] = plan[k];
+  static const bool nofold = std::getenv("MGMC_NO_RES_FOLD") != nullptr;
+  P.res_stage = (restrict_ && omega == 1.0 && S > 0 && plan[S - 1].mode == STAGE_FULL && !nofold) ? S - 1 : -1;
   P.HXL = up4(halo.v[0]);
   const int HXR = up4(halo.v[1]);
   P.TX = 128 - P.HXL - HXR;
-  P.TY = fused_tile_rows(L.g.ny, nc, c->strip.on());
+  P.TY = fused_tile_rows(L.g.ny, nc, c->strip.on(), restrict_);
   P.hl = halo.v[2];
   const int hh = halo.v[3];
   P.RY = P.TY + P.hl + hh;
@@ -766,7 +772,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     P.RY = P.TY + P.hl + hh;
     smem = (size_t)2 * P.RY * 128 * sizeof(double) + (use_lr ? lr_tile_smem(c->d.m_lowrank) : 0);
   }
-  if (c->strip.on() && P.TY != fused_tile_rows(L.g.ny, nc, true)) fail(MGMC_ERR_UNSUPPORTED, "row strips: too many measurements for the tile geometry");
+  if (c->strip.on() && P.TY != fused_tile_rows(L.g.ny, nc, true, restrict_)) fail(MGMC_ERR_UNSUPPORTED, "row strips: too many measurements for the tile geometry");
   if (smem > (size_t)kFusedSmemMax) fail(MGMC_ERR_INVALID, "internal: fused tile does not fit in shared memory");
   P.tiles_x = (L.g.nx + P.TX - 1) / P.TX;
   int tiles_y = (L.g.ny - 1 + P.TY - 1) / P.TY;
@@ -849,6 +855,19 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     }
     P.lr_slot = c->lr_slot_next;
     c->lr_slot_next += P.nfix + 1;
+    if (c->d_lr_flag_pool) {
+      // flags are a function of the launch geometry and of what the launch looks at (fix-up directions, residual)
+      char key[160];
+      std::snprintf(key, sizeof(key), "%d:%.17g:%d,%d,%d,%d,%d,%d,%d,%d:%d,%d,%d:%d,%d", level, omega, P.HXL, P.TX, P.TY, P.hl, P.RY, P.tiles_x, tiles_y, P.by0, P.nfix,
+                    P.nfix > 0 ? P.fix_dir[0] : -1, P.nfix > 1 ? P.fix_dir[1] : -1, (int)restrict_, P.sk.on);
+      const size_t ntile = (size_t)P.tiles_x * tiles_y;
+      auto it = c->lr_flag_slots.find(key);
+      if (it == c->lr_flag_slots.end() && c->lr_flag_pool_used + ntile <= c->lr_flag_pool_size) {
+        it = c->lr_flag_slots.emplace(key, c->lr_flag_pool_used).first;
+        c->lr_flag_pool_used += (ntile + 15) / 16 * 16;
+      }
+      if (it != c->lr_flag_slots.end()) P.lr_flags = c->d_lr_flag_pool + it->second;  // (pool exhausted: every tile runs the tests)
+    }
     if (c->lr_slot_next > mgmc_ctx::kLrSlots) fail(MGMC_ERR_UNSUPPORTED, "too many low-rank fix-ups in one cycle (W-cycle too deep)");
   }
   dim3 grid(P.tiles_x * tiles_y, 1, c->d.nchains);
@@ -1320,6 +1339,9 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
       const size_t n = (size_t)mgmc_ctx::kLrSlots * desc->nchains * desc->m_lowrank;
       c->d_lr_vbuf = c->strip.on() ? (LrPkt *)carve(4 * n) : c->dalloc<LrPkt>(2 * n);
       c->d_lr_epoch = c->dalloc<int>(1);
+      c->lr_flag_pool_size = (size_t)1 << 20;
+      c->d_lr_flag_pool = c->dalloc<unsigned char>(c->lr_flag_pool_size, false);
+      CUDA_CHECK(cudaMemsetAsync(c->d_lr_flag_pool, 0xFF, c->lr_flag_pool_size, c->stream));  // 0xFF: not known yet
     }
     for (int l = 0; l < desc->nlevel; ++l) {
       DevLevel &L = c->lv[l];
