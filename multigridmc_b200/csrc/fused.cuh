@@ -29,7 +29,16 @@ namespace mgmc {
 
 constexpr int kGX = 16;  // allocated doubles left of i = 0
 constexpr int kGY = 2;   // allocated rows below j = 0 / above j = ny
-constexpr int kFusedThreads = 512;
+#ifndef MGMC_FUSED_THREADS
+#define MGMC_FUSED_THREADS 512
+#endif
+#ifndef MGMC_LOAD_ROWS
+#define MGMC_LOAD_ROWS 2
+#endif
+#ifndef MGMC_PASS_ILP
+#define MGMC_PASS_ILP 1
+#endif
+constexpr int kFusedThreads = MGMC_FUSED_THREADS;
 constexpr int kFusedWarps = kFusedThreads / 32;
 
 struct LrPkt;
@@ -255,7 +264,23 @@ template <bool NINE, bool GIBBS, bool W1, int Q, bool RES = false>
 __device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, double *fl, int nrows, int dl, uint32_t c0, uint32_t dc0, uint32_t c1,
                                           uint32_t sample, uint32_t chain, const double *ntab, bool v0, bool v1) {
   const double winv = P.winv, nscale = P.noise_scale;
-  for (int n = 0; n < nrows; ++n) {
+  int n = 0;
+#if MGMC_PASS_ILP == 2
+  // two rows of the warp per iteration: two independent Philox / Box-Muller / update chains in flight
+  for (; n + 1 < nrows; n += 2) {
+    double z0 = 0.0, z1 = 0.0, y0 = 0.0, y1 = 0.0;
+    if (GIBBS) {
+      normal_pair(P.nz.keys, c0, c1, sample, chain, P.nz.mc, ntab, z0, z1);
+      normal_pair(P.nz.keys, c0 + dc0, c1, sample, chain, P.nz.mc, ntab, y0, y1);
+    }
+    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, xl, fl, 0, v0, v1, winv, nscale, z0, z1);
+    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, xl + dl, fl + dl, 0, v0, v1, winv, nscale, y0, y1);
+    xl += 2 * dl;
+    fl += 2 * dl;
+    c0 += 2 * dc0;
+  }
+#endif
+  for (; n < nrows; ++n) {
     double z0 = 0.0, z1 = 0.0;
     if (GIBBS) normal_pair(P.nz.keys, c0, c1, sample, chain, P.nz.mc, ntab, z0, z1);
     update_pair<NINE, GIBBS, W1, Q, RES>(P.a, xl, fl, 0, v0, v1, winv, nscale, z0, z1);
@@ -347,10 +372,11 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const int pa = 2 * (lane & 1), ia = lane >> 1;          // plane / index of column 2l; column 64+2l is at index ia + 16
   const int gia = i_r0 + 2 * lane, gib = gia + 64;        // global columns of the two pairs
   const bool oka = (gia >= -kGX) && (gia + 1 < pitch - kGX), okb = (gib >= -kGX) && (gib + 1 < pitch - kGX);
-  for (int r = warp; r < RY; r += 2 * kFusedWarps) {
-    double2 xa[2], xb[2], fa[2], fb[2];
+  constexpr int LU = MGMC_LOAD_ROWS;  // rows of a warp whose loads are in flight together (4 x 128-bit loads per lane and row)
+  for (int r = warp; r < RY; r += LU * kFusedWarps) {
+    double2 xa[LU], xb[LU], fa[LU], fb[LU];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < LU; ++u) {
       const int gj = j_r0 + r + u * kFusedWarps;
       xa[u] = xb[u] = fa[u] = fb[u] = make_double2(0.0, 0.0);
       if (gj >= -kGY && gj <= ny + kGY && r + u * kFusedWarps < RY) {
@@ -366,7 +392,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < LU; ++u) {
       const int rr = r + u * kFusedWarps;
       if (rr >= RY) break;
       const int gj = j_r0 + rr;

@@ -94,6 +94,7 @@ struct mgmc_ctx {
   mgmc_desc d;
   std::vector<double> Sigma;
   int device = 0;
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
   std::vector<DevLevel> lv;
   std::vector<void *> allocs;
@@ -1306,6 +1307,7 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
       if (!(s > 0.0)) fail(MGMC_ERR_INVALID, "Sigma entries must be positive");
     c->device = desc->device;
     CUDA_CHECK(cudaSetDevice(c->device));
+    CUDA_CHECK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->use_graph = (std::getenv("MGMC_NO_GRAPH") == nullptr);
     c->perf_no_noise = (std::getenv("MGMC_PERF_NO_NOISE") != nullptr);

@@ -1,6 +1,7 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 200 --warmup 5 > gpurun_out/bench_r01_v4.log 2>&1 || exit 1
-grep -o '"value": [0-9.]*' gpurun_out/bench_r01_v4.log | head -1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01_v4.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_v4.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"fused_smooth_kernel|trimv_kernel" -s 48 -c 16 -o gpurun_out/prof_r01_v4_cycle -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_v4.log 2>&1
-ls -la gpurun_out/prof_r01_v4_cycle.ncu-rep
+for v in b200 lu3; do
+for t in 40,46,24,8,44 38,46,24,8,42 38,38,24,8,42; do
+  lib=build/libmgmc_$v.so; [ $v = b200 ] && lib=multigridmc_b200/csrc/libmgmc_b200.so
+  MGMC_LIB=$lib MGMC_TILE_ROWS=$t python bench.py --steps 60 --warmup 5 --no-cpu-baseline > gpurun_out/bench_lu_${v}_$t.log 2>&1
+  echo "$v $t $(grep -o '"value": [0-9.]*' gpurun_out/bench_lu_${v}_$t.log | head -1) $(grep -o '"qoi_mean": [-0-9.e]*' gpurun_out/bench_lu_${v}_$t.log)"
+done
+done
