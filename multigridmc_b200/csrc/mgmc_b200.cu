@@ -759,7 +759,10 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   const Margin halo = plan_stages(nc, plan, fixes, use_lr, omega == 1.0, restrict_, P.lr_mx, P.lr_my);
   for (int k = 0; k < S; ++k) P.st[k] = plan[k];
   static const bool nofold = std::getenv("MGMC_NO_RES_FOLD") != nullptr;
-  P.res_stage = (restrict_ && omega == 1.0 && S > 0 && plan[S - 1].mode == STAGE_FULL && !nofold) ? S - 1 : -1;
+  // (not with a low-rank term: tiles next to a measurement could not fold, and which tiles those are depends on the
+  //  tiling -- the folded residual differs from the stencil one in the last bit, and the chain must not depend on the
+  //  tiling / the strip decomposition)
+  P.res_stage = (restrict_ && omega == 1.0 && S > 0 && plan[S - 1].mode == STAGE_FULL && !use_lr && !nofold) ? S - 1 : -1;
   P.HXL = up4(halo.v[0]);
   const int HXR = up4(halo.v[1]);
   P.TX = 128 - P.HXL - HXR;
