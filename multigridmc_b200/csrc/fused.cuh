@@ -161,6 +161,7 @@ struct FusedP {
   int fix_stage[2], fix_dir[2];
   uint32_t fix_c1[2];
   unsigned char *lr_flags; // [tiles of the launch] see "Per-tile flag" in the kernel
+  int lr_u_from_fix;      // RESTRICT: the launch ends with a fix-up, u = s - d (see the fix-up block)
   int lr_slot, nchains;   // first vbuf / flag slot of this launch (nfix fix-ups, then u)
 };
 
@@ -304,8 +305,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const int tile_bx = tile_id % P.tiles_x, tile_by = tile_row + P.by0;
 #ifdef MGMC_TILE_TIMING
   const int cta_id = blockIdx.z * gridDim.x + blockIdx.x;
-#define TSTAMP(k) if (threadIdx.x == 0 && P.timing) P.timing[(long long)cta_id * 10 + (k)] = gtimer();
-  if (threadIdx.x == 0 && P.timing) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); P.timing[(long long)cta_id * 10 + 9] = smid; }
+#define TSTAMP(k) if (threadIdx.x == 0 && P.timing) P.timing[(long long)cta_id * 16 + (k)] = gtimer();
+  if (threadIdx.x == 0 && P.timing) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); P.timing[(long long)cta_id * 16 + 15] = smid; }
 #else
 #define TSTAMP(k)
 #endif
@@ -333,12 +334,13 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   double *spre = sarr + lrm;    /* [2][m] noise of fix-up q for owned k */                                            \
   double *cms = spre + 2 * lrm; /* [2][m] Ms_kk per direction (owned k) */                                            \
   double *cmn = cms + 2 * lrm;  /* [2][m] Mneg_kk */                                                                  \
-  int *own_list = reinterpret_cast<int *>(cmn + 2 * lrm), *need_list = own_list + lrm; /* need_list: [3][m] */        \
+  double *uarr = cmn + 2 * lrm; /* u_k = s_k - d_k of the last fix-up (low-rank part of the residual) */               \
+  int *own_list = reinterpret_cast<int *>(uarr + lrm), *need_list = own_list + lrm; /* need_list: [3][m] */           \
   int *is_own = need_list + 3 * lrm;                                                                                  \
   const int lr_epoch = *P.lr.epoch;                                                                                   \
   const bool lr_to_dn = P.sk.on && P.sk.lr_peer_dn != 0 && (tile_by - P.by0 < P.sk.edge_rows);                        \
   const bool lr_to_up = P.sk.on && P.sk.lr_peer_up != 0 && (tile_by - P.by0 >= P.sk.tiles_y - P.sk.edge_rows);        \
-  (void)darr; (void)tarr; (void)sarr; (void)spre; (void)cms; (void)cmn; (void)own_list; (void)need_list; (void)is_own; \
+  (void)darr; (void)tarr; (void)sarr; (void)spre; (void)cms; (void)cmn; (void)uarr; (void)own_list; (void)need_list; (void)is_own; \
   (void)lr_epoch; (void)lr_to_dn; (void)lr_to_up;
   // Per-tile flag of this launch geometry (self-initialising: 0xFF = not known yet): 0 = the tile is nowhere near a
   // measurement and skips every low-rank block -- set-up, tests and their loads included -- on one uniform branch
@@ -434,27 +436,32 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     const int k = threadIdx.x;
     const int4 bb = reinterpret_cast<const int4 *>(R.bbox)[k];  // i0, i1, j0, j1 of supp(B_k)
     const int4 b0 = reinterpret_cast<const int4 *>(R.wbox[0])[k], b1 = reinterpret_cast<const int4 *>(R.wbox[1])[k];
-    if (b0.y >= i_r0 && b0.x < i_r0 + 128 && b0.w >= j_r0 && b0.z < j_r0 + RY) need_list[atomicAdd(&lr_cnt[1], 1)] = k;
-    if (b1.y >= i_r0 && b1.x < i_r0 + 128 && b1.w >= j_r0 && b1.z < j_r0 + RY) need_list[lrm + atomicAdd(&lr_cnt[2], 1)] = k;
-    if (RESTRICT && bb.y >= max(1, i_t0 - 1) && bb.x <= min(nx - 1, i_t0 + TX - 1) && bb.w >= j_t0 && bb.z <= min(j_t0 + TY, ny - 1))
-      need_list[2 * lrm + atomicAdd(&lr_cnt[3], 1)] = k;
-    if (bb.x >= i_t0 && bb.x < i_t0 + TX && bb.z >= j_t0 && bb.z < j_t0 + TY) {  // owner: the tile that holds the lower left corner
+    const bool hit_res = RESTRICT && bb.y >= max(1, i_t0 - 1) && bb.x <= min(nx - 1, i_t0 + TX - 1) && bb.w >= j_t0 && bb.z <= min(j_t0 + TY, ny - 1);
+    // (a measurement that enters the residual of this tile is also needed at the fix-ups: u_k = s_k - d_k below)
+    if (hit_res || (b0.y >= i_r0 && b0.x < i_r0 + 128 && b0.w >= j_r0 && b0.z < j_r0 + RY)) need_list[atomicAdd(&lr_cnt[1], 1)] = k;
+    if (hit_res || (b1.y >= i_r0 && b1.x < i_r0 + 128 && b1.w >= j_r0 && b1.z < j_r0 + RY)) need_list[lrm + atomicAdd(&lr_cnt[2], 1)] = k;
+    if (hit_res) need_list[2 * lrm + atomicAdd(&lr_cnt[3], 1)] = k;
+    const bool owner = bb.x >= i_t0 && bb.x < i_t0 + TX && bb.z >= j_t0 && bb.z < j_t0 + TY;  // the tile that holds the lower left corner
+    if (owner) {
       own_list[atomicAdd(&lr_cnt[0], 1)] = k;
       is_own[k] = 1;
+    }
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (q >= P.nfix) break;
-        const int dir = P.fix_dir[q];
+    for (int q = 0; q < 2; ++q) {
+      if (q >= P.nfix) break;
+      const int dir = P.fix_dir[q];
+      if (owner) {
         cms[q * lrm + k] = R.Ms[dir][(size_t)k * lrm + k];
         cmn[q * lrm + k] = R.Mneg[dir][(size_t)k * lrm + k];
-        double sv = 0.0;
-        if (GIBBS) {
-          double z0, z1;
-          normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[q], *P.nz.sample, P.nz.chain0 + blockIdx.z, P.nz.mc, kNormalTabDev, z0, z1);
-          sv = R.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
-        }
-        spre[q * lrm + k] = sv;
       }
+      // the low-rank noise s_k = Sigma_k^{-1/2} xi_k is a pure function of the counters: every tile forms it itself
+      double sv = 0.0;
+      if (GIBBS) {
+        double z0, z1;
+        normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[q], *P.nz.sample, P.nz.chain0 + blockIdx.z, P.nz.mc, ntab, z0, z1);
+        sv = R.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
+      }
+      spre[q * lrm + k] = sv;
     }
   }
   __syncthreads();
@@ -536,8 +543,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
     }
     __syncthreads();
-    TSTAMP(2 + (s < 4 ? s : 3))
    }
+    TSTAMP(2 + 2 * seg)
     if (LOWRANK && seg < P.nfix && lr_tile) {
       MGMC_LR_PTRS
       const int fixq = seg;
@@ -643,13 +650,18 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
           xs[(j - j_r0) * 128 + (di & 3) * 32 + (di >> 2)] += acc;
         }
         __syncthreads();
+        // Low-rank part of the residual for free: after the last fix-up x = x' + W d, hence Sigma^{-1} B^T x =
+        // K (t + G s) = s - d  (d = (I - K G) s - K t, K = (Sigma + G)^{-1}): no second exchange for u.
+        if (RESTRICT && P.lr_u_from_fix && seg == P.nfix - 1)
+          for (int n = threadIdx.x; n < n_need; n += kFusedThreads) uarr[nlist[n]] = spre[fixq * lrm + nlist[n]] - darr[nlist[n]];
         for (int n = threadIdx.x; n < n_need; n += kFusedThreads) darr[nlist[n]] = 0.0;  // (ordered before the next use by the pass barriers)
       }
     }
+    TSTAMP(3 + 2 * seg)
   }
 
-  if (LOWRANK && RESTRICT && lr_own) {
-    // owners: u_k = (Sigma^{-1} B^T x)_k of the final iterate, for the low-rank part of the residual
+  if (LOWRANK && RESTRICT && lr_own && !P.lr_u_from_fix) {
+    // (launch without a closing fix-up) owners: u_k = (Sigma^{-1} B^T x)_k of the final iterate, for the low-rank part of the residual
     MGMC_LR_PTRS
     const LowRankTile &R = P.lr;
     const size_t slot = (size_t)(P.lr_slot + P.nfix) * P.nchains + blockIdx.z;
@@ -673,6 +685,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     }
   }
 
+  TSTAMP(7 + 0)
   // ---- write the tile to the output buffer (skipped by a pure residual + restrict launch):
   //      same coalesced column-pair mapping as the load ----
   if (PROLONG || S > 0) {
@@ -702,7 +715,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     }
   }
 
-  TSTAMP(6)
+  TSTAMP(8)
   // ---- residual on [i_t0 - 1, i_t0 + TX - 1] x [j_t0, j_t0 + TY], then full-weighting restriction ----
   if (RESTRICT) {
     for (int rr = warp; rr <= TY; rr += kFusedWarps) {
@@ -740,6 +753,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
     }
     __syncthreads();
+    TSTAMP(9)
     if (lr_res) {
       // low-rank part of the residual: r -= B u, u = Sigma^{-1} B^T x of the final state (linear_operator.hh:71-75)
       MGMC_LR_PTRS
@@ -749,7 +763,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       const int *nlist = need_list + 2 * lrm;
       for (int n = threadIdx.x; n < lr_cnt[3]; n += kFusedThreads) {
         const int k = nlist[n];
-        darr[k] = is_own[k] ? tarr[k] : pkt_wait(vb + k, lr_epoch);
+        darr[k] = P.lr_u_from_fix ? uarr[k] : (is_own[k] ? tarr[k] : pkt_wait(vb + k, lr_epoch));
       }
       __syncthreads();
       for (int u = threadIdx.x; u < R.nbu; u += kFusedThreads) {
@@ -762,6 +776,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
       __syncthreads();
     }
+    TSTAMP(10)
     const long long ccb = (long long)blockIdx.z * P.gc.stride;
     const int I = gi0 >> 1;  // coarse columns I (fine 4p) and I + 1 (fine 4p + 2) of this lane
     const bool mine = (gi0 >= i_t0) && (gi0 < i_t0 + TX);
@@ -805,7 +820,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       }
     }
   }
-  TSTAMP(7)
+  TSTAMP(11)
 }
 
 }  // namespace mgmc

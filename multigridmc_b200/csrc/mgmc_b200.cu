@@ -594,7 +594,7 @@ void lr_begin_epoch(mgmc_ctx *c) {
 }
 
 // shared memory the low-rank bookkeeping of a tile needs behind the tile itself
-inline size_t lr_tile_smem(int m) { return (size_t)9 * m * sizeof(double) + (size_t)6 * m * sizeof(int); }
+inline size_t lr_tile_smem(int m) { return (size_t)10 * m * sizeof(double) + (size_t)6 * m * sizeof(int); }
 
 // Can the fix-ups of this level run inside the fused launch?  Always when the measurements do not interact;
 // otherwise every tile that needs a fix-up waits for ALL owner tiles, so the whole grid must be resident at once.
@@ -857,6 +857,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
       P.fix_dir[q] = fixes[q].dir;
       P.fix_c1[q] = fixes[q].c1;
     }
+    P.lr_u_from_fix = (restrict_ && P.nfix > 0 && fixes.back().stage == S - 1) ? 1 : 0;
     P.lr_slot = c->lr_slot_next;
     c->lr_slot_next += P.nfix + 1;
     if (c->d_lr_flag_pool) {
@@ -889,8 +890,8 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   const size_t ncta = (size_t)grid.x * grid.z;
   static const char *tlev = std::getenv("MGMC_TIMING_LEVEL");
   if (tfile && level == (tlev ? std::atoi(tlev) : 0) && dumped[name]++ == 3) {
-    CUDA_CHECK(cudaMalloc(&d_timing, ncta * 10 * sizeof(long long)));
-    CUDA_CHECK(cudaMemset(d_timing, 0, ncta * 10 * sizeof(long long)));
+    CUDA_CHECK(cudaMalloc(&d_timing, ncta * 16 * sizeof(long long)));
+    CUDA_CHECK(cudaMemset(d_timing, 0, ncta * 16 * sizeof(long long)));
     P.timing = d_timing;
   }
 #endif
@@ -909,12 +910,12 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
 #ifdef MGMC_TILE_TIMING
   if (d_timing) {
     c->sync();
-    std::vector<long long> h(ncta * 10);
+    std::vector<long long> h(ncta * 16);
     CUDA_CHECK(cudaMemcpy(h.data(), d_timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(d_timing);
     FILE *fp = std::fopen((std::string(tfile) + "." + name + ".txt").c_str(), "w");
     for (size_t k = 0; k < ncta; ++k) {
-      for (int q = 0; q < 10; ++q) std::fprintf(fp, "%lld ", h[k * 10 + q]);
+      for (int q = 0; q < 16; ++q) std::fprintf(fp, "%lld ", h[k * 16 + q]);
       std::fprintf(fp, "\n");
     }
     std::fclose(fp);
