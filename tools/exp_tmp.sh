@@ -1,2 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench_q7.log 2>&1; grep -o '"value": [0-9.]*' gpurun_out/bench_q7.log | head -1; grep -o '"qoi_mean": [-0-9.e]*' gpurun_out/bench_q7.log
+python -m pytest tests/test_gpu_invariance.py -x -q 2>&1 | tail -15
+python profiles/run_configs.py > gpurun_out/configs_r01_v4.log 2>&1; cat gpurun_out/configs_r01_v4.log | tail -8
