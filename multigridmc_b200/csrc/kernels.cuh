@@ -31,6 +31,12 @@ struct GridP {
   long long stride;  // doubles between chains
 };
 
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // y = A_0 x  (LinearOperator::apply sparse part, linear_operator.hh:69) or r = f - A_0 x
 // ------------------------------------------------------------------------------------------------
@@ -169,12 +175,16 @@ __device__ __forceinline__ double stencil25(const double *__restrict__ a, const 
 }
 
 // y = A_0 x, or r = f - A_0 x
+// (row strips: only the rows [rows.j0, rows.j1]; the grid is sized for that range)
+struct RowRange {
+  int j0, j1;
+};
 template <bool RESIDUAL>
 __global__ void __launch_bounds__(256) apply25_kernel(GridP g, const double *__restrict__ st, const double *__restrict__ x, const double *__restrict__ f,
-                                                     double *__restrict__ y) {
+                                                     double *__restrict__ y, RowRange rows) {
   const int i = 1 + blockIdx.x * 64 + threadIdx.x;
-  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
-  if (i >= g.nx || j >= g.ny) return;
+  const int j = rows.j0 + blockIdx.y * 4 + threadIdx.y;
+  if (i >= g.nx || j > rows.j1) return;
   const long long o = (long long)blockIdx.z * g.stride + (long long)j * g.pitch + i;
   const double s = stencil25(st + 25 * (pos_class_dev(i, g.nx) + 3 * pos_class_dev(j, g.ny)), x + o, g.pitch);
   y[o] = RESIDUAL ? (f[o] - s) : s;
@@ -205,25 +215,120 @@ __global__ void __launch_bounds__(256) residual_norm25_kernel(GridP g, const dou
   }
 }
 
+// Row strips (one process per GPU): the colour launch itself exchanges the halo.  A rank sweeps its own rows
+// [lo, hi]; the sites it updates in the `halo` rows next to a neighbour are stored a second time straight into the
+// neighbour's copy of x (CUDA IPC mapping, NVLink) -- the per-colour halo exchange.  CTAs that touch those rows first
+// wait (device side) until the neighbour has finished the previous launch -- its rows have arrived AND it no longer
+// reads the rows about to be overwritten -- and the last of them raises the neighbour's flag.  Same counting protocol
+// as the tile kernel (fused.cuh StripK): the flag value launch k of a cycle must see is cycle * per_cycle + k.
+struct StripR2 {
+  int on, lo, hi, halo;
+  double *peer_dn, *peer_up;                 // the neighbours' x (same layout); nullptr at the ends of the lattice
+  int *peer_flag_dn, *peer_flag_up;
+  const int *flag_from_dn, *flag_from_up;
+  const int *cycle_no;
+  int per_cycle, index;
+  unsigned int *ticket_dn, *ticket_up;
+  unsigned int n_edge_dn, n_edge_up;         // CTAs of this launch that touch the rows next to the neighbour
+  int *err;
+};
+__device__ __forceinline__ void r2_spin(const int *flag, int target, int *err) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < target) {
+    if (clock64() - t0 > 6000000000ll) {  // a peer died: raise the error word instead of hanging the GPU
+      *err = 1;
+      break;
+    }
+  }
+}
+__device__ __forceinline__ void r2_arrive(unsigned int *ticket, unsigned int n_expected, int *peer_flag) {
+  if (atomicAdd(ticket, 1u) == n_expected - 1) {
+    *ticket = 0u;
+    __threadfence_system();
+    atomicAdd_system(peer_flag, 1);
+  }
+}
+
+// Transfers of a distributed radius-2 level run without exchange on own + mirrored rows, but they must not start before
+// the neighbours have finished the launch that wrote those rows (sync), and -- where they modify mirrored rows
+// (prolongation) -- the neighbours' next colour launch must not push into them before they are done (raise).
+__global__ void strip_sync_kernel(const int *flag_dn, const int *flag_up, const int *cycle_no, int per_cycle, int index, int *err) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int target = *cycle_no * per_cycle + index;
+  if (flag_dn) r2_spin(flag_dn, target, err);
+  if (flag_up) r2_spin(flag_up, target, err);
+}
+// one CTA: copy `n` doubles per chain into a neighbour's array (the first own row of the restricted right-hand side:
+// the neighbour below forms its residual one row beyond its strip), then raise both neighbours' flags
+__global__ void __launch_bounds__(256) strip_row_push_kernel(const double *__restrict__ src, double *__restrict__ dst, long long n, long long stride, int nchains,
+                                                             int *peer_flag_dn, int *peer_flag_up) {
+  if (dst)
+    for (int ch = 0; ch < nchains; ++ch)
+      for (long long k = threadIdx.x; k < n; k += blockDim.x) dst[ch * stride + k] = src[ch * stride + k];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (peer_flag_dn) atomicAdd_system(peer_flag_dn, 1);
+    if (peer_flag_up) atomicAdd_system(peer_flag_up, 1);
+  }
+}
+__global__ void strip_raise_kernel(int *peer_flag_dn, int *peer_flag_up) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __threadfence_system();
+  if (peer_flag_dn) atomicAdd_system(peer_flag_dn, 1);
+  if (peer_flag_up) atomicAdd_system(peer_flag_up, 1);
+}
+
 // one colour (0..8) of a 9-colour SOR / Gibbs sweep; the noise of a site is the same pure function of the
-// site as in the radius-1 kernels (philox.cuh)
+// site as in the radius-1 kernels (philox.cuh).  jfirst = first row of this colour in the launch.
 template <bool GIBBS>
 __global__ void __launch_bounds__(256) sweep_colour25_kernel(GridP g, const double *__restrict__ st, double *__restrict__ x, const double *__restrict__ f, int colour,
-                                                            double omega, NoiseP nz) {
-  const int ci = colour % 3, cj = colour / 3;
+                                                            double omega, NoiseP nz, int jfirst, StripR2 sk) {
+  const int ci = colour % 3;
   const int i = ((ci == 0) ? 3 : ci) + 3 * (blockIdx.x * 64 + threadIdx.x);
-  const int j = ((cj == 0) ? 3 : cj) + 3 * (blockIdx.y * 4 + threadIdx.y);
-  if (i >= g.nx || j >= g.ny) return;
-  const long long o = (long long)blockIdx.z * g.stride + (long long)j * g.pitch + i;
-  const double *a = st + 25 * (pos_class_dev(i, g.nx) + 3 * pos_class_dev(j, g.ny));
-  const double diag = a[12];
-  double b = f[o];
-  if (GIBBS) {
-    double z0, z1;
-    normal_pair(nz.keys, (((uint32_t)j * nz.G + (uint32_t)(i >> 2)) << 1) | (uint32_t)(i & 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.z, nz.mc, kNormalTabDev, z0, z1);
-    b = fma(sqrt(diag * (2. - omega) / omega), (i & 2) ? z1 : z0, b);  // sor_sampler.cc:24-27
+  // row strips: the CTA rows at both ends of the strip run first (they feed the neighbours, whose next launch waits)
+  const int by = sk.on ? ((blockIdx.y & 1) ? (int)(gridDim.y - 1 - (blockIdx.y >> 1)) : (int)(blockIdx.y >> 1)) : (int)blockIdx.y;
+  const int j = jfirst + 3 * (by * 4 + threadIdx.y);
+  const int jmax = sk.on ? min(sk.hi, g.ny - 1) : g.ny - 1;
+  bool edge_dn = false, edge_up = false;
+  if (sk.on) {
+    const int jc0 = jfirst + 12 * by, jc1 = jc0 + 9;
+    edge_dn = sk.peer_dn && jc0 < sk.lo + sk.halo;
+    edge_up = sk.peer_up && jc1 > sk.hi - sk.halo && jc0 <= sk.hi;
+    if (edge_dn || edge_up) {
+      if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const int target = *sk.cycle_no * sk.per_cycle + sk.index;
+        if (edge_dn) r2_spin(sk.flag_from_dn, target, sk.err);
+        if (edge_up) r2_spin(sk.flag_from_up, target, sk.err);
+      }
+      __syncthreads();
+    }
   }
-  x[o] += omega * (b - stencil25(a, x + o, g.pitch)) / diag;
+  if (i < g.nx && j <= jmax) {
+    const long long o = (long long)blockIdx.z * g.stride + (long long)j * g.pitch + i;
+    const double *a = st + 25 * (pos_class_dev(i, g.nx) + 3 * pos_class_dev(j, g.ny));
+    const double diag = a[12];
+    double b = f[o];
+    if (GIBBS) {
+      double z0, z1;
+      normal_pair(nz.keys, (((uint32_t)j * nz.G + (uint32_t)(i >> 2)) << 1) | (uint32_t)(i & 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.z, nz.mc, kNormalTabDev, z0, z1);
+      b = fma(sqrt(diag * (2. - omega) / omega), (i & 2) ? z1 : z0, b);  // sor_sampler.cc:24-27
+    }
+    const double v = x[o] + omega * (b - stencil25(a, x + o, g.pitch)) / diag;
+    x[o] = v;
+    if (sk.on) {
+      if (sk.peer_dn && j < sk.lo + sk.halo) sk.peer_dn[o] = v;
+      if (sk.peer_up && j > sk.hi - sk.halo) sk.peer_up[o] = v;
+    }
+  }
+  if (edge_dn || edge_up) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      if (edge_dn) r2_arrive(sk.ticket_dn, sk.n_edge_dn, sk.peer_flag_dn);
+      if (edge_up) r2_arrive(sk.ticket_up, sk.n_edge_up, sk.peer_flag_up);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -234,10 +339,10 @@ __global__ void __launch_bounds__(256) sweep_colour25_kernel(GridP g, const doub
 // ------------------------------------------------------------------------------------------------
 template <bool NINE, bool PLAIN>
 __global__ void __launch_bounds__(256) residual_restrict_kernel(GridP g, GridP gc, Coef9 a, const double *__restrict__ x,
-                                                               const double *__restrict__ f, double *__restrict__ fc) {
+                                                               const double *__restrict__ f, double *__restrict__ fc, RowRange crows) {
   const int I = 1 + blockIdx.x * 64 + threadIdx.x;
-  const int J = 1 + blockIdx.y * 4 + threadIdx.y;
-  if (I >= gc.nx || J >= gc.ny) return;
+  const int J = crows.j0 + blockIdx.y * 4 + threadIdx.y;
+  if (I >= gc.nx || J > crows.j1) return;
   const long long of = (long long)blockIdx.z * g.stride + (long long)(2 * J) * g.pitch + 2 * I;
   double acc = 0.0;
 #pragma unroll
@@ -264,10 +369,11 @@ __global__ void __launch_bounds__(256) residual_restrict_kernel(GridP g, GridP g
 // x += alpha R^T x_c in gather form (IntergridOperator::prolongate_add, intergrid_operator.hh:106-120):
 // every fine vertex reads its (up to) 4 coarse parents; boundary parents are the zero ghost lines.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prolongate_add_kernel(GridP g, GridP gc, double alpha, const double *__restrict__ xc, double *__restrict__ x) {
+__global__ void __launch_bounds__(256) prolongate_add_kernel(GridP g, GridP gc, double alpha, const double *__restrict__ xc, double *__restrict__ x,
+                                                            RowRange rows) {
   const int i = 1 + blockIdx.x * 64 + threadIdx.x;
-  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
-  if (i >= g.nx || j >= g.ny) return;
+  const int j = rows.j0 + blockIdx.y * 4 + threadIdx.y;
+  if (i >= g.nx || j > rows.j1) return;
   const double *c = xc + (long long)blockIdx.z * gc.stride;
   const int I0 = i >> 1, J0 = j >> 1, I1 = (i + 1) >> 1, J1 = (j + 1) >> 1;
   // even index: I0 == I1 -> weight 1/2 + 1/2 = 1; odd index: the two neighbours with weight 1/2
@@ -509,11 +615,6 @@ __global__ void __launch_bounds__(256) strip_push_kernel(const __grid_constant__
   }
 }
 
-__device__ __forceinline__ int ld_acquire_sys(const int *p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // wait until flag[f] >= per_wait[f] * (number of this wait, counted in *waitno) - lag[f]; a time-out
 // (a peer died) raises *err instead of hanging the GPU

@@ -264,13 +264,15 @@ StripPlan make_strip_plan(const mgmc_desc &d, const std::vector<HostLevel> &H) {
   const long long min_sites = ms ? std::atoll(ms) : (1ll << 20);
   for (int l = 0; l + 1 < (int)H.size(); ++l) {  // the coarsest level is always replicated
     const HostLevel &h = H[l];
-    if (h.st.radius > 1) break;  // radius-2 operators: not decomposed yet
+    const bool r2 = h.st.radius > 1;  // radius-2 operators: per-colour exchange inside the colour launches (kernels.cuh StripR2)
+    if (r2 && d.m_lowrank > 0) break;
     const int nc = h.st.ncolours;
-    const int ty = fused_tile_rows(h.ny, nc, true, true);
+    const int ty = r2 ? 2 : fused_tile_rows(h.ny, nc, true, true);
     const int rows = h.ny / p.nranks;
     // rows exchanged with a neighbour: what a launch of 2 sweeps (+ residual) reads beyond the own rows; with a
-    // low-rank term additionally the windows of the measurements near the strip boundary (patch CTAs)
-    const int halo = (d.m_lowrank > 0) ? ((nc == 2) ? 12 : 20) : ((nc == 2) ? 8 : 12);
+    // low-rank term additionally the windows of the measurements near the strip boundary.  Radius 2: the stencil
+    // reach (2) + the residual row beyond the strip (1) + prolongation of the mirrored rows.
+    const int halo = r2 ? 4 : ((d.m_lowrank > 0) ? ((nc == 2) ? 12 : 20) : ((nc == 2) ? 8 : 12));
     if (h.ny % p.nranks || rows % ty || rows < std::max(min_rows, 2 * halo)) break;
     if (l > 0 && (long long)h.nx * h.ny < min_sites) break;
     // every rank runs the measurement windows near its strip on its own: only while the measurements do not interact
@@ -539,7 +541,7 @@ void normalize_x(mgmc_ctx *c, int level) {
 void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
   const DevLevel &L = c->lv[level];
   c->launch("apply", level, [&] {
-    if (L.r2) apply25_kernel<false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.d_st, x, nullptr, y);
+    if (L.r2) apply25_kernel<false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.d_st, x, nullptr, y, RowRange{1, L.g.ny - 1});
     else if (L.nine) apply_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
     else apply_kernel<false, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
   });
@@ -1025,40 +1027,128 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
   DevLevel &L = c->lv[level];
   const int nch = c->d.nchains;
   const bool lowrank = c->d.m_lowrank > 0;
-  const double n = (double)L.h.ndof() * nch;
+  // Row strips: this rank sweeps its own rows; the colour launches exchange the `halo` rows next to a neighbour
+  // themselves (kernels.cuh StripR2).  Transfers need no exchange: the prolongation is also applied to the mirrored
+  // rows (same arithmetic as on the owner), the residual is formed one row beyond the own rows for the restriction.
+  const bool strip_level = c->strip.on() && c->strip_connected && level < c->strip.ndist;
+  const StripPlan &sp = c->strip;
+  const int lo = strip_level ? sp.lo[level] : 1, hi = strip_level ? sp.hi[level] : L.g.ny - 1;
+  const int halo = strip_level ? sp.halo[level] : 0;
+  const bool has_dn = strip_level && sp.rank > 0, has_up = strip_level && sp.rank + 1 < sp.nranks;
+  if (strip_level && lowrank) fail(MGMC_ERR_UNSUPPORTED, "row strips of a radius-2 operator with a low-rank term are not implemented");
+  const double n = (double)(hi - lo + 1) * (L.g.nx - 1) * nch;
+  auto rows_grid = [&](int j0, int j1) { return dim3((L.g.nx - 1 + 63) / 64, (std::max(j1 - j0 + 1, 1) + 3) / 4, nch); };
+  int *ctl = c->d_strip_ctl;
+  auto strip_sync = [&] {  // wait until the neighbours have finished every distributed launch emitted so far
+    if (!strip_level) return;
+    const int idx = c->strip_index, per = c->strip_per_cycle;
+    c->launch("strip_sync", level, [&] { strip_sync_kernel<<<1, 32, 0, c->stream>>>(has_dn ? ctl + 0 : nullptr, has_up ? ctl + 1 : nullptr, ctl + 9, per, idx, ctl + 3); });
+  };
   if (prolong) {
     DevLevel &C = c->lv[level + 1];
-    c->launch("prolongate_add", level, [&] { prolongate_add_kernel<<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, C.g, alpha, C.x, L.x); }, 18.0 * n);
+    const RowRange rr{std::max(1, lo - (has_dn ? halo : 0)), std::min(L.g.ny - 1, hi + (has_up ? halo : 0))};
+    strip_sync();
+    c->launch("prolongate_add", level, [&] { prolongate_add_kernel<<<rows_grid(rr.j0, rr.j1), kBlockSites, 0, c->stream>>>(L.g, C.g, alpha, C.x, L.x, rr); }, 18.0 * n);
+    if (strip_level) {  // counts as a distributed launch: the neighbours' next colour launch waits for it
+      c->strip_index++;
+      c->launch("strip_raise", level, [&] {
+        strip_raise_kernel<<<1, 32, 0, c->stream>>>(has_dn ? peer_ptr(c, sp.rank - 1, ctl + 1) : nullptr, has_up ? peer_ptr(c, sp.rank + 1, ctl + 0) : nullptr);
+      });
+    }
   }
-  dim3 grid((L.g.nx / 3 + 1 + 63) / 64, (L.g.ny / 3 + 1 + 3) / 4, nch);
+  // The coarse iterate of a distributed next level is zeroed BEFORE the sweeps: the neighbours' first coarse colour
+  // launch pushes into my mirrored rows of it as soon as my last colour launch here has raised their flag.
+  const bool zero_first = strip_level && restrict_ && level + 1 < sp.ndist;
+  if (zero_first) dev_zero(c, level + 1, c->lv[level + 1].x);
   for (const SweepSpec &sw : sweeps) {
     const uint32_t c1 = next_c1(c, level, gibbs);
     NoiseP nz = noise_params(c, level, c1);
     for (int cc = 0; cc < 9; ++cc) {
       const int colour = sw.fwd ? cc : 8 - cc;
+      const int cj = colour / 3;
+      // first row of this colour at or above lo: rows j = cj (mod 3), j >= 1 (row 0 is the boundary)
+      int jfirst = (cj == 0) ? 3 : cj;
+      if (jfirst < lo) jfirst += (lo - jfirst + 2) / 3 * 3;
+      const int nrows3 = (hi >= jfirst) ? (hi - jfirst) / 3 + 1 : 0;
+      dim3 grid((L.g.nx / 3 + 1 + 63) / 64, std::max((nrows3 + 3) / 4, 1), nch);
+      StripR2 K;
+      std::memset(&K, 0, sizeof(K));
+      if (strip_level) {
+        K.on = 1;
+        K.lo = lo;
+        K.hi = hi;
+        K.halo = halo;
+        if (has_dn) {
+          K.peer_dn = peer_ptr(c, sp.rank - 1, L.x);
+          K.peer_flag_dn = peer_ptr(c, sp.rank - 1, ctl + 1);
+          K.flag_from_dn = ctl + 0;
+        }
+        if (has_up) {
+          K.peer_up = peer_ptr(c, sp.rank + 1, L.x);
+          K.peer_flag_up = peer_ptr(c, sp.rank + 1, ctl + 0);
+          K.flag_from_up = ctl + 1;
+        }
+        K.cycle_no = ctl + 9;
+        K.per_cycle = c->strip_per_cycle;
+        K.index = c->strip_index++;
+        K.ticket_dn = (unsigned int *)(ctl + 7);
+        K.ticket_up = (unsigned int *)(ctl + 8);
+        K.err = ctl + 3;
+        unsigned int ndn = 0, nup = 0;
+        for (unsigned int by = 0; by < grid.y; ++by) {  // the kernel's own tests
+          const int jc0 = jfirst + 12 * (int)by, jc1 = jc0 + 9;
+          if (has_dn && jc0 < lo + halo) ++ndn;
+          if (has_up && jc1 > hi - halo && jc0 <= hi) ++nup;
+        }
+        K.n_edge_dn = ndn * grid.x * grid.z;
+        K.n_edge_up = nup * grid.x * grid.z;
+        if ((has_dn && ndn == 0) || (has_up && nup == 0)) fail(MGMC_ERR_INVALID, "internal: strip too short for the radius-2 halo exchange");
+      }
       c->launch(gibbs ? "gibbs_9c1" : "sor_9c1", level, [&] {
-        if (gibbs) sweep_colour25_kernel<true><<<grid, kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, colour, omega, nz);
-        else sweep_colour25_kernel<false><<<grid, kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, colour, omega, nz);
+        if (gibbs) sweep_colour25_kernel<true><<<grid, kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, colour, omega, nz, jfirst, K);
+        else sweep_colour25_kernel<false><<<grid, kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, colour, omega, nz, jfirst, K);
       }, 24.0 * n / 9.0);
     }
     if (lowrank && sw.fix_after) dev_lowrank_fix(c, level, sw.fwd, gibbs, omega, c1);
   }
   if (restrict_) {
     DevLevel &C = c->lv[level + 1];
-    c->launch("residual", level, [&] { apply25_kernel<true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, L.r); }, 16.0 * n);
+    // the restriction to the own coarse rows reads the residual one fine row beyond the own rows
+    const RowRange rr{lo, std::min(L.g.ny - 1, hi + (has_up ? 1 : 0))};
+    strip_sync();
+    c->launch("residual", level, [&] { apply25_kernel<true><<<rows_grid(rr.j0, rr.j1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, L.r, rr); }, 16.0 * n);
     if (lowrank)
       c->launch("lowrank_residual", level, [&] {
         lowrank_apply_kernel<<<nch, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, L.B.rows, c->d_sigma_inv_neg, L.g.stride, L.x, L.r);
       });
-    dev_restrict_plain(c, level, L.r, C.f);
-    dev_zero(c, level + 1, C.x);
+    if (strip_level) {
+      const RowRange cr{(lo - 1) / 2 + 1, std::min(hi / 2, C.g.ny - 1)};
+      c->launch("restrict", level, [&] {
+        residual_restrict_kernel<false, true><<<dim3((C.g.nx - 1 + 63) / 64, (cr.j1 - cr.j0 + 1 + 3) / 4, nch), kBlockSites, 0, c->stream>>>(L.g, C.g, L.coef, nullptr, L.r, C.f, cr);
+      });
+      if (level + 1 == sp.ndist) {
+        strip_allgather_rhs(c, level);  // (zeroes the coarse iterate as well)
+      } else {
+        // the neighbour below forms its coarse residual one row beyond its strip: it needs my first row of f_c
+        // (counts as a distributed launch: both flags go up)
+        c->strip_index++;
+        const long long off = (long long)cr.j0 * C.g.pitch - GX;
+        c->launch("strip_row_push", level, [&] {
+          strip_row_push_kernel<<<1, 256, 0, c->stream>>>(C.f + off, has_dn ? peer_ptr(c, sp.rank - 1, C.f + off) : nullptr, C.g.pitch, C.g.stride, nch,
+                                                        has_dn ? peer_ptr(c, sp.rank - 1, ctl + 1) : nullptr, has_up ? peer_ptr(c, sp.rank + 1, ctl + 0) : nullptr);
+        });
+      }
+    } else {
+      dev_restrict_plain(c, level, L.r, C.f);
+      dev_zero(c, level + 1, C.x);
+    }
   }
 }
 
 void dev_restrict_plain(mgmc_ctx *c, int level, const double *r, double *fc) {
   const DevLevel &L = c->lv[level], &C = c->lv[level + 1];
   c->launch("restrict", level, [&] {
-    residual_restrict_kernel<false, true><<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, L.coef, nullptr, r, fc);
+    residual_restrict_kernel<false, true><<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, L.coef, nullptr, r, fc, RowRange{1, C.g.ny - 1});
   });
 }
 

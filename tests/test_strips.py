@@ -73,7 +73,7 @@ def test_host_plumbing_gloo_world2():
     assert res == {0: True, 1: True}
 
 
-def _gpu_worker(rank, world, port, q, n, nlevel, nsamples, nmeas):
+def _gpu_worker(rank, world, port, q, n, nlevel, nsamples, nmeas, pde="shiftedlaplace_fd"):
     sys.path.insert(0, ROOT)
     os.environ["MGMC_STRIP_MIN_SITES"] = "1"  # small test lattices: distribute as many levels as the strips allow
     import torch
@@ -105,9 +105,9 @@ def _gpu_worker(rank, world, port, q, n, nlevel, nsamples, nmeas):
         z = ctx.sample(nsamples)[:, 0]
         return ctx.get_state(), z
 
-    ref = m.Context(n, n, nlevel, B=B, device=rank, seed=99)
+    ref = m.Context(n, n, nlevel, B=B, device=rank, seed=99, pde=pde)
     x_ref, z_ref = run(ref)
-    ctx = m.Context(n, n, nlevel, B=B, device=rank, seed=99, strip_rank=rank, strip_nranks=world)
+    ctx = m.Context(n, n, nlevel, B=B, device=rank, seed=99, strip_rank=rank, strip_nranks=world, pde=pde)
     strips.connect(ctx, dist, dev)
     x_loc, z_part = run(ctx)
     err = ctx.strip_error()
@@ -126,13 +126,13 @@ def _gpu_worker(rank, world, port, q, n, nlevel, nsamples, nmeas):
     q.put(res)
 
 
-def _run_gpu_case(n, nlevel, nsamples, nmeas, world=2):
+def _run_gpu_case(n, nlevel, nsamples, nmeas, world=2, pde="shiftedlaplace_fd"):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + os.getpid() % 2000
-    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, q, n, nlevel, nsamples, nmeas)) for r in range(world)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, q, n, nlevel, nsamples, nmeas, pde)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
@@ -158,3 +158,15 @@ def test_two_rank_chain_is_bit_identical_to_single_gpu(n, nlevel, nmeas):
         assert r["err"] == 0, r
         assert r["own"] == 0.0 and r["glob"] == 0.0 and r["series"] <= 1e-12 * max(r["scale"], 1.0), r
         assert r["far_untouched"] and r["launches"] > r["ref_launches"], r  # really decomposed: wait / push launches, untouched far rows
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("n,nlevel", [(256, 4), (512, 5)])
+def test_two_rank_biharmonic_chain_is_bit_identical_to_single_gpu(n, nlevel):
+    """BASELINE config 4: squared shifted Laplacian (radius-2 stencils, 9 colours) on row strips, halo rows exchanged
+    per colour inside the colour launches over NVLink peer memory."""
+    for r in _run_gpu_case(n, nlevel, 4, 0, pde="squared_shiftedlaplace_fd"):
+        assert r["err"] == 0, r
+        assert r["own"] == 0.0 and r["glob"] == 0.0 and r["series"] <= 1e-12 * max(r["scale"], 1.0), r
+        assert r["far_untouched"], r
