@@ -1060,11 +1060,16 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
   // launch pushes into my mirrored rows of it as soon as my last colour launch here has raised their flag.
   const bool zero_first = strip_level && restrict_ && level + 1 < sp.ndist;
   if (zero_first) dev_zero(c, level + 1, c->lv[level + 1].x);
-  for (const SweepSpec &sw : sweeps) {
+  static const bool noskip = std::getenv("MGMC_NO_DEAD_PASS") != nullptr;
+  for (size_t si = 0; si < sweeps.size(); ++si) {
+    const SweepSpec &sw = sweeps[si];
     const uint32_t c1 = next_c1(c, level, gibbs);
     NoiseP nz = noise_params(c, level, c1);
     for (int cc = 0; cc < 9; ++cc) {
       const int colour = sw.fwd ? cc : 8 - cc;
+      // omega = 1: an update does not read the site's own value, so the last colour of this sweep is dead if the next
+      // sweep starts with the same colour and nothing reads x in between (see plan_stages for the tile kernel)
+      if (cc == 8 && omega == 1.0 && !noskip && si + 1 < sweeps.size() && sweeps[si + 1].fwd != sw.fwd && !(lowrank && sw.fix_after)) continue;
       const int cj = colour / 3;
       // first row of this colour at or above lo: rows j = cj (mod 3), j >= 1 (row 0 is the boundary)
       int jfirst = (cj == 0) ? 3 : cj;
