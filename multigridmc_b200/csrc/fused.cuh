@@ -7,14 +7,14 @@
 //   reference: SSORSampler::apply + LinearOperator::apply + IntergridOperator::restrict /
 //   prolongate_add (ssor_sampler.cc:9-16, multigridmc_sampler.cc:116-127).
 //
-// Correctness of the overlapped tiles: stage k of S may only update sites whose neighbours held
-// correct values after stage k-1, so the updated region shrinks by the stencil radius (1) per stage
-// from tile +- (S - 1 [+ extra for the residual]) down to the tile; halo sites are recomputed by the
-// neighbouring tiles with IDENTICAL results because the Gibbs noise is a pure function of
-// (seed, chain, sample, level, sweep, site) -- see philox.cuh.  Because tiles overlap the sweep is out
-// of place (x_in -> x_out, ping-pong).
+// Correctness of the overlapped tiles: a colour pass may only update sites whose neighbours hold correct values, so
+// the updated rectangle shrinks from pass to pass down to the tile (+ the halo of the fused residual); the host
+// plans the rectangles backwards from what the launch must deliver (plan_stages in mgmc_b200.cu, see "Stage" below:
+// directional margins, dead passes).  Halo sites are recomputed by the neighbouring tiles with IDENTICAL results
+// because the Gibbs noise is a pure function of (seed, chain, sample, level, sweep, site) -- see philox.cuh.
+// Because tiles overlap the sweep is out of place (x_in -> x_out, ping-pong).
 //
-// Geometry (all index arithmetic is compile-time): a region is always 128 columns = 32 aligned groups
+// Geometry: a region is always 128 columns = 32 aligned groups
 // of 4 columns wide (one warp lane per group -- the unit that shares a Philox call) and RY rows tall.
 // Shared memory holds row r as 4 planes of 32 doubles, plane k = columns 4p + k: for every neighbour
 // access consecutive lanes read consecutive doubles of one plane (bank-conflict free), and every
@@ -244,18 +244,28 @@ __device__ __forceinline__ double offdiag_at(const Coef9 &a, double *row, int p)
 template <bool NINE, bool GIBBS, bool W1, int Q, bool RES>
 __device__ __forceinline__ void update_pair(const Coef9 &a, double *xrow, double *frow, int p, bool v0, bool v1, double winv, double nscale, double z0,
                                             double z1) {
+  // both sites are evaluated before either is stored (same-colour sites are never neighbours): the neighbour the two
+  // stencils share is loaded once, the two dependent chains overlap, and the stores are the only predicated part
+  // (masked lanes read in-bounds shared memory and drop the result)
+  double b0 = frow[Q * 32 + p], b1 = frow[(Q + 2) * 32 + p];
+  if (GIBBS) {
+    b0 = fma(nscale, z0, b0);
+    b1 = fma(nscale, z1, b1);
+  }
+  double r0, r1;
+  if (W1) {
+    r0 = winv * (b0 - offdiag_at<NINE, Q>(a, xrow, p));
+    r1 = winv * (b1 - offdiag_at<NINE, Q + 2>(a, xrow, p));
+  } else {
+    r0 = sat<Q>(xrow, p) + winv * (b0 - stencil_at<NINE, Q>(a, xrow, p));
+    r1 = sat<Q + 2>(xrow, p) + winv * (b1 - stencil_at<NINE, Q + 2>(a, xrow, p));
+  }
   if (v0) {
-    double b = frow[Q * 32 + p];
-    if (GIBBS) b = fma(nscale, z0, b);
-    if (W1) sat<Q>(xrow, p) = winv * (b - offdiag_at<NINE, Q>(a, xrow, p));
-    else sat<Q>(xrow, p) += winv * (b - stencil_at<NINE, Q>(a, xrow, p));
+    sat<Q>(xrow, p) = r0;
     if (RES) frow[Q * 32 + p] = GIBBS ? -(nscale * z0) : 0.0;
   }
   if (v1) {
-    double b = frow[(Q + 2) * 32 + p];
-    if (GIBBS) b = fma(nscale, z1, b);
-    if (W1) sat<Q + 2>(xrow, p) = winv * (b - offdiag_at<NINE, Q + 2>(a, xrow, p));
-    else sat<Q + 2>(xrow, p) += winv * (b - stencil_at<NINE, Q + 2>(a, xrow, p));
+    sat<Q + 2>(xrow, p) = r1;
     if (RES) frow[(Q + 2) * 32 + p] = GIBBS ? -(nscale * z1) : 0.0;
   }
 }
@@ -479,10 +489,17 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const uint32_t chain = P.nz.chain0 + blockIdx.z;
   // the colour passes run in segments that end at a low-rank fix-up (or at the last pass): the fix-up code stays out
   // of the body of the pass loop
+#ifdef MGMC_TILE_TIMING
+  long long tacc_setup = 0, tacc_pass = 0, tacc_bar = 0, tq0 = 0, tq1 = 0, tq2 = 0;
+#define TCLK(v) v = clock64();
+#else
+#define TCLK(v)
+#endif
   int s = 0;
   for (int seg = 0; seg <= (LOWRANK ? P.nfix : 0); ++seg) {
    const int s_end = (LOWRANK && seg < P.nfix) ? P.fix_stage[seg] + 1 : S;
    for (; s < s_end; ++s) {
+    TCLK(tq0)
     const int colour = P.st[s].colour;
     const uint32_t c1 = P.st[s].c1;
     const int mode = P.st[s].mode;
@@ -520,6 +537,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     // the rows of a warp advance by an even number: the column parity q of the colour, the validity of the two sites
     // of the lane and the stride of every pointer are invariants of the pass
     const int jw = jlo + warp * step;
+    TCLK(tq1)
     if (jw <= jhi) {
       const int q = (NC == 2) ? ((colour ^ jw) & 1) : (colour & 1);
       const int i0 = gi0 + q;
@@ -542,7 +560,13 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
         }
       }
     }
+    TCLK(tq2)
     __syncthreads();
+#ifdef MGMC_TILE_TIMING
+    tacc_setup += tq1 - tq0;
+    tacc_pass += tq2 - tq1;
+    tacc_bar += clock64() - tq2;
+#endif
    }
     TSTAMP(2 + 2 * seg)
     if (LOWRANK && seg < P.nfix && lr_tile) {
@@ -821,6 +845,13 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     }
   }
   TSTAMP(11)
+#ifdef MGMC_TILE_TIMING
+  if (threadIdx.x == 0 && P.timing) {  // warp 0: cycles spent in pass set-up / rows / waiting at the pass barriers
+    P.timing[(long long)cta_id * 16 + 12] = tacc_setup;
+    P.timing[(long long)cta_id * 16 + 13] = tacc_pass;
+    P.timing[(long long)cta_id * 16 + 14] = tacc_bar;
+  }
+#endif
 }
 
 }  // namespace mgmc

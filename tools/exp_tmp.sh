@@ -1,2 +1,4 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python profiles/run_c4_strips.py > gpurun_out/c4_n1b.log 2>&1; tail -1 gpurun_out/c4_n1b.log
+for k in 1 2 3; do
+python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench_rep_$k.log 2>&1; echo "rep $k rc=$? $(grep -o '"value": [0-9.]*' gpurun_out/bench_rep_$k.log | head -1) illegal=$(grep -c 'illegal' gpurun_out/bench_rep_$k.log)"
+done
+python bench.py > gpurun_out/bench_rep_default.log 2>&1; echo "default rc=$? $(grep -o '"value": [0-9.]*' gpurun_out/bench_rep_default.log | head -1) illegal=$(grep -c 'illegal' gpurun_out/bench_rep_default.log)"
