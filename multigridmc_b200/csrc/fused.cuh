@@ -35,6 +35,9 @@ constexpr int kGY = 2;   // allocated rows below j = 0 / above j = ny
 #ifndef MGMC_LOAD_ROWS
 #define MGMC_LOAD_ROWS 2
 #endif
+#ifndef MGMC_PASS_PIPELINE
+#define MGMC_PASS_PIPELINE 0
+#endif
 #ifndef MGMC_PASS_ILP
 #define MGMC_PASS_ILP 1
 #endif
@@ -291,6 +294,22 @@ __device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, double *f
     c0 += 2 * dc0;
   }
 #endif
+#if MGMC_PASS_PIPELINE
+  // software pipeline: the normals of the next row are generated before the current row is updated, so that the
+  // shared-memory latency and the dependent chain of the update overlap the (independent) Philox rounds
+  double z0 = 0.0, z1 = 0.0;
+  if (GIBBS && n < nrows) normal_pair(P.nz.keys, c0, c1, sample, chain, P.nz.mc, ntab, z0, z1);
+  for (; n < nrows; ++n) {
+    double y0 = 0.0, y1 = 0.0;
+    c0 += dc0;
+    if (GIBBS && n + 1 < nrows) normal_pair(P.nz.keys, c0, c1, sample, chain, P.nz.mc, ntab, y0, y1);
+    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, xl, fl, 0, v0, v1, winv, nscale, z0, z1);
+    xl += dl;
+    fl += dl;
+    z0 = y0;
+    z1 = y1;
+  }
+#else
   for (; n < nrows; ++n) {
     double z0 = 0.0, z1 = 0.0;
     if (GIBBS) normal_pair(P.nz.keys, c0, c1, sample, chain, P.nz.mc, ntab, z0, z1);
@@ -299,6 +318,7 @@ __device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, double *f
     fl += dl;
     c0 += dc0;
   }
+#endif
 }
 
 template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT, bool LOWRANK>

@@ -557,7 +557,7 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
 inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_) {
   if (strips) return ny > 1024 ? 32 : (ny > 256 ? 16 : 8);  // strips must start on tile boundaries: powers of two only
   static const char *ov = std::getenv("MGMC_TILE_ROWS");    // perf experiments: "rb_big,4c_big,4c_mid,small,rb_big_prolong"
-  static int t[5] = {40, 46, 24, 8, 44};
+  static int t[5] = {36, 46, 24, 8, 40};
   static bool parsed = false;
   if (!parsed) {
     parsed = true;
