@@ -139,6 +139,8 @@ __device__ __forceinline__ long long gtimer() {
 struct FusedP {
   GridP g, gc;  // this level, next coarser level
   Coef9 a;
+  Coef9 aw;   // a * winv (omega = 1 updates)
+  double wn;  // noise_scale * winv
   const double *x_in;
   double *x_out;
   const double *f;
@@ -245,21 +247,27 @@ __device__ __forceinline__ double offdiag_at(const Coef9 &a, double *row, int p)
 // RES (omega = 1, last pass before a fused residual): the residual of a site that has just been updated is known
 // without a stencil evaluation, f_i - sum_j a_ij x_j = f_i - b_i = -(noise), so the pass leaves it in the slot of f_i
 template <bool NINE, bool GIBBS, bool W1, int Q, bool RES>
-__device__ __forceinline__ void update_pair(const Coef9 &a, double *xrow, double *frow, int p, bool v0, bool v1, double winv, double nscale, double z0,
-                                            double z1) {
+__device__ __forceinline__ void update_pair(const Coef9 &a, const Coef9 &aw, double *xrow, double *frow, int p, bool v0, bool v1, double winv, double nscale,
+                                            double wn, double z0, double z1) {
   // both sites are evaluated before either is stored (same-colour sites are never neighbours): the neighbour the two
   // stencils share is loaded once, the two dependent chains overlap, and the stores are the only predicated part
   // (masked lanes read in-bounds shared memory and drop the result)
   double b0 = frow[Q * 32 + p], b1 = frow[(Q + 2) * 32 + p];
-  if (GIBBS) {
-    b0 = fma(nscale, z0, b0);
-    b1 = fma(nscale, z1, b1);
-  }
   double r0, r1;
   if (W1) {
-    r0 = winv * (b0 - offdiag_at<NINE, Q>(a, xrow, p));
-    r1 = winv * (b1 - offdiag_at<NINE, Q + 2>(a, xrow, p));
+    // omega = 1: x_i = (f_i + n z_i - sum_{j != i} a_ij x_j) / a_ii with the division folded into the coefficients
+    // (aw = a / a_ii, wn = n / a_ii: one instruction less per site)
+    r0 = fma(winv, b0, -offdiag_at<NINE, Q>(aw, xrow, p));
+    r1 = fma(winv, b1, -offdiag_at<NINE, Q + 2>(aw, xrow, p));
+    if (GIBBS) {
+      r0 = fma(wn, z0, r0);
+      r1 = fma(wn, z1, r1);
+    }
   } else {
+    if (GIBBS) {
+      b0 = fma(nscale, z0, b0);
+      b1 = fma(nscale, z1, b1);
+    }
     r0 = sat<Q>(xrow, p) + winv * (b0 - stencil_at<NINE, Q>(a, xrow, p));
     r1 = sat<Q + 2>(xrow, p) + winv * (b1 - stencil_at<NINE, Q + 2>(a, xrow, p));
   }
@@ -277,7 +285,7 @@ __device__ __forceinline__ void update_pair(const Coef9 &a, double *xrow, double
 template <bool NINE, bool GIBBS, bool W1, int Q, bool RES = false>
 __device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, double *fl, int nrows, int dl, uint32_t c0, uint32_t dc0, uint32_t c1,
                                           uint32_t sample, uint32_t chain, const double *ntab, bool v0, bool v1) {
-  const double winv = P.winv, nscale = P.noise_scale;
+  const double winv = P.winv, nscale = P.noise_scale, wn = P.wn;
   int n = 0;
 #if MGMC_PASS_ILP == 2
   // two rows of the warp per iteration: two independent Philox / Box-Muller / update chains in flight
@@ -287,8 +295,8 @@ __device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, double *f
       normal_pair(P.nz.keys, c0, c1, sample, chain, P.nz.mc, ntab, z0, z1);
       normal_pair(P.nz.keys, c0 + dc0, c1, sample, chain, P.nz.mc, ntab, y0, y1);
     }
-    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, xl, fl, 0, v0, v1, winv, nscale, z0, z1);
-    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, xl + dl, fl + dl, 0, v0, v1, winv, nscale, y0, y1);
+    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, P.aw, xl, fl, 0, v0, v1, winv, nscale, wn, z0, z1);
+    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, P.aw, xl + dl, fl + dl, 0, v0, v1, winv, nscale, wn, y0, y1);
     xl += 2 * dl;
     fl += 2 * dl;
     c0 += 2 * dc0;
@@ -303,7 +311,7 @@ __device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, double *f
     double y0 = 0.0, y1 = 0.0;
     c0 += dc0;
     if (GIBBS && n + 1 < nrows) normal_pair(P.nz.keys, c0, c1, sample, chain, P.nz.mc, ntab, y0, y1);
-    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, xl, fl, 0, v0, v1, winv, nscale, z0, z1);
+    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, P.aw, xl, fl, 0, v0, v1, winv, nscale, wn, z0, z1);
     xl += dl;
     fl += dl;
     z0 = y0;
@@ -313,7 +321,7 @@ __device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, double *f
   for (; n < nrows; ++n) {
     double z0 = 0.0, z1 = 0.0;
     if (GIBBS) normal_pair(P.nz.keys, c0, c1, sample, chain, P.nz.mc, ntab, z0, z1);
-    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, xl, fl, 0, v0, v1, winv, nscale, z0, z1);
+    update_pair<NINE, GIBBS, W1, Q, RES>(P.a, P.aw, xl, fl, 0, v0, v1, winv, nscale, wn, z0, z1);
     xl += dl;
     fl += dl;
     c0 += dc0;

@@ -748,6 +748,12 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   P.winv = omega / L.coef.c;
   P.omega_is_one = (omega == 1.0) ? 1 : 0;
   P.noise_scale = std::sqrt(L.coef.c * (2. - omega) / omega);  // sor_sampler.cc:24-27
+  P.wn = P.noise_scale * P.winv;
+  {
+    const double *src = &L.coef.c;
+    double *dst = &P.aw.c;
+    for (int k = 0; k < 9; ++k) dst[k] = src[k] * P.winv;
+  }
   P.nz = noise_params(c, level, 0);
   auto up4 = [](int v) { return (v + 3) / 4 * 4; };
   if (use_lr) {
