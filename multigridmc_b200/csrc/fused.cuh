@@ -165,7 +165,7 @@ struct FusedP {
   int nfix;
   int fix_stage[2], fix_dir[2];
   uint32_t fix_c1[2];
-  unsigned char *lr_flags; // [tiles of the launch] see "Per-tile flag" in the kernel
+  unsigned char *lr_flags; // [chains][tiles of the launch] see "Per-tile flag" in the kernel
   int lr_u_from_fix;      // RESTRICT: the launch ends with a fix-up, u = s - d (see the fix-up block)
   int lr_slot, nchains;   // first vbuf / flag slot of this launch (nfix fix-ups, then u)
 };
@@ -383,7 +383,10 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   // Per-tile flag of this launch geometry (self-initialising: 0xFF = not known yet): 0 = the tile is nowhere near a
   // measurement and skips every low-rank block -- set-up, tests and their loads included -- on one uniform branch
   int lr_flag = 0;
-  if (LOWRANK) lr_flag = P.lr_flags ? (int)P.lr_flags[blockIdx.x] : 0xFF;
+  // (one flag per tile AND chain: a flag shared by the chains could change under the threads of a CTA that is still
+  //  reading it -- the CTA of another chain writes it -- and split the CTA at the barriers below)
+  const size_t lr_flag_idx = (size_t)blockIdx.z * gridDim.x + blockIdx.x;
+  if (LOWRANK) lr_flag = P.lr_flags ? (int)P.lr_flags[lr_flag_idx] : 0xFF;
   if (LOWRANK && lr_flag) {
     MGMC_LR_PTRS
     if (threadIdx.x < 4) lr_cnt[threadIdx.x] = 0;
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const bool lr_own = LOWRANK && lr_flag && lr_cnt[0] > 0;
   const bool lr_tile = LOWRANK && lr_flag && (lr_cnt[0] | lr_cnt[1] | lr_cnt[2]) != 0;
   const bool lr_res = LOWRANK && lr_flag && lr_cnt[3] > 0;
-  if (LOWRANK && lr_flag == 0xFF && P.lr_flags && threadIdx.x == 0) P.lr_flags[blockIdx.x] = (lr_cnt[0] | lr_cnt[1] | lr_cnt[2] | lr_cnt[3]) ? 1 : 0;
+  if (LOWRANK && lr_flag == 0xFF && P.lr_flags && threadIdx.x == 0) P.lr_flags[lr_flag_idx] = (lr_cnt[0] | lr_cnt[1] | lr_cnt[2] | lr_cnt[3]) ? 1 : 0;
 
   // ---- colour passes: one warp per row, lane = group ----
   const int S = P.nstages;

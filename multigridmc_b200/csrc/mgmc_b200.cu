@@ -873,7 +873,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
       char key[160];
       std::snprintf(key, sizeof(key), "%d:%.17g:%d,%d,%d,%d,%d,%d,%d,%d:%d,%d,%d:%d,%d", level, omega, P.HXL, P.TX, P.TY, P.hl, P.RY, P.tiles_x, tiles_y, P.by0, P.nfix,
                     P.nfix > 0 ? P.fix_dir[0] : -1, P.nfix > 1 ? P.fix_dir[1] : -1, (int)restrict_, P.sk.on);
-      const size_t ntile = (size_t)P.tiles_x * tiles_y;
+      const size_t ntile = (size_t)P.tiles_x * tiles_y * c->d.nchains;  // one flag per tile and chain
       auto it = c->lr_flag_slots.find(key);
       if (it == c->lr_flag_slots.end() && c->lr_flag_pool_used + ntile <= c->lr_flag_pool_size) {
         it = c->lr_flag_slots.emplace(key, c->lr_flag_pool_used).first;
