@@ -1,2 +1,6 @@
-for k in 1 2 3 4 5 6; do python tools/debug_batched.py c 2>&1 | tail -1; done
-for k in 1 2; do python bench.py --steps 200 --warmup 5 --no-cpu-baseline > gpurun_out/bench_fix_$k.log 2>&1; echo "rc=$? $(grep -o '"value": [0-9.]*' gpurun_out/bench_fix_$k.log | head -1) illegal=$(grep -c illegal gpurun_out/bench_fix_$k.log) $(grep -o '"batched_chains": {"chains": 4, "value": [0-9.]*' gpurun_out/bench_fix_$k.log)"; done
+timeout 700 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 200 --warmup 5 > gpurun_out/bench_r01_v5.log 2>&1 || exit 1
+grep -o '"value": [0-9.]*' gpurun_out/bench_r01_v5.log | head -1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01_v5.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-batched > gpurun_out/ncu_launches_v5.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"fused_smooth_kernel|trimv_kernel" -s 48 -c 16 -o gpurun_out/prof_r01_v5_cycle -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-batched > gpurun_out/ncu_full_v5.log 2>&1
+ls -la gpurun_out/prof_r01_v5_cycle.ncu-rep
