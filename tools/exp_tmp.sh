@@ -1,2 +1,2 @@
-timeout 500 python -m pytest tests/test_strips.py -x -q 2>&1 | tail -2
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n2_v5.log 2>&1; grep -o "\"value\": [0-9.]*" gpurun_out/bench_n2_v5.log | head -1; grep -o "\"strips\": {[^}]*}" gpurun_out/bench_n2_v5.log | cut -c1-120
+python __graft_entry__.py smoke 2>&1 | tail -2
+python profiles/run_configs.py > gpurun_out/configs_r01_v5.log 2>&1; grep '^{' gpurun_out/configs_r01_v5.log | cut -c1-230
