@@ -46,7 +46,7 @@ struct DevSparse {  // device copies of a sparse n x m matrix in both groupings
 struct LowRankDev {
   LowRankFix fix[2];  // [0] forward, [1] backward
   size_t smem = 0;
-  // in-kernel fix-up (patch CTAs of the fused kernel)
+  // in-kernel fix-up (owner / consumer tiles of the fused kernel)
   LowRankTile tile;               // descriptor of the in-kernel fix-up (passed to the kernel by value)
   int bw = 0, bh = 0;             // largest extent of supp(B_k)
   int wreach = 0;                 // largest distance of a site of supp(W_k) from the bounding box of supp(B_k)
@@ -971,8 +971,8 @@ std::vector<SweepSpec> sweep_list(int kind, int direction, int nsmooth, bool gib
 
 // A smoothing step of a level: [prolongate_add] sweeps... [residual + restrict].  Consecutive sweeps are
 // fused into launches of up to 2 sweeps (4 / 8 colour passes).  The Woodbury fix-up of the low-rank
-// term after a sweep is a grid-wide dependency: normally it is resolved inside the launch by the patch
-// CTAs (fused.cuh); if the measurement windows do not fit, every sweep becomes its own launch followed
+// term after a sweep is a grid-wide dependency: normally it is resolved inside the launch by the owner
+// tiles of the measurements (fused.cuh 4.2); where that scheme does not apply, every sweep becomes its own launch followed
 // by a fix-up kernel, and the low-rank part of the residual is a separate kernel.
 void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps, bool gibbs, double omega, bool prolong, double alpha, bool restrict_);
 
