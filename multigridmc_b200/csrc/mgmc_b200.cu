@@ -981,7 +981,10 @@ void emit_smoothing(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps
   if (L.r2) return emit_smoothing_r2(c, level, sweeps, gibbs, omega, prolong, alpha, restrict_);
   const int nc = L.h.st.ncolours;
   const bool lowrank = c->d.m_lowrank > 0;
-  const int max_stages = (nc == 2) ? 4 : 8;  // keeps the tile + halo of x and f below ~100 KB (2 CTAs / SM)
+  // colour passes per launch: 2 sweeps (tile + halo of x and f stay below ~100 KB, 2 CTAs / SM, and a launch carries at
+  // most two low-rank fix-ups); red-black levels without a low-rank term take 4 sweeps -- V(2,2): with omega = 1 only
+  // 5 of the 8 passes are live (plan_stages), one launch instead of two per smoothing step
+  const int max_stages = (nc == 2 && (lowrank || omega != 1.0)) ? 4 : 8;
   bool fusedlr = false;
   if (lowrank) {
     // (tile count of the widest launch geometry: an upper bound is all that matters here)
