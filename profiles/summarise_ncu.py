@@ -40,8 +40,8 @@ def main():
         u = units[h.index(key)].split("/")[0]
         return {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u] / want
 
-    print("| slot | us | DRAM read MB | DRAM write MB | issue active % | fp64 pipe % | LSU wavefronts % | warps active % | inst (M warp) | grid | regs | smem KB |")
-    print("|---|---|---|---|---|---|---|---|---|---|---|---|")
+    print("| slot | us | DRAM read MB | DRAM write MB | DRAM GB/s | issue active % | fp64 pipe % | LSU wavefronts % | warps active % | inst (M warp) | grid | regs | smem KB |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     traffic = {}
     tot = 0.0
     for r in recs:
@@ -50,7 +50,7 @@ def main():
         us = f(r, "gpu__time_duration.sum") * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[h.index("gpu__time_duration.sum")], 1.0)
         tot += us
         traffic[names[r["ID"]]] = (rd + wr) * 1e6
-        print(f"| {names[r['ID']]} | {us:.1f} | {rd:.1f} | {wr:.1f} | {f(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
+        print(f"| {names[r['ID']]} | {us:.1f} | {rd:.1f} | {wr:.1f} | {(rd + wr) / us * 1e3:.0f} | {f(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
               f"{f(r, 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'):.1f} | "
               f"{f(r, 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed'):.1f} | "
               f"{f(r, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {f(r, 'smsp__inst_executed.sum') / 1e6:.1f} | "
