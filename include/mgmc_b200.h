@@ -151,6 +151,16 @@ int mgmc_strip_connect(mgmc_ctx *, const void *all_handles);
 /* nonzero if a device-side wait for a neighbour timed out since the last call (then the state is invalid) */
 int mgmc_strip_error(mgmc_ctx *);
 
+/* ---- introspection (host-only, needs no device; used by the CPU tests) ---- */
+/* Plan of the colour passes of one fused launch (DESIGN.md 4.1 "Pass planning"): for the colour sequence
+ * colours[0..npass) of a level with `ncolours` colours (2: red-black, 4: 4-colour ordering), fix-ups after the passes
+ * fix_after[0..nfix), omega == 1 or not, a fused residual + restriction behind or not, and the extent (lr_mx, lr_my) of
+ * supp(B_k) beyond its lower left corner (0, 0 without a low-rank term), returns per pass mode[s] (0 = full rectangle,
+ * 1 = skipped, 2 = only supp(B_k) of the owned measurements) and the margins margins[4 s .. 4 s + 3] = (xl, xh, yl, yh)
+ * of the updated rectangle around the tile, and in halo[0..3] the margins of the input the launch loads. */
+int mgmc_plan_passes(int ncolours, int npass, const int *colours, int nfix, const int *fix_after, int omega_is_one, int restrict_behind, int lr_mx,
+                     int lr_my, int *mode, int *margins, int *halo);
+
 /* ---- instrumentation ---- */
 /* number of kernels launched by this context so far */
 int64_t mgmc_launch_count(const mgmc_ctx *);

@@ -93,6 +93,7 @@ def lib():
         "mgmc_sample_moments": (i, [vp, i64, c_dp, c_dp]),
         "mgmc_sample_timed": (i, [vp, i64, c_dp, c_dp]),
         "mgmc_strip_partition": (i, [C.POINTER(Desc), i, i, ip, ip, ip]),
+        "mgmc_plan_passes": (i, [i, i, ip, i, ip, i, i, i, i, ip, ip, ip]),
         "mgmc_strip_handle_bytes": (i, []),
         "mgmc_strip_export": (i, [vp, vp]),
         "mgmc_strip_connect": (i, [vp, vp]),
@@ -116,7 +117,7 @@ EXPORTS = [
     "mgmc_loop_solve", "mgmc_set_philox_position", "mgmc_set_rhs", "mgmc_set_state", "mgmc_get_state", "mgmc_set_qoi",
     "mgmc_sample", "mgmc_sample_moments", "mgmc_sample_timed", "mgmc_launch_count", "mgmc_profile_cycle",
     "mgmc_cycle_model", "mgmc_strip_partition", "mgmc_strip_handle_bytes", "mgmc_strip_export", "mgmc_strip_connect",
-    "mgmc_strip_error",
+    "mgmc_strip_error", "mgmc_plan_passes",
 ]
 
 
@@ -162,6 +163,18 @@ def make_desc(nx, ny, nlevel, pde="shiftedlaplace_fd", Lambda=0.2, B=None, smoot
     d.strip_rank, d.strip_nranks = strip_rank, strip_nranks
     d._keep = keep
     return d
+
+
+def plan_passes(ncolours, colours, fix_after=(), omega_is_one=True, restrict_behind=False, lr_mx=0, lr_my=0):
+    """Pass plan of one fused launch (host-only): (modes, margins[npass][4], input halo[4]) -- include/mgmc_b200.h."""
+    n = len(colours)
+    col = (C.c_int * max(n, 1))(*colours)
+    fx = (C.c_int * max(len(fix_after), 1))(*fix_after)
+    mode = (C.c_int * max(n, 1))()
+    marg = (C.c_int * max(4 * n, 1))()
+    halo = (C.c_int * 4)()
+    _chk(lib().mgmc_plan_passes(ncolours, n, col, len(fix_after), fx, int(omega_is_one), int(restrict_behind), lr_mx, lr_my, mode, marg, halo))
+    return list(mode)[:n], [list(marg)[4 * s:4 * s + 4] for s in range(n)], list(halo)
 
 
 def strip_partition(desc, level, rank):

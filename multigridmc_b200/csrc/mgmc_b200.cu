@@ -1900,6 +1900,30 @@ int mgmc_strip_partition(const mgmc_desc *desc, int level, int rank, int *row_lo
   API_END
 }
 
+int mgmc_plan_passes(int ncolours, int npass, const int *colours, int nfix, const int *fix_after, int omega_is_one, int restrict_behind, int lr_mx,
+                     int lr_my, int *mode, int *margins, int *halo) {
+  API_BEGIN
+  if ((ncolours != 2 && ncolours != 4) || npass < 0 || npass > 8 || !colours || !mode || !margins || !halo || nfix < 0 || (nfix > 0 && !fix_after))
+    fail(MGMC_ERR_INVALID, "invalid argument");
+  std::vector<Stage> st(npass);
+  for (int s = 0; s < npass; ++s) {
+    if (colours[s] < 0 || colours[s] >= ncolours) fail(MGMC_ERR_INVALID, "colour out of range");
+    st[s] = Stage{colours[s], 0u, 0, 0, 0, 0, STAGE_FULL};
+  }
+  std::vector<FixSpec> fixes;
+  for (int q = 0; q < nfix; ++q) fixes.push_back(FixSpec{fix_after[q], 0, 0u});
+  const Margin in = plan_stages(ncolours, st, fixes, nfix > 0, omega_is_one != 0, restrict_behind != 0, lr_mx, lr_my);
+  for (int s = 0; s < npass; ++s) {
+    mode[s] = st[s].mode;
+    margins[4 * s] = st[s].xl;
+    margins[4 * s + 1] = st[s].xh;
+    margins[4 * s + 2] = st[s].yl;
+    margins[4 * s + 3] = st[s].yh;
+  }
+  for (int k = 0; k < 4; ++k) halo[k] = in.v[k];
+  API_END
+}
+
 int mgmc_strip_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
 
 int mgmc_strip_export(mgmc_ctx *c, void *handle_out) {
