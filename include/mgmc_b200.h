@@ -169,6 +169,11 @@ int64_t mgmc_launch_count(const mgmc_ctx *);
  * in the model of mgmc_cycle_model.  names: caller buffer of nslots_max * 64 chars. */
 int mgmc_profile_cycle(mgmc_ctx *, int nsamples, int nslots_max, char *names, double *ms_total, int64_t *launches, double *alg_bytes,
                        int *nslots);
+/* Levels below ~512 x 512 and the coarsest-level solve run as phases of ONE persistent cooperative launch
+ * (csrc/tail.cuh).  With MGMC_TAIL_STAMPS=1 in the environment the kernel records a time stamp per phase; this
+ * returns the duration (us) of every phase of the most recent such launch and its kind: 100 + tiles = smoothing +
+ * residual + restriction, 200 + tiles = prolongation + smoothing, -1 = coarse solve, -2 / -3 = copy / zero. */
+int mgmc_tail_stamps(mgmc_ctx *, int nmax, int *kinds, double *us, int *nphases);
 /* algorithmic bytes and site updates of one MGMC cycle */
 int mgmc_cycle_model(const mgmc_ctx *, double *bytes, double *site_updates);
 

@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
 ]
 SOURCES = ["mgmc_b200.cu"]
-HEADERS = ["fused.cuh", "kernels.cuh", "philox.cuh", "normal_tables.inc", "setup.hh", "../../include/mgmc_b200.h"]
+HEADERS = ["fused.cuh", "tail.cuh", "kernels.cuh", "philox.cuh", "normal_tables.inc", "setup.hh", "../../include/mgmc_b200.h"]
 
 
 def build(force=False, verbose=False):
@@ -101,6 +101,7 @@ def lib():
         "mgmc_launch_count": (i64, [vp]),
         "mgmc_profile_cycle": (i, [vp, i, i, C.c_char_p, c_dp, C.POINTER(i64), c_dp, ip]),
         "mgmc_cycle_model": (i, [vp, c_dp, c_dp]),
+        "mgmc_tail_stamps": (i, [vp, i, ip, c_dp, ip]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)  # AttributeError = header / library mismatch
@@ -117,7 +118,7 @@ EXPORTS = [
     "mgmc_loop_solve", "mgmc_set_philox_position", "mgmc_set_rhs", "mgmc_set_state", "mgmc_get_state", "mgmc_set_qoi",
     "mgmc_sample", "mgmc_sample_moments", "mgmc_sample_timed", "mgmc_launch_count", "mgmc_profile_cycle",
     "mgmc_cycle_model", "mgmc_strip_partition", "mgmc_strip_handle_bytes", "mgmc_strip_export", "mgmc_strip_connect",
-    "mgmc_strip_error", "mgmc_plan_passes",
+    "mgmc_strip_error", "mgmc_plan_passes", "mgmc_tail_stamps",
 ]
 
 
@@ -360,6 +361,14 @@ class Context:
         for k in range(n.value):
             out.append((names.raw[k * 64:(k + 1) * 64].split(b"\0")[0].decode(), float(ms[k]), int(launches[k]), float(byts[k])))
         return out
+
+    def tail_stamps(self, nmax=256):
+        """[(kind, us)] per phase of the last persistent tail launch (needs MGMC_TAIL_STAMPS=1)"""
+        kinds = (C.c_int * nmax)()
+        us = np.zeros(nmax)
+        n = C.c_int()
+        _chk(lib().mgmc_tail_stamps(self.h, nmax, kinds, us.ctypes.data_as(c_dp), C.byref(n)))
+        return [(int(kinds[k]), float(us[k])) for k in range(n.value)]
 
     def cycle_model(self):
         b, u = C.c_double(), C.c_double()

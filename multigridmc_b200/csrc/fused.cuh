@@ -168,6 +168,10 @@ struct FusedP {
   unsigned char *lr_flags; // [chains][tiles of the launch] see "Per-tile flag" in the kernel
   int lr_u_from_fix;      // RESTRICT: the launch ends with a fix-up, u = s - d (see the fix-up block)
   int lr_slot, nchains;   // first vbuf / flag slot of this launch (nfix fix-ups, then u)
+  int rt_prolong, rt_restrict;  // persistent kernel of the small levels (tail.cuh): the flavour of the phase
+  int chain_off;                // first chain of this launch (chains launched in groups)
+  int nz_off, nz_cap;           // persistent kernel: noise generated ahead of the passes -- buffer offset in doubles behind
+                                // the tile (0: off) and its capacity in (row, pass) items
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -282,11 +286,23 @@ __device__ __forceinline__ void update_pair(const Coef9 &a, const Coef9 &aw, dou
 }
 
 // one colour pass over the rows of a warp: xl / fl point at the lane's group (plane 0) in the first row
-template <bool NINE, bool GIBBS, bool W1, int Q, bool RES = false>
+// PRE: the normals were generated ahead of the passes (fused_tile "noise ahead of the passes"); zp points at the pair of
+// this lane for the first row, consecutive rows of the warp are dz pairs apart
+template <bool NINE, bool GIBBS, bool W1, int Q, bool RES = false, bool PRE = false>
 __device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, double *fl, int nrows, int dl, uint32_t c0, uint32_t dc0, uint32_t c1,
-                                          uint32_t sample, uint32_t chain, const double *ntab, bool v0, bool v1) {
+                                          uint32_t sample, uint32_t chain, const double *ntab, bool v0, bool v1, const double2 *zp = nullptr, int dz = 0) {
   const double winv = P.winv, nscale = P.noise_scale, wn = P.wn;
   int n = 0;
+  if (PRE) {
+    for (; n < nrows; ++n) {
+      const double2 z = *zp;
+      update_pair<NINE, GIBBS, W1, Q, RES>(P.a, P.aw, xl, fl, 0, v0, v1, winv, nscale, wn, z.x, z.y);
+      xl += dl;
+      fl += dl;
+      zp += dz;
+    }
+    return;
+  }
 #if MGMC_PASS_ILP == 2
   // two rows of the warp per iteration: two independent Philox / Box-Muller / update chains in flight
   for (; n + 1 < nrows; n += 2) {
@@ -329,20 +345,28 @@ __device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, double *f
 #endif
 }
 
-template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT, bool LOWRANK>
-__global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {
-  extern __shared__ double sm[];
-  __shared__ int lr_cnt[4];  // LOWRANK: measurements owned by this tile, needed for the forward / backward fix-up, for the residual
-  __shared__ __align__(16) double ntab[128];  // GIBBS: tables of the normal generator (philox.cuh), published by the barrier of the tile load
-  if (GIBBS && threadIdx.x < 128) ntab[threadIdx.x] = kNormalTabDev[threadIdx.x];
+// One tile job: tile `tile_id` of chain `chain` of the launch / phase described by P.  `njob_x` = tiles per chain
+// (index of the per-tile flags).  sm = dynamic shared memory of the CTA; lr_cnt[4], ntab[128] = static shared memory
+// (LOWRANK: measurements owned by this tile, needed for the forward / backward fix-up, for the residual; GIBBS: tables
+// of the normal generator (philox.cuh), published by the barrier of the tile load).
+// PR / RS = 0, 1: prolongation in front / residual + restriction behind compiled out / in; 2: decided at run time by
+// P.rt_prolong / P.rt_restrict (the persistent kernel of the small levels runs both flavours, tail.cuh).
+template <int NC, bool GIBBS, int PR, int RS, bool LOWRANK>
+__device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, const int chain_idx, const int njob_x, double *sm, int *lr_cnt, double *ntab) {
+  const bool PROLONG = (PR == 2) ? (P.rt_prolong != 0) : (PR == 1);
+  const bool RESTRICT = (RS == 2) ? (P.rt_restrict != 0) : (RS == 1);
   constexpr bool NINE = (NC == 4);
-  const int tile_id = (int)blockIdx.x;
+  // Persistent kernel of the small levels: a warp has at most a row or two per colour pass there, and a pass is the
+  // in-order latency of ONE Philox + Box-Muller + update chain (~1400 cycles, 80 % of it the normals) times the number
+  // of passes.  The normals do not depend on x: all of them -- every (row, pass) item of the launch -- are generated
+  // ahead of the passes by all warps, two independent chains per warp in flight, and parked in shared memory.
+  constexpr bool TAILMODE = (PR == 2);
   int tile_row = tile_id / P.tiles_x;
   // row strips: the tile rows at both ends of the strip run first (they feed the neighbours)
   if (P.sk.on) tile_row = (tile_row & 1) ? (P.sk.tiles_y - 1 - (tile_row >> 1)) : (tile_row >> 1);
   const int tile_bx = tile_id % P.tiles_x, tile_by = tile_row + P.by0;
 #ifdef MGMC_TILE_TIMING
-  const int cta_id = blockIdx.z * gridDim.x + blockIdx.x;
+  const int cta_id = chain_idx * njob_x + tile_id;
 #define TSTAMP(k) if (threadIdx.x == 0 && P.timing) P.timing[(long long)cta_id * 16 + (k)] = gtimer();
   if (threadIdx.x == 0 && P.timing) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); P.timing[(long long)cta_id * 16 + 15] = smid; }
 #else
@@ -356,7 +380,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const int nx = P.g.nx, ny = P.g.ny, pitch = P.g.pitch;
   const int i_t0 = TX * tile_bx, j_t0 = 1 + TY * tile_by;
   const int i_r0 = i_t0 - P.HXL, j_r0 = j_t0 - P.hl;
-  const long long cbase = (long long)blockIdx.z * P.g.stride;
+  const long long cbase = (long long)chain_idx * P.g.stride;
   const double *xg = P.x_in + cbase;
   double *xo = P.x_out + cbase;
   const double *fg = P.f + cbase;
@@ -385,8 +409,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   int lr_flag = 0;
   // (one flag per tile AND chain: a flag shared by the chains could change under the threads of a CTA that is still
   //  reading it -- the CTA of another chain writes it -- and split the CTA at the barriers below)
-  const size_t lr_flag_idx = (size_t)blockIdx.z * gridDim.x + blockIdx.x;
-  if (LOWRANK) lr_flag = P.lr_flags ? (int)P.lr_flags[lr_flag_idx] : 0xFF;
+  const size_t lr_flag_idx = (size_t)chain_idx * njob_x + tile_id;
+  if (LOWRANK) lr_flag = (P.lr.m > 0) ? (P.lr_flags ? (int)P.lr_flags[lr_flag_idx] : 0xFF) : 0;  // (m = 0: a phase without low-rank work inside a LOWRANK kernel)
   if (LOWRANK && lr_flag) {
     MGMC_LR_PTRS
     if (threadIdx.x < 4) lr_cnt[threadIdx.x] = 0;
@@ -395,6 +419,86 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       is_own[k] = 0;
     }
     __syncthreads();
+  }
+  // ---- persistent kernel of the small levels: pass descriptors and noise ahead of the passes ----
+  // A warp has a row or two per colour pass there, and a pass costs the in-order latency of its set-up (~60 dependent
+  // integer instructions) plus one Philox + Box-Muller + update chain (~1400 cycles, 80 % of it the normals).  Both are
+  // taken off the pass loop: one thread per (pass, warp) works out what the warp does in the pass (descriptor), and
+  // all normals of the launch -- one item per (row, live pass) -- are generated by all warps, three independent
+  // chains per warp in flight, and parked in shared memory.
+  double2 *nzb = nullptr;
+  int *aux = nullptr;  // [0..7] first item of a pass, [8..15] first row, [16..23] rows, [32 + 4 (16 s + w)] descriptor of
+                       // (pass s, warp w): row offset, rows | q << 16, ilo, ihi; [32 + 512 + 2 t] (row, pass) of item t
+  bool pre_on = false;
+  if (TAILMODE) {
+    nzb = reinterpret_cast<double2 *>(sm + P.nz_off);
+    aux = reinterpret_cast<int *>(nzb + (size_t)P.nz_cap * 32);
+    const int S0 = P.nstages;
+    if ((int)threadIdx.x < S0 * kFusedWarps) {
+      const int st = threadIdx.x / kFusedWarps, w = threadIdx.x % kFusedWarps;
+      int n = 0, jlo = 0, rowoff = 0, nrows = 0, q = 0, ilo = 0, ihi = -1;
+      if (P.st[st].mode == STAGE_FULL) {
+        const int colour = P.st[st].colour;
+        ilo = max(1, i_t0 - P.st[st].xl);
+        ihi = min(nx - 1, i_t0 + TX - 1 + P.st[st].xh);
+        jlo = max(1, j_t0 - P.st[st].yl);
+        const int jhi = min(ny - 1, j_t0 + TY - 1 + P.st[st].yh);
+        const int step = (NC == 4) ? 2 : 1;
+        if (NC == 4 && (jlo & 1) != (colour >> 1)) ++jlo;
+        n = (jhi >= jlo) ? (jhi - jlo) / step + 1 : 0;
+        const int jw = jlo + w * step;
+        if (jw <= jhi) {
+          nrows = (jhi - jw) / (kFusedWarps * step) + 1;
+          rowoff = (jw - j_r0) * 128;
+          q = (NC == 2) ? ((colour ^ jw) & 1) : (colour & 1);
+        }
+      }
+      reinterpret_cast<int4 *>(aux + 32)[threadIdx.x] = make_int4(rowoff, nrows | (q << 16), ilo, ihi);
+      if (w == 0) {
+        aux[8 + st] = jlo;
+        aux[16 + st] = n;
+      }
+    }
+    __syncthreads();
+    if (GIBBS && P.nz_cap > 0) {
+      int tot = 0;
+      {
+        // item t = (pass, k-th row of the pass): every thread walks the (at most 8) passes
+        const int t = threadIdx.x;
+        for (int st = 0; st < S0; ++st) {
+          const int n = aux[16 + st];
+          if (t == 0) aux[st] = tot;
+          if (t >= tot && t < tot + n) {
+            aux[32 + 512 + 2 * t] = aux[8 + st] + (t - tot) * ((NC == 4) ? 2 : 1);
+            aux[33 + 512 + 2 * t] = st;
+          }
+          tot += n;
+        }
+      }
+      pre_on = tot <= P.nz_cap;  // (uniform)
+      __syncthreads();
+      if (pre_on) {
+        const uint32_t pg0 = (uint32_t)((i_r0 >> 2) + lane);
+        const uint32_t sample0 = *P.nz.sample, chain0 = P.nz.chain0 + chain_idx;
+        constexpr int NI = 3;
+        for (int it0 = warp; it0 < tot; it0 += NI * kFusedWarps) {
+          double z0[NI], z1[NI];
+#pragma unroll
+          for (int u = 0; u < NI; ++u) {
+            const int it = min(it0 + u * kFusedWarps, tot - 1);  // (a surplus chain recomputes the last item)
+            const int jr = aux[32 + 512 + 2 * it], sr = aux[33 + 512 + 2 * it];
+            const int cr = P.st[sr].colour;
+            const uint32_t qr = (NC == 2) ? ((cr ^ jr) & 1) : (cr & 1);
+            normal_pair(P.nz.keys, (((uint32_t)jr * P.nz.G + pg0) << 1) | qr, P.st[sr].c1, sample0, chain0, P.nz.mc, ntab, z0[u], z1[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < NI; ++u) {
+            const int it = it0 + u * kFusedWarps;
+            if (it < tot) nzb[it * 32 + lane] = make_double2(z0[u], z1[u]);
+          }
+        }
+      }
+    }
   }
   if (P.sk.on) {
     const bool wdn = P.sk.flag_from_dn && (j_r0 < P.sk.own_lo), wup = P.sk.flag_from_up && (j_r0 + RY - 1 > P.sk.own_hi);
@@ -442,7 +546,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       if (PROLONG) {
         if (gj >= 1 && gj < ny) {
           // x += alpha R^T x_c in gather form: every fine vertex reads its (up to) 4 coarse parents
-          const double *xc = P.xc_in + (long long)blockIdx.z * P.gc.stride;
+          const double *xc = P.xc_in + (long long)chain_idx * P.gc.stride;
           const double *r0 = xc + (long long)(gj >> 1) * P.gc.pitch, *r1 = xc + (long long)((gj + 1) >> 1) * P.gc.pitch;
           const double al = P.alpha;
           if (oka && gia >= -1 && gia <= nx) {  // gia is even: coarse columns I, I + 1
@@ -499,7 +603,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       double sv = 0.0;
       if (GIBBS) {
         double z0, z1;
-        normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[q], *P.nz.sample, P.nz.chain0 + blockIdx.z, P.nz.mc, ntab, z0, z1);
+        normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[q], *P.nz.sample, P.nz.chain0 + chain_idx, P.nz.mc, ntab, z0, z1);
         sv = R.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
       }
       spre[q * lrm + k] = sv;
@@ -517,7 +621,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
   const int S = P.nstages;
   const uint32_t pg = (uint32_t)((i_r0 >> 2) + lane);
   const uint32_t sample = GIBBS ? *P.nz.sample : 0u;
-  const uint32_t chain = P.nz.chain0 + blockIdx.z;
+  const uint32_t chain = P.nz.chain0 + chain_idx;
   // the colour passes run in segments that end at a low-rank fix-up (or at the last pass): the fix-up code stays out
   // of the body of the pass loop
 #ifdef MGMC_TILE_TIMING
@@ -555,6 +659,53 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
         }
       }
       __syncthreads();
+      continue;
+    }
+    if (TAILMODE) {
+      // persistent kernel of the small levels: what this warp does in the pass was worked out ahead (descriptor)
+      const int4 d = reinterpret_cast<const int4 *>(aux + 32)[s * kFusedWarps + warp];
+      const int nrows = d.y & 0xffff, q = d.y >> 16;
+      const int i0 = gi0 + q;
+      const bool v0 = (i0 >= d.z) && (i0 <= d.w), v1 = (i0 + 2 >= d.z) && (i0 + 2 <= d.w);
+      TCLK(tq1)
+      if (nrows > 0 && (v0 || v1)) {
+        double *xl = xs + d.x + lane, *fl = fs + d.x + lane;
+        const int dl = kFusedWarps * ((NC == 4) ? 2 : 1) * 128;
+        const bool res = RESTRICT && s == P.res_stage && !lr_tile;
+        if (GIBBS && pre_on) {
+          // normals generated ahead of the passes: item of this warp's first row, 16 items per round of rows
+          const double2 *zp = nzb + (size_t)(aux[s] + warp) * 32 + lane;
+          const int dz = kFusedWarps * 32;
+#define MGMC_TAIL_PASS(W1_, RES_)                                                                                           \
+  {                                                                                                                         \
+    if (q == 0) pass_rows<NINE, GIBBS, W1_, 0, RES_, true>(P, xl, fl, nrows, dl, 0u, 0u, c1, sample, chain, ntab, v0, v1, zp, dz); \
+    else pass_rows<NINE, GIBBS, W1_, 1, RES_, true>(P, xl, fl, nrows, dl, 0u, 0u, c1, sample, chain, ntab, v0, v1, zp, dz);       \
+  }
+          if (res) MGMC_TAIL_PASS(true, true)
+          else if (P.omega_is_one) MGMC_TAIL_PASS(true, false)
+          else MGMC_TAIL_PASS(false, false)
+#undef MGMC_TAIL_PASS
+        } else {
+          const int jw = d.x / 128 + j_r0;
+          const uint32_t c0 = (((uint32_t)jw * P.nz.G + pg) << 1) | (uint32_t)q, dc0 = ((uint32_t)(kFusedWarps * ((NC == 4) ? 2 : 1)) * P.nz.G) << 1;
+#define MGMC_TAIL_PASS(W1_, RES_)                                                                                     \
+  {                                                                                                                   \
+    if (q == 0) pass_rows<NINE, GIBBS, W1_, 0, RES_>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1); \
+    else pass_rows<NINE, GIBBS, W1_, 1, RES_>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);       \
+  }
+          if (res) MGMC_TAIL_PASS(true, true)
+          else if (P.omega_is_one) MGMC_TAIL_PASS(true, false)
+          else MGMC_TAIL_PASS(false, false)
+#undef MGMC_TAIL_PASS
+        }
+      }
+      TCLK(tq2)
+      __syncthreads();
+#ifdef MGMC_TILE_TIMING
+      tacc_setup += tq1 - tq0;
+      tacc_pass += tq2 - tq1;
+      tacc_bar += clock64() - tq2;
+#endif
       continue;
     }
     const int ilo = max(1, i_t0 - P.st[s].xl), ihi = min(nx - 1, i_t0 + TX - 1 + P.st[s].xh);
@@ -606,7 +757,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       const LowRankTile &R = P.lr;
       const int dir = P.fix_dir[fixq];
       const bool diag = R.diag[dir] != 0;
-      const size_t slot = (size_t)(P.lr_slot + fixq) * P.nchains + blockIdx.z;
+      const size_t slot = (size_t)(P.lr_slot + fixq) * P.nchains + chain_idx;
       LrPkt *vb = R.vbuf + slot * 2 * lrm;
       // (1) owners: t_k = (B^T x)_k from shared memory, published as d_k (diagonal capacitance matrix) or as (t_k, s_k);
       //     the tile keeps its own values in shared memory
@@ -719,7 +870,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     // (launch without a closing fix-up) owners: u_k = (Sigma^{-1} B^T x)_k of the final iterate, for the low-rank part of the residual
     MGMC_LR_PTRS
     const LowRankTile &R = P.lr;
-    const size_t slot = (size_t)(P.lr_slot + P.nfix) * P.nchains + blockIdx.z;
+    const size_t slot = (size_t)(P.lr_slot + P.nfix) * P.nchains + chain_idx;
     LrPkt *vb = R.vbuf + slot * 2 * lrm;
     for (int o = warp; o < lr_cnt[0]; o += kFusedWarps) {
       const int k = own_list[o];
@@ -813,7 +964,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       // low-rank part of the residual: r -= B u, u = Sigma^{-1} B^T x of the final state (linear_operator.hh:71-75)
       MGMC_LR_PTRS
       const LowRankTile &R = P.lr;
-      const size_t slot = (size_t)(P.lr_slot + P.nfix) * P.nchains + blockIdx.z;
+      const size_t slot = (size_t)(P.lr_slot + P.nfix) * P.nchains + chain_idx;
       const LrPkt *vb = R.vbuf + slot * 2 * lrm;
       const int *nlist = need_list + 2 * lrm;
       for (int n = threadIdx.x; n < lr_cnt[3]; n += kFusedThreads) {
@@ -832,7 +983,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
       __syncthreads();
     }
     TSTAMP(10)
-    const long long ccb = (long long)blockIdx.z * P.gc.stride;
+    const long long ccb = (long long)chain_idx * P.gc.stride;
     const int I = gi0 >> 1;  // coarse columns I (fine 4p) and I + 1 (fine 4p + 2) of this lane
     const bool mine = (gi0 >= i_t0) && (gi0 < i_t0 + TX);
     for (int rr = warp; rr < TY / 2; rr += kFusedWarps) {
@@ -883,6 +1034,15 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __
     P.timing[(long long)cta_id * 16 + 14] = tacc_bar;
   }
 #endif
+}
+
+template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT, bool LOWRANK>
+__global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {
+  extern __shared__ double sm[];
+  __shared__ int lr_cnt[4];
+  __shared__ __align__(16) double ntab[128];
+  if (GIBBS && threadIdx.x < 128) ntab[threadIdx.x] = kNormalTabDev[threadIdx.x];
+  fused_tile<NC, GIBBS, PROLONG ? 1 : 0, RESTRICT ? 1 : 0, LOWRANK>(P, (int)blockIdx.x, (int)blockIdx.z + P.chain_off, (int)gridDim.x, sm, lr_cnt, ntab);
 }
 
 }  // namespace mgmc

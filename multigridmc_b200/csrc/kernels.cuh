@@ -112,47 +112,6 @@ __global__ void __launch_bounds__(256) axpy_kernel(GridP g, double *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// One colour of a multicolour SOR / Gibbs sweep (SORSmoother::apply_sparse sor_smoother.cc:56-78
-// with the rows visited colour by colour; SORSampler noise sor_sampler.cc:42-46 generated in
-// registers).  NC = 2: red-black for the 5-point stencil, colour = (i + j) & 1.
-// NC = 4: colour = (i & 1) + 2 (j & 1) for the 9-point Galerkin stencils.
-// Each thread owns one aligned group of 4 columns in one row and updates the (up to) two sites of
-// the colour in it: (i0, i0 + 2) -- they share one Philox call.
-// ------------------------------------------------------------------------------------------------
-template <int NC, bool GIBBS>
-__global__ void __launch_bounds__(256) sweep_colour_kernel(GridP g, Coef9 a, double *__restrict__ x, const double *__restrict__ f, int colour,
-                                                          double omega, double noise_scale, NoiseP nz) {
-  const int p = blockIdx.x * 32 + threadIdx.x;
-  const int jj = blockIdx.y * 8 + threadIdx.y;
-  int j, q;
-  if (NC == 2) {
-    j = 1 + jj;
-    q = (colour ^ j) & 1;
-  } else {
-    j = 2 * jj + ((colour >> 1) ? 1 : 2);
-    q = colour & 1;
-  }
-  const int i0 = 4 * p + q;
-  if (j >= g.ny || i0 >= g.nx) return;
-  const long long o = (long long)blockIdx.z * g.stride + (long long)j * g.pitch + i0;
-  double z0 = 0.0, z1 = 0.0;
-  if (GIBBS) normal_pair(nz.keys, (((uint32_t)j * nz.G + (uint32_t)p) << 1) | (uint32_t)q, nz.c1, *nz.sample, nz.chain0 + blockIdx.z, nz.mc, kNormalTabDev, z0, z1);
-  const double winv = omega / a.c;
-  double *xp = x + o;
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int i = i0 + 2 * k;
-    if (i < 1 || i >= g.nx) continue;
-    double *pc = xp + 2 * k;
-    double s = a.c * pc[0] + a.w * pc[-1] + a.e * pc[1] + a.s * pc[-g.pitch] + a.n * pc[g.pitch];
-    if (NC == 4) s += a.sw * pc[-g.pitch - 1] + a.se * pc[-g.pitch + 1] + a.nw * pc[g.pitch - 1] + a.ne * pc[g.pitch + 1];
-    double b = f[o + 2 * k];
-    if (GIBBS) b += noise_scale * (k ? z1 : z0);
-    pc[0] += winv * (b - s);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Radius-2 operators (SquaredShiftedLaplaceFDOperator, squared_shiftedlaplace_fd_operator.cc:9-96, and
 // its Galerkin coarsenings): 13-point stencil on the finest level, 21-point below, constant in the
 // interior but with different coefficients on the first / last interior line of either direction
@@ -332,14 +291,12 @@ __global__ void __launch_bounds__(256) sweep_colour25_kernel(GridP g, const doub
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused residual + restriction: f_c = R (f - A_0 x) with R = {1/2,1,1/2}^(x)2 un-normalised
-// (multigridmc_sampler.cc:118-120, intergrid_operator.hh:74-88, intergrid_operator_linear.cc:13).
-// One thread per coarse vertex (I, J) <-> fine (2I, 2J); the residual is never stored.
-// PLAIN = true: restrict a given fine vector (IntergridOperator::restrict).
+// Restriction f_c = R r with R = {1/2,1,1/2}^(x)2 un-normalised (IntergridOperator::restrict,
+// intergrid_operator.hh:74-88, intergrid_operator_linear.cc:13): one thread per coarse vertex
+// (I, J) <-> fine (2I, 2J).  (Inside a cycle the residual is never stored: the tile kernel restricts it
+// from shared memory, fused.cuh.)
 // ------------------------------------------------------------------------------------------------
-template <bool NINE, bool PLAIN>
-__global__ void __launch_bounds__(256) residual_restrict_kernel(GridP g, GridP gc, Coef9 a, const double *__restrict__ x,
-                                                               const double *__restrict__ f, double *__restrict__ fc, RowRange crows) {
+__global__ void __launch_bounds__(256) restrict_kernel(GridP g, GridP gc, const double *__restrict__ r, double *__restrict__ fc, RowRange crows) {
   const int I = 1 + blockIdx.x * 64 + threadIdx.x;
   const int J = crows.j0 + blockIdx.y * 4 + threadIdx.y;
   if (I >= gc.nx || J > crows.j1) return;
@@ -348,20 +305,7 @@ __global__ void __launch_bounds__(256) residual_restrict_kernel(GridP g, GridP g
 #pragma unroll
   for (int dj = -1; dj <= 1; ++dj)
 #pragma unroll
-    for (int di = -1; di <= 1; ++di) {
-      const double wgt = ((di == 0) ? 1.0 : 0.5) * ((dj == 0) ? 1.0 : 0.5);
-      const long long o = of + (long long)dj * g.pitch + di;
-      double r;
-      if (PLAIN) {
-        r = f[o];
-      } else {
-        const double *p = x + o;
-        double s = a.c * p[0] + a.w * p[-1] + a.e * p[1] + a.s * p[-g.pitch] + a.n * p[g.pitch];
-        if (NINE) s += a.sw * p[-g.pitch - 1] + a.se * p[-g.pitch + 1] + a.nw * p[g.pitch - 1] + a.ne * p[g.pitch + 1];
-        r = f[o] - s;
-      }
-      acc += wgt * r;
-    }
+    for (int di = -1; di <= 1; ++di) acc += ((di == 0) ? 1.0 : 0.5) * ((dj == 0) ? 1.0 : 0.5) * r[of + (long long)dj * g.pitch + di];
   fc[(long long)blockIdx.z * gc.stride + (long long)J * gc.pitch + I] = acc;
 }
 
@@ -517,63 +461,6 @@ __global__ void __launch_bounds__(256) lowrank_fix_kernel(LowRankFix F, long lon
     for (int e = 0; e < F.EW; ++e) acc += F.wval[u * F.EW + e] * d[F.wcol[u * F.EW + e]];
     xc[F.usite[u]] += acc;
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Coarsest level: dense lower Cholesky factor of A_0 + B Sigma^{-1} B^T resident on the device.
-//   SAMPLE:  x = L^{-T} (xi + L^{-1} f)   (CholeskySampler::apply, cholesky_sampler.hh:50-66)
-//   SOLVE:   x = L^{-T} L^{-1} b          (CholeskySolver::apply, cholesky_solver.cc:30-41; the low-rank
-//            term is folded into the factorised matrix instead of the reference's Woodbury update)
-// A substitution with N = 961 unknowns is a chain of N dependent steps (or N/32 block steps): latency
-// bound at ~0.6 ms on one SM.  The triangular solves are therefore applied in their fully blocked
-// form -- block size N, i.e. through the triangular inverses T = L^{-1} (row-major lower) and
-// T^T (row-major upper) computed by substitution on the host at setup -- as two triangular
-// matrix-vector products that spread over the whole chip (one warp per row, rows read coalesced from
-// L2).  Vectors are gathered from / scattered to the padded lattice layout through `cidx`.
-//   pass 1: y = T f (+ xi)      pass 2: x = T^T y
-// ------------------------------------------------------------------------------------------------
-template <bool LOWER, bool NOISE, bool GATHER_IN, bool SCATTER_OUT>
-__global__ void __launch_bounds__(256) trimv_kernel(const double *__restrict__ T, int N, int Np, const int *__restrict__ cidx,
-                                                   const double *__restrict__ in, long long in_stride, double *__restrict__ out, long long out_stride,
-                                                   NoiseP nz) {
-  // the input vector is staged in shared memory once per CTA (the gather through cidx is two dependent
-  // loads per element otherwise), the noise of the row is computed while the loads are in flight
-  extern __shared__ double vsh[];
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const double *vin = in + (long long)blockIdx.y * in_stride;
-  const int r_hi = min(blockIdx.x * 8 + 7, N - 1);
-  const int s_lo = LOWER ? 0 : blockIdx.x * 8, s_hi = LOWER ? r_hi + 1 : N;  // columns any row of this CTA touches
-  for (int c = s_lo + threadIdx.x; c < s_hi; c += 256) vsh[c] = vin[GATHER_IN ? cidx[c] : c];
-  double zn = 0.0;
-  if (NOISE && row < N && lane == 0) {
-    double z0, z1;
-    normal_pair(nz.keys, 0x40000000u | ((uint32_t)row >> 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.y, nz.mc, kNormalTabDev, z0, z1);
-    zn = (row & 1) ? z1 : z0;
-  }
-  __syncthreads();
-  if (row >= N) return;
-  const double *Trow = T + (long long)row * Np;
-  const int c_lo = LOWER ? 0 : row, c_hi = LOWER ? row + 1 : N;  // non-zero range of the row
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int c = c_lo + lane;
-  for (; c + 224 < c_hi; c += 256) {  // 8 independent loads in flight per lane
-    const double t0 = Trow[c], t1 = Trow[c + 32], t2 = Trow[c + 64], t3 = Trow[c + 96];
-    const double t4 = Trow[c + 128], t5 = Trow[c + 160], t6 = Trow[c + 192], t7 = Trow[c + 224];
-    a0 = fma(t0, vsh[c], a0);
-    a1 = fma(t1, vsh[c + 32], a1);
-    a2 = fma(t2, vsh[c + 64], a2);
-    a3 = fma(t3, vsh[c + 96], a3);
-    a0 = fma(t4, vsh[c + 128], a0);
-    a1 = fma(t5, vsh[c + 160], a1);
-    a2 = fma(t6, vsh[c + 192], a2);
-    a3 = fma(t7, vsh[c + 224], a3);
-  }
-  for (; c < c_hi; c += 32) a0 = fma(Trow[c], vsh[c], a0);
-  double acc = (a0 + a1) + (a2 + a3);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) out[(long long)blockIdx.y * out_stride + (SCATTER_OUT ? cidx[row] : row)] = acc + zn;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -15,6 +15,9 @@
 #include "fused.cuh"
 #include "kernels.cuh"
 #include "setup.hh"
+#include "tail.cuh"
+
+#include <set>
 
 using namespace mgmc;
 
@@ -100,8 +103,7 @@ struct mgmc_ctx {
   std::vector<void *> allocs;
   // coarse factor
   int Nc = 0, Ncp = 0;
-  double *dT = nullptr, *dTT = nullptr, *d_cy = nullptr;  // L^{-1}, L^{-T}, intermediate vector (Np per chain)
-  int *d_cidx = nullptr;                                  // lexicographic index -> offset in the padded layout
+  double *dTT = nullptr;  // L^{-T} of the coarsest level (dense, row-major upper triangular)
   double *d_sigma_inv = nullptr, *d_sigma_inv_sqrt = nullptr, *d_sigma_inv_neg = nullptr;
   // in-kernel low-rank fix-up: slots of one cycle / API call (d vectors, exchange buffers, flags)
   static constexpr int kLrSlots = 1024;
@@ -146,6 +148,18 @@ struct mgmc_ctx {
   cudaGraphExec_t mg_graph = nullptr;  // one LoopSolver iteration: V-cycle, x -= Pr, next residual and its norm
   int64_t mg_graph_launches = 0;
   bool use_graph = true;
+  // persistent kernel of the small levels (tail.cuh): levels >= tail_level and the coarse solve are phases of one launch
+  int tail_level = -1;             // -1: not planned yet; nlevel: off
+  bool tail_rec = false;           // the recursion below tail_level is being recorded instead of launched
+  std::vector<TailPhase> tail_ph;
+  size_t tail_smem = 0;
+  double tail_bytes = 0.0;
+  bool tail_lowrank = false;
+  unsigned long long *d_tail_bar = nullptr;
+  long long *d_tail_stamps = nullptr;  // MGMC_TAIL_STAMPS=1: per-phase time stamps of the last tail launch
+  std::vector<int> tail_stamp_kinds;
+  double *dAinv = nullptr;         // A^{-1} of the coarsest level (one-pass coarse phase)
+  std::set<const void *> func_attr_done;  // kernels whose dynamic shared memory limit has been raised on this device
   bool perf_no_noise = false;  // MGMC_PERF_NO_NOISE=1: run the sampling cycle with the deterministic kernels (perf experiments only)
   // instrumentation
   int64_t launch_count = 0;
@@ -523,8 +537,19 @@ uint32_t next_c1(mgmc_ctx *c, int level, bool advance) {
 // ---------------------------------------------------------------------------------------------
 // single-level building blocks (device vectors)
 // ---------------------------------------------------------------------------------------------
+void tail_push_simple(mgmc_ctx *c, int kind, const GridP &g, const double *src, double *dst) {
+  TailPhase ph;
+  std::memset(&ph, 0, sizeof(ph));
+  ph.kind = kind;
+  ph.P.g = g;
+  ph.P.x_in = src;
+  ph.P.x_out = dst;
+  c->tail_ph.push_back(ph);
+}
+
 void dev_zero(mgmc_ctx *c, int level, double *x) {
   const DevLevel &L = c->lv[level];
+  if (c->tail_rec) return tail_push_simple(c, TAIL_ZERO, L.g, nullptr, x);
   c->launch("zero", level, [&] { axpy_kernel<1><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, x, nullptr); });
 }
 
@@ -533,6 +558,11 @@ void dev_zero(mgmc_ctx *c, int level, double *x) {
 void normalize_x(mgmc_ctx *c, int level) {
   DevLevel &L = c->lv[level];
   if (L.x == L.x_primary) return;
+  if (c->tail_rec) {
+    tail_push_simple(c, TAIL_COPY, L.g, L.x, L.x_primary);
+    std::swap(L.x, L.x_alt);
+    return;
+  }
   c->launch("copy_back", level, [&] { axpy_kernel<2><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.x_primary, L.x); });
   std::swap(L.x, L.x_alt);
 }
@@ -572,14 +602,24 @@ inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_) {
   return t[3];
 }
 constexpr int kFusedSmemMax = 112 * 1024;  // 2 CTAs per SM: 2 x (112 + 1 KB reserved) <= 227 KB
+constexpr int kTailTileRowsMax = 40;
+constexpr int kTailSmemMax = 200 * 1024;  // the persistent kernel runs one CTA per SM
+
+// Persistent kernel of the small levels (tail.cuh): every tile job of a chain must be resident at once (the low-rank
+// exchange between the tiles may wait for any of them), so the tiles are made as tall as that needs (dev_fused).
+// Conservative tile count of one chain for the planning: tiles at least 96 columns wide, as tall as allowed.
+inline int tail_tiles_bound(int nx, int ny, int nc) {
+  const int ty = std::max(std::min(fused_tile_rows(ny, nc, false, true), fused_tile_rows(ny, nc, false, false)), 8);
+  int best = ((nx + 95) / 96) * ((ny - 1 + ty - 1) / ty);
+  for (int t = ty; t <= kTailTileRowsMax; t += 2) best = std::min(best, ((nx + 95) / 96) * ((ny - 1 + t - 1) / t));
+  return best;
+}
 
 template <int NC, bool G, bool PR, bool RS, bool LR>
 void launch_fused_t(mgmc_ctx *c, const FusedP &P, dim3 grid, size_t smem) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(fused_smooth_kernel<NC, G, PR, RS, LR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
-    attr_set = true;
-  }
+  // (the attribute is per device and function: tracked per context, not per process)
+  const void *fn = (const void *)fused_smooth_kernel<NC, G, PR, RS, LR>;
+  if (c->func_attr_done.insert(fn).second) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
   fused_smooth_kernel<NC, G, PR, RS, LR><<<grid, kFusedThreads, smem, c->stream>>>(P);
 }
 
@@ -599,12 +639,16 @@ void lr_begin_epoch(mgmc_ctx *c) {
 inline size_t lr_tile_smem(int m) { return (size_t)10 * m * sizeof(double) + (size_t)6 * m * sizeof(int); }
 
 // Can the fix-ups of this level run inside the fused launch?  Always when the measurements do not interact;
-// otherwise every tile that needs a fix-up waits for ALL owner tiles, so the whole grid must be resident at once.
-bool lr_fusable(mgmc_ctx *c, const LowRankDev &lr, int ntiles) {
+// otherwise every tile that needs a fix-up waits for ALL owner tiles of its chain, so all tiles of a chain must be
+// resident at once: the tiles of such a level are made tall enough for one CTA per SM (dev_fused), and chains are
+// launched in groups that fit.  The answer must not depend on nchains or on whether the level runs as a phase of the
+// persistent kernel: the in-kernel and the separate fix-up differ in rounding, and chains are compared bit for bit.
+bool lr_fusable(mgmc_ctx *c, const LowRankDev &lr, int level) {
   const int m = c->d.m_lowrank;
   if (!c->lr_fuse || m > 256 || lr.bw > 16 || lr.bh > 16) return false;
   if (lr.diag[0] && lr.diag[1]) return true;
-  return (long long)ntiles * c->d.nchains <= 148;
+  const DevLevel &L = c->lv[level];
+  return tail_tiles_bound(L.g.nx, L.g.ny, L.h.st.ncolours) <= c->num_sms;
 }
 
 const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega);
@@ -774,7 +818,22 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   P.HXL = up4(halo.v[0]);
   const int HXR = up4(halo.v[1]);
   P.TX = 128 - P.HXL - HXR;
-  P.TY = fused_tile_rows(L.g.ny, nc, c->strip.on(), restrict_);
+  P.TY = fused_tile_rows(L.g.ny, nc, c->strip.on() && !c->tail_rec, restrict_);
+  // persistent kernel of the small levels / interacting measurements: all tiles of a chain must be resident at once
+  // (one CTA per SM)
+  bool lr_coupled = false;
+  if (use_lr) {
+    const LowRankDev &lr = get_lowrank(c, level, omega);
+    lr_coupled = !(lr.diag[0] && lr.diag[1]);
+  }
+  if (c->tail_rec) {
+    // persistent kernel: the phases are latency bound -- as many (low) tiles as there are SMs for the chains of a wave
+    const int target = std::max(1, c->num_sms / std::min(c->d.nchains, 2));
+    P.TY = 2;
+    while (((L.g.nx + P.TX - 1) / P.TX) * ((L.g.ny - 1 + P.TY - 1) / P.TY) > target && P.TY < kTailTileRowsMax) P.TY += 2;
+  }
+  if (c->tail_rec || lr_coupled)
+    while (((L.g.nx + P.TX - 1) / P.TX) * ((L.g.ny - 1 + P.TY - 1) / P.TY) > c->num_sms && P.TY < kTailTileRowsMax) P.TY += 2;
   P.hl = halo.v[2];
   const int hh = halo.v[3];
   P.RY = P.TY + P.hl + hh;
@@ -784,7 +843,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     P.RY = P.TY + P.hl + hh;
     smem = (size_t)2 * P.RY * 128 * sizeof(double) + (use_lr ? lr_tile_smem(c->d.m_lowrank) : 0);
   }
-  if (c->strip.on() && P.TY != fused_tile_rows(L.g.ny, nc, true, restrict_)) fail(MGMC_ERR_UNSUPPORTED, "row strips: too many measurements for the tile geometry");
+  if (c->strip.on() && !c->tail_rec && P.TY != fused_tile_rows(L.g.ny, nc, true, restrict_)) fail(MGMC_ERR_UNSUPPORTED, "row strips: too many measurements for the tile geometry");
   if (smem > (size_t)kFusedSmemMax) fail(MGMC_ERR_INVALID, "internal: fused tile does not fit in shared memory");
   P.tiles_x = (L.g.nx + P.TX - 1) / P.TX;
   int tiles_y = (L.g.ny - 1 + P.TY - 1) / P.TY;
@@ -903,7 +962,48 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     P.timing = d_timing;
   }
 #endif
+  if (c->tail_rec) {
+    if (strip_level) fail(MGMC_ERR_INVALID, "internal: distributed level inside the persistent tail kernel");
+    {
+      // behind the tile: noise generated ahead of the passes (fused.cuh; one item per (row, live pass), 32 pairs of
+      // normals each) and the pass descriptors
+      int items = 0;
+      const int step = (nc == 4) ? 2 : 1;
+      if (gibbs)
+        for (int k = 0; k < S; ++k)
+          if (plan[k].mode == STAGE_FULL) items += (P.TY - 1 + plan[k].yl + plan[k].yh) / step + 1;
+      if (items > kFusedThreads) items = 0;  // (cannot happen with the tile heights of the persistent kernel)
+      const size_t off = (smem + 15) / 16 * 16;
+      P.nz_off = (int)(off / sizeof(double));
+      P.nz_cap = items;
+      smem = off + (size_t)items * 32 * sizeof(double2) + (32 + 512 + 2 * kFusedThreads) * sizeof(int);
+    }
+    TailPhase ph;
+    std::memset(&ph, 0, sizeof(ph));
+    ph.kind = TAIL_FUSED;
+    ph.nc = nc;
+    ph.ntiles = P.tiles_x * tiles_y;
+    if (ph.ntiles > c->num_sms) fail(MGMC_ERR_INVALID, "internal: level too large for the persistent tail kernel");
+    ph.P = P;
+    ph.P.rt_prolong = prolong ? 1 : 0;
+    ph.P.rt_restrict = restrict_ ? 1 : 0;
+    c->tail_ph.push_back(ph);
+    c->tail_smem = std::max(c->tail_smem, smem);
+    c->tail_bytes += alg_bytes;
+    c->tail_lowrank = c->tail_lowrank || use_lr;
+    if (S > 0 || prolong) std::swap(L.x, L.x_alt);
+    return;
+  }
+  // interacting measurements: the chains are launched in groups whose tiles are all resident at once
+  int chain_group = c->d.nchains;
+  if (lr_coupled) {
+    if ((int)grid.x > c->num_sms) fail(MGMC_ERR_INVALID, "internal: level with interacting measurements does not fit on the chip");
+    chain_group = std::max(1, c->num_sms / (int)grid.x);
+  }
   c->launch(name.c_str(), level, [&] {
+   for (int c0 = 0; c0 < c->d.nchains; c0 += chain_group) {
+    P.chain_off = c0;
+    grid.z = std::min(chain_group, c->d.nchains - c0);
 #define FUSED_CASE(NC_, G_, PR_, RS_)                                             \
   if (nc == NC_ && gibbs == G_ && prolong == PR_ && restrict_ == RS_) {            \
     if (use_lr) launch_fused_t<NC_, G_, PR_, RS_, true>(c, P, grid, smem);        \
@@ -914,6 +1014,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     FUSED_CASE(4, false, false, false) FUSED_CASE(4, false, false, true) FUSED_CASE(4, false, true, false) FUSED_CASE(4, false, true, true)
     FUSED_CASE(4, true, false, false) FUSED_CASE(4, true, false, true) FUSED_CASE(4, true, true, false) FUSED_CASE(4, true, true, true)
 #undef FUSED_CASE
+   }
   }, alg_bytes);
 #ifdef MGMC_TILE_TIMING
   if (d_timing) {
@@ -987,9 +1088,7 @@ void emit_smoothing(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps
   const int max_stages = (nc == 2 && (lowrank || omega != 1.0)) ? 4 : 8;
   bool fusedlr = false;
   if (lowrank) {
-    // (tile count of the widest launch geometry: an upper bound is all that matters here)
-    const int ntiles = ((L.g.nx + 87) / 88) * ((L.g.ny + 7) / 8);
-    fusedlr = lr_fusable(c, get_lowrank(c, level, omega), ntiles);
+    fusedlr = lr_fusable(c, get_lowrank(c, level, omega), level);
   }
   std::vector<Stage> cur;
   std::vector<FixSpec> fixes;
@@ -1138,7 +1237,7 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
     if (strip_level) {
       const RowRange cr{(lo - 1) / 2 + 1, std::min(hi / 2, C.g.ny - 1)};
       c->launch("restrict", level, [&] {
-        residual_restrict_kernel<false, true><<<dim3((C.g.nx - 1 + 63) / 64, (cr.j1 - cr.j0 + 1 + 3) / 4, nch), kBlockSites, 0, c->stream>>>(L.g, C.g, L.coef, nullptr, L.r, C.f, cr);
+        restrict_kernel<<<dim3((C.g.nx - 1 + 63) / 64, (cr.j1 - cr.j0 + 1 + 3) / 4, nch), kBlockSites, 0, c->stream>>>(L.g, C.g, L.r, C.f, cr);
       });
       if (level + 1 == sp.ndist) {
         strip_allgather_rhs(c, level);  // (zeroes the coarse iterate as well)
@@ -1162,14 +1261,14 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
 void dev_restrict_plain(mgmc_ctx *c, int level, const double *r, double *fc) {
   const DevLevel &L = c->lv[level], &C = c->lv[level + 1];
   c->launch("restrict", level, [&] {
-    residual_restrict_kernel<false, true><<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, L.coef, nullptr, r, fc, RowRange{1, C.g.ny - 1});
+    restrict_kernel<<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, r, fc, RowRange{1, C.g.ny - 1});
   });
 }
 
 // dense factor of the coarsest level (cholesky_sampler.cc:25-38), built at first use: contexts that only
 // serve single-level operations (apply, smoothers, transfers) never need it
 void ensure_coarse(mgmc_ctx *c) {
-  if (c->dT) return;
+  if (c->dTT) return;
   const DevLevel &LC = c->lv[c->d.nlevel - 1];
   if (LC.h.ndof() > 4096) fail(MGMC_ERR_UNSUPPORTED, "coarsest level has more than 4096 unknowns: increase nlevel (dense coarse factor)");
   CoarseFactor cf;
@@ -1180,36 +1279,212 @@ void ensure_coarse(mgmc_ctx *c) {
   }
   c->Nc = cf.N;
   c->Ncp = cf.Np;
-  c->dT = c->dupload(cf.T);
   c->dTT = c->dupload(cf.TT);
-  c->d_cy = c->dalloc<double>((size_t)cf.Np * c->d.nchains);
-  std::vector<int> cidx(cf.Np, 0);
-  const int w = LC.g.nx - 1;
-  for (int e = 0; e < cf.N; ++e) cidx[e] = (e / w + 1) * LC.g.pitch + (e % w + 1);
-  c->d_cidx = c->dupload(cidx);
+  {
+    // A^{-1} = L^{-T} L^{-1} for the one-pass coarse phase (tail.cuh): row i of TT times T
+    const int Np = cf.Np;
+    std::vector<double> Ainv((size_t)Np * Np, 0.0);
+    for (int i = 0; i < cf.N; ++i) {
+      double *ai = &Ainv[(size_t)i * Np];
+      for (int k = i; k < cf.N; ++k) {
+        const double a = cf.TT[(size_t)i * Np + k];
+        const double *tk = &cf.T[(size_t)k * Np];
+        for (int j = 0; j <= k; ++j) ai[j] += a * tk[j];
+      }
+    }
+    c->dAinv = c->dupload(Ainv);
+  }
+  if (!c->d_tail_bar) c->d_tail_bar = c->dalloc<unsigned long long>(1);
   c->sync();
 }
 
+void tail_flush(mgmc_ctx *c, bool gibbs, int level);
+
+// Coarsest level: x = A^{-1} f (+ L^{-T} xi) in one pass over the chip (tail.cuh coarse_phase) -- a phase of the
+// persistent kernel of the small levels, or a launch of its own when called on its own
 void dev_coarse(mgmc_ctx *c, bool sample, const double *f, double *x) {
   ensure_coarse(c);
   const int lc = c->d.nlevel - 1;
   const DevLevel &L = c->lv[lc];
-  NoiseP nz = noise_params(c, lc, next_c1(c, lc, sample));
-  dim3 grid((c->Nc + 7) / 8, c->d.nchains);
-  // pass 1: y = L^{-1} f (+ xi);  pass 2: x = L^{-T} y
-  c->launch(sample ? "coarse_sample_fwd" : "coarse_solve_fwd", lc, [&] {
-    if (sample) trimv_kernel<true, true, true, false><<<grid, 256, c->Ncp * sizeof(double), c->stream>>>(c->dT, c->Nc, c->Ncp, c->d_cidx, f, L.g.stride, c->d_cy, c->Ncp, nz);
-    else trimv_kernel<true, false, true, false><<<grid, 256, c->Ncp * sizeof(double), c->stream>>>(c->dT, c->Nc, c->Ncp, c->d_cidx, f, L.g.stride, c->d_cy, c->Ncp, nz);
-  }, 4.0 * c->Nc * c->Nc);
-  c->launch(sample ? "coarse_sample_bwd" : "coarse_solve_bwd", lc, [&] {
-    trimv_kernel<false, false, false, true><<<grid, 256, c->Ncp * sizeof(double), c->stream>>>(c->dTT, c->Nc, c->Ncp, c->d_cidx, c->d_cy, c->Ncp, x, L.g.stride, nz);
-  }, 4.0 * c->Nc * c->Nc);
+  if (f != L.f || x != L.x) fail(MGMC_ERR_INVALID, "internal: coarse phase on foreign vectors");
+  const uint32_t c1 = next_c1(c, lc, sample);
+  const bool standalone = !c->tail_rec;
+  TailPhase ph;
+  std::memset(&ph, 0, sizeof(ph));
+  ph.kind = TAIL_COARSE;
+  ph.nc = sample ? 1 : 0;
+  ph.c1 = (int)c1;
+  c->tail_ph.push_back(ph);
+  c->tail_smem = std::max(c->tail_smem, coarse_phase_smem(c->Ncp, c->Nc, c->num_sms, c->d.nchains));
+  c->tail_bytes += 8.0 * c->Nc * c->Nc * c->d.nchains;
+  if (standalone) tail_flush(c, sample, lc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent kernel of the small levels (tail.cuh)
+// ---------------------------------------------------------------------------------------------
+// First level of the tail: every level from there down must be a radius-1 level that is not distributed over row
+// strips, small enough that all tile jobs of a chain are resident at once (<= one CTA per SM) and that the chains
+// take at most two waves, and -- with a low-rank term -- able to run its fix-ups inside the launch.
+void plan_tail(mgmc_ctx *c) {
+  if (c->tail_level >= 0) return;
+  const int nl = c->d.nlevel;
+  c->tail_level = nl;
+  static const bool off = std::getenv("MGMC_NO_TAIL") != nullptr;
+  if (off) return;
+  static const char *ms = std::getenv("MGMC_TAIL_MAX_SITES");  // (perf experiments)
+  const long long max_sites = ms ? std::atoll(ms) : 512ll * 512ll;
+  for (int l = nl - 1; l >= 0; --l) {
+    const DevLevel &L = c->lv[l];
+    if (L.r2 || (c->strip.on() && l < c->strip.ndist)) break;
+    const bool smoothed = (l < nl - 1) || c->d.coarse_solver != MGMC_COARSE_CHOLESKY;
+    if (l == nl - 1 && !smoothed && L.h.ndof() > 4096) break;
+    if (smoothed) {
+      if ((long long)L.g.nx * L.g.ny > max_sites) break;
+      const int nt = tail_tiles_bound(L.g.nx, L.g.ny, L.h.st.ncolours);
+      if (nt > c->num_sms || (long long)nt * c->d.nchains > 2ll * c->num_sms) break;
+      if (c->d.m_lowrank > 0) {
+        const LowRankDev &lr = get_lowrank(c, l, c->d.omega);
+        if (!lr_fusable(c, lr, l)) break;
+      }
+    }
+    c->tail_level = l;
+  }
+  if (c->tail_level < nl) {
+    if (!c->d_tail_bar) c->d_tail_bar = c->dalloc<unsigned long long>(1);
+    static const bool stamps = std::getenv("MGMC_TAIL_STAMPS") != nullptr;
+    if (stamps && !c->d_tail_stamps) c->d_tail_stamps = c->dalloc<long long>(256);
+    if (c->d.coarse_solver == MGMC_COARSE_CHOLESKY) ensure_coarse(c);
+    c->sync();
+  }
+}
+
+template <bool G_, bool LR_>
+void launch_tail_t(mgmc_ctx *c, const TailP &T, size_t smem) {
+  const void *fn = (const void *)tail_kernel<G_, LR_>;
+  if (c->func_attr_done.insert(fn).second) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemMax));
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(c->num_sms, 1, 1);  // one CTA per SM: the cooperative launch guarantees that all of them are resident
+  cfg.blockDim = dim3(kFusedThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, tail_kernel<G_, LR_>, T));
+}
+
+// launch what the recursion below tail_level has recorded
+void tail_flush(mgmc_ctx *c, bool gibbs, int level) {
+  const std::vector<TailPhase> ph = c->tail_ph;
+  const size_t smem = std::max(c->tail_smem, (size_t)1024);
+  const double bytes = c->tail_bytes;
+  const bool lr = c->tail_lowrank;
+  c->tail_ph.clear();
+  c->tail_smem = 0;
+  c->tail_bytes = 0.0;
+  c->tail_lowrank = false;
+  if (smem > (size_t)kTailSmemMax) fail(MGMC_ERR_INVALID, "internal: tail phase does not fit in shared memory");
+  const int lc = c->d.nlevel - 1;
+  for (size_t p0 = 0; p0 < ph.size(); p0 += kMaxTailPhases) {
+    // (more phases than the parameter space holds -- deep W-cycles: several launches, the kernel boundary is the barrier)
+    TailP T;
+    std::memset(&T, 0, sizeof(T));
+    T.nphase = (int)std::min<size_t>(kMaxTailPhases, ph.size() - p0);
+    T.nchains = c->d.nchains;
+    T.bar = c->d_tail_bar;
+    T.stamps = (p0 == 0) ? c->d_tail_stamps : nullptr;
+    T.nz = noise_params(c, lc, 0);
+    if (c->dAinv) {
+      const DevLevel &LC = c->lv[lc];
+      T.coarse.Ainv = c->dAinv;
+      T.coarse.TT = c->dTT;
+      T.coarse.N = c->Nc;
+      T.coarse.Np = c->Ncp;
+      T.coarse.w = LC.g.nx - 1;
+      T.coarse.pitch = LC.g.pitch;
+      T.coarse.stride = LC.g.stride;
+      T.coarse.f = LC.f;
+      T.coarse.x = LC.x;
+    }
+    if (p0 == 0) c->tail_stamp_kinds.clear();
+    for (int k = 0; k < T.nphase; ++k) {
+      T.ph[k] = ph[p0 + k];
+      if (k > 0 && T.ph[k].kind == TAIL_COARSE) T.prefetch_coarse = 1;
+      if (p0 == 0) c->tail_stamp_kinds.push_back(T.ph[k].kind == TAIL_FUSED ? 100 * (T.ph[k].P.rt_restrict ? 1 : 2) + T.ph[k].ntiles : -T.ph[k].kind);
+    }
+    const std::string name = std::string(gibbs ? "tail_gibbs" : "tail_sor") + std::to_string(T.nphase);
+#ifdef MGMC_TILE_TIMING
+    // debug build: per-CTA phase stamps of the 6th multi-phase tail launch (tile stamps of fused.cuh + barrier stamps)
+    static int tail_dumped = 0;
+    const char *tfile = std::getenv("MGMC_TIMING_FILE");
+    long long *d_tt = nullptr, *d_cs = nullptr;
+    const size_t G_ = (size_t)c->num_sms;
+    if (tfile && T.nphase > 1 && tail_dumped++ == 5) {
+      CUDA_CHECK(cudaMalloc(&d_tt, T.nphase * G_ * 16 * sizeof(long long)));
+      CUDA_CHECK(cudaMemset(d_tt, 0, T.nphase * G_ * 16 * sizeof(long long)));
+      CUDA_CHECK(cudaMalloc(&d_cs, T.nphase * G_ * 4 * sizeof(long long)));
+      CUDA_CHECK(cudaMemset(d_cs, 0, T.nphase * G_ * 4 * sizeof(long long)));
+      for (int k = 0; k < T.nphase; ++k) T.ph[k].P.timing = d_tt + (size_t)k * G_ * 16;
+      T.cta_stamps = d_cs;
+    }
+#endif
+    c->launch(name.c_str(), level, [&] {
+      if (gibbs) {
+        if (lr) launch_tail_t<true, true>(c, T, smem);
+        else launch_tail_t<true, false>(c, T, smem);
+      } else {
+        if (lr) launch_tail_t<false, true>(c, T, smem);
+        else launch_tail_t<false, false>(c, T, smem);
+      }
+    }, p0 == 0 ? bytes : 0.0);
+#ifdef MGMC_TILE_TIMING
+    if (d_tt) {
+      c->sync();
+      std::vector<long long> h(T.nphase * G_ * 16), hc(T.nphase * G_ * 4);
+      CUDA_CHECK(cudaMemcpy(h.data(), d_tt, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(hc.data(), d_cs, hc.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(d_tt);
+      cudaFree(d_cs);
+      FILE *fp = std::fopen((std::string(tfile) + ".tail.txt").c_str(), "w");
+      for (int k = 0; k < T.nphase; ++k)
+        for (size_t b = 0; b < G_; ++b) {
+          std::fprintf(fp, "%d %d %d %zu ", k, T.ph[k].kind, T.ph[k].ntiles, b);
+          for (int q = 0; q < 4; ++q) std::fprintf(fp, "%lld ", hc[(k * G_ + b) * 4 + q]);
+          for (int q = 0; q < 16; ++q) std::fprintf(fp, "%lld ", h[(k * G_ + b) * 16 + q]);
+          std::fprintf(fp, "\n");
+        }
+      std::fclose(fp);
+    }
+#endif
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // multilevel recursions
 // ---------------------------------------------------------------------------------------------
+void mgmc_sample_level_body(mgmc_ctx *c, int level);
 void mgmc_sample_level(mgmc_ctx *c, int level) {  // multigridmc_sampler.cc:103-130
+  if (level == c->tail_level && !c->tail_rec) {
+    // this level and everything below it: phases of one persistent launch
+    c->tail_rec = true;
+    try {
+      mgmc_sample_level_body(c, level);
+    } catch (...) {
+      c->tail_rec = false;
+      c->tail_ph.clear();
+      throw;
+    }
+    c->tail_rec = false;
+    tail_flush(c, !c->perf_no_noise, level);
+    return;
+  }
+  mgmc_sample_level_body(c, level);
+}
+void mgmc_sample_level_body(mgmc_ctx *c, int level) {
   const mgmc_desc &d = c->d;
   if (level == d.nlevel - 1) {
     DevLevel &L = c->lv[level];
@@ -1233,7 +1508,24 @@ void mgmc_sample_level(mgmc_ctx *c, int level) {  // multigridmc_sampler.cc:103-
   }
 }
 
+void mg_solve_level_body(mgmc_ctx *c, int level);
 void mg_solve_level(mgmc_ctx *c, int level) {  // multigrid_preconditioner.cc:74-101
+  if (level == c->tail_level && !c->tail_rec) {
+    c->tail_rec = true;
+    try {
+      mg_solve_level_body(c, level);
+    } catch (...) {
+      c->tail_rec = false;
+      c->tail_ph.clear();
+      throw;
+    }
+    c->tail_rec = false;
+    tail_flush(c, false, level);
+    return;
+  }
+  mg_solve_level_body(c, level);
+}
+void mg_solve_level_body(mgmc_ctx *c, int level) {
   const mgmc_desc &d = c->d;
   DevLevel &L = c->lv[level];
   if (level == d.nlevel - 1) {
@@ -1321,6 +1613,7 @@ void strip_count_launches(mgmc_ctx *c) {
 }
 
 void run_cycles(mgmc_ctx *c, int64_t nsamples) {
+  plan_tail(c);
   strip_count_launches(c);
   const unsigned long long zero = 0ull;
   CUDA_CHECK(cudaMemcpyAsync(c->d_pos, &zero, sizeof(zero), cudaMemcpyHostToDevice, c->stream));
@@ -1656,6 +1949,7 @@ int mgmc_sampler_mgmc_apply(mgmc_ctx *c, const double *f, double *x) {
   API_BEGIN
   check_level(c, 0);
   if (c->strip.on() && c->strip_connected) fail(MGMC_ERR_UNSUPPORTED, "row strips: the chain state is distributed; use mgmc_set_state / mgmc_sample / mgmc_get_state");
+  plan_tail(c);
   if (f) upload_vec(c, 0, c->lv[0].f, f);  // f == NULL: right-hand side fixed earlier (Sampler::fix_rhs, sampler.hh:56)
   upload_vec(c, 0, c->lv[0].x, x);
   emit_mgmc_cycle(c);
@@ -1667,6 +1961,7 @@ int mgmc_sampler_mgmc_apply(mgmc_ctx *c, const double *f, double *x) {
 int mgmc_mgprec_apply(mgmc_ctx *c, const double *b, double *x) {
   API_BEGIN
   check_level(c, 0);
+  plan_tail(c);
   upload_vec(c, 0, c->lv[0].f, b);
   mg_solve_level(c, 0);
   download_vec(c, 0, c->lv[0].x, x);
@@ -1679,6 +1974,7 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
   API_BEGIN
   check_level(c, 0);
   if (c->d.nchains != 1) fail(MGMC_ERR_UNSUPPORTED, "mgmc_loop_solve works on a single right-hand side (nchains = 1)");
+  plan_tail(c);
   DevLevel &L = c->lv[0];
   const size_t total = (size_t)L.g.stride;
   const size_t origin = (size_t)GY * L.g.pitch + GX;
@@ -2003,6 +2299,25 @@ int mgmc_profile_cycle(mgmc_ctx *c, int nsamples, int nslots_max, char *names, d
     if (alg_bytes) alg_bytes[k] = slots[k].bytes;
   }
   if (nslots) *nslots = n;
+  API_END
+}
+
+int mgmc_tail_stamps(mgmc_ctx *c, int nmax, int *kinds, double *us, int *nphases) {
+  API_BEGIN
+  check_level(c, 0);
+  c->sync();
+  const int n = (int)c->tail_stamp_kinds.size();
+  if (!c->d_tail_stamps || n == 0) {
+    if (nphases) *nphases = 0;
+    return MGMC_OK;
+  }
+  std::vector<long long> st(n + 1);
+  CUDA_CHECK(cudaMemcpy(st.data(), c->d_tail_stamps, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < n && k < nmax; ++k) {
+    kinds[k] = c->tail_stamp_kinds[k];
+    us[k] = 1e-3 * (double)(st[k + 1] - st[k]);
+  }
+  if (nphases) *nphases = std::min(n, nmax);
   API_END
 }
 

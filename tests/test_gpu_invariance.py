@@ -52,6 +52,9 @@ def test_chain_independent_of_tiling_and_dead_pass_skipping(tmp_path, n, nlevel,
         "low_tiles": {"MGMC_TILE_ROWS": "32,32,16,8,32"},
         "tall_tiles": {"MGMC_TILE_ROWS": "24,40,32,16,36"},
         "no_fold": {"MGMC_NO_RES_FOLD": "1", "MGMC_TILE_ROWS": "16,16,8,8,16"},
+        # every level as its own launch instead of phases of the persistent kernel of the small levels (tail.cuh)
+        "no_tail": {"MGMC_NO_TAIL": "1"},
+        "short_tail": {"MGMC_TAIL_MAX_SITES": "20000"},
     }
     for tag, env in variants.items():
         x = _run(tmp_path, tag, env, **kw)
