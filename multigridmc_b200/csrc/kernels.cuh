@@ -82,8 +82,20 @@ __global__ void __launch_bounds__(256) residual_norm_kernel(GridP g, Coef9 a, co
   }
 }
 
-// deterministic final reduction of the per-block partial sums: out[0] = sum(partial)
-__global__ void __launch_bounds__(1024) reduce_sum_kernel(const double *__restrict__ partial, int n, double *__restrict__ out) {
+// Device-resident control of the Richardson loop (LoopSolver::apply, loop_solver.cc:21-41): the residual norm of every
+// evaluation goes into a device-side history and the convergence test "rel < rtol AND abs < atol" (loop_solver.cc:33) is
+// made on the device; once it holds the update x -= P r is suppressed, so the host may launch iterations in batches and
+// look at the outcome afterwards -- x stays the iterate at which the reference would have stopped.
+struct SolverCtl {
+  double r0, rtol, atol;
+  int maxiter;  // residual evaluations recorded at most
+  int iter;     // residual evaluations so far
+  int conv;     // converged
+  int it_conv;  // iteration index at which the test held
+};
+
+// deterministic final reduction of the per-block partial sums of r^2, then history + convergence test
+__global__ void __launch_bounds__(1024) reduce_check_kernel(const double *__restrict__ partial, int n, SolverCtl *ctl, double *__restrict__ hist) {
   __shared__ double ws[32];
   double v = 0.0;
   for (int k = threadIdx.x; k < n; k += 1024) v += partial[k];
@@ -95,11 +107,30 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const double *__restri
     v = ws[threadIdx.x];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    if (threadIdx.x == 0) out[0] = v;
+    if (threadIdx.x == 0 && !ctl->conv && ctl->iter < ctl->maxiter) {
+      const double r = sqrt(v);
+      const int k = ctl->iter;
+      hist[k] = r;
+      ctl->iter = k + 1;
+      if ((r / ctl->r0 < ctl->rtol) && (r < ctl->atol)) {
+        ctl->conv = 1;
+        ctl->it_conv = k;
+      }
+    }
   }
 }
 
-// x -= y on the interior (LoopSolver update x -= Pr, loop_solver.cc:41); or x = 0
+// x -= y unless the loop has converged (LoopSolver update x -= Pr, loop_solver.cc:41)
+__global__ void __launch_bounds__(256) axpy_guard_kernel(GridP g, double *__restrict__ x, const double *__restrict__ y, const SolverCtl *ctl) {
+  if (ctl->conv) return;
+  const int i = 1 + blockIdx.x * 64 + threadIdx.x;
+  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  const long long o = (long long)j * g.pitch + i;
+  x[o] -= y[o];
+}
+
+// x -= y on the interior; or x = 0
 template <int MODE>  // 0: x -= y, 1: x = 0, 2: x = y
 __global__ void __launch_bounds__(256) axpy_kernel(GridP g, double *__restrict__ x, const double *__restrict__ y) {
   const int i = 1 + blockIdx.x * 64 + threadIdx.x;

@@ -135,8 +135,9 @@ struct mgmc_ctx {
   long long series_cap = 0;
   unsigned long long *d_pos = nullptr;
   // loop solver scratch
-  double *sol_x = nullptr, *sol_b = nullptr, *d_partial = nullptr, *d_norm = nullptr;
-  int npartial = 0;
+  double *sol_x = nullptr, *sol_b = nullptr, *d_partial = nullptr, *d_sol_hist = nullptr;
+  SolverCtl *d_solver = nullptr;
+  int npartial = 0, sol_hist_cap = 0;
   // moments
   double *d_mean = nullptr, *d_second = nullptr;
   // graph of one MGMC cycle (+ end-of-cycle kernel)
@@ -828,7 +829,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   }
   if (c->tail_rec) {
     // persistent kernel: the phases are latency bound -- as many (low) tiles as there are SMs for the chains of a wave
-    const int target = std::max(1, c->num_sms / std::min(c->d.nchains, 2));
+    const int target = std::max(1, c->num_sms / c->d.nchains);
     P.TY = 2;
     while (((L.g.nx + P.TX - 1) / P.TX) * ((L.g.ny - 1 + P.TY - 1) / P.TY) > target && P.TY < kTailTileRowsMax) P.TY += 2;
   }
@@ -1330,8 +1331,12 @@ void plan_tail(mgmc_ctx *c) {
   if (c->tail_level >= 0) return;
   const int nl = c->d.nlevel;
   c->tail_level = nl;
-  static const bool off = std::getenv("MGMC_NO_TAIL") != nullptr;
-  if (off) return;
+  // Measured (profiles/r02_tail.md): a phase of the persistent kernel costs what a launch inside the CUDA graph costs
+  // (5-7 us: the in-order latency of the tile code, not the launch), so the kernel is at parity with the launch
+  // sequence -- it is opt-in (MGMC_TAIL=1) until the per-phase latency is below that of a launch; the coarsest-level
+  // solve always runs as its one-pass phase.
+  static const bool on = std::getenv("MGMC_TAIL") != nullptr && std::getenv("MGMC_NO_TAIL") == nullptr;
+  if (!on) return;
   static const char *ms = std::getenv("MGMC_TAIL_MAX_SITES");  // (perf experiments)
   const long long max_sites = ms ? std::atoll(ms) : 512ll * 512ll;
   for (int l = nl - 1; l >= 0; --l) {
@@ -1974,6 +1979,7 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
   API_BEGIN
   check_level(c, 0);
   if (c->d.nchains != 1) fail(MGMC_ERR_UNSUPPORTED, "mgmc_loop_solve works on a single right-hand side (nchains = 1)");
+  if (maxiter < 0) fail(MGMC_ERR_INVALID, "maxiter must be >= 0");
   plan_tail(c);
   DevLevel &L = c->lv[0];
   const size_t total = (size_t)L.g.stride;
@@ -1984,7 +1990,16 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
     dim3 g = grid_sites(L.g, 1);
     c->npartial = (int)(g.x * g.y);
     c->d_partial = c->dalloc<double>(c->npartial);
-    c->d_norm = c->dalloc<double>(1);
+    c->d_solver = c->dalloc<SolverCtl>(1);
+  }
+  if (maxiter + 1 > c->sol_hist_cap) {
+    // (the captured iteration holds the pointer: a larger history needs a new graph)
+    if (c->mg_graph) {
+      cudaGraphExecDestroy(c->mg_graph);
+      c->mg_graph = nullptr;
+    }
+    c->sol_hist_cap = std::max(maxiter + 1, 256);
+    c->d_sol_hist = c->dalloc<double>(c->sol_hist_cap);
   }
   upload_vec(c, 0, c->sol_b, b);
   c->launch("zero", 0, [&] { axpy_kernel<1><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, c->sol_x, nullptr); });
@@ -1992,15 +2007,21 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
   const size_t n = (size_t)L.h.ndof();
   for (size_t k = 0; k < n; ++k) r0 += b[k] * b[k];
   r0 = std::sqrt(r0);
-  bool conv = false;
-  int it = maxiter, nh = 0;
-  // r = A x - b (into f_ell[0], the preconditioner's input) and ||r||^2 (into d_norm)
+  SolverCtl ctl;
+  std::memset(&ctl, 0, sizeof(ctl));
+  ctl.r0 = r0;
+  ctl.rtol = rtol;
+  ctl.atol = atol;
+  ctl.maxiter = maxiter;
+  CUDA_CHECK(cudaMemcpyAsync(c->d_solver, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, c->stream));
+  c->sync();  // (ctl is a stack variable)
+  // r = A x - b (into f_ell[0], the preconditioner's input), ||r|| into the device-side history + convergence test
   auto emit_residual = [&] {
     c->launch("residual_norm", 0, [&] {
       if (L.r2) residual_norm25_kernel<<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, c->sol_x, c->sol_b, L.f, c->d_partial);
       else if (L.nine) residual_norm_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
       else residual_norm_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
-    });
+    }, 24.0 * (double)L.h.ndof());
     if (c->d.m_lowrank > 0) {
       // low-rank part of A x is added to r, then the norm is recomputed from r
       c->launch("lowrank_apply", 0, [&] {
@@ -2010,12 +2031,13 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
         residual_norm_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, Coef9{0, 0, 0, 0, 0, 0, 0, 0, 0}, c->sol_x, L.f, L.r, c->d_partial);
       });
     }
-    c->launch("reduce_sum", 0, [&] { reduce_sum_kernel<<<1, 1024, 0, c->stream>>>(c->d_partial, c->npartial, c->d_norm); });
+    c->launch("reduce_check", 0, [&] { reduce_check_kernel<<<1, 1024, 0, c->stream>>>(c->d_partial, c->npartial, c->d_solver, c->d_sol_hist); });
   };
-  // one iteration = V-cycle on r, x -= Pr (loop_solver.cc:40-41), residual of the new iterate: captured once, replayed
+  // one iteration = V-cycle on r, x -= Pr (loop_solver.cc:40-41; suppressed once converged), residual of the new iterate:
+  // captured once, replayed
   auto emit_iteration = [&] {
     mg_solve_level(c, 0);  // Pr = x_ell[0]
-    c->launch("axpy", 0, [&] { axpy_kernel<0><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, c->sol_x, L.x); });
+    c->launch("axpy", 0, [&] { axpy_guard_kernel<<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, c->sol_x, L.x, c->d_solver); });
     emit_residual();
   };
   if (c->use_graph && !c->mg_graph && !c->prof_on) {
@@ -2040,30 +2062,41 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
     c->launch_count = count0;
   }
   emit_residual();
-  for (int k = 0; k < maxiter; ++k) {
-    double nrm2 = 0.0;
-    CUDA_CHECK(cudaMemcpyAsync(&nrm2, c->d_norm, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  // The reference evaluates the residual, tests, updates -- at most maxiter times.  Here the iterations are launched in
+  // batches without a host round trip in between; the batch size follows the observed convergence rate, so that only a
+  // few iterations run past the one at which the test holds (they leave x alone).
+  std::vector<double> hist(std::max(maxiter, 1), 0.0);
+  int launched = 0, batch = std::min(4, maxiter);
+  while (true) {
+    for (int k = 0; k < batch; ++k) {
+      if (c->mg_graph && !c->prof_on) {
+        CUDA_CHECK(cudaGraphLaunch(c->mg_graph, c->stream));
+        c->launch_count += c->mg_graph_launches;
+      } else {
+        emit_iteration();
+      }
+    }
+    launched += batch;
+    CUDA_CHECK(cudaMemcpyAsync(&ctl, c->d_solver, sizeof(ctl), cudaMemcpyDeviceToHost, c->stream));
     c->sync();
-    const double r_nrm = std::sqrt(nrm2);
-    if (history) history[nh] = r_nrm;
-    nh++;
-    if ((r_nrm / r0 < rtol) && (r_nrm < atol)) {
-      it = k;
-      conv = true;
-      break;
+    if (ctl.conv || launched >= maxiter) break;
+    CUDA_CHECK(cudaMemcpy(hist.data(), c->d_sol_hist, sizeof(double) * ctl.iter, cudaMemcpyDeviceToHost));
+    int pred = 8;
+    const int q = std::min(ctl.iter - 1, 4);
+    if (q >= 1 && hist[ctl.iter - 1] > 0.0 && hist[ctl.iter - 1 - q] > hist[ctl.iter - 1]) {
+      const double rho = std::pow(hist[ctl.iter - 1] / hist[ctl.iter - 1 - q], 1.0 / q);
+      const double target = std::min(rtol * r0, atol);
+      if (target > 0.0 && rho < 1.0) pred = (int)std::ceil(std::log(target / hist[ctl.iter - 1]) / std::log(rho));
     }
-    if (c->mg_graph && !c->prof_on) {
-      CUDA_CHECK(cudaGraphLaunch(c->mg_graph, c->stream));
-      c->launch_count += c->mg_graph_launches;
-    } else {
-      emit_iteration();
-    }
+    batch = std::min(std::max(pred, 1), std::min(32, maxiter - launched));
   }
+  const int nh = ctl.iter;
+  if (history && nh > 0) CUDA_CHECK(cudaMemcpy(history, c->d_sol_hist, sizeof(double) * nh, cudaMemcpyDeviceToHost));
   download_vec(c, 0, c->sol_x, x);
   c->sync();
   if (nhist) *nhist = nh;
-  if (niter) *niter = it;
-  if (converged) *converged = conv ? 1 : 0;
+  if (niter) *niter = ctl.conv ? ctl.it_conv : maxiter;
+  if (converged) *converged = ctl.conv ? 1 : 0;
   API_END
 }
 

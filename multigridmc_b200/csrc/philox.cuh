@@ -1,4 +1,4 @@
-// Counter-based noise for the Gibbs sweeps: Philox4x32-10 (Salmon et al., SC'11) generated in
+// Counter-based noise for the Gibbs sweeps: Philox4x32-7 (Salmon et al., SC'11; rounds: see kPhiloxRounds) generated in
 // registers, two N(0,1) per call via Box-Muller on two 52-bit uniforms.
 //
 // Replaces the reference's sequential std::mt19937_64 + std::normal_distribution stream
@@ -163,7 +163,17 @@ MGMC_HD void sincos2pi_u52(uint64_t b, const NormalConsts &mc, const double *tab
   cs = fma_(-S, sy, fma_(C, cm, C));
 }
 
-// Round keys of Philox4x32-10 for a 64-bit seed: computed once on the host and passed by value in the
+// Rounds: Philox4x32-R with R = 7, the smallest round count of the family that passes BigCrush (Salmon, Moraes, Dror,
+// Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11, table 2: Philox4x32-7 is "Crush-resistant"; R = 10 is
+// Random123's default for its safety margin).  The sweeps are instruction-issue bound and the generator is a third of
+// their instructions: 7 rounds save 12 of the 149 instructions of a row iteration.  -DMGMC_PHILOX_ROUNDS=10 restores the
+// default of Random123 / cuRAND (the oracle has the same switch and must be built with the same value).
+#ifndef MGMC_PHILOX_ROUNDS
+#define MGMC_PHILOX_ROUNDS 7
+#endif
+constexpr int kPhiloxRounds = MGMC_PHILOX_ROUNDS;
+
+// Round keys of Philox4x32-R for a 64-bit seed: computed once on the host and passed by value in the
 // kernel parameters, so that every round is 2 IMAD.WIDE + 2 LOP3 with the key read from the constant bank.
 struct PhiloxKeys {
   uint32_t k[20];
@@ -171,7 +181,7 @@ struct PhiloxKeys {
 inline PhiloxKeys philox_round_keys(uint64_t seed) {
   PhiloxKeys K;
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < 10; ++r) {  // (room for 10 rounds; kPhiloxRounds of them are used)
     K.k[2 * r] = k0;
     K.k[2 * r + 1] = k1;
     k0 += 0x9E3779B9u;
@@ -180,11 +190,11 @@ inline PhiloxKeys philox_round_keys(uint64_t seed) {
   return K;
 }
 
-MGMC_HD void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, const PhiloxKeys &K) {
+MGMC_HD void philox4x32(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, const PhiloxKeys &K) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kPhiloxRounds; ++r) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k[2 * r], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k[2 * r + 1];
     c0 = n0;
@@ -206,7 +216,7 @@ MGMC_HD void box_muller(uint64_t a, uint64_t b, const NormalConsts &mc, const do
 // two independent N(0,1) variates from one counter; tab = the 128-entry table above (shared, global or host memory)
 MGMC_HD void normal_pair(const PhiloxKeys &K, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const NormalConsts &mc, const double *tab, double &z0,
                          double &z1) {
-  philox4x32_10(c0, c1, c2, c3, K);
+  philox4x32(c0, c1, c2, c3, K);
   box_muller((uint64_t)c0 | ((uint64_t)c1 << 32), (uint64_t)c2 | ((uint64_t)c3 << 32), mc, tab, z0, z1);
 }
 

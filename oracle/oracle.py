@@ -22,7 +22,11 @@ c_lp = C.POINTER(C.c_long)
 def build(force=False):
     """Compile liboracle.so with the Makefile next to this file (g++ only, no dependencies)."""
     so = os.path.join(_HERE, "liboracle.so")
-    if force or not os.path.exists(so):
+    if force and os.path.exists(so):
+        os.remove(so)
+    # (make rebuilds only when a source is newer than the library; without the sources -- never the case in this
+    #  repository -- the prebuilt library is used as it is)
+    if os.path.exists(os.path.join(_HERE, "oracle_core.cc")):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
 

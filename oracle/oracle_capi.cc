@@ -407,7 +407,7 @@ void orc_philox_normal_pair(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2
 }
 void orc_philox_raw(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out4) {
   uint32_t c[4] = {c0, c1, c2, c3};
-  Philox::philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  Philox::philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   for (int k = 0; k < 4; ++k) out4[k] = c[k];
 }
 

@@ -652,14 +652,18 @@ std::vector<long> make_order(const Lattice &lat, const CSR &A, int ordering);
 // (sampler/sampler.hh:31-34,69-71).  PhiloxNoise is the counter-based stream of the B200 path.
 // ---------------------------------------------------------------------------------------------
 struct Philox {
-  // Philox4x32-10 (Salmon et al. 2011, Random123), key = 64-bit seed, counter = 4 x 32 bit
+  // Philox4x32-R (Salmon et al. 2011, Random123), key = 64-bit seed, counter = 4 x 32 bit
   static inline void round_(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
     c0 = n0; c1 = n1; c2 = n2; c3 = n3;
   }
-  static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-    for (int r = 0; r < 10; ++r) {
+  // rounds: the CUDA path runs Philox4x32-7 (multigridmc_b200/csrc/philox.cuh kPhiloxRounds; same switch)
+#ifndef MGMC_PHILOX_ROUNDS
+#define MGMC_PHILOX_ROUNDS 7
+#endif
+  static inline void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < MGMC_PHILOX_ROUNDS; ++r) {
       round_(c[0], c[1], c[2], c[3], k0, k1);
       k0 += 0x9E3779B9u;
       k1 += 0xBB67AE85u;
@@ -668,7 +672,7 @@ struct Philox {
   // two N(0,1) from one counter: Box-Muller on two 52-bit uniforms (k + 1/2) 2^-52 in (0,1)
   static inline void normal_pair(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, double &z0, double &z1) {
     uint32_t c[4] = {c0, c1, c2, c3};
-    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     const uint64_t a = (uint64_t)c[0] | ((uint64_t)c[1] << 32), b = (uint64_t)c[2] | ((uint64_t)c[3] << 32);
     const double u1 = ((double)(a >> 12) + 0.5) * (1.0 / 4503599627370496.0);
     const double u2 = ((double)(b >> 12) + 0.5) * (1.0 / 4503599627370496.0);

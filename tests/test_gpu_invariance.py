@@ -52,9 +52,10 @@ def test_chain_independent_of_tiling_and_dead_pass_skipping(tmp_path, n, nlevel,
         "low_tiles": {"MGMC_TILE_ROWS": "32,32,16,8,32"},
         "tall_tiles": {"MGMC_TILE_ROWS": "24,40,32,16,36"},
         "no_fold": {"MGMC_NO_RES_FOLD": "1", "MGMC_TILE_ROWS": "16,16,8,8,16"},
-        # every level as its own launch instead of phases of the persistent kernel of the small levels (tail.cuh)
-        "no_tail": {"MGMC_NO_TAIL": "1"},
-        "short_tail": {"MGMC_TAIL_MAX_SITES": "20000"},
+        # the small levels and the coarse solve as phases of ONE persistent cooperative kernel (tail.cuh) instead of a
+        # launch per level visit
+        "tail": {"MGMC_TAIL": "1"},
+        "short_tail": {"MGMC_TAIL": "1", "MGMC_TAIL_MAX_SITES": "20000"},
     }
     for tag, env in variants.items():
         x = _run(tmp_path, tag, env, **kw)
