@@ -8,9 +8,17 @@ statement; one JSON line on stdout from rank 0.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 4096] [--nlevel 8]
 
-N > 1 (launched under torchrun, one rank per GPU): every rank advances an independent Markov chain
-on the same lattice (Philox chain id = rank) -- "small lattices run independent chains per GPU" of
-the north star applied to the benchmark lattice; no data-path collective, weak scaling.
+N > 1 (launched under torchrun, one rank per GPU): ONE chain of the benchmark lattice on row strips over all ranks
+("large lattices are domain-decomposed" of the north star; strong scaling: `value` = samples/s of that chain, halo
+rows exchanged inside the tile kernel over NVLink peer memory).  The other mode of the north star -- independent
+chains per GPU, no data-path collective, weak scaling -- is timed in the same run and reported under
+`independent_chains`; `--decomp chains` makes it the headline instead.
+
+`--impl reference`: the CPU oracle (restatement of the reference; the reference itself needs Eigen 3.4 + libconfig++,
+absent here) on the SAME workload -- 4096 x 4096, 8 levels, 32 measurements -- for --steps samples after --warmup,
+single-threaded like the reference (one sequential RNG stream, lexicographic Gauss-Seidel); "time per sample" as
+driver_mgmc.cc:72-80 defines it.  Needs ~30 GB of host memory (dense n x m low-rank matrices, sor_smoother.cc:17-38);
+on a smaller host the largest lattice that fits is run and named in config.workload.
 """
 import argparse
 import json
@@ -37,9 +45,11 @@ def parse():
     p.add_argument("--nmeas", type=int, default=32)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-batched", action="store_true", help="skip the 4-chains-per-launch figure")
-    p.add_argument("--decomp", default="chains", choices=["chains", "strips"],
-                   help="N > 1: independent chains per GPU (weak scaling, default) or ONE chain on row strips of the lattice (strong scaling)")
-    p.add_argument("--cpu-n", type=int, default=1024, help="lattice of the bounded CPU sample")
+    p.add_argument("--decomp", default="strips", choices=["chains", "strips"],
+                   help="N > 1: ONE chain on row strips of the lattice (strong scaling, default) or independent chains per GPU (weak scaling)")
+    p.add_argument("--cpu-n", type=int, default=0, help="lattice of the CPU arm (0: the benchmark lattice if the host memory allows)")
+    p.add_argument("--cpu-samples", type=int, default=2, help="samples of the in-line cpu_baseline (bounded sample of the workload)")
+    p.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other BASELINE configurations")
     return p.parse_args()
 
 
@@ -61,17 +71,52 @@ def cycle_model(n, nlevel):
 
 
 # ------------------------------------------------------------------------------------ CPU arm
+def host_info():
+    info = {"cores_available": os.cpu_count()}
+    try:
+        import cpuinfo
+
+        info["cpu"] = cpuinfo.get_cpu_info().get("brand_raw")
+    except Exception:
+        pass
+    try:
+        import psutil
+
+        info["mem_available_gb"] = round(psutil.virtual_memory().available / 1e9, 1)
+    except Exception:
+        pass
+    return info
+
+
+def cpu_lattice(a):
+    """The lattice the CPU arm runs: the benchmark lattice itself unless the host cannot hold the reference's data
+    structures (4 dense n x m matrices per level: ~1.8 KB per fine-level unknown at m = 32 -> 30 GB at 4096^2)."""
+    n, nlevel = a.n, a.nlevel
+    if a.cpu_n:
+        while n > a.cpu_n and nlevel > 2:
+            n, nlevel = n // 2, nlevel - 1
+        return n, nlevel
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64e9
+    need = lambda n_: 1.25 * (30e9 * (n_ / 4096.0) ** 2 * max(a.nmeas, 4) / 32.0)
+    while need(n) > avail and nlevel > 2:
+        n, nlevel = n // 2, nlevel - 1
+    return n, nlevel
+
+
 def cpu_reference_run(a, nsamples, nwarm):
-    """Times the CPU oracle (faithful restatement of the reference: lexicographic sweeps,
-    std::mt19937_64, CSR Galerkin hierarchy, dense n x m low-rank correction) on a bounded sample:
-    the same operator family on a cpu_n x cpu_n lattice with nlevel chosen so that the coarsest level
-    is the same 31 x 31; converted to samples/s of the benchmark lattice through site-updates/s."""
+    """Times the CPU oracle (faithful restatement of the reference: lexicographic sweeps, std::mt19937_64, CSR Galerkin
+    hierarchy, dense n x m low-rank correction; one thread) on the benchmark workload: MultigridMCSampler::apply in the
+    loop of measure_sampling_time (driver_mgmc.cc:66-80), "time per sample" = elapsed / nsamples."""
     from multigridmc_b200 import workloads as w
     from oracle import oracle as orc
 
-    n = a.cpu_n
-    nlevel = a.nlevel - int(round(np.log2(a.n / n)))
-    loc, sample_loc, mean, var = w.measurement_set(a.nmeas)
+    n, nlevel = cpu_lattice(a)
+    loc, sample_loc, mean, var = w.measurement_set(a.nmeas) if a.nmeas else (None, np.array([0.5, 0.5]), None, None)
     t0 = time.time()
     prior = orc.Operator.prior((n, n), "shiftedlaplace_fd", Lambda=0.2)
     op = prior.measured(loc, var, variance_scaling=1e-6) if a.nmeas else prior
@@ -84,20 +129,26 @@ def cpu_reference_run(a, nsamples, nwarm):
     f = op.apply(u)
     b_obs = op.measurement_vector(sample_loc, 0.0)
     x = np.zeros(op.ndof)
-    x, _ = sampler.run(f, x, b_obs, nwarm)
+    if nwarm > 0:
+        x, _ = sampler.run(f, x, b_obs, nwarm)
     t0 = time.time()
     x, series = sampler.run(f, x, b_obs, nsamples)
     dt = time.time() - t0
-    _, upd_small = cycle_model(n, nlevel)
+    _, upd_run = cycle_model(n, nlevel)
     _, upd_full = cycle_model(a.n, a.nlevel)
-    updates_per_s = upd_small * nsamples / dt
+    same = (n, nlevel) == (a.n, a.nlevel)
+    updates_per_s = upd_run * nsamples / dt
+    value = nsamples / dt  # samples/s on the lattice that was run
+    value_full = value if same else updates_per_s / upd_full
+    what = (f"{nsamples} MGMC samples (after {nwarm} warm-up) of the workload itself: {n}x{n}, {nlevel} levels, m={a.nmeas}, "
+            f"time per sample {1e3 * dt / nsamples:.0f} ms (driver_mgmc.cc:72-80)" if same else
+            f"{nsamples} MGMC samples (after {nwarm} warm-up) on {n}x{n}, {nlevel} levels, m={a.nmeas} -- the largest lattice of the "
+            f"family this host's memory holds; site-updates/s converted to samples/s of {a.n}x{a.n}")
     return {
-        "samples_per_s_equiv": updates_per_s / upd_full,
-        "site_updates_per_s": updates_per_s,
-        "ms_per_sample_on_sample_lattice": 1e3 * dt / nsamples,
-        "sample": f"{nsamples} MGMC samples (after {nwarm} warm-up) of the same operator on {n}x{n}, {nlevel} levels, m={a.nmeas}; "
-                  f"site-updates/s converted to samples/s of the {a.n}x{a.n} workload; setup {t_setup:.1f} s untimed",
-        "seconds": dt,
+        "value": value, "value_full_lattice": value_full, "same_config": same, "lattice": [n, n], "nlevel": nlevel,
+        "site_updates_per_s": updates_per_s, "ms_per_sample": 1e3 * dt / nsamples,
+        "sample": what + f"; set-up {t_setup:.0f} s untimed (threaded over the measurements; sampling on 1 thread)",
+        "seconds": dt, "setup_seconds": t_setup, "host": host_info(),
     }
 
 
@@ -107,15 +158,19 @@ def run_reference(a):
         return
     r = cpu_reference_run(a, max(a.steps, 1), max(a.warmup, 0))
     cfg = workload_config(a)
+    if not r["same_config"]:
+        n, nl = r["lattice"][0], r["nlevel"]
+        cfg["workload"] = cfg["workload"].replace(f"{a.n}x{a.n}", f"{n}x{n}").replace(f"{a.nlevel} levels", f"{nl} levels")
+        cfg["lattice"], cfg["nlevel"] = r["lattice"], nl
     line = {
-        "impl": "reference", "metric": "mgmc_samples_per_sec", "value": r["samples_per_s_equiv"], "unit": "samples/s",
-        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 / r["samples_per_s_equiv"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "impl": "reference", "metric": "mgmc_samples_per_sec", "value": r["value"], "unit": "samples/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_sample"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "site_updates_per_sec": r["site_updates_per_s"],
-        "cpu_baseline": {"value": r["samples_per_s_equiv"], "unit": "samples/s", "cores": 1, "kind": "port", "sample": r["sample"]},
-        "e2e": {"value": r["samples_per_s_equiv"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": 1, "kind": "port", "sample": r["sample"], "host": r["host"]},
+        "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is single-threaded by construction (one sequential RNG stream, lexicographic Gauss-Seidel); "
-                "the reference itself needs Eigen 3.4 + libconfig++ (absent): this is the oracle port",
+                "the reference itself needs Eigen 3.4 + libconfig++ (absent): this is the oracle port, timed per sample like driver_mgmc.cc:72-80",
     }
     print(json.dumps(line), flush=True)
 
@@ -164,6 +219,55 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def other_configs(m, peak):
+    """Driver-run numbers for the other BASELINE configurations (C1, C2, C4, C5) on one GPU, through
+    the C ABI, device-timed -- sub-records of the bench line, not bench lines of their own."""
+    out = []
+
+    def mgmc(name, n, nlevel, nchains=1, pde="shiftedlaplace_fd", steps=100, target=None):
+        try:
+            ctx = m.Context(n, n, nlevel, Lambda=0.2, pde=pde, nchains=nchains)
+            nd = ctx.ndof()
+            xs = np.arange(1, n) / n
+            u = np.outer(np.sin(np.pi * xs), np.sin(np.pi * xs)).ravel()
+            ctx.set_rhs(ctx.op_apply(0, np.tile(u, nchains)))
+            ctx.set_state(np.zeros(nd * nchains))
+            ctx.set_qoi([nd // 2], [1.0])
+            ctx.sample(10, series=False)
+            ms, _ = ctx.sample_timed(steps)
+            byts, upd = ctx.cycle_model()
+            t = ms / steps * 1e-3
+            rec = {"config": name, "ms_per_cycle": ms / steps, "chain_samples_per_s": nchains / t, "site_updates_per_s": nchains * upd / t,
+                   "algorithmic_gbs": nchains * byts / t / 1e9, "frac_of_peak": nchains * byts / t / 1e9 / peak}
+            if target:
+                rec["target"] = target
+            ctx.close()
+        except m.MgmcError as e:
+            rec = {"config": name, "unavailable": str(e)}
+        out.append(rec)
+
+    mgmc("C1 driver_mgmc 64x64, 3 levels, prior, V(1,1) SSOR (latency bound: us per cycle, not a roofline fraction)", 64, 3, steps=1000)
+    try:
+        n, nlevel = 1024, 6
+        ctx = m.Context(n, n, nlevel, Lambda=0.2, npresmooth=2, npostsmooth=2)
+        b = np.random.default_rng(1482817).standard_normal(ctx.ndof())  # (driver_mg.cc:165-172 draws it from std::mt19937_64(1482817))
+        ctx.loop_solve(b, rtol=1e-12, atol=1e-15, maxiter=3)
+        t0 = time.perf_counter()
+        x, hist, it, cv = ctx.loop_solve(b, rtol=1e-12, atol=1e-15, maxiter=100)
+        dt = time.perf_counter() - t0
+        out.append({"config": "C2 driver_mg 1024x1024, 6 levels, V(2,2) SSOR, rtol 1e-12 / atol 1e-15 / maxiter 100", "iterations": len(hist),
+                    "ms_per_iteration": 1e3 * dt / len(hist), "residual_reduction": float(hist[-1] / hist[0]),
+                    "rate_first_10": float((hist[10] / hist[0]) ** 0.1), "timed": "wall clock of the whole LoopSolver call incl. H2D of b and D2H of x",
+                    "target": "<= 0.09 ms / iteration at 60 % of the model"})
+        ctx.close()
+    except Exception as e:  # noqa: BLE001
+        out.append({"config": "C2", "unavailable": str(e)})
+    mgmc("C4 squared_shiftedlaplace_fd 2048x2048, 7 levels, prior, V(1,1) SSOR, one GPU", 2048, 7, pde="squared_shiftedlaplace_fd", steps=20,
+         target="<= 0.193 ms / cycle at 60 % of the model")
+    mgmc("C5 256 chains x 512x512, 5 levels, prior, one GPU", 512, 5, nchains=256, steps=20, target=">= 8.4e4 chain-samples/s per GPU at 60 % of the model")
+    return out
+
+
 def run_b200(a):
     import torch
 
@@ -201,6 +305,7 @@ def run_b200(a):
         ctx = m.Context(n, n, nlevel, Lambda=0.2, B=B, smoother="SSOR", coarse_solver="Cholesky", npresmooth=1, npostsmooth=1,
                         cycle=1, omega=1.0, seed=5418513, device=local, nchains=1, first_chain=rank)
     nchains_total = 1 if strips_on else world
+    strip_err = 0
     nd = ctx.ndof()
     # synthetic right-hand side f = A u, u = sin(pi x) sin(pi y); pinned host buffers for the e2e path
     xs = np.arange(1, n) / n
@@ -232,7 +337,8 @@ def run_b200(a):
     value = nchains_total * a.steps / (ms_max * 1e-3)
     if strips_on:
         series = strips.reduce_series(series, dist, torch.device("cuda", local))
-        if ctx.strip_error():
+        strip_err = ctx.strip_error()
+        if strip_err:
             raise SystemExit("bench.py: a device-side wait for a neighbour rank timed out")
 
     # ---- end to end through the reference-facing call with HOST buffers ----
@@ -274,9 +380,29 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_resident = nchains_total * a.steps / float(t.item())
 
-    # ---- N > 1, default mode (independent chains): additionally time ONE chain on row strips of the same lattice
-    #      (strong scaling; halo rows exchanged inside the tile kernel over NVLink peer memory) ----
+    # ---- N > 1: the other multi-GPU mode of the north star next to the headline one.  Headline = row strips (default):
+    #      additionally every rank advances an independent chain (Philox chain id = rank; no data-path collective, weak
+    #      scaling).  Headline = chains (--decomp chains): additionally ONE chain on row strips. ----
     strips_extra = None
+    chains_extra = None
+    if world > 1 and strips_on:
+        try:
+            cctx = m.Context(n, n, nlevel, Lambda=0.2, B=B, smoother="SSOR", coarse_solver="Cholesky", npresmooth=1, npostsmooth=1,
+                             cycle=1, omega=1.0, seed=5418513, device=local, nchains=1, first_chain=rank)
+            cctx.set_rhs(f_np)
+            cctx.set_state(np.zeros(nd))
+            cctx.set_philox_position(0)
+            cctx.sample(a.warmup, series=False)
+            barrier()
+            cms, _ = cctx.sample_timed(a.steps, series=False)
+            barrier()
+            t = torch.tensor([cms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            chains_extra = {"value": world * a.steps / (float(t.item()) * 1e-3), "unit": "samples/s", "ms_per_step": float(t.item()) / a.steps,
+                            "scaling": "weak", "what": "every rank advances an independent chain of the same lattice (Philox chain id = rank), no data-path collective"}
+            cctx.close()
+        except m.MgmcError as e:
+            chains_extra = {"unavailable": str(e)}
     if world > 1 and not strips_on:
         from multigridmc_b200 import strips as _strips
 
@@ -386,12 +512,18 @@ def run_b200(a):
     }
     if strips_extra is not None:
         line["strips"] = strips_extra
+    if chains_extra is not None:
+        line["independent_chains"] = chains_extra
+    if strips_on:
+        line["strips_error_flag"] = int(strip_err)
     if batched is not None:
         line["batched_chains"] = batched
+    if world == 1 and not a.no_configs:
+        line["other_configs"] = other_configs(m, peak)
     if not a.no_cpu_baseline and world == 1:
-        r = cpu_reference_run(a, 10, 1)
-        line["cpu_baseline"] = {"value": r["samples_per_s_equiv"], "unit": "samples/s", "cores": 1, "kind": "port", "sample": r["sample"],
-                                "site_updates_per_sec": r["site_updates_per_s"]}
+        r = cpu_reference_run(a, max(a.cpu_samples, 1), 0)
+        line["cpu_baseline"] = {"value": r["value_full_lattice"], "unit": "samples/s", "cores": 1, "kind": "port", "sample": r["sample"],
+                                "same_config": r["same_config"], "site_updates_per_sec": r["site_updates_per_s"], "host": r["host"]}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

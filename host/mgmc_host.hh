@@ -336,8 +336,12 @@ class MeasuredOperator : public LinearOperator {
       double d_min = 2.0;
       unsigned int ell_min = 0;
       const int ci = (int)std::floor(x0[0] * nx), cj = (int)std::floor(x0[1] * ny);
-      for (int j = std::max(cj, 1); j <= std::min(cj + 1, ny - 1); ++j)
-        for (int i = std::max(ci, 1); i <= std::min(ci + 1, nx - 1); ++i) {
+      // (candidates clamped to the interior: a point on or beyond the upper boundary picks the last interior line, as
+      //  the reference's scan over all vertices does)
+      const int j0 = std::min(std::max(cj, 1), ny - 1), j1 = std::min(std::max(cj + 1, 1), ny - 1);
+      const int i0 = std::min(std::max(ci, 1), nx - 1), i1 = std::min(std::max(ci + 1, 1), nx - 1);
+      for (int j = j0; j <= j1; ++j)
+        for (int i = i0; i <= i1; ++i) {
           const double dist = std::sqrt((i * hx - x0[0]) * (i * hx - x0[0]) + (j * hy - x0[1]) * (j * hy - x0[1]));
           if (dist < d_min) {
             d_min = dist;

@@ -114,7 +114,7 @@ __device__ __forceinline__ int ld_acquire_sys_i(const int *p) {
 __device__ __forceinline__ void strip_spin(const int *flag, int target, int *err) {
   const long long t0 = clock64();
   while (ld_acquire_sys_i(flag) < target) {
-    if (clock64() - t0 > 6000000000ll) {
+    if (clock64() - t0 > 6000000000ll) {  // (= kWaitTimeoutClocks)
       *err = 1;
       break;
     }
@@ -170,6 +170,7 @@ struct FusedP {
   int lr_slot, nchains;   // first vbuf / flag slot of this launch (nfix fix-ups, then u)
   int rt_prolong, rt_restrict;  // persistent kernel of the small levels (tail.cuh): the flavour of the phase
   int chain_off;                // first chain of this launch (chains launched in groups)
+  int *err;                     // error word of the context: a device-side wait that timed out sets it
   int nz_off, nz_cap;           // persistent kernel: noise generated ahead of the passes -- buffer offset in doubles behind
                                 // the tile (0: off) and its capacity in (row, pass) items
 };
@@ -192,14 +193,22 @@ __device__ __forceinline__ void pkt_store(LrPkt *p, double v, int epoch) {
   const unsigned long long b = (unsigned long long)__double_as_longlong(v);
   asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"((unsigned)(b >> 32)), "r"(epoch), "r"(0) : "memory");
 }
-// bounded wait: a bug (or a dead peer) must not hang the GPU
-__device__ __forceinline__ double pkt_wait(const LrPkt *p, int epoch) {
+// bounded wait: a bug (or a dead peer) must not hang the GPU -- a time-out raises the context's error word (the API
+// call that finds it set fails with MGMC_ERR_CUDA instead of returning a chain built on a stale value).  The epoch
+// comparison is wrap-safe.
+constexpr long long kWaitTimeoutClocks = 6000000000ll;  // ~3 s at 1.9 GHz
+__device__ __forceinline__ double pkt_wait(const LrPkt *p, int epoch, int *err) {
   unsigned lo, hi;
   int e, pad;
   const long long t0 = clock64();
-  do {
+  while (true) {
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(e), "=r"(pad) : "l"(p) : "memory");
-  } while (e < epoch && clock64() - t0 < 4000000000ll);
+    if ((int)(e - epoch) >= 0) break;
+    if (clock64() - t0 > kWaitTimeoutClocks) {
+      if (err) *err = 2;
+      break;
+    }
+  }
   return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
@@ -815,14 +824,14 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
         if (diag) {
           for (int n = threadIdx.x; n < n_need; n += kFusedThreads) {
             const int k = nlist[n];
-            if (!is_own[k]) darr[k] = pkt_wait(vb + k, lr_epoch);
+            if (!is_own[k]) darr[k] = pkt_wait(vb + k, lr_epoch, P.err);
           }
         } else {
           // the measurements interact: every needed d_k is a full row of Ms s + Mneg t
           for (int k = threadIdx.x; k < lrm; k += kFusedThreads) {
             if (is_own[k]) continue;
-            tarr[k] = pkt_wait(vb + k, lr_epoch);
-            sarr[k] = pkt_wait(vb + lrm + k, lr_epoch);
+            tarr[k] = pkt_wait(vb + k, lr_epoch, P.err);
+            sarr[k] = pkt_wait(vb + lrm + k, lr_epoch, P.err);
           }
           __syncthreads();
           for (int n = warp; n < n_need; n += kFusedWarps) {
@@ -969,7 +978,7 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
       const int *nlist = need_list + 2 * lrm;
       for (int n = threadIdx.x; n < lr_cnt[3]; n += kFusedThreads) {
         const int k = nlist[n];
-        darr[k] = P.lr_u_from_fix ? uarr[k] : (is_own[k] ? tarr[k] : pkt_wait(vb + k, lr_epoch));
+        darr[k] = P.lr_u_from_fix ? uarr[k] : (is_own[k] ? tarr[k] : pkt_wait(vb + k, lr_epoch, P.err));
       }
       __syncthreads();
       for (int u = threadIdx.x; u < R.nbu; u += kFusedThreads) {

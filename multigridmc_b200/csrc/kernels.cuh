@@ -561,6 +561,8 @@ __global__ void strip_wait_kernel(const int *flag0, const int *flag1, int per_wa
 __global__ void __launch_bounds__(256) end_of_cycle_kernel(int nnz, const long long *__restrict__ qsite, const double *__restrict__ qval,
                                                           const double *__restrict__ x, long long stride, int nchains, double *__restrict__ series,
                                                           long long series_cap, uint32_t *sample, unsigned long long *pos, int *cycle_no) {
+  // series_cap = capacity of `series` in SAMPLES (rows of nchains values): a call that does not ask for the series may
+  // run more cycles than the buffer of an earlier call holds -- they are not recorded
   const unsigned long long p = *pos;
   if (series != nullptr && nnz > 0 && p < (unsigned long long)series_cap) {
     for (int c = threadIdx.x >> 5; c < nchains; c += 8) {

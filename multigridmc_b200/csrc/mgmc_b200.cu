@@ -122,12 +122,15 @@ struct mgmc_ctx {
                                    // the edge CTAs (below / above), [9] cycle number
   int strip_index = 0;             // distributed fused launches emitted so far in this cycle
   int strip_per_cycle = 0;         // ... per cycle (counted by a dry run before the first capture)
+  int *d_err = nullptr;  // error word: set by a device-side wait (low-rank packets, strip flags) that timed out
   // noise position
   uint32_t *d_sample = nullptr;
   uint32_t h_sample = 0;
   std::vector<uint32_t> sweep_counter;
   PhiloxKeys keys;
   // QoI / series
+  std::vector<long long> h_qsite;  // what d_qsite / d_qval hold (mgmc_set_qoi returns early when nothing changes)
+  std::vector<double> h_qval;
   int qoi_nnz = 0;
   long long *d_qsite = nullptr;
   double *d_qval = nullptr;
@@ -184,6 +187,15 @@ struct mgmc_ctx {
     return p;
   }
   void sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
+  void dfree(void *p) {
+    if (!p) return;
+    for (size_t k = 0; k < allocs.size(); ++k)
+      if (allocs[k] == p) {
+        allocs.erase(allocs.begin() + k);
+        break;
+      }
+    cudaFree(p);
+  }
 
   // alg_bytes: algorithmic bytes of this launch in the model of SURVEY.md section 8(d)
   template <class F>
@@ -309,6 +321,9 @@ std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
   if (!(d.Lambda > 0.0)) fail(MGMC_ERR_INVALID, "Lambda must be positive");
   if (!(d.omega > 0.0 && d.omega < 2.0)) fail(MGMC_ERR_INVALID, "omega must be in (0,2)");
   if (d.nx >= (1 << 20) || d.ny >= (1 << 20)) fail(MGMC_ERR_INVALID, "lattice too large");
+  // Philox counter word 0 of a site is ((j G + i / 4) << 1) | (i & 1), G = nx / 4 + 1; 0x40000000 / 0x80000000 tag the
+  // coarse-sampler / low-rank streams (philox.cuh): the site counters must stay below 2^30
+  if (2ll * ((long long)d.ny + 1) * ((long long)d.nx / 4 + 1) >= (1ll << 30)) fail(MGMC_ERR_UNSUPPORTED, "lattice too large for the 32-bit site counter of the noise streams (about 46000 x 46000)");
   std::vector<HostLevel> L(d.nlevel);
   L[0].nx = d.nx;
   L[0].ny = d.ny;
@@ -616,11 +631,28 @@ inline int tail_tiles_bound(int nx, int ny, int nc) {
   return best;
 }
 
+// coop: tiles of this launch wait for packets of ANY other tile of their chain (interacting measurements): launched
+// cooperatively, so that the runtime guarantees (and checks) that the whole grid is resident at once
 template <int NC, bool G, bool PR, bool RS, bool LR>
-void launch_fused_t(mgmc_ctx *c, const FusedP &P, dim3 grid, size_t smem) {
+void launch_fused_t(mgmc_ctx *c, const FusedP &P, dim3 grid, size_t smem, bool coop = false) {
   // (the attribute is per device and function: tracked per context, not per process)
   const void *fn = (const void *)fused_smooth_kernel<NC, G, PR, RS, LR>;
   if (c->func_attr_done.insert(fn).second) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+  if (coop) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kFusedThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_smooth_kernel<NC, G, PR, RS, LR>, P));
+    return;
+  }
   fused_smooth_kernel<NC, G, PR, RS, LR><<<grid, kFusedThreads, smem, c->stream>>>(P);
 }
 
@@ -915,6 +947,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     K.err = ctl + 3;
   }
   P.nchains = c->d.nchains;
+  P.err = c->d_err;
   if (use_lr) {
     const LowRankDev &lr = get_lowrank(c, level, omega);
     P.lr = lr.tile;
@@ -1007,7 +1040,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     grid.z = std::min(chain_group, c->d.nchains - c0);
 #define FUSED_CASE(NC_, G_, PR_, RS_)                                             \
   if (nc == NC_ && gibbs == G_ && prolong == PR_ && restrict_ == RS_) {            \
-    if (use_lr) launch_fused_t<NC_, G_, PR_, RS_, true>(c, P, grid, smem);        \
+    if (use_lr) launch_fused_t<NC_, G_, PR_, RS_, true>(c, P, grid, smem, lr_coupled); \
     else launch_fused_t<NC_, G_, PR_, RS_, false>(c, P, grid, smem);              \
   }
     FUSED_CASE(2, false, false, false) FUSED_CASE(2, false, false, true) FUSED_CASE(2, false, true, false) FUSED_CASE(2, false, true, true)
@@ -1560,10 +1593,21 @@ void emit_mgmc_cycle(mgmc_ctx *c) {
 void emit_end_of_cycle(mgmc_ctx *c) {
   const DevLevel &L = c->lv[0];
   c->launch("end_of_cycle", 0, [&] {
-    end_of_cycle_kernel<<<1, 256, 0, c->stream>>>(c->qoi_nnz, c->d_qsite, c->d_qval, L.x, L.g.stride, c->d.nchains, c->d_series, c->series_cap, c->d_sample,
+    end_of_cycle_kernel<<<1, 256, 0, c->stream>>>(c->qoi_nnz, c->d_qsite, c->d_qval, L.x, L.g.stride, c->d.nchains, c->d_series, c->series_cap / c->d.nchains, c->d_sample,
                                                  c->d_pos, (c->strip.on() && c->strip_connected) ? c->d_strip_ctl + 9 : nullptr);
   });
   c->h_sample++;
+}
+
+// after the stream has been synchronised: did a device-side wait time out?  (then the state is invalid)
+void check_device_error(mgmc_ctx *c) {
+  if (!c->d_err || c->d.m_lowrank == 0) return;
+  int e = 0;
+  CUDA_CHECK(cudaMemcpy(&e, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) {
+    CUDA_CHECK(cudaMemset(c->d_err, 0, sizeof(int)));
+    fail(MGMC_ERR_CUDA, "a device-side wait for a low-rank packet of another tile timed out (co-residency lost or a peer died); the chain state is invalid");
+  }
 }
 
 void set_sample_index(mgmc_ctx *c, uint32_t s) {
@@ -1581,7 +1625,9 @@ void drop_graph(mgmc_ctx *c) {
 
 void ensure_series(mgmc_ctx *c, long long n) {
   if (n > c->series_cap) {
+    c->sync();
     drop_graph(c);
+    c->dfree(c->d_series);
     c->d_series = c->dalloc<double>((size_t)n);
     c->series_cap = n;
   }
@@ -1681,8 +1727,11 @@ void run_cycles(mgmc_ctx *c, int64_t nsamples) {
   }                                               \
   return MGMC_OK;
 
+// every entry point that takes a context passes through here: argument check + the context's device becomes current
+// (a host thread may hold contexts on several devices)
 static void check_level(const mgmc_ctx *c, int level, bool need_coarser = false) {
   if (!c) fail(MGMC_ERR_INVALID, "null context");
+  CUDA_CHECK(cudaSetDevice(c->device));
   if (level < 0 || level >= c->d.nlevel - (need_coarser ? 1 : 0)) fail(MGMC_ERR_INVALID, "level out of range");
 }
 
@@ -1697,6 +1746,9 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
     if (desc->device < 0 || desc->device >= ndev) fail(MGMC_ERR_INVALID, "invalid device ordinal");
     if (desc->nchains < 1) fail(MGMC_ERR_INVALID, "nchains must be >= 1");
     if (desc->m_lowrank < 0 || desc->m_lowrank > 1024) fail(MGMC_ERR_UNSUPPORTED, "m_lowrank must be in [0, 1024]");
+    if (desc->B_nnz < 0 || (desc->m_lowrank > 0 && !desc->Sigma) || (desc->B_nnz > 0 && (!desc->B_rows || !desc->B_cols || !desc->B_vals)))
+      fail(MGMC_ERR_INVALID, "low-rank term: Sigma / B_rows / B_cols / B_vals must not be null when m_lowrank / B_nnz > 0");
+    if (desc->m_lowrank == 0 && desc->B_nnz > 0) fail(MGMC_ERR_INVALID, "B entries given but m_lowrank = 0");
     if (desc->smoother != MGMC_SMOOTHER_SOR && desc->smoother != MGMC_SMOOTHER_SSOR) fail(MGMC_ERR_INVALID, "invalid smoother");
     if (desc->coarse_solver != MGMC_COARSE_SSOR && desc->coarse_solver != MGMC_COARSE_CHOLESKY) fail(MGMC_ERR_INVALID, "invalid coarse solver");
     std::vector<HostLevel> H = build_host_levels(*desc);
@@ -1789,6 +1841,7 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
     }
     c->d_sample = c->dalloc<uint32_t>(1);
     c->d_pos = c->dalloc<unsigned long long>(1);
+    c->d_err = c->dalloc<int>(1);
     c->sync();
     *out = c;
     return MGMC_OK;
@@ -1876,6 +1929,7 @@ int mgmc_prolongate_add(mgmc_ctx *c, int level, double alpha, const double *x_co
   normalize_x(c, level);
   download_vec(c, level, c->lv[level].x, x_fine);
   c->sync();
+  check_device_error(c);
   API_END
 }
 
@@ -1888,6 +1942,7 @@ int mgmc_residual_restrict(mgmc_ctx *c, int level, const double *f, const double
   emit_smoothing(c, level, {}, false, c->d.omega, false, 0.0, true);
   download_vec(c, level + 1, c->lv[level + 1].f, f_coarse);
   c->sync();
+  check_device_error(c);
   API_END
 }
 
@@ -1910,6 +1965,7 @@ int mgmc_smoother_apply(mgmc_ctx *c, int level, int kind, int direction, double 
   normalize_x(c, level);
   download_vec(c, level, L.x, x);
   c->sync();
+  check_device_error(c);
   API_END
 }
 
@@ -1925,6 +1981,7 @@ int mgmc_sampler_apply(mgmc_ctx *c, int level, int kind, int direction, double o
   normalize_x(c, level);
   download_vec(c, level, L.x, x);
   c->sync();
+  check_device_error(c);
   API_END
 }
 
@@ -1960,6 +2017,7 @@ int mgmc_sampler_mgmc_apply(mgmc_ctx *c, const double *f, double *x) {
   emit_mgmc_cycle(c);
   download_vec(c, 0, c->lv[0].x, x);
   set_sample_index(c, c->h_sample + 1);
+  check_device_error(c);
   API_END
 }
 
@@ -1971,6 +2029,7 @@ int mgmc_mgprec_apply(mgmc_ctx *c, const double *b, double *x) {
   mg_solve_level(c, 0);
   download_vec(c, 0, c->lv[0].x, x);
   c->sync();
+  check_device_error(c);
   API_END
 }
 
@@ -2094,6 +2153,7 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
   if (history && nh > 0) CUDA_CHECK(cudaMemcpy(history, c->d_sol_hist, sizeof(double) * nh, cudaMemcpyDeviceToHost));
   download_vec(c, 0, c->sol_x, x);
   c->sync();
+  check_device_error(c);
   if (nhist) *nhist = nh;
   if (niter) *niter = ctl.conv ? ctl.it_conv : maxiter;
   if (converged) *converged = ctl.conv ? 1 : 0;
@@ -2144,9 +2204,16 @@ int mgmc_set_qoi(mgmc_ctx *c, int64_t nnz, const int64_t *idx, const double *val
     // row strips: every rank sums the entries it owns; the caller adds the partial series of all ranks
     if (c->strip.on() && (j < c->strip.lo[0] || j > c->strip.hi[0])) v[e] = 0.0;
   }
-  drop_graph(c);
+  // (the drivers set the same functional before every series: nothing to do then -- no new buffers, no re-capture)
+  if (c->d_qsite && site == c->h_qsite && v == c->h_qval) return MGMC_OK;
+  c->sync();
+  drop_graph(c);  // the captured cycle holds the old pointers
+  c->dfree(c->d_qsite);
+  c->dfree(c->d_qval);
   c->d_qsite = c->dupload(site);
   c->d_qval = c->dupload(v);
+  c->h_qsite = site;
+  c->h_qval = v;
   c->qoi_nnz = (int)nnz;
   API_END
 }
@@ -2160,6 +2227,7 @@ int mgmc_sample(mgmc_ctx *c, int64_t nsamples, double *qoi_series) {
   if (qoi_series && c->qoi_nnz > 0)
     CUDA_CHECK(cudaMemcpyAsync(qoi_series, c->d_series, sizeof(double) * nsamples * c->d.nchains, cudaMemcpyDeviceToHost, c->stream));
   c->sync();
+  check_device_error(c);
   API_END
 }
 
@@ -2185,6 +2253,7 @@ int mgmc_sample_timed(mgmc_ctx *c, int64_t nsamples, double *qoi_series, double 
   if (qoi_series && c->qoi_nnz > 0)
     CUDA_CHECK(cudaMemcpyAsync(qoi_series, c->d_series, sizeof(double) * nsamples * c->d.nchains, cudaMemcpyDeviceToHost, c->stream));
   c->sync();
+  check_device_error(c);
   API_END
 }
 
@@ -2211,6 +2280,7 @@ int mgmc_sample_moments(mgmc_ctx *c, int64_t nsamples, double *mean_field, doubl
                                  cudaMemcpyDeviceToHost, c->stream));
   }
   c->sync();
+  check_device_error(c);
   API_END
 }
 

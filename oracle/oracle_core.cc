@@ -1,6 +1,9 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle_core.hh).  Implementation of the CPU restatement.
 #include "oracle_core.hh"
 
+#include <atomic>
+#include <thread>
+
 namespace orc {
 
 // ---------------------------------------------------------------------------------------------
@@ -369,6 +372,24 @@ std::vector<long> make_order(const Lattice &lat, const CSR &A, int ordering) {
 // ---------------------------------------------------------------------------------------------
 // SORSmoother
 // ---------------------------------------------------------------------------------------------
+// SET-UP helper: independent pieces of the low-rank smoother data (one per measurement) on the host's threads.
+// Nothing on the sampling / smoothing path uses it.
+template <class F>
+static void setup_parallel_for(int n, F &&body) {
+  const int nt = (int)std::max(1u, std::min((unsigned)n, std::thread::hardware_concurrency()));
+  if (nt <= 1) {
+    for (int k = 0; k < n; ++k) body(k);
+    return;
+  }
+  std::atomic<int> next(0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&] {
+      for (int k = next++; k < n; k = next++) body(k);
+    });
+  for (auto &t : th) t.join();
+}
+
 SORSmoother::SORSmoother(const LinearOperator *op_, double omega_, int nsmooth_, Direction dir_, const std::vector<long> &order_)
     : op(op_), omega(omega_), nsmooth(nsmooth_), direction(dir_), order(order_), diag(op_->A.diagonal()) {
   const int m = op->m_lowrank;
@@ -377,13 +398,14 @@ SORSmoother::SORSmoother(const LinearOperator *op_, double omega_, int nsmooth_,
     // from x = 0 with right-hand side b (and (L^T + D/omega)^{-1} b one backward sweep); this is
     // the triangular solve of the reference expressed for an arbitrary visiting order.
     const long n = op->ndof();
+    // (SET-UP only is threaded -- the m columns are independent; the sampling / smoothing path below stays on one
+    //  thread like the reference: one sequential RNG stream, lexicographic Gauss-Seidel)
     std::vector<Vec> W(m, Vec(n, 0.0));
-    Vec col(n);
-    for (int k = 0; k < m; ++k) {
-      std::fill(col.begin(), col.end(), 0.0);
+    setup_parallel_for(m, [&](int k) {
+      Vec col(n, 0.0);
       for (long p = op->BT.rowptr[k]; p < op->BT.rowptr[k + 1]; ++p) col[op->BT.col[p]] = op->BT.val[p];
       sweep_once(col.data(), W[k].data());
-    }
+    });
     std::vector<double> S(m * m, 0.0);
     for (int a = 0; a < m; ++a)
       for (int b = 0; b < m; ++b) {
@@ -393,7 +415,7 @@ SORSmoother::SORSmoother(const LinearOperator *op_, double omega_, int nsmooth_,
       }
     std::vector<double> Sinv = dense_inverse(S, m);
     B_bar.assign(m, Vec(n, 0.0));
-    for (int b = 0; b < m; ++b)
+    setup_parallel_for(m, [&](int b) {
       for (int a = 0; a < m; ++a) {
         const double s = Sinv[a * m + b];
         if (s == 0.0) continue;
@@ -401,6 +423,7 @@ SORSmoother::SORSmoother(const LinearOperator *op_, double omega_, int nsmooth_,
         Vec &o = B_bar[b];
         for (long i = 0; i < n; ++i) o[i] += w[i] * s;
       }
+    });
   }
 }
 

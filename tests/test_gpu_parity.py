@@ -396,3 +396,42 @@ def test_full_size_properties(m, n, nlevel):
     x, hist, niter, conv = ctx.loop_solve(b, rtol=1e-11, atol=1e300, maxiter=40)
     assert conv and niter < 25
     assert rel(x, x_exact) < 1e-8
+
+
+def test_series_shorter_than_a_later_run_without_series(m):
+    """Round-1 advisor finding: the QoI series buffer is sized by the call that asks for it; a later call WITHOUT series
+    that runs more cycles must not write past it (several chains per launch).  The chain must simply continue: the state
+    after series(4) + no-series(12) + series(2) equals the state after one run of 18 cycles, and the recorded values are
+    the first 4 and the last 2 of that run's series."""
+    from multigridmc_b200 import workloads as w
+
+    n, nlevel, nchains = 256, 4, 4
+    loc, _, _, var = w.measurement_set(8)
+    B = w.point_measurement_matrix(n, n, loc, var, 1e-3)
+    nd = (n - 1) ** 2
+    rng = np.random.default_rng(0)
+    f = np.tile(rng.standard_normal(nd), nchains)
+
+    def fresh():
+        ctx = m.Context(n, n, nlevel, B=B, nchains=nchains, seed=3)
+        ctx.set_rhs(f)
+        ctx.set_state(np.zeros(nd * nchains))
+        ctx.set_qoi([nd // 2, 7], [1.0, 0.5])
+        ctx.set_philox_position(0)
+        return ctx
+
+    a = fresh()
+    z1 = a.sample(4, series=True)
+    a.sample(12, series=False)
+    z2 = a.sample(2, series=True)
+    xa = a.get_state()
+    b = fresh()
+    zb = b.sample(18, series=True)
+    assert np.array_equal(xa, b.get_state())
+    assert np.array_equal(z1, zb[:4]) and np.array_equal(z2, zb[16:])
+    # setting the same functional again is a no-op (no re-capture, no new buffers); a different one takes effect
+    b.set_qoi([nd // 2, 7], [1.0, 0.5])
+    z3 = b.sample(1, series=True)
+    b.set_qoi([7], [2.0])
+    z4 = b.sample(1, series=True)
+    assert np.all(np.isfinite(z3)) and np.allclose(z4[0], 2.0 * b.get_state().reshape(nchains, nd)[:, 7])
