@@ -58,7 +58,10 @@ struct Stage {
   uint32_t c1;  // (level << 24) | sweep counter of the sweep this colour pass belongs to
   short xl, xh, yl, yh;
   int mode;
+  uint32_t soff;  // added to the sample index (1: the pass belongs to the pre-smoothing of the NEXT cycle, merged level-0 launch)
 };
+constexpr int kMaxFix = 4;   // low-rank fix-ups per launch (merged level-0 launch: 2 sweeps of cycle k + 2 of cycle k + 1)
+constexpr int kMaxQoi = 8;   // observed sites a merged level-0 launch can record (more: the launches are not merged)
 
 // Device-resident data of the low-rank (measurement) term of one level for the in-kernel Woodbury
 // fix-up (see "Low-rank term inside the launch" below).  Sparse matrices carry explicit (i, j) coordinates.
@@ -163,8 +166,18 @@ struct FusedP {
   LowRankTile lr;         // by value: its pointers sit in the constant bank, no dependent load to reach the tables
   int lr_mx, lr_my;       // extent of supp(B_k) beyond its lower left corner: extra halo on the high sides
   int nfix;
-  int fix_stage[2], fix_dir[2];
-  uint32_t fix_c1[2];
+  int fix_stage[kMaxFix], fix_dir[kMaxFix];
+  uint32_t fix_c1[kMaxFix], fix_soff[kMaxFix];
+  // Merged level-0 launch (post-smoothing of cycle k + pre-smoothing of cycle k + 1): the sample x^(k) only exists
+  // inside the launch, after stage qoi_stage (and its fix-up).  The tile that holds an observed site records its value
+  // there: qoi_out[chain * nqoi + e] (end_of_cycle_kernel forms sample_vector . x from them, driver_mgmc.cc:76).
+  int nqoi, qoi_stage;
+  int qoi_i[kMaxQoi], qoi_j[kMaxQoi];
+  double *qoi_out;
+  // The iterate this launch starts from is zero by construction (multigridmc_sampler.cc:122, x_{l+1} = 0 before the
+  // recursion) and is not read.  Set for the first launch of level 1 behind a merged level-0 launch, which cannot zero
+  // the coarse iterate itself: its tiles read it (prolongation) while others would already be zeroing it.
+  int x_in_zero;
   unsigned char *lr_flags; // [chains][tiles of the launch] see "Per-tile flag" in the kernel
   int lr_u_from_fix;      // RESTRICT: the launch ends with a fix-up, u = s - d (see the fix-up block)
   int lr_slot, nchains;   // first vbuf / flag slot of this launch (nfix fix-ups, then u)
@@ -173,7 +186,14 @@ struct FusedP {
   int *err;                     // error word of the context: a device-side wait that timed out sets it
   int nz_off, nz_cap;           // persistent kernel: noise generated ahead of the passes -- buffer offset in doubles behind
                                 // the tile (0: off) and its capacity in (row, pass) items
+  // NZG kernels: the normals of the full colour passes were generated ahead of the launch by noise_gen_kernel
+  // (noise_ahead.cuh) while the latency-bound small levels left the chip idle.  nzg[s] = plane of pass s, one pair per
+  // (row, aligned group of 4 columns): [row index][nzg_gp] double2, group p at index p + kNzgPad
+  const double2 *nzg[8];
+  int nzg_gp;
 };
+constexpr int kNzgPad = 4;   // groups left of column 0 in a noise plane (= kGX / 4)
+constexpr int kNzgRows = 3;  // rows of a warp per colour pass a NZG kernel can hold in registers (host: RY <= 16 * kNzgRows ...)
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
   int v;
@@ -354,13 +374,23 @@ __device__ __forceinline__ void pass_rows(const FusedP &P, double *xl, double *f
 #endif
 }
 
+// NZG kernels: one colour pass over the (at most kNzgRows) rows of a warp with the normals already in registers
+template <bool NINE, bool W1, int Q, bool RES>
+__device__ __forceinline__ void pass_rows_z(const FusedP &P, double *xl, double *fl, int nrows, int dl, bool v0, bool v1, const double2 (&z)[kNzgRows]) {
+  const double winv = P.winv, nscale = P.noise_scale, wn = P.wn;
+#pragma unroll
+  for (int n = 0; n < kNzgRows; ++n) {
+    if (n < nrows) update_pair<NINE, true, W1, Q, RES>(P.a, P.aw, xl + n * dl, fl + n * dl, 0, v0, v1, winv, nscale, wn, z[n].x, z[n].y);
+  }
+}
+
 // One tile job: tile `tile_id` of chain `chain` of the launch / phase described by P.  `njob_x` = tiles per chain
 // (index of the per-tile flags).  sm = dynamic shared memory of the CTA; lr_cnt[4], ntab[128] = static shared memory
 // (LOWRANK: measurements owned by this tile, needed for the forward / backward fix-up, for the residual; GIBBS: tables
 // of the normal generator (philox.cuh), published by the barrier of the tile load).
 // PR / RS = 0, 1: prolongation in front / residual + restriction behind compiled out / in; 2: decided at run time by
 // P.rt_prolong / P.rt_restrict (the persistent kernel of the small levels runs both flavours, tail.cuh).
-template <int NC, bool GIBBS, int PR, int RS, bool LOWRANK>
+template <int NC, bool GIBBS, int PR, int RS, bool LOWRANK, bool NZG = false>
 __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, const int chain_idx, const int njob_x, double *sm, int *lr_cnt, double *ntab) {
   const bool PROLONG = (PR == 2) ? (P.rt_prolong != 0) : (PR == 1);
   const bool RESTRICT = (RS == 2) ? (P.rt_restrict != 0) : (RS == 1);
@@ -402,10 +432,10 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
 #define MGMC_LR_PTRS                                                                                                  \
   const int lrm = P.lr.m;                                                                                             \
   double *darr = sm + 2 * P.RY * 128, *tarr = darr + lrm, *sarr = tarr + lrm;                                         \
-  double *spre = sarr + lrm;    /* [2][m] noise of fix-up q for owned k */                                            \
-  double *cms = spre + 2 * lrm; /* [2][m] Ms_kk per direction (owned k) */                                            \
-  double *cmn = cms + 2 * lrm;  /* [2][m] Mneg_kk */                                                                  \
-  double *uarr = cmn + 2 * lrm; /* u_k = s_k - d_k of the last fix-up (low-rank part of the residual) */               \
+  double *spre = sarr + lrm;    /* [kMaxFix][m] noise of fix-up q for owned k */                                      \
+  double *cms = spre + kMaxFix * lrm; /* [kMaxFix][m] Ms_kk per fix-up (owned k) */                                   \
+  double *cmn = cms + kMaxFix * lrm;  /* [kMaxFix][m] Mneg_kk */                                                      \
+  double *uarr = cmn + kMaxFix * lrm; /* u_k = s_k - d_k of the last fix-up (low-rank part of the residual) */         \
   int *own_list = reinterpret_cast<int *>(uarr + lrm), *need_list = own_list + lrm; /* need_list: [3][m] */           \
   int *is_own = need_list + 3 * lrm;                                                                                  \
   const int lr_epoch = *P.lr.epoch;                                                                                   \
@@ -498,7 +528,7 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
             const int jr = aux[32 + 512 + 2 * it], sr = aux[33 + 512 + 2 * it];
             const int cr = P.st[sr].colour;
             const uint32_t qr = (NC == 2) ? ((cr ^ jr) & 1) : (cr & 1);
-            normal_pair(P.nz.keys, (((uint32_t)jr * P.nz.G + pg0) << 1) | qr, P.st[sr].c1, sample0, chain0, P.nz.mc, ntab, z0[u], z1[u]);
+            normal_pair(P.nz.keys, (((uint32_t)jr * P.nz.G + pg0) << 1) | qr, P.st[sr].c1, sample0 + P.st[sr].soff, chain0, P.nz.mc, ntab, z0[u], z1[u]);
           }
 #pragma unroll
           for (int u = 0; u < NI; ++u) {
@@ -521,6 +551,54 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
     }
   }
 
+  // ---- NZG kernels: what this warp does in colour pass s, and the normals of that pass (generated ahead of the launch,
+  //      noise_ahead.cuh) fetched into registers one pass ahead -- the first pass before the tile load ----
+  auto pass_geom = [&](int s_, int &jw_, int &nrows_, int &q_, bool &v0_, bool &v1_) {
+    const int colour_ = P.st[s_].colour;
+    const int ilo_ = max(1, i_t0 - P.st[s_].xl), ihi_ = min(nx - 1, i_t0 + TX - 1 + P.st[s_].xh);
+    int jlo_ = max(1, j_t0 - P.st[s_].yl);
+    const int jhi_ = min(ny - 1, j_t0 + TY - 1 + P.st[s_].yh);
+    const int step_ = (NC == 4) ? 2 : 1;
+    if (NC == 4 && (jlo_ & 1) != (colour_ >> 1)) ++jlo_;
+    jw_ = jlo_ + warp * step_;
+    nrows_ = (jw_ <= jhi_) ? (jhi_ - jw_) / (kFusedWarps * step_) + 1 : 0;
+    q_ = (NC == 2) ? ((colour_ ^ jw_) & 1) : (colour_ & 1);
+    const int i0_ = gi0 + q_;
+    v0_ = (i0_ >= ilo_) && (i0_ <= ihi_);
+    v1_ = (i0_ + 2 >= ilo_) && (i0_ + 2 <= ihi_);
+  };
+  // (two register sets used alternately: a copy "current = next" would wait for the loads in flight)
+  double2 za[kNzgRows], zb[kNzgRows];
+  bool z_flip = false;  // false: the current pass reads za and loads the next one into zb
+  auto nzg_load = [&](int s_, double2 (&zd)[kNzgRows]) {
+    int jw_, nrows_, q_;
+    bool v0_, v1_;
+    pass_geom(s_, jw_, nrows_, q_, v0_, v1_);
+    const double2 *zp = P.nzg[s_] + ((long long)((NC == 4) ? (jw_ >> 1) : jw_) * P.nzg_gp + ((i_r0 >> 2) + lane + kNzgPad));
+#pragma unroll
+    for (int n = 0; n < kNzgRows; ++n)
+      if (n < nrows_ && (v0_ || v1_)) zd[n] = __ldcs(zp + (long long)n * kFusedWarps * P.nzg_gp);
+  };
+  auto next_full = [&](int s_) {
+    while (s_ < P.nstages && P.st[s_].mode != STAGE_FULL) ++s_;
+    return s_;
+  };
+  if (NZG) {
+#pragma unroll
+    for (int n = 0; n < kNzgRows; ++n) za[n] = zb[n] = make_double2(0.0, 0.0);
+    const int s0_ = next_full(0);
+    if (s0_ < P.nstages) nzg_load(s0_, za);
+    // the planes of the later passes: pulled into L2 now (a pass is too short to cover an HBM access issued one pass ahead)
+    for (int s_ = next_full(s0_ + 1); s_ < P.nstages; s_ = next_full(s_ + 1)) {
+      int jw_, nrows_, q_;
+      bool v0_, v1_;
+      pass_geom(s_, jw_, nrows_, q_, v0_, v1_);
+      const double2 *zp = P.nzg[s_] + ((long long)((NC == 4) ? (jw_ >> 1) : jw_) * P.nzg_gp + ((i_r0 >> 2) + lane + kNzgPad));
+      if (((lane & 7) == 0 || lane == 31) && cols_alloc)  // (one request per 128-byte line; rows need not be line aligned)
+        for (int n = 0; n < nrows_; ++n) asm volatile("prefetch.global.L2 [%0];" ::"l"(zp + (long long)n * kFusedWarps * P.nzg_gp));
+    }
+  }
+
   // ---- stage the region: one warp per row.  Lane l loads the column pairs (2l, 2l+1) and
   //      (64+2l, 64+2l+1): each 128-bit load instruction covers 512 contiguous bytes (fully coalesced);
   //      the pair is then scattered into planes 2(l&1), 2(l&1)+1 at index l/2 (+16), conflict free.
@@ -538,11 +616,11 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
       if (gj >= -kGY && gj <= ny + kGY && r + u * kFusedWarps < RY) {
         const long long o = (long long)gj * pitch;
         if (oka) {
-          xa[u] = *reinterpret_cast<const double2 *>(xg + o + gia);
+          if (!P.x_in_zero) xa[u] = *reinterpret_cast<const double2 *>(xg + o + gia);
           fa[u] = *reinterpret_cast<const double2 *>(fg + o + gia);
         }
         if (okb) {
-          xb[u] = *reinterpret_cast<const double2 *>(xg + o + gib);
+          if (!P.x_in_zero) xb[u] = *reinterpret_cast<const double2 *>(xg + o + gib);
           fb[u] = *reinterpret_cast<const double2 *>(fg + o + gib);
         }
       }
@@ -601,7 +679,7 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
       is_own[k] = 1;
     }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < kMaxFix; ++q) {
       if (q >= P.nfix) break;
       const int dir = P.fix_dir[q];
       if (owner) {
@@ -612,7 +690,7 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
       double sv = 0.0;
       if (GIBBS) {
         double z0, z1;
-        normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[q], *P.nz.sample, P.nz.chain0 + chain_idx, P.nz.mc, ntab, z0, z1);
+        normal_pair(P.nz.keys, 0x80000000u | ((uint32_t)k >> 1), P.fix_c1[q], *P.nz.sample + P.fix_soff[q], P.nz.chain0 + chain_idx, P.nz.mc, ntab, z0, z1);
         sv = R.sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
       }
       spre[q * lrm + k] = sv;
@@ -639,32 +717,57 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
 #else
 #define TCLK(v)
 #endif
+  // observed sites of a merged level-0 launch that this tile holds (uniform over the CTA)
+  bool tile_qoi = false;
+  for (int e = 0; e < P.nqoi; ++e)
+    tile_qoi = tile_qoi || (P.qoi_i[e] >= i_t0 && P.qoi_i[e] < i_t0 + TX && P.qoi_j[e] >= j_t0 && P.qoi_j[e] < j_t0 + TY);
+  // segments of passes: each ends at a low-rank fix-up; without fix-ups, at the stage after which the observed sites
+  // are recorded
+  const int nsegfix = LOWRANK ? P.nfix : 0;
+  const int nbreak = nsegfix > 0 ? nsegfix : (P.nqoi > 0 ? 1 : 0);
   int s = 0;
-  for (int seg = 0; seg <= (LOWRANK ? P.nfix : 0); ++seg) {
-   const int s_end = (LOWRANK && seg < P.nfix) ? P.fix_stage[seg] + 1 : S;
+  for (int seg = 0; seg <= nbreak; ++seg) {
+   const int s_end = (seg < nbreak) ? ((nsegfix > 0) ? P.fix_stage[seg] : P.qoi_stage) + 1 : S;
    for (; s < s_end; ++s) {
     TCLK(tq0)
     const int colour = P.st[s].colour;
     const uint32_t c1 = P.st[s].c1;
+    const uint32_t smp = sample + P.st[s].soff;
     const int mode = P.st[s].mode;
     if (mode == STAGE_SKIP) continue;  // (uniform over the launch)
-    if (LOWRANK && mode == STAGE_SPARSE) {
-      // dead pass that a fix-up still looks at: only supp(B_k) of the owned measurements (omega = 1 here)
-      if (!lr_own) continue;
-      MGMC_LR_PTRS
-      for (int o = warp; o < lr_cnt[0]; o += kFusedWarps) {
-        const int4 bb = reinterpret_cast<const int4 *>(P.lr.bbox)[own_list[o]];  // i0, i1, j0, j1
-        for (int j = bb.z; j <= bb.w; ++j) {
+    if (mode == STAGE_SPARSE) {
+      // dead pass that a fix-up (or the recording of the observed sites) still looks at: only supp(B_k) of the owned
+      // measurements and the observed sites of this tile (omega = 1 here)
+      if (!(lr_own || tile_qoi)) continue;
+      auto sparse_box = [&](int bi0, int bi1, int bj0, int bj1) {
+        for (int j = bj0; j <= bj1; ++j) {
           if (NC == 4 && (j & 1) != (colour >> 1)) continue;
           const int q = (NC == 2) ? ((colour ^ j) & 1) : (colour & 1);
           const int i0 = gi0 + q;
-          const bool v0 = (i0 >= bb.x) && (i0 <= bb.y), v1 = (i0 + 2 >= bb.x) && (i0 + 2 <= bb.y);
+          const bool v0 = (i0 >= bi0) && (i0 <= bi1), v1 = (i0 + 2 >= bi0) && (i0 + 2 <= bi1);
           if (!(v0 || v1)) continue;
           double *xl = xs + (j - j_r0) * 128 + lane;
           double *fl = fs + (j - j_r0) * 128 + lane;
           const uint32_t c0 = (((uint32_t)j * P.nz.G + pg) << 1) | (uint32_t)q;
-          if (q == 0) pass_rows<NINE, GIBBS, true, 0>(P, xl, fl, 1, 0, c0, 0u, c1, sample, chain, ntab, v0, v1);
-          else pass_rows<NINE, GIBBS, true, 1>(P, xl, fl, 1, 0, c0, 0u, c1, sample, chain, ntab, v0, v1);
+          if (q == 0) pass_rows<NINE, GIBBS, true, 0>(P, xl, fl, 1, 0, c0, 0u, c1, smp, chain, ntab, v0, v1);
+          else pass_rows<NINE, GIBBS, true, 1>(P, xl, fl, 1, 0, c0, 0u, c1, smp, chain, ntab, v0, v1);
+        }
+      };
+      // (an observed site inside supp(B_k) of an owned measurement is updated by that box: the boxes of one tile must
+      //  not update a site twice in a pass -- a second update would draw the same normal and give the same value, but
+      //  two warps would write it concurrently; same value, benign, and excluded here for the observed sites)
+      if (LOWRANK && lr_own) {
+        MGMC_LR_PTRS
+        for (int o = warp; o < lr_cnt[0]; o += kFusedWarps) {
+          const int4 bb = reinterpret_cast<const int4 *>(P.lr.bbox)[own_list[o]];  // i0, i1, j0, j1
+          sparse_box(bb.x, bb.y, bb.z, bb.w);
+        }
+      }
+      if (tile_qoi) {
+        for (int e = warp; e < P.nqoi; e += kFusedWarps) {
+          const int qi = P.qoi_i[e], qj = P.qoi_j[e];
+          if (!(qi >= i_t0 && qi < i_t0 + TX && qj >= j_t0 && qj < j_t0 + TY)) continue;
+          sparse_box(qi, qi, qj, qj);
         }
       }
       __syncthreads();
@@ -687,8 +790,8 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
           const int dz = kFusedWarps * 32;
 #define MGMC_TAIL_PASS(W1_, RES_)                                                                                           \
   {                                                                                                                         \
-    if (q == 0) pass_rows<NINE, GIBBS, W1_, 0, RES_, true>(P, xl, fl, nrows, dl, 0u, 0u, c1, sample, chain, ntab, v0, v1, zp, dz); \
-    else pass_rows<NINE, GIBBS, W1_, 1, RES_, true>(P, xl, fl, nrows, dl, 0u, 0u, c1, sample, chain, ntab, v0, v1, zp, dz);       \
+    if (q == 0) pass_rows<NINE, GIBBS, W1_, 0, RES_, true>(P, xl, fl, nrows, dl, 0u, 0u, c1, smp, chain, ntab, v0, v1, zp, dz); \
+    else pass_rows<NINE, GIBBS, W1_, 1, RES_, true>(P, xl, fl, nrows, dl, 0u, 0u, c1, smp, chain, ntab, v0, v1, zp, dz);       \
   }
           if (res) MGMC_TAIL_PASS(true, true)
           else if (P.omega_is_one) MGMC_TAIL_PASS(true, false)
@@ -699,8 +802,8 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
           const uint32_t c0 = (((uint32_t)jw * P.nz.G + pg) << 1) | (uint32_t)q, dc0 = ((uint32_t)(kFusedWarps * ((NC == 4) ? 2 : 1)) * P.nz.G) << 1;
 #define MGMC_TAIL_PASS(W1_, RES_)                                                                                     \
   {                                                                                                                   \
-    if (q == 0) pass_rows<NINE, GIBBS, W1_, 0, RES_>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1); \
-    else pass_rows<NINE, GIBBS, W1_, 1, RES_>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);       \
+    if (q == 0) pass_rows<NINE, GIBBS, W1_, 0, RES_>(P, xl, fl, nrows, dl, c0, dc0, c1, smp, chain, ntab, v0, v1); \
+    else pass_rows<NINE, GIBBS, W1_, 1, RES_>(P, xl, fl, nrows, dl, c0, dc0, c1, smp, chain, ntab, v0, v1);       \
   }
           if (res) MGMC_TAIL_PASS(true, true)
           else if (P.omega_is_one) MGMC_TAIL_PASS(true, false)
@@ -708,6 +811,42 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
 #undef MGMC_TAIL_PASS
         }
       }
+      TCLK(tq2)
+      __syncthreads();
+#ifdef MGMC_TILE_TIMING
+      tacc_setup += tq1 - tq0;
+      tacc_pass += tq2 - tq1;
+      tacc_bar += clock64() - tq2;
+#endif
+      continue;
+    }
+    if (NZG) {
+      int jw, nrows, q;
+      bool v0, v1;
+      pass_geom(s, jw, nrows, q, v0, v1);
+      const int s2 = next_full(s + 1);
+      auto run_pass = [&](const double2 (&zc)[kNzgRows], double2 (&zd)[kNzgRows]) {
+        if (s2 < S) nzg_load(s2, zd);  // in flight while this pass runs
+        TCLK(tq1)
+        if (nrows > 0 && (v0 || v1)) {
+          double *xl = xs + (jw - j_r0) * 128 + lane;
+          double *fl = fs + (jw - j_r0) * 128 + lane;
+          const int dl = kFusedWarps * ((NC == 4) ? 2 : 1) * 128;
+          if (RESTRICT && s == P.res_stage && !lr_tile) {
+            if (q == 0) pass_rows_z<NINE, true, 0, true>(P, xl, fl, nrows, dl, v0, v1, zc);
+            else pass_rows_z<NINE, true, 1, true>(P, xl, fl, nrows, dl, v0, v1, zc);
+          } else if (P.omega_is_one) {
+            if (q == 0) pass_rows_z<NINE, true, 0, false>(P, xl, fl, nrows, dl, v0, v1, zc);
+            else pass_rows_z<NINE, true, 1, false>(P, xl, fl, nrows, dl, v0, v1, zc);
+          } else {
+            if (q == 0) pass_rows_z<NINE, false, 0, false>(P, xl, fl, nrows, dl, v0, v1, zc);
+            else pass_rows_z<NINE, false, 1, false>(P, xl, fl, nrows, dl, v0, v1, zc);
+          }
+        }
+      };
+      if (z_flip) run_pass(zb, za);
+      else run_pass(za, zb);
+      z_flip = !z_flip;
       TCLK(tq2)
       __syncthreads();
 #ifdef MGMC_TILE_TIMING
@@ -740,14 +879,14 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
         const uint32_t c0 = (((uint32_t)jw * P.nz.G + pg) << 1) | (uint32_t)q, dc0 = ((uint32_t)(kFusedWarps * step) * P.nz.G) << 1;
         const int dl = kFusedWarps * step * 128;
         if (RESTRICT && s == P.res_stage && !lr_tile) {  // last pass before the residual (omega = 1): leaves the residual of its sites in fs
-          if (q == 0) pass_rows<NINE, GIBBS, true, 0, true>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
-          else pass_rows<NINE, GIBBS, true, 1, true>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
+          if (q == 0) pass_rows<NINE, GIBBS, true, 0, true>(P, xl, fl, nrows, dl, c0, dc0, c1, smp, chain, ntab, v0, v1);
+          else pass_rows<NINE, GIBBS, true, 1, true>(P, xl, fl, nrows, dl, c0, dc0, c1, smp, chain, ntab, v0, v1);
         } else if (P.omega_is_one) {
-          if (q == 0) pass_rows<NINE, GIBBS, true, 0>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
-          else pass_rows<NINE, GIBBS, true, 1>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
+          if (q == 0) pass_rows<NINE, GIBBS, true, 0>(P, xl, fl, nrows, dl, c0, dc0, c1, smp, chain, ntab, v0, v1);
+          else pass_rows<NINE, GIBBS, true, 1>(P, xl, fl, nrows, dl, c0, dc0, c1, smp, chain, ntab, v0, v1);
         } else {
-          if (q == 0) pass_rows<NINE, GIBBS, false, 0>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
-          else pass_rows<NINE, GIBBS, false, 1>(P, xl, fl, nrows, dl, c0, dc0, c1, sample, chain, ntab, v0, v1);
+          if (q == 0) pass_rows<NINE, GIBBS, false, 0>(P, xl, fl, nrows, dl, c0, dc0, c1, smp, chain, ntab, v0, v1);
+          else pass_rows<NINE, GIBBS, false, 1>(P, xl, fl, nrows, dl, c0, dc0, c1, smp, chain, ntab, v0, v1);
         }
       }
     }
@@ -759,8 +898,8 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
     tacc_bar += clock64() - tq2;
 #endif
    }
-    TSTAMP(2 + 2 * seg)
-    if (LOWRANK && seg < P.nfix && lr_tile) {
+    if (seg < 2) { TSTAMP(2 + 2 * seg) }
+    if (LOWRANK && seg < nsegfix && lr_tile) {
       MGMC_LR_PTRS
       const int fixq = seg;
       const LowRankTile &R = P.lr;
@@ -872,7 +1011,18 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
         for (int n = threadIdx.x; n < n_need; n += kFusedThreads) darr[nlist[n]] = 0.0;  // (ordered before the next use by the pass barriers)
       }
     }
-    TSTAMP(3 + 2 * seg)
+    if (P.nqoi > 0 && seg < nbreak && s_end - 1 == P.qoi_stage && tile_qoi) {
+      // the sample x^(k) of a merged launch: record the observed sites this tile holds (tile_qoi is uniform over the CTA)
+      if ((int)threadIdx.x < P.nqoi) {
+        const int qi = P.qoi_i[threadIdx.x], qj = P.qoi_j[threadIdx.x];
+        if (qi >= i_t0 && qi < i_t0 + TX && qj >= j_t0 && qj < j_t0 + TY) {
+          const int di = qi - i_r0;
+          P.qoi_out[(size_t)chain_idx * P.nqoi + threadIdx.x] = xs[(qj - j_r0) * 128 + (di & 3) * 32 + (di >> 2)];
+        }
+      }
+      __syncthreads();  // (the next pass may overwrite the site)
+    }
+    if (seg < 2) { TSTAMP(3 + 2 * seg) }
   }
 
   if (LOWRANK && RESTRICT && lr_own && !P.lr_u_from_fix) {
@@ -1045,13 +1195,13 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
 #endif
 }
 
-template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT, bool LOWRANK>
+template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT, bool LOWRANK, bool NZG = false>
 __global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {
   extern __shared__ double sm[];
   __shared__ int lr_cnt[4];
   __shared__ __align__(16) double ntab[128];
   if (GIBBS && threadIdx.x < 128) ntab[threadIdx.x] = kNormalTabDev[threadIdx.x];
-  fused_tile<NC, GIBBS, PROLONG ? 1 : 0, RESTRICT ? 1 : 0, LOWRANK>(P, (int)blockIdx.x, (int)blockIdx.z + P.chain_off, (int)gridDim.x, sm, lr_cnt, ntab);
+  fused_tile<NC, GIBBS, PROLONG ? 1 : 0, RESTRICT ? 1 : 0, LOWRANK, NZG>(P, (int)blockIdx.x, (int)blockIdx.z + P.chain_off, (int)gridDim.x, sm, lr_cnt, ntab);
 }
 
 }  // namespace mgmc

@@ -560,14 +560,17 @@ __global__ void strip_wait_kernel(const int *flag0, const int *flag1, int per_wa
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) end_of_cycle_kernel(int nnz, const long long *__restrict__ qsite, const double *__restrict__ qval,
                                                           const double *__restrict__ x, long long stride, int nchains, double *__restrict__ series,
-                                                          long long series_cap, uint32_t *sample, unsigned long long *pos, int *cycle_no) {
+                                                          long long series_cap, uint32_t *sample, unsigned long long *pos, int *cycle_no,
+                                                          const double *__restrict__ qpart, int *lr_epoch) {
   // series_cap = capacity of `series` in SAMPLES (rows of nchains values): a call that does not ask for the series may
   // run more cycles than the buffer of an earlier call holds -- they are not recorded
+  // qpart != nullptr (after a merged level-0 launch, fused.cuh): the sample only existed inside that launch, which
+  // recorded the observed sites: x_site(e) of chain c at qpart[c * nnz + e]; same summation order as below
   const unsigned long long p = *pos;
   if (series != nullptr && nnz > 0 && p < (unsigned long long)series_cap) {
     for (int c = threadIdx.x >> 5; c < nchains; c += 8) {
       double v = 0.0;
-      for (int e = threadIdx.x & 31; e < nnz; e += 32) v += qval[e] * x[(long long)c * stride + qsite[e]];
+      for (int e = threadIdx.x & 31; e < nnz; e += 32) v += qval[e] * (qpart ? qpart[(long long)c * nnz + e] : x[(long long)c * stride + qsite[e]]);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
       if ((threadIdx.x & 31) == 0) series[p * nchains + c] = v;
@@ -578,6 +581,7 @@ __global__ void __launch_bounds__(256) end_of_cycle_kernel(int nnz, const long l
     *sample = *sample + 1u;
     *pos = p + 1ull;
     if (cycle_no) *cycle_no = *cycle_no + 1;  // row strips: flag values are counted in cycles
+    if (lr_epoch) *lr_epoch = *lr_epoch + 1;  // merged launches: the next unit starts a new epoch of the low-rank packets
   }
 }
 

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "setup.hh"
 #include "tail.cuh"
+#include "noise_ahead.cuh"
 
 #include <set>
 
@@ -145,6 +146,17 @@ struct mgmc_ctx {
   double *d_mean = nullptr, *d_second = nullptr;
   // graph of one MGMC cycle (+ end-of-cycle kernel)
   cudaGraphExec_t graph = nullptr;
+  // Merged level-0 launch: the post-smoothing of cycle k and the pre-smoothing of cycle k + 1 are adjacent launches on
+  // level 0 -- one launch does both (prolongation, the sweeps of both, residual + restriction): one load / store of the
+  // fine level and, with omega = 1, one colour pass less per cycle.  A run of K cycles is
+  //   pre-smoothing, levels >= 1 | (K - 1) x { merged launch, end of cycle, levels >= 1 } | post-smoothing, end of cycle
+  // and the unit in braces is the CUDA graph (one per parity of the ping-pong buffers of level 0).
+  bool merge_on = false;
+  int merge_qoi_stage = -1;          // >= 0 while the merged launch is being emitted: last stage of cycle k
+  bool next_x_zero = false;          // the next fused launch starts from a zero iterate that nobody has zeroed (FusedP::x_in_zero)
+  cudaGraphExec_t graph_unit[2] = {nullptr, nullptr};
+  int64_t unit_launches = 0;
+  double *d_qpart = nullptr;         // [nchains][kMaxQoi] observed sites recorded by the merged launch
   // per-tile low-rank flags of the fused launches (fused.cuh): a pool allocated with the context, handed out per launch geometry
   unsigned char *d_lr_flag_pool = nullptr;
   size_t lr_flag_pool_size = 0, lr_flag_pool_used = 0;
@@ -164,6 +176,26 @@ struct mgmc_ctx {
   std::vector<int> tail_stamp_kinds;
   double *dAinv = nullptr;         // A^{-1} of the coarsest level (one-pass coarse phase)
   std::set<const void *> func_attr_done;  // kernels whose dynamic shared memory limit has been raised on this device
+  // noise generated ahead of the fine-level launches (noise_ahead.cuh): a second branch of the cycle graph generates
+  // the normals of the next level-0 launches while the latency-bound small levels leave the chip idle
+  struct NzaSlot {
+    int level = 0;
+    bool post = false;               // consumed by the post-smoothing of the same cycle (else: pre-smoothing of the next)
+    std::vector<NzJob> jobs;         // one per full colour pass of the launch (sample_off = 0)
+    std::vector<int> stage;          // stage index of jobs[k] in the launch
+  };
+  int nza_planned = 0;               // 0: not yet, 1: planned (nza_on says whether it is in use)
+  bool nza_on = false;
+  int nza_fork_level = -1;           // the branch forks before the first launch of this level
+  std::vector<int> nza_levels;
+  std::vector<NzaSlot> nza_slots;    // in launch order per level
+  std::vector<int> nza_cursor;       // per level: launches of the level emitted so far in this cycle
+  bool nza_dry = false, nza_dry_post = false;  // planning run: dev_fused records the launch instead of emitting it
+  bool nza_forked = false, nza_joined = false, nza_in_cycle = false;
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_post = nullptr, ev_done = nullptr;
+  uint32_t *d_nza_tag = nullptr;     // [nlevel] sample index the pre-smoothing planes of a level hold
+  unsigned int *d_nza_ticket = nullptr;
   bool perf_no_noise = false;  // MGMC_PERF_NO_NOISE=1: run the sampling cycle with the deterministic kernels (perf experiments only)
   // instrumentation
   int64_t launch_count = 0;
@@ -633,11 +665,21 @@ inline int tail_tiles_bound(int nx, int ny, int nc) {
 
 // coop: tiles of this launch wait for packets of ANY other tile of their chain (interacting measurements): launched
 // cooperatively, so that the runtime guarantees (and checks) that the whole grid is resident at once
-template <int NC, bool G, bool PR, bool RS, bool LR>
+#ifdef MGMC_NOISE_AHEAD
+constexpr bool kNoiseAheadBuilt = true;
+#else
+constexpr bool kNoiseAheadBuilt = false;  // the NZG kernels are not instantiated
+#endif
+template <int NC, bool G, bool PR, bool RS, bool LR, bool NZ = false>
 void launch_fused_t(mgmc_ctx *c, const FusedP &P, dim3 grid, size_t smem, bool coop = false) {
   // (the attribute is per device and function: tracked per context, not per process)
-  const void *fn = (const void *)fused_smooth_kernel<NC, G, PR, RS, LR>;
-  if (c->func_attr_done.insert(fn).second) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+  const void *fn = (const void *)fused_smooth_kernel<NC, G, PR, RS, LR, NZ>;
+  if (c->func_attr_done.insert(fn).second) {
+    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    // (always the largest shared-memory carve-out: an SM that has to change its L1 / shared split for a new CTA first
+    //  drains -- a small-level launch would wait for the co-resident noise_gen_kernel CTA to finish, noise_ahead.cuh)
+    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
   if (coop) {
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
@@ -650,16 +692,17 @@ void launch_fused_t(mgmc_ctx *c, const FusedP &P, dim3 grid, size_t smem, bool c
     at[0].val.cooperative = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_smooth_kernel<NC, G, PR, RS, LR>, P));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_smooth_kernel<NC, G, PR, RS, LR, NZ>, P));
     return;
   }
-  fused_smooth_kernel<NC, G, PR, RS, LR><<<grid, kFusedThreads, smem, c->stream>>>(P);
+  fused_smooth_kernel<NC, G, PR, RS, LR, NZ><<<grid, kFusedThreads, smem, c->stream>>>(P);
 }
 
 struct FixSpec {
   int stage;    // the fix-up follows this stage of the launch
   int dir;      // 0: forward sweep, 1: backward sweep
   uint32_t c1;  // Philox word of the sweep (low-rank noise)
+  uint32_t soff = 0;  // added to the sample index (merged level-0 launch: sweeps of the next cycle)
 };
 
 // start of every cycle and API call: a new epoch invalidates everything the owner tiles published before
@@ -669,7 +712,7 @@ void lr_begin_epoch(mgmc_ctx *c) {
 }
 
 // shared memory the low-rank bookkeeping of a tile needs behind the tile itself
-inline size_t lr_tile_smem(int m) { return (size_t)10 * m * sizeof(double) + (size_t)6 * m * sizeof(int); }
+inline size_t lr_tile_smem(int m) { return (size_t)(4 + 3 * kMaxFix) * m * sizeof(double) + (size_t)6 * m * sizeof(int); }
 
 // Can the fix-ups of this level run inside the fused launch?  Always when the measurements do not interact;
 // otherwise every tile that needs a fix-up waits for ALL owner tiles of its chain, so all tiles of a chain must be
@@ -752,7 +795,7 @@ struct Margin {
     return m;
   }
 };
-Margin plan_stages(int nc, std::vector<Stage> &st, const std::vector<FixSpec> &fixes, bool use_lr, bool w1, bool restrict_, int lr_mx, int lr_my) {
+Margin plan_stages(int nc, std::vector<Stage> &st, const std::vector<FixSpec> &fixes, bool use_lr, bool w1, bool restrict_, int lr_mx, int lr_my, int qoi_stage = -1) {
   static const bool noskip = std::getenv("MGMC_NO_DEAD_PASS") != nullptr;  // (experiments: run every pass in full)
   Margin end;
   end.on = true;
@@ -768,6 +811,8 @@ Margin plan_stages(int nc, std::vector<Stage> &st, const std::vector<FixSpec> &f
     if (use_lr)
       for (const FixSpec &fx : fixes)
         if (fx.stage == s) std::fill(sparse.begin(), sparse.end(), 1);
+    // (merged level-0 launch: the observed sites are recorded after this stage -- every colour is needed there)
+    if (s == qoi_stage) std::fill(sparse.begin(), sparse.end(), 1);
     const int cs = st[s].colour;
     Margin r = req[cs];
     const bool sp = sparse[cs] != 0;
@@ -821,6 +866,12 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     P.fc_out = C.f;
     P.xc_zero = C.x;
   }
+  if (prolong && restrict_) P.xc_zero = nullptr;  // (merged level-0 launch: see FusedP::x_in_zero)
+  if (c->next_x_zero) {
+    if (prolong || level == 0) fail(MGMC_ERR_INVALID, "internal: zero-iterate launch out of place");
+    P.x_in_zero = 1;
+    c->next_x_zero = false;
+  }
   P.nstages = S;
   P.winv = omega / L.coef.c;
   P.omega_is_one = (omega == 1.0) ? 1 : 0;
@@ -841,7 +892,18 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     P.lr_my = lr.bh - 1;
   }
   std::vector<Stage> plan = stages;
-  const Margin halo = plan_stages(nc, plan, fixes, use_lr, omega == 1.0, restrict_, P.lr_mx, P.lr_my);
+  const int nqoi = (c->merge_qoi_stage >= 0) ? c->qoi_nnz : 0;
+  const Margin halo = plan_stages(nc, plan, fixes, use_lr, omega == 1.0, restrict_, P.lr_mx, P.lr_my, nqoi > 0 ? c->merge_qoi_stage : -1);
+  if (nqoi > 0) {
+    if (nqoi > kMaxQoi) fail(MGMC_ERR_INVALID, "internal: too many observed sites for a merged launch");
+    P.nqoi = nqoi;
+    P.qoi_stage = c->merge_qoi_stage;
+    for (int e = 0; e < nqoi; ++e) {
+      P.qoi_i[e] = (int)(c->h_qsite[e] % L.g.pitch);
+      P.qoi_j[e] = (int)(c->h_qsite[e] / L.g.pitch);
+    }
+    P.qoi_out = c->d_qpart;
+  }
   for (int k = 0; k < S; ++k) P.st[k] = plan[k];
   static const bool nofold = std::getenv("MGMC_NO_RES_FOLD") != nullptr;
   // (not with a low-rank term: tiles next to a measurement could not fold, and which tiles those are depends on the
@@ -878,6 +940,54 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   }
   if (c->strip.on() && !c->tail_rec && P.TY != fused_tile_rows(L.g.ny, nc, true, restrict_)) fail(MGMC_ERR_UNSUPPORTED, "row strips: too many measurements for the tile geometry");
   if (smem > (size_t)kFusedSmemMax) fail(MGMC_ERR_INVALID, "internal: fused tile does not fit in shared memory");
+  // ---- normals generated ahead of the launch (noise_ahead.cuh) ----
+  bool nzg = false;
+  if (gibbs && !c->tail_rec && (c->nza_dry || (c->nza_on && c->nza_in_cycle)) && std::find(c->nza_levels.begin(), c->nza_levels.end(), level) != c->nza_levels.end()) {
+    const int step = (nc == 4) ? 2 : 1;
+    const bool fits = ((P.RY + step - 1) / step + kFusedWarps - 1) / kFusedWarps <= kNzgRows;  // rows of a warp per pass held in registers
+    if (c->nza_dry) {
+      // planning run: record the launch (one plane of normals per full colour pass) instead of emitting it
+      mgmc_ctx::NzaSlot sl;
+      sl.level = level;
+      sl.post = c->nza_dry_post;
+      if (fits) {
+        const size_t rows = (size_t)((nc == 4) ? L.g.ny / 2 : L.g.ny) + 1;
+        for (int k = 0; k < S; ++k) {
+          if (plan[k].mode != STAGE_FULL) continue;
+          NzJob jb;
+          jb.buf = c->dalloc<double2>(rows * (size_t)(L.g.pitch / 4));
+          jb.colour = plan[k].colour;
+          jb.c1 = plan[k].c1;
+          jb.sample_off = 0u;
+          sl.jobs.push_back(jb);
+          sl.stage.push_back(k);
+        }
+      }
+      c->nza_slots.push_back(sl);
+      return;
+    }
+    int idx = c->nza_cursor[level]++, at = -1;
+    for (size_t q = 0; q < c->nza_slots.size(); ++q)
+      if (c->nza_slots[q].level == level && idx-- == 0) at = (int)q;
+    if (at < 0) fail(MGMC_ERR_INVALID, "internal: launch without a planned noise slot");
+    const mgmc_ctx::NzaSlot &sl = c->nza_slots[at];
+    if (!sl.jobs.empty()) {
+      size_t nfull = 0;
+      for (int k = 0; k < S; ++k) nfull += plan[k].mode == STAGE_FULL;
+      if (nfull != sl.jobs.size()) fail(MGMC_ERR_INVALID, "internal: noise slot does not match the launch");
+      for (size_t q = 0; q < sl.jobs.size(); ++q) {
+        const Stage &st = plan[sl.stage[q]];
+        if (st.mode != STAGE_FULL || st.colour != sl.jobs[q].colour || st.c1 != sl.jobs[q].c1) fail(MGMC_ERR_INVALID, "internal: noise slot does not match the launch");
+        P.nzg[sl.stage[q]] = sl.jobs[q].buf;
+      }
+      P.nzg_gp = L.g.pitch / 4;
+      nzg = true;
+      if (sl.post && c->nza_forked && !c->nza_joined) {
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_post, 0));  // the planes of this cycle's post-smoothing are complete
+        c->nza_joined = true;
+      }
+    }
+  }
   P.tiles_x = (L.g.nx + P.TX - 1) / P.TX;
   int tiles_y = (L.g.ny - 1 + P.TY - 1) / P.TY;
   const bool strip_level = c->strip.on() && c->strip_connected && level < c->strip.ndist;
@@ -952,11 +1062,12 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     const LowRankDev &lr = get_lowrank(c, level, omega);
     P.lr = lr.tile;
     P.nfix = (int)fixes.size();
-    if (P.nfix > 2) fail(MGMC_ERR_INVALID, "internal: more than 2 fix-ups in one fused launch");
+    if (P.nfix > kMaxFix) fail(MGMC_ERR_INVALID, "internal: too many fix-ups in one fused launch");
     for (int q = 0; q < P.nfix; ++q) {
       P.fix_stage[q] = fixes[q].stage;
       P.fix_dir[q] = fixes[q].dir;
       P.fix_c1[q] = fixes[q].c1;
+      P.fix_soff[q] = fixes[q].soff;
     }
     P.lr_u_from_fix = (restrict_ && P.nfix > 0 && fixes.back().stage == S - 1) ? 1 : 0;
     P.lr_slot = c->lr_slot_next;
@@ -964,8 +1075,8 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     if (c->d_lr_flag_pool) {
       // flags are a function of the launch geometry and of what the launch looks at (fix-up directions, residual)
       char key[160];
-      std::snprintf(key, sizeof(key), "%d:%.17g:%d,%d,%d,%d,%d,%d,%d,%d:%d,%d,%d:%d,%d", level, omega, P.HXL, P.TX, P.TY, P.hl, P.RY, P.tiles_x, tiles_y, P.by0, P.nfix,
-                    P.nfix > 0 ? P.fix_dir[0] : -1, P.nfix > 1 ? P.fix_dir[1] : -1, (int)restrict_, P.sk.on);
+      std::snprintf(key, sizeof(key), "%d:%.17g:%d,%d,%d,%d,%d,%d,%d,%d:%d,%d,%d:%d,%d,%d", level, omega, P.HXL, P.TX, P.TY, P.hl, P.RY, P.tiles_x, tiles_y, P.by0, P.nfix,
+                    P.nfix > 0 ? P.fix_dir[0] : -1, P.nfix > 1 ? P.fix_dir[1] : -1, (int)restrict_, P.sk.on, (int)prolong);
       const size_t ntile = (size_t)P.tiles_x * tiles_y * c->d.nchains;  // one flag per tile and chain
       auto it = c->lr_flag_slots.find(key);
       if (it == c->lr_flag_slots.end() && c->lr_flag_pool_used + ntile <= c->lr_flag_pool_size) {
@@ -1034,13 +1145,22 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     if ((int)grid.x > c->num_sms) fail(MGMC_ERR_INVALID, "internal: level with interacting measurements does not fit on the chip");
     chain_group = std::max(1, c->num_sms / (int)grid.x);
   }
+  // A cooperative launch is not co-scheduled with the kernels of another stream: it would wait for the branch that
+  // generates noise ahead (noise_ahead.cuh), and that branch for it.  With the branch in use the launch is an ordinary
+  // one: its grid is at most one CTA per SM, the only other resident kernel leaves room for exactly that on every SM
+  // and terminates without waiting for anything, so all tiles of the chain become resident; a wait that still times
+  // out raises the error word of the context.
+  const bool coop = lr_coupled && !c->nza_on;
   c->launch(name.c_str(), level, [&] {
    for (int c0 = 0; c0 < c->d.nchains; c0 += chain_group) {
     P.chain_off = c0;
     grid.z = std::min(chain_group, c->d.nchains - c0);
 #define FUSED_CASE(NC_, G_, PR_, RS_)                                             \
   if (nc == NC_ && gibbs == G_ && prolong == PR_ && restrict_ == RS_) {            \
-    if (use_lr) launch_fused_t<NC_, G_, PR_, RS_, true>(c, P, grid, smem, lr_coupled); \
+    if (G_ && nzg) {                                                               \
+      if (use_lr) launch_fused_t<NC_, G_, PR_, RS_, true, G_ && kNoiseAheadBuilt>(c, P, grid, smem, coop); \
+      else launch_fused_t<NC_, G_, PR_, RS_, false, G_ && kNoiseAheadBuilt>(c, P, grid, smem);        \
+    } else if (use_lr) launch_fused_t<NC_, G_, PR_, RS_, true>(c, P, grid, smem, coop); \
     else launch_fused_t<NC_, G_, PR_, RS_, false>(c, P, grid, smem);              \
   }
     FUSED_CASE(2, false, false, false) FUSED_CASE(2, false, false, true) FUSED_CASE(2, false, true, false) FUSED_CASE(2, false, true, true)
@@ -1341,6 +1461,7 @@ void dev_coarse(mgmc_ctx *c, bool sample, const double *f, double *x) {
   const int lc = c->d.nlevel - 1;
   const DevLevel &L = c->lv[lc];
   if (f != L.f || x != L.x) fail(MGMC_ERR_INVALID, "internal: coarse phase on foreign vectors");
+  c->next_x_zero = false;  // (the coarse solve overwrites x: nothing to zero)
   const uint32_t c1 = next_c1(c, lc, sample);
   const bool standalone = !c->tail_rec;
   TailPhase ph;
@@ -1400,7 +1521,10 @@ void plan_tail(mgmc_ctx *c) {
 template <bool G_, bool LR_>
 void launch_tail_t(mgmc_ctx *c, const TailP &T, size_t smem) {
   const void *fn = (const void *)tail_kernel<G_, LR_>;
-  if (c->func_attr_done.insert(fn).second) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemMax));
+  if (c->func_attr_done.insert(fn).second) {
+    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemMax));
+    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(c->num_sms, 1, 1);  // one CTA per SM: the cooperative launch guarantees that all of them are resident
@@ -1502,10 +1626,163 @@ void tail_flush(mgmc_ctx *c, bool gibbs, int level) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// noise ahead of the fine-level launches (noise_ahead.cuh)
+// ---------------------------------------------------------------------------------------------
+// In use for one chain on one GPU when the cycle has a latency-bound part to hide the generation in: level 0 has
+// >= 4 M sites and at least two smoothed levels have <= 512 x 512 sites.  The branch forks before the first of them.
+void plan_nza(mgmc_ctx *c) {
+  if (c->nza_planned) return;
+  c->nza_planned = 1;
+#ifndef MGMC_NOISE_AHEAD
+  return;  // (measured: no gain, profiles/r02_noise_ahead.md -- compiled in by -DMGMC_NOISE_AHEAD only)
+#endif
+  static const bool off = std::getenv("MGMC_NO_NOISE_AHEAD") != nullptr || std::getenv("MGMC_NO_MERGE") == nullptr;  // (not with merged level-0 launches)
+  const mgmc_desc &d = c->d;
+  if (off || c->perf_no_noise || d.nchains != 1 || c->strip.on() || d.nlevel < 4) return;
+  int small = 0, fork = -1;
+  for (int l = 1; l + 1 < d.nlevel; ++l)
+    if ((long long)c->lv[l].g.nx * c->lv[l].g.ny <= 512ll * 512ll) {
+      if (fork < 0) fork = l;
+      ++small;
+    }
+  if (small < 2) return;
+  static const char *nl = std::getenv("MGMC_NOISE_AHEAD_LEVELS");  // (perf experiments: how many of the big levels)
+  const int nlev = nl ? std::atoi(nl) : 1;
+  for (int l = 0; l < std::min(nlev, fork); ++l) {
+    const DevLevel &L = c->lv[l];
+    if (L.r2 || (long long)L.g.nx * L.g.ny < (l == 0 ? (1ll << 22) : (1ll << 20))) break;
+    if (l > 0 && d.cycle != 1) break;  // (W-cycles visit the levels below 0 more than once per cycle)
+    c->nza_levels.push_back(l);
+  }
+  if (c->nza_levels.empty()) return;
+  if (d.m_lowrank > 0)
+    for (int l : c->nza_levels) get_lowrank(c, l, d.omega);
+  // planning run: the launches of these levels in one cycle, in order
+  const std::vector<uint32_t> sweeps0 = c->sweep_counter;
+  const int64_t count0 = c->launch_count;
+  const int lr_slot0 = c->lr_slot_next;
+  c->nza_dry = true;
+  try {
+    for (int l : c->nza_levels) {
+      c->sweep_counter[l] = 0u;
+      c->nza_dry_post = false;
+      emit_smoothing(c, l, sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true), true, d.omega, false, 0.0, true);
+      c->nza_dry_post = true;
+      emit_smoothing(c, l, sweep_list(d.smoother, MGMC_BACKWARD, d.npostsmooth, true), true, d.omega, true, d.coarse_scaling, false);
+    }
+  } catch (...) {
+    c->nza_dry = false;
+    c->sweep_counter = sweeps0;
+    throw;
+  }
+  c->nza_dry = false;
+  c->sweep_counter = sweeps0;
+  c->launch_count = count0;
+  c->lr_slot_next = lr_slot0;
+  bool any = false;
+  for (const auto &sl : c->nza_slots) any = any || !sl.jobs.empty();
+  if (!any) return;
+  int lo = 0, hi = 0;
+  CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CUDA_CHECK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, lo));  // lowest priority: fills idle SMs
+  CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_post, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+  c->d_nza_tag = c->dalloc<uint32_t>((size_t)d.nlevel, false);
+  CUDA_CHECK(cudaMemsetAsync(c->d_nza_tag, 0xFF, (size_t)d.nlevel * sizeof(uint32_t), c->stream));  // (no plane is valid yet)
+  c->d_nza_ticket = c->dalloc<unsigned int>((size_t)d.nlevel);
+  c->nza_cursor.assign(d.nlevel, 0);
+  c->nza_fork_level = fork;
+  c->nza_on = true;
+  c->sync();
+}
+
+// generate the planes of one group of launches of a level: post = false: the pre-smoothing launches (tagged with the
+// sample index they are for), post = true: the post-smoothing launches
+void nza_launch_gen(mgmc_ctx *c, int level, bool post, uint32_t sample_off, bool only_if_stale, cudaStream_t stream) {
+  std::vector<NzJob> jobs;
+  for (const auto &sl : c->nza_slots)
+    if (sl.level == level && sl.post == post)
+      for (NzJob jb : sl.jobs) {
+        jb.sample_off = sample_off;
+        jobs.push_back(jb);
+      }
+  if (jobs.empty()) return;
+  const DevLevel &L = c->lv[level];
+  const int nc = L.h.st.ncolours;
+  for (size_t j0 = 0; j0 < jobs.size(); j0 += kMaxNzJobs) {
+    NzGenP G;
+    std::memset(&G, 0, sizeof(G));
+    G.nz = noise_params(c, level, 0);
+    G.nc = nc;
+    G.nx = L.g.nx;
+    G.ny = L.g.ny;
+    G.gp = L.g.pitch / 4;
+    G.njobs = (int)std::min<size_t>(kMaxNzJobs, jobs.size() - j0);
+    for (int k = 0; k < G.njobs; ++k) G.job[k] = jobs[j0 + k];
+    const bool last = j0 + kMaxNzJobs >= jobs.size();
+    if (!post) {
+      // (every launch of the group tests the tag, the last one writes it)
+      G.tag = c->d_nza_tag + level;
+      G.tag_off = sample_off;
+      G.only_if_stale = only_if_stale ? 1 : 0;
+      G.ticket = last ? c->d_nza_ticket + level : nullptr;
+    }
+    ++c->launch_count;
+    const void *fn = (nc == 2) ? (const void *)noise_gen_kernel<2> : (const void *)noise_gen_kernel<4>;
+    if (c->func_attr_done.insert(fn).second) {
+      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kNzGenSmem));
+      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->prof_on) {  // (timed on the stream it runs on)
+      CUDA_CHECK(cudaEventCreate(&e0));
+      CUDA_CHECK(cudaEventCreate(&e1));
+      CUDA_CHECK(cudaEventRecord(e0, stream));
+    }
+    if (nc == 2) noise_gen_kernel<2><<<c->num_sms, kNzGenThreads, kNzGenSmem, stream>>>(G);
+    else noise_gen_kernel<4><<<c->num_sms, kNzGenThreads, kNzGenSmem, stream>>>(G);
+    CUDA_CHECK(cudaGetLastError());
+    if (c->prof_on) {
+      CUDA_CHECK(cudaEventRecord(e1, stream));
+      c->prof_events.push_back({std::string(only_if_stale ? "noise_check" : (post ? "noise_ahead_post" : "noise_ahead_pre")) + "/L" + std::to_string(level), e0, e1, 0.0});
+    }
+  }
+}
+
+// head of a cycle: the planes of the pre-smoothing launches must hold the normals of the current sample index -- they
+// do when the previous cycle generated them; otherwise (first cycle, sample index moved) they are generated now
+void nza_begin_cycle(mgmc_ctx *c) {
+  if (!c->nza_on) return;
+  std::fill(c->nza_cursor.begin(), c->nza_cursor.end(), 0);
+  c->nza_forked = c->nza_joined = false;
+  c->nza_in_cycle = true;
+  for (int l : c->nza_levels) nza_launch_gen(c, l, false, 0u, true, c->stream);
+}
+
+// the branch: normals of this cycle's post-smoothing launches, then of the next cycle's pre-smoothing launches
+void nza_fork(mgmc_ctx *c) {
+  c->nza_forked = true;
+  CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  for (int l = (int)c->nza_levels.size() - 1; l >= 0; --l) nza_launch_gen(c, c->nza_levels[l], true, 0u, false, c->stream2);  // (coarser levels are read first)
+  CUDA_CHECK(cudaEventRecord(c->ev_post, c->stream2));
+  for (int l : c->nza_levels) nza_launch_gen(c, l, false, 1u, false, c->stream2);
+  CUDA_CHECK(cudaEventRecord(c->ev_done, c->stream2));
+}
+
+void nza_end_cycle(mgmc_ctx *c) {
+  if (!c->nza_on) return;
+  c->nza_in_cycle = false;
+  if (c->nza_forked) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_done, 0));  // joins the branch (before the sample index moves)
+}
+
+// ---------------------------------------------------------------------------------------------
 // multilevel recursions
 // ---------------------------------------------------------------------------------------------
 void mgmc_sample_level_body(mgmc_ctx *c, int level);
 void mgmc_sample_level(mgmc_ctx *c, int level) {  // multigridmc_sampler.cc:103-130
+  if (c->nza_on && c->nza_in_cycle && level == c->nza_fork_level && !c->nza_forked) nza_fork(c);
   if (level == c->tail_level && !c->tail_rec) {
     // this level and everything below it: phases of one persistent launch
     c->tail_rec = true;
@@ -1587,16 +1864,122 @@ void emit_mgmc_cycle(mgmc_ctx *c) {
   lr_begin_epoch(c);
   c->strip_index = 0;
   std::fill(c->sweep_counter.begin(), c->sweep_counter.end(), 0u);
-  mgmc_sample_level(c, 0);
+  nza_begin_cycle(c);
+  try {
+    mgmc_sample_level(c, 0);
+  } catch (...) {
+    c->nza_in_cycle = false;
+    throw;
+  }
+  nza_end_cycle(c);
 }
 
-void emit_end_of_cycle(mgmc_ctx *c) {
+void emit_end_of_cycle(mgmc_ctx *c, bool merged = false) {
   const DevLevel &L = c->lv[0];
   c->launch("end_of_cycle", 0, [&] {
     end_of_cycle_kernel<<<1, 256, 0, c->stream>>>(c->qoi_nnz, c->d_qsite, c->d_qval, L.x, L.g.stride, c->d.nchains, c->d_series, c->series_cap / c->d.nchains, c->d_sample,
-                                                 c->d_pos, (c->strip.on() && c->strip_connected) ? c->d_strip_ctl + 9 : nullptr);
+                                                 c->d_pos, (c->strip.on() && c->strip_connected) ? c->d_strip_ctl + 9 : nullptr, merged ? c->d_qpart : nullptr,
+                                                 merged ? c->d_lr_epoch : nullptr);
   });
   c->h_sample++;
+}
+
+// ---- merged level-0 launches (mgmc_ctx::merge_on) ----
+// Level 0 is visited once per cycle (also in a W-cycle): post-smoothing of cycle k, then pre-smoothing of cycle k + 1.
+// Merged they are one launch of at most 8 colour passes -- red-black levels, SOR / SSOR with one sweep pair each --
+// with up to 4 low-rank fix-ups; with omega = 1 the passes that are recomputed before anybody reads them are dead
+// (plan_stages): red-black SSOR V(1,1) runs 5 full passes of 8 (+ the observed / measured sites of a sixth).
+void plan_merge(mgmc_ctx *c) {
+  static const bool off = std::getenv("MGMC_NO_MERGE") != nullptr;
+  const mgmc_desc &d = c->d;
+  c->merge_on = false;
+  if (off || c->strip.on() || d.nlevel < 2 || c->tail_level == 0 || c->perf_no_noise) return;
+  const DevLevel &L = c->lv[0];
+  if (L.r2 || L.h.st.ncolours != 2 || d.omega != 1.0) return;
+  const size_t npre = sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true).size(), npost = sweep_list(d.smoother, MGMC_BACKWARD, d.npostsmooth, true).size();
+  if (npre == 0 || npost == 0 || 2 * (npre + npost) > 8) return;
+  if (d.m_lowrank > 0 && ((int)(npre + npost) > kMaxFix || !lr_fusable(c, get_lowrank(c, 0, d.omega), 0))) return;
+  if (c->qoi_nnz > kMaxQoi) return;
+  if (!c->d_qpart) c->d_qpart = c->dalloc<double>((size_t)d.nchains * kMaxQoi);
+  c->merge_on = true;
+}
+
+void emit_merged_level0(mgmc_ctx *c) {
+  const mgmc_desc &d = c->d;
+  const bool lowrank = d.m_lowrank > 0;
+  const std::vector<SweepSpec> pre = sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true), post = sweep_list(d.smoother, MGMC_BACKWARD, d.npostsmooth, true);
+  std::vector<Stage> st;
+  std::vector<FixSpec> fixes;
+  auto add = [&](const std::vector<SweepSpec> &sweeps, uint32_t first_sweep, uint32_t soff) {
+    uint32_t k = first_sweep;
+    for (const SweepSpec &sw : sweeps) {
+      const uint32_t c1 = k++ & 0xFFFFFFu;  // level 0: (0 << 24) | sweep counter (next_c1)
+      for (int cc = 0; cc < 2; ++cc) {
+        Stage sg;
+        std::memset(&sg, 0, sizeof(sg));
+        sg.colour = sw.fwd ? cc : 1 - cc;
+        sg.c1 = c1;
+        sg.soff = soff;
+        st.push_back(sg);
+      }
+      if (lowrank && sw.fix_after) {
+        FixSpec fx{(int)st.size() - 1, sw.fwd ? 0 : 1, c1};
+        fx.soff = soff;
+        fixes.push_back(fx);
+      }
+    }
+  };
+  add(post, (uint32_t)pre.size(), 0u);  // cycle k: the sweep counters of level 0 continue behind the pre-smoothing sweeps
+  c->merge_qoi_stage = (int)st.size() - 1;
+  add(pre, 0u, 1u);                     // cycle k + 1
+  try {
+    dev_fused(c, 0, st, fixes, lowrank, true, d.omega, true, d.coarse_scaling, true);
+  } catch (...) {
+    c->merge_qoi_stage = -1;
+    throw;
+  }
+  c->merge_qoi_stage = -1;
+  c->sweep_counter[0] = (uint32_t)pre.size();
+}
+
+// pre-smoothing of the first cycle + the levels below
+void emit_merge_prologue(mgmc_ctx *c) {
+  const mgmc_desc &d = c->d;
+  lr_begin_epoch(c);
+  std::fill(c->sweep_counter.begin(), c->sweep_counter.end(), 0u);
+  emit_smoothing(c, 0, sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true), true, d.omega, false, 0.0, true);
+  mgmc_sample_level(c, 1);
+  // (the merged launch that follows reuses the packet slots of the pre-smoothing: new epoch)
+  if (c->d_lr_epoch) c->launch("lr_epoch", 0, [&] { bump_kernel<<<1, 1, 0, c->stream>>>(c->d_lr_epoch); });
+}
+
+// the unit of a run: merged launch (end of cycle k, start of cycle k + 1), end of cycle k, levels >= 1 of cycle k + 1
+void emit_merge_unit(mgmc_ctx *c) {
+  c->lr_slot_next = 0;
+  std::fill(c->sweep_counter.begin(), c->sweep_counter.end(), 0u);
+  emit_merged_level0(c);
+  emit_end_of_cycle(c, true);
+  c->next_x_zero = true;  // the merged launch does not zero the iterate of level 1
+  try {
+    mgmc_sample_level(c, 1);
+  } catch (...) {
+    c->next_x_zero = false;
+    throw;
+  }
+  if (c->next_x_zero) {
+    c->next_x_zero = false;
+    fail(MGMC_ERR_INVALID, "internal: level 1 did not start with a fused launch");
+  }
+}
+
+// post-smoothing of the last cycle
+void emit_merge_epilogue(mgmc_ctx *c) {
+  const mgmc_desc &d = c->d;
+  c->lr_slot_next = 0;
+  c->sweep_counter[0] = (uint32_t)sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true).size();
+  emit_smoothing(c, 0, sweep_list(d.smoother, MGMC_BACKWARD, d.npostsmooth, true), true, d.omega, true, d.coarse_scaling, false);
+  normalize_x(c, 0);
+  emit_end_of_cycle(c);
 }
 
 // after the stream has been synchronised: did a device-side wait time out?  (then the state is invalid)
@@ -1621,6 +2004,11 @@ void drop_graph(mgmc_ctx *c) {
     cudaGraphExecDestroy(c->graph);
     c->graph = nullptr;
   }
+  for (cudaGraphExec_t &g : c->graph_unit)
+    if (g) {
+      cudaGraphExecDestroy(g);
+      g = nullptr;
+    }
 }
 
 void ensure_series(mgmc_ctx *c, long long n) {
@@ -1663,11 +2051,75 @@ void strip_count_launches(mgmc_ctx *c) {
   c->sweep_counter = sweeps0;
 }
 
+// K >= 2 cycles with merged level-0 launches (mgmc_ctx::merge_on); nsamples = 0: only instantiate the graphs
+void run_cycles_merged(mgmc_ctx *c, int64_t nsamples) {
+  DevLevel &L0 = c->lv[0];
+  if (L0.x != L0.x_primary) fail(MGMC_ERR_INVALID, "internal: level-0 iterate not in its primary buffer at the start of a run");
+  const bool use_g = c->use_graph && !c->prof_on;
+  if (use_g && !c->graph_unit[0]) {
+    // (lazily built low-rank data must exist before capture: uploads are not capturable)
+    if (c->d.m_lowrank > 0)
+      for (int l = 0; l < c->d.nlevel; ++l) get_lowrank(c, l, c->d.omega);
+    if (c->d.coarse_solver == MGMC_COARSE_CHOLESKY) ensure_coarse(c);
+    c->sync();
+    const int64_t count0 = c->launch_count;
+    const uint32_t sample0 = c->h_sample;
+    const std::vector<uint32_t> sweeps0 = c->sweep_counter;
+    const int slot0 = c->lr_slot_next;
+    // one graph per parity of the ping-pong buffers of level 0 (the merged launch is out of place: x -> x_alt); the
+    // capture swaps the host-side pointers like a launch does, so the second capture is the other parity
+    for (int parity = 0; parity < 2; ++parity) {
+      const int64_t before = c->launch_count;
+      cudaGraph_t g = nullptr;
+      CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        emit_merge_unit(c);
+      } catch (...) {
+        cudaStreamEndCapture(c->stream, &g);
+        if (g) cudaGraphDestroy(g);
+        if (L0.x != L0.x_primary) std::swap(L0.x, L0.x_alt);
+        throw;
+      }
+      CUDA_CHECK(cudaStreamEndCapture(c->stream, &g));
+      CUDA_CHECK(cudaGraphInstantiate(&c->graph_unit[parity], g, 0));
+      CUDA_CHECK(cudaGraphDestroy(g));
+      c->unit_launches = c->launch_count - before;
+    }
+    c->launch_count = count0;  // capture itself launched nothing
+    c->h_sample = sample0;
+    c->sweep_counter = sweeps0;
+    c->lr_slot_next = slot0;
+    if (L0.x != L0.x_primary) fail(MGMC_ERR_INVALID, "internal: parity of the level-0 buffers after capture");
+  }
+  if (nsamples == 0) return;
+  emit_merge_prologue(c);
+  for (int64_t k = 1; k < nsamples; ++k) {
+    if (use_g) {
+      CUDA_CHECK(cudaGraphLaunch(c->graph_unit[L0.x == L0.x_primary ? 0 : 1], c->stream));
+      c->launch_count += c->unit_launches;
+      c->h_sample++;
+      std::swap(L0.x, L0.x_alt);
+    } else {
+      const int64_t before = c->launch_count;
+      emit_merge_unit(c);
+      c->unit_launches = c->launch_count - before;
+    }
+  }
+  emit_merge_epilogue(c);
+  c->launches_per_cycle = c->unit_launches;
+}
+
 void run_cycles(mgmc_ctx *c, int64_t nsamples) {
   plan_tail(c);
+  plan_nza(c);
   strip_count_launches(c);
+  plan_merge(c);
   const unsigned long long zero = 0ull;
   CUDA_CHECK(cudaMemcpyAsync(c->d_pos, &zero, sizeof(zero), cudaMemcpyHostToDevice, c->stream));
+  if (c->merge_on && nsamples != 1) {
+    run_cycles_merged(c, nsamples);
+    if (nsamples > 0) return;
+  }
   if (c->use_graph && !c->prof_on) {
     if (!c->graph) {
       // make sure lazily built low-rank data exists before capture (uploads are not capturable)
@@ -1766,7 +2218,12 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
     c->device = desc->device;
     CUDA_CHECK(cudaSetDevice(c->device));
     CUDA_CHECK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
-    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+      // (highest priority: the branch that generates noise ahead of the launches runs at the lowest, noise_ahead.cuh)
+      int plo = 0, phi = 0;
+      CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&plo, &phi));
+      CUDA_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, phi));
+    }
     c->use_graph = (std::getenv("MGMC_NO_GRAPH") == nullptr);
     c->perf_no_noise = (std::getenv("MGMC_PERF_NO_NOISE") != nullptr);
     c->lr_fuse = (std::getenv("MGMC_NO_LR_FUSE") == nullptr);
@@ -1861,10 +2318,18 @@ void mgmc_destroy(mgmc_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->graph) cudaGraphExecDestroy(c->graph);
+  for (cudaGraphExec_t g : c->graph_unit)
+    if (g) cudaGraphExecDestroy(g);
   if (c->mg_graph) cudaGraphExecDestroy(c->mg_graph);
   for (char *p : c->peer_arena)
     if (p) cudaIpcCloseMemHandle(p);
   for (void *p : c->allocs) cudaFree(p);
+  if (c->stream2) {
+    cudaStreamSynchronize(c->stream2);
+    cudaStreamDestroy(c->stream2);
+  }
+  for (cudaEvent_t e : {c->ev_fork, c->ev_post, c->ev_done})
+    if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -2012,6 +2477,7 @@ int mgmc_sampler_mgmc_apply(mgmc_ctx *c, const double *f, double *x) {
   check_level(c, 0);
   if (c->strip.on() && c->strip_connected) fail(MGMC_ERR_UNSUPPORTED, "row strips: the chain state is distributed; use mgmc_set_state / mgmc_sample / mgmc_get_state");
   plan_tail(c);
+  plan_nza(c);
   if (f) upload_vec(c, 0, c->lv[0].f, f);  // f == NULL: right-hand side fixed earlier (Sampler::fix_rhs, sampler.hh:56)
   upload_vec(c, 0, c->lv[0].x, x);
   emit_mgmc_cycle(c);

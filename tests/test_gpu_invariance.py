@@ -56,6 +56,10 @@ def test_chain_independent_of_tiling_and_dead_pass_skipping(tmp_path, n, nlevel,
         # launch per level visit
         "tail": {"MGMC_TAIL": "1"},
         "short_tail": {"MGMC_TAIL": "1", "MGMC_TAIL_MAX_SITES": "20000"},
+        # post-smoothing of cycle k and pre-smoothing of cycle k + 1 as separate level-0 launches (the default merges
+        # them into one launch per cycle, the observed sites recorded inside it)
+        "no_merge": {"MGMC_NO_MERGE": "1"},
+        "no_merge_all_passes": {"MGMC_NO_MERGE": "1", "MGMC_NO_DEAD_PASS": "1"},
     }
     for tag, env in variants.items():
         x = _run(tmp_path, tag, env, **kw)
@@ -64,3 +68,52 @@ def test_chain_independent_of_tiling_and_dead_pass_skipping(tmp_path, n, nlevel,
             assert np.max(np.abs(x - ref)) <= 1e-9 * np.max(np.abs(ref)), tag
         else:
             assert np.array_equal(x, ref), f"{tag}: max abs diff {np.max(np.abs(x - ref)):.3e}"
+
+
+SNIPPET_AHEAD = r'''
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+import multigridmc_b200 as m
+from multigridmc_b200 import workloads as w
+n, nlevel, nmeas, omega, out = %(n)d, %(nlevel)d, %(nmeas)d, %(omega)r, %(out)r
+B = None
+if nmeas:
+    loc, _, _, var = w.measurement_set(nmeas)
+    B = w.point_measurement_matrix(n, n, loc, var, 1e-3)
+ctx = m.Context(n, n, nlevel, B=B, seed=99, omega=omega)
+rng = np.random.default_rng(5)
+nd = ctx.ndof()
+f = rng.standard_normal(nd)
+ctx.set_rhs(f)
+ctx.set_state(rng.standard_normal(nd))
+ctx.set_qoi([nd // 3], [1.0])
+ctx.set_philox_position(0)
+z1 = ctx.sample(3)                      # graph replays: planes of cycle k + 1 generated during cycle k
+x = ctx.mgmc_apply(f, ctx.get_state())  # one cycle outside the graph, host vectors
+ctx.set_state(x)
+ctx.set_philox_position(100)            # the sample index jumps: the planes in memory are stale
+z2 = ctx.sample(2)
+np.save(out, np.concatenate([ctx.get_state(), x, np.asarray(z1).ravel(), np.asarray(z2).ravel()]))
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nlevel,nmeas,omega", [(2048, 6, 0, 1.0), (2048, 6, 8, 1.0), (2048, 6, 8, 1.3)])
+def test_chain_independent_of_noise_generated_ahead(tmp_path, n, nlevel, nmeas, omega):
+    """Normals of the level-0 launches generated ahead of the launch by a second branch of the cycle graph
+    (noise_ahead.cuh) vs generated in registers by the launch itself: the same chain bit for bit -- through graph
+    replays, a cycle outside the graph and a jump of the sample index (stale planes must be regenerated)."""
+    kw = dict(n=n, nlevel=nlevel, nmeas=nmeas, omega=omega)
+
+    def run(tag, env):
+        out = str(tmp_path / f"{tag}.npy")
+        e = dict(os.environ)
+        e.update(env)
+        subprocess.check_call([sys.executable, "-c", SNIPPET_AHEAD % dict(root=ROOT, out=out, **kw)], env=e)
+        return np.load(out)
+
+    ref = run("in_register", {"MGMC_NO_NOISE_AHEAD": "1"})
+    assert np.all(np.isfinite(ref))
+    for tag, env in {"ahead": {}, "ahead_two_levels": {"MGMC_NOISE_AHEAD_LEVELS": "2"}, "ahead_no_graph": {"MGMC_NO_GRAPH": "1"}}.items():
+        x = run(tag, env)
+        assert np.array_equal(x, ref), f"{tag}: max abs diff {np.max(np.abs(x - ref)):.3e}"
