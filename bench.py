@@ -28,6 +28,8 @@ import sys
 import threading
 import time
 
+NPROF = 11  # cycles of the per-kernel profile: a run of K cycles is K - 1 merged level-0 launches + one split pair
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -452,7 +454,7 @@ def run_b200(a):
     prof = None
     if strips_on:  # cooperative: every rank has to run the profiled cycles
         barrier()
-        prof = ctx.profile_cycle(nsamples=3)
+        prof = ctx.profile_cycle(nsamples=NPROF)
         barrier()
     if rank != 0:
         if dist is not None:
@@ -461,7 +463,7 @@ def run_b200(a):
 
     # ---- per-kernel CUDA-event timing of the cycle (rank 0): roofline of the dominant kernel ----
     if prof is None:
-        prof = ctx.profile_cycle(nsamples=3)
+        prof = ctx.profile_cycle(nsamples=NPROF)
     total_ms = sum(p[1] for p in prof)
     top = max(prof, key=lambda p: p[1])
     byts, upd = ctx.cycle_model()
@@ -506,8 +508,8 @@ def run_b200(a):
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
                      "kernel_share_of_cycle": top[1] / total_ms if total_ms else None},
-        "kernels": [{"name": p[0], "ms_per_cycle": p[1] / 3.0, "launches_per_cycle": p[2] / 3.0,
-                     "algorithmic_gbs": (p[3] / (p[1] * 1e-3) / 1e9) if p[1] > 0 else None} for p in sorted(prof, key=lambda p: -p[1])[:12]],
+        "kernels": [{"name": p[0], "ms_per_cycle": p[1] / NPROF, "launches_per_cycle": p[2] / NPROF,
+                     "algorithmic_gbs": (p[3] / (p[1] * 1e-3) / 1e9) if p[1] > 0 else None} for p in sorted(prof, key=lambda p: -p[1])[:24]],
         "qoi_mean": float(np.mean(series)),
     }
     if strips_extra is not None:

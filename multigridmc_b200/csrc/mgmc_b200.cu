@@ -307,7 +307,7 @@ Coef9 to_coef9(const StencilSet &s) {
   return a;
 }
 
-inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_);
+inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool merged = false);
 
 StripPlan make_strip_plan(const mgmc_desc &d, const std::vector<HostLevel> &H) {
   StripPlan p;
@@ -632,15 +632,19 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
 // ---- fused tile kernel dispatch ----
 // tile height: 32 rows on the big (bandwidth / issue bound) levels; the small levels are latency bound,
 // there short tiles give every warp at most one row per colour pass and spread over more SMs
-inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_) {
+inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool merged) {
   if (strips) return ny > 1024 ? 32 : (ny > 256 ? 16 : 8);  // strips must start on tile boundaries: powers of two only
-  static const char *ov = std::getenv("MGMC_TILE_ROWS");    // perf experiments: "rb_big,4c_big,4c_mid,small,rb_big_prolong"
-  static int t[5] = {36, 46, 24, 8, 40};
+  static const char *ov = std::getenv("MGMC_TILE_ROWS");    // perf experiments: "rb_big,4c_big,4c_mid,small,rb_big_prolong,rb_big_merged"
+  static int t[6] = {36, 46, 24, 8, 40, 40};
   static bool parsed = false;
   if (!parsed) {
     parsed = true;
-    if (ov) std::sscanf(ov, "%d,%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3], &t[4]);
+    if (ov) std::sscanf(ov, "%d,%d,%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3], &t[4], &t[5]);
   }
+  // (merged level-0 launch, restrict_ and prolongation: 40 rows + the 13 halo rows of its 5 live passes + residual is
+  //  the tallest tile that leaves two CTAs per SM; also on mid-size lattices -- the 16-row tiles of their two-sweep
+  //  launches would nearly double the rows a merged launch stages)
+  if (ny > 256 && nc == 2 && merged) return t[5];
   // The rows of a colour pass are dealt out to 16 warps, so the tile heights are chosen to make the passes come out
   // at whole rounds (plan_stages: a red-black launch with restriction updates TY + 7 / 5 / 3 rows, without TY + 4 / 2 / 0;
   // a 4-colour launch every other row of TY + 7 ... TY + 3).
@@ -913,7 +917,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   P.HXL = up4(halo.v[0]);
   const int HXR = up4(halo.v[1]);
   P.TX = 128 - P.HXL - HXR;
-  P.TY = fused_tile_rows(L.g.ny, nc, c->strip.on() && !c->tail_rec, restrict_);
+  P.TY = fused_tile_rows(L.g.ny, nc, c->strip.on() && !c->tail_rec, restrict_, prolong && restrict_);
   // persistent kernel of the small levels / interacting measurements: all tiles of a chain must be resident at once
   // (one CTA per SM)
   bool lr_coupled = false;

@@ -117,3 +117,37 @@ def test_chain_independent_of_noise_generated_ahead(tmp_path, n, nlevel, nmeas, 
     for tag, env in {"ahead": {}, "ahead_two_levels": {"MGMC_NOISE_AHEAD_LEVELS": "2"}, "ahead_no_graph": {"MGMC_NO_GRAPH": "1"}}.items():
         x = run(tag, env)
         assert np.array_equal(x, ref), f"{tag}: max abs diff {np.max(np.abs(x - ref)):.3e}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nlevel,nmeas,nchains", [(1024, 6, 8, 1), (512, 5, 8, 3)])
+def test_repeated_runs_are_bit_identical(n, nlevel, nmeas, nchains):
+    """Race detector of our own (compute-sanitizer is closed on the GPU pool): the chain is a pure function of its inputs,
+    so two contexts fed the same inputs must agree bit for bit -- run after run, with the scheduling noise of 60-1000
+    CTAs per launch in between.  A data race between CTAs (e.g. one tile zeroing what another still reads) or between
+    the warps of a CTA shows up as a difference here within a few repetitions."""
+    import multigridmc_b200 as m
+    from multigridmc_b200 import workloads as w
+
+    loc, _, _, var = w.measurement_set(nmeas)
+    B = w.point_measurement_matrix(n, n, loc, var, 1e-3)
+    rng = np.random.default_rng(11)
+    ref = None
+    for rep in range(4):
+        ctx = m.Context(n, n, nlevel, B=B, seed=99, nchains=nchains)
+        nd = ctx.ndof()
+        if rep == 0:
+            f, x0 = rng.standard_normal(nd * nchains), rng.standard_normal(nd * nchains)
+        ctx.set_rhs(f)
+        ctx.set_state(x0)
+        ctx.set_qoi([nd // 2, nd // 3], [1.0, -0.5])
+        ctx.set_philox_position(0)
+        z = ctx.sample(2 + rep % 2 * 3)[:2]  # (2 or 5 cycles: one or several merged level-0 launches; compare the first two samples)
+        out = np.concatenate([z.ravel()] + ([ctx.get_state()] if rep % 2 == 0 else []))
+        ctx.close()
+        if ref is None:
+            ref, ref_z = out, z.copy()
+        elif rep % 2 == 0:
+            assert np.array_equal(out, ref), f"repetition {rep}: max abs diff {np.max(np.abs(out - ref)):.3e}"
+        else:
+            assert np.array_equal(z, ref_z), f"repetition {rep}: series differs"

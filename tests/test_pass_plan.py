@@ -76,3 +76,18 @@ def test_plan_with_fixups_keeps_measurement_sites_alive():
     assert halo[1] >= 2 + 1 and halo[3] >= 1 + 1        # supp(B_k) (+ its neighbours) lies inside the loaded region
     modes4, _, halo4 = capi.plan_passes(4, [0, 1, 2, 3, 3, 2, 1, 0])
     assert modes4.count(SKIP) == 1 and halo4 == [7, 7, 3, 3]  # directional margins: y-halo 3 rows for 8 passes
+
+
+def test_plan_of_the_merged_level0_launch():
+    """Post-smoothing of cycle k + pre-smoothing of cycle k + 1 in one launch (emit_merged_level0, mgmc_b200.cu): red-black
+    SSOR V(1,1) is R B | B R || R B | B R with a low-rank fix-up behind every sweep; with omega = 1 three passes are dead
+    (run on the measured / observed sites only), and the 5 live passes + the fused residual need 13 halo rows."""
+    from multigridmc_b200 import capi
+
+    modes, margins, halo = capi.plan_passes(2, [0, 1, 1, 0, 0, 1, 1, 0], fix_after=[1, 3, 5, 7], restrict_behind=True)
+    assert modes == [FULL, SPARSE, FULL, SPARSE, FULL, SPARSE, FULL, FULL]
+    assert halo == [7, 6, 6, 7]
+    live = [mg for md, mg in zip(modes, margins) if md == FULL]
+    assert all(a[k] >= b[k] for a, b in zip(live, live[1:]) for k in range(4))  # the rectangles shrink towards the tile
+    # without measurements the dead passes are skipped altogether
+    assert capi.plan_passes(2, [0, 1, 1, 0, 0, 1, 1, 0], restrict_behind=True)[0] == [FULL, SKIP, FULL, SKIP, FULL, SKIP, FULL, FULL]
