@@ -646,6 +646,53 @@ class SORSamplerFactory : public SamplerFactory {
   const Direction direction;
 };
 
+/** CholeskySampler (sampler/cholesky_sampler.hh:27-146, cholesky_sampler.cc:9-38): exact sampler x = A^{-1} f + L^{-T} xi for a
+ *  small operator (<= 4096 unknowns: the dense factor, low-rank term folded in, is resident on the device -- the coarse
+ *  phase of the V-cycle, csrc/tail.cuh).  Sparse / Dense name the reference's two factorisation back ends; here both are
+ *  the same device factor.  xi is drawn from the Philox stream keyed by one draw of rng (as for the other samplers). */
+class CholeskySampler : public Sampler {
+ public:
+  CholeskySampler(const std::shared_ptr<LinearOperator> op, std::mt19937_64 &rng_) : Sampler(op, rng_) {
+    MultigridParameters p;
+    p.nlevel = (unsigned int)op->get_level() + 1;  // the operator is the coarsest level of this hierarchy
+    p.coarse_solver = "Cholesky";
+    dev = std::make_shared<DeviceHierarchy>(op->get_data(), p, rng());
+  }
+  void apply(const Eigen::VectorXd &f, Eigen::VectorXd &x) const override {
+    mgmc_host::check(mgmc_set_philox_position(dev->ctx, sample_index++, 0), "set_philox_position");
+    mgmc_host::check(mgmc_coarse_sample(dev->ctx, f.data(), x.data()), "CholeskySampler::apply");
+  }
+
+ protected:
+  std::shared_ptr<DeviceHierarchy> dev;
+  mutable uint32_t sample_index = 0;
+};
+class SparseCholeskySampler : public CholeskySampler {
+ public:
+  using CholeskySampler::CholeskySampler;
+};
+class DenseCholeskySampler : public CholeskySampler {
+ public:
+  using CholeskySampler::CholeskySampler;
+};
+/** factories (sampler/cholesky_sampler.hh:151-196) */
+class SparseCholeskySamplerFactory : public SamplerFactory {
+ public:
+  explicit SparseCholeskySamplerFactory(std::mt19937_64 &rng_) : rng(rng_) {}
+  std::shared_ptr<Sampler> get(std::shared_ptr<LinearOperator> op) override { return std::make_shared<SparseCholeskySampler>(op, rng); }
+
+ protected:
+  std::mt19937_64 &rng;
+};
+class DenseCholeskySamplerFactory : public SamplerFactory {
+ public:
+  explicit DenseCholeskySamplerFactory(std::mt19937_64 &rng_) : rng(rng_) {}
+  std::shared_ptr<Sampler> get(std::shared_ptr<LinearOperator> op) override { return std::make_shared<DenseCholeskySampler>(op, rng); }
+
+ protected:
+  std::mt19937_64 &rng;
+};
+
 // ------------------------------------------------------------------------------------------------
 // Preconditioner / solvers (preconditioner/multigrid_preconditioner.hh, solver/loop_solver.hh)
 // ------------------------------------------------------------------------------------------------
@@ -726,6 +773,37 @@ class LoopSolver : public LinearSolver {
  protected:
   std::shared_ptr<Preconditioner> preconditioner;
   const IterativeSolverParameters params;
+};
+
+/** linear solver factory base class (solver/linear_solver.hh:43-48) */
+class LinearSolverFactory {
+ public:
+  virtual ~LinearSolverFactory() = default;
+  virtual std::shared_ptr<LinearSolver> get(std::shared_ptr<LinearOperator> linear_operator) = 0;
+};
+
+/** CholeskySolver (solver/cholesky_solver.hh:21-52, cholesky_solver.cc:8-41): direct solve A x = b for a small operator
+ *  (<= 4096 unknowns).  The reference factorises A_0 and treats the low-rank term by the Woodbury identity; the device
+ *  factor has the term folded in -- the same x to rounding. */
+class CholeskySolver : public LinearSolver {
+ public:
+  explicit CholeskySolver(std::shared_ptr<LinearOperator> op) : LinearSolver(op) {
+    MultigridParameters p;
+    p.nlevel = (unsigned int)op->get_level() + 1;
+    p.coarse_solver = "Cholesky";
+    dev = std::make_shared<DeviceHierarchy>(op->get_data(), p, 0);
+  }
+  void apply(const Eigen::VectorXd &b, Eigen::VectorXd &x) override {
+    mgmc_host::check(mgmc_coarse_solve(dev->ctx, b.data(), x.data()), "CholeskySolver::apply");
+  }
+
+ protected:
+  std::shared_ptr<DeviceHierarchy> dev;
+};
+/** CholeskySolverFactory (solver/cholesky_solver.hh:57-68) */
+class CholeskySolverFactory : public LinearSolverFactory {
+ public:
+  std::shared_ptr<LinearSolver> get(std::shared_ptr<LinearOperator> op) override { return std::make_shared<CholeskySolver>(op); }
 };
 
 // ---- LinearOperator members that need the solver classes ----

@@ -186,8 +186,8 @@ struct FusedP {
   int *err;                     // error word of the context: a device-side wait that timed out sets it
   int nz_off, nz_cap;           // persistent kernel: noise generated ahead of the passes -- buffer offset in doubles behind
                                 // the tile (0: off) and its capacity in (row, pass) items
-  // NZG kernels: the normals of the full colour passes were generated ahead of the launch by noise_gen_kernel
-  // (noise_ahead.cuh) while the latency-bound small levels left the chip idle.  nzg[s] = plane of pass s, one pair per
+  // NZG kernels (small levels): the normals of the full colour passes were generated ahead of the launch by
+  // noise_gen_kernel (noise_ahead.cuh) while the big levels ran.  nzg[s] = plane of pass s, one pair per
   // (row, aligned group of 4 columns): [row index][nzg_gp] double2, group p at index p + kNzgPad
   const double2 *nzg[8];
   int nzg_gp;
@@ -577,7 +577,7 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
     const double2 *zp = P.nzg[s_] + ((long long)((NC == 4) ? (jw_ >> 1) : jw_) * P.nzg_gp + ((i_r0 >> 2) + lane + kNzgPad));
 #pragma unroll
     for (int n = 0; n < kNzgRows; ++n)
-      if (n < nrows_ && (v0_ || v1_)) zd[n] = __ldcs(zp + (long long)n * kFusedWarps * P.nzg_gp);
+      if (n < nrows_ && (v0_ || v1_)) zd[n] = __ldg(zp + (long long)n * kFusedWarps * P.nzg_gp);
   };
   auto next_full = [&](int s_) {
     while (s_ < P.nstages && P.st[s_].mode != STAGE_FULL) ++s_;
@@ -588,15 +588,6 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
     for (int n = 0; n < kNzgRows; ++n) za[n] = zb[n] = make_double2(0.0, 0.0);
     const int s0_ = next_full(0);
     if (s0_ < P.nstages) nzg_load(s0_, za);
-    // the planes of the later passes: pulled into L2 now (a pass is too short to cover an HBM access issued one pass ahead)
-    for (int s_ = next_full(s0_ + 1); s_ < P.nstages; s_ = next_full(s_ + 1)) {
-      int jw_, nrows_, q_;
-      bool v0_, v1_;
-      pass_geom(s_, jw_, nrows_, q_, v0_, v1_);
-      const double2 *zp = P.nzg[s_] + ((long long)((NC == 4) ? (jw_ >> 1) : jw_) * P.nzg_gp + ((i_r0 >> 2) + lane + kNzgPad));
-      if (((lane & 7) == 0 || lane == 31) && cols_alloc)  // (one request per 128-byte line; rows need not be line aligned)
-        for (int n = 0; n < nrows_; ++n) asm volatile("prefetch.global.L2 [%0];" ::"l"(zp + (long long)n * kFusedWarps * P.nzg_gp));
-    }
   }
 
   // ---- stage the region: one warp per row.  Lane l loads the column pairs (2l, 2l+1) and
@@ -1196,7 +1187,7 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
 }
 
 template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT, bool LOWRANK, bool NZG = false>
-__global__ void __launch_bounds__(kFusedThreads, 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {
+__global__ void __launch_bounds__(kFusedThreads, NZG ? 1 : 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {  // (NZG: small levels, at most one CTA per SM -- no register cap)
   extern __shared__ double sm[];
   __shared__ int lr_cnt[4];
   __shared__ __align__(16) double ntab[128];

@@ -176,12 +176,11 @@ struct mgmc_ctx {
   std::vector<int> tail_stamp_kinds;
   double *dAinv = nullptr;         // A^{-1} of the coarsest level (one-pass coarse phase)
   std::set<const void *> func_attr_done;  // kernels whose dynamic shared memory limit has been raised on this device
-  // noise generated ahead of the fine-level launches (noise_ahead.cuh): a second branch of the cycle graph generates
-  // the normals of the next level-0 launches while the latency-bound small levels leave the chip idle
+  // noise of the small levels generated ahead of their launches (noise_ahead.cuh): a second branch of the cycle graph
+  // generates the normals of the latency-bound levels while the big levels run
   struct NzaSlot {
     int level = 0;
-    bool post = false;               // consumed by the post-smoothing of the same cycle (else: pre-smoothing of the next)
-    std::vector<NzJob> jobs;         // one per full colour pass of the launch (sample_off = 0)
+    std::vector<NzJob> jobs;         // one per full colour pass of the launch
     std::vector<int> stage;          // stage index of jobs[k] in the launch
   };
   int nza_planned = 0;               // 0: not yet, 1: planned (nza_on says whether it is in use)
@@ -190,12 +189,10 @@ struct mgmc_ctx {
   std::vector<int> nza_levels;
   std::vector<NzaSlot> nza_slots;    // in launch order per level
   std::vector<int> nza_cursor;       // per level: launches of the level emitted so far in this cycle
-  bool nza_dry = false, nza_dry_post = false;  // planning run: dev_fused records the launch instead of emitting it
+  bool nza_dry = false;              // planning run: dev_fused records the launch instead of emitting it
   bool nza_forked = false, nza_joined = false, nza_in_cycle = false;
   cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_post = nullptr, ev_done = nullptr;
-  uint32_t *d_nza_tag = nullptr;     // [nlevel] sample index the pre-smoothing planes of a level hold
-  unsigned int *d_nza_ticket = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_gen = nullptr;
   bool perf_no_noise = false;  // MGMC_PERF_NO_NOISE=1: run the sampling cycle with the deterministic kernels (perf experiments only)
   // instrumentation
   int64_t launch_count = 0;
@@ -635,11 +632,11 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
 inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool merged) {
   if (strips) return ny > 1024 ? 32 : (ny > 256 ? 16 : 8);  // strips must start on tile boundaries: powers of two only
   static const char *ov = std::getenv("MGMC_TILE_ROWS");    // perf experiments: "rb_big,4c_big,4c_mid,small,rb_big_prolong,rb_big_merged"
-  static int t[6] = {36, 46, 24, 8, 40, 40};
+  static int t[7] = {36, 46, 24, 8, 40, 40, 36};  // (... ,rb_big_merged,4c_1024)
   static bool parsed = false;
   if (!parsed) {
     parsed = true;
-    if (ov) std::sscanf(ov, "%d,%d,%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3], &t[4], &t[5]);
+    if (ov) std::sscanf(ov, "%d,%d,%d,%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3], &t[4], &t[5], &t[6]);
   }
   // (merged level-0 launch, restrict_ and prolongation: 40 rows + the 13 halo rows of its 5 live passes + residual is
   //  the tallest tile that leaves two CTAs per SM; also on mid-size lattices -- the 16-row tiles of their two-sweep
@@ -650,6 +647,8 @@ inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool mer
   // a 4-colour launch every other row of TY + 7 ... TY + 3).
   if (ny > 2048 && nc == 2) return restrict_ ? t[0] : t[4];
   if (ny > 1024) return nc == 2 ? 32 : t[1];
+  // (a 1024 x 1024 4-colour level in 36-row tiles is 290 tiles: one wave of 2 CTAs per SM instead of 1.45 with 24 rows)
+  if (ny > 512) return nc == 2 ? 16 : t[6];
   if (ny > 256) return nc == 2 ? 16 : t[2];
   return t[3];
 }
@@ -669,11 +668,6 @@ inline int tail_tiles_bound(int nx, int ny, int nc) {
 
 // coop: tiles of this launch wait for packets of ANY other tile of their chain (interacting measurements): launched
 // cooperatively, so that the runtime guarantees (and checks) that the whole grid is resident at once
-#ifdef MGMC_NOISE_AHEAD
-constexpr bool kNoiseAheadBuilt = true;
-#else
-constexpr bool kNoiseAheadBuilt = false;  // the NZG kernels are not instantiated
-#endif
 template <int NC, bool G, bool PR, bool RS, bool LR, bool NZ = false>
 void launch_fused_t(mgmc_ctx *c, const FusedP &P, dim3 grid, size_t smem, bool coop = false) {
   // (the attribute is per device and function: tracked per context, not per process)
@@ -946,23 +940,20 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   if (smem > (size_t)kFusedSmemMax) fail(MGMC_ERR_INVALID, "internal: fused tile does not fit in shared memory");
   // ---- normals generated ahead of the launch (noise_ahead.cuh) ----
   bool nzg = false;
-  if (gibbs && !c->tail_rec && (c->nza_dry || (c->nza_on && c->nza_in_cycle)) && std::find(c->nza_levels.begin(), c->nza_levels.end(), level) != c->nza_levels.end()) {
-    const int step = (nc == 4) ? 2 : 1;
-    const bool fits = ((P.RY + step - 1) / step + kFusedWarps - 1) / kFusedWarps <= kNzgRows;  // rows of a warp per pass held in registers
+  if (gibbs && nc == 4 && !c->tail_rec && (c->nza_dry || (c->nza_on && c->nza_in_cycle)) && std::find(c->nza_levels.begin(), c->nza_levels.end(), level) != c->nza_levels.end()) {
+    const bool fits = ((P.RY + 1) / 2 + kFusedWarps - 1) / kFusedWarps <= kNzgRows;  // rows of a warp per pass held in registers
     if (c->nza_dry) {
       // planning run: record the launch (one plane of normals per full colour pass) instead of emitting it
       mgmc_ctx::NzaSlot sl;
       sl.level = level;
-      sl.post = c->nza_dry_post;
       if (fits) {
-        const size_t rows = (size_t)((nc == 4) ? L.g.ny / 2 : L.g.ny) + 1;
+        const size_t rows = (size_t)L.g.ny / 2 + 1;
         for (int k = 0; k < S; ++k) {
           if (plan[k].mode != STAGE_FULL) continue;
           NzJob jb;
           jb.buf = c->dalloc<double2>(rows * (size_t)(L.g.pitch / 4));
           jb.colour = plan[k].colour;
           jb.c1 = plan[k].c1;
-          jb.sample_off = 0u;
           sl.jobs.push_back(jb);
           sl.stage.push_back(k);
         }
@@ -975,19 +966,19 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
       if (c->nza_slots[q].level == level && idx-- == 0) at = (int)q;
     if (at < 0) fail(MGMC_ERR_INVALID, "internal: launch without a planned noise slot");
     const mgmc_ctx::NzaSlot &sl = c->nza_slots[at];
-    if (!sl.jobs.empty()) {
+    if (!sl.jobs.empty() && c->nza_forked) {
       size_t nfull = 0;
       for (int k = 0; k < S; ++k) nfull += plan[k].mode == STAGE_FULL;
       if (nfull != sl.jobs.size()) fail(MGMC_ERR_INVALID, "internal: noise slot does not match the launch");
       for (size_t q = 0; q < sl.jobs.size(); ++q) {
         const Stage &st = plan[sl.stage[q]];
-        if (st.mode != STAGE_FULL || st.colour != sl.jobs[q].colour || st.c1 != sl.jobs[q].c1) fail(MGMC_ERR_INVALID, "internal: noise slot does not match the launch");
+        if (st.mode != STAGE_FULL || st.colour != sl.jobs[q].colour || st.c1 != sl.jobs[q].c1 || st.soff != 0u) fail(MGMC_ERR_INVALID, "internal: noise slot does not match the launch");
         P.nzg[sl.stage[q]] = sl.jobs[q].buf;
       }
       P.nzg_gp = L.g.pitch / 4;
       nzg = true;
-      if (sl.post && c->nza_forked && !c->nza_joined) {
-        CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_post, 0));  // the planes of this cycle's post-smoothing are complete
+      if (!c->nza_joined) {
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_gen, 0));  // the planes of this cycle are complete
         c->nza_joined = true;
       }
     }
@@ -1105,7 +1096,9 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   long long *d_timing = nullptr;
   const size_t ncta = (size_t)grid.x * grid.z;
   static const char *tlev = std::getenv("MGMC_TIMING_LEVEL");
-  if (tfile && level == (tlev ? std::atoi(tlev) : 0) && dumped[name]++ == 3) {
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(c->stream, &cap_status);  // (the dump allocates and synchronises: eager launches only)
+  if (cap_status == cudaStreamCaptureStatusNone && tfile && level == (tlev ? std::atoi(tlev) : 0) && dumped[name]++ == 3) {
     CUDA_CHECK(cudaMalloc(&d_timing, ncta * 16 * sizeof(long long)));
     CUDA_CHECK(cudaMemset(d_timing, 0, ncta * 16 * sizeof(long long)));
     P.timing = d_timing;
@@ -1149,21 +1142,16 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
     if ((int)grid.x > c->num_sms) fail(MGMC_ERR_INVALID, "internal: level with interacting measurements does not fit on the chip");
     chain_group = std::max(1, c->num_sms / (int)grid.x);
   }
-  // A cooperative launch is not co-scheduled with the kernels of another stream: it would wait for the branch that
-  // generates noise ahead (noise_ahead.cuh), and that branch for it.  With the branch in use the launch is an ordinary
-  // one: its grid is at most one CTA per SM, the only other resident kernel leaves room for exactly that on every SM
-  // and terminates without waiting for anything, so all tiles of the chain become resident; a wait that still times
-  // out raises the error word of the context.
-  const bool coop = lr_coupled && !c->nza_on;
+  const bool coop = lr_coupled;
   c->launch(name.c_str(), level, [&] {
    for (int c0 = 0; c0 < c->d.nchains; c0 += chain_group) {
     P.chain_off = c0;
     grid.z = std::min(chain_group, c->d.nchains - c0);
 #define FUSED_CASE(NC_, G_, PR_, RS_)                                             \
   if (nc == NC_ && gibbs == G_ && prolong == PR_ && restrict_ == RS_) {            \
-    if (G_ && nzg) {                                                               \
-      if (use_lr) launch_fused_t<NC_, G_, PR_, RS_, true, G_ && kNoiseAheadBuilt>(c, P, grid, smem, coop); \
-      else launch_fused_t<NC_, G_, PR_, RS_, false, G_ && kNoiseAheadBuilt>(c, P, grid, smem);        \
+    if (G_ && nzg && NC_ == 4) { /* (the small levels are 4-colour levels: Galerkin 9-point operators) */ \
+      if (use_lr) launch_fused_t<NC_, G_, PR_, RS_, true, G_ && NC_ == 4>(c, P, grid, smem, coop); \
+      else launch_fused_t<NC_, G_, PR_, RS_, false, G_ && NC_ == 4>(c, P, grid, smem);        \
     } else if (use_lr) launch_fused_t<NC_, G_, PR_, RS_, true>(c, P, grid, smem, coop); \
     else launch_fused_t<NC_, G_, PR_, RS_, false>(c, P, grid, smem);              \
   }
@@ -1630,32 +1618,26 @@ void tail_flush(mgmc_ctx *c, bool gibbs, int level) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// noise ahead of the fine-level launches (noise_ahead.cuh)
+// noise of the small levels ahead of their launches (noise_ahead.cuh)
 // ---------------------------------------------------------------------------------------------
-// In use for one chain on one GPU when the cycle has a latency-bound part to hide the generation in: level 0 has
-// >= 4 M sites and at least two smoothed levels have <= 512 x 512 sites.  The branch forks before the first of them.
+// In use for one chain per context when the cycle has big levels to hide the generation behind: level 0 has >= 1 M
+// sites and the first small level (<= 512 x 512 sites) is level 2 or deeper.  V-cycles only (a W-cycle visits the
+// small levels several times per cycle).  The branch forks where the recursion enters level 1.
 void plan_nza(mgmc_ctx *c) {
   if (c->nza_planned) return;
   c->nza_planned = 1;
-#ifndef MGMC_NOISE_AHEAD
-  return;  // (measured: no gain, profiles/r02_noise_ahead.md -- compiled in by -DMGMC_NOISE_AHEAD only)
-#endif
-  static const bool off = std::getenv("MGMC_NO_NOISE_AHEAD") != nullptr || std::getenv("MGMC_NO_MERGE") == nullptr;  // (not with merged level-0 launches)
+  // Measured (profiles/r02_noise_ahead.md): no gain -- a small-level launch is a chain of many latencies (tile load,
+  // pass set-up, fix-up exchanges) of which the normals are one; reading them costs an L2 round trip per pass instead.
+  // Opt-in (MGMC_NOISE_AHEAD=1) for experiments; tests/test_gpu_invariance.py keeps it bit-identical.
+  static const bool on = std::getenv("MGMC_NOISE_AHEAD") != nullptr;
   const mgmc_desc &d = c->d;
-  if (off || c->perf_no_noise || d.nchains != 1 || c->strip.on() || d.nlevel < 4) return;
-  int small = 0, fork = -1;
-  for (int l = 1; l + 1 < d.nlevel; ++l)
-    if ((long long)c->lv[l].g.nx * c->lv[l].g.ny <= 512ll * 512ll) {
-      if (fork < 0) fork = l;
-      ++small;
-    }
-  if (small < 2) return;
-  static const char *nl = std::getenv("MGMC_NOISE_AHEAD_LEVELS");  // (perf experiments: how many of the big levels)
-  const int nlev = nl ? std::atoi(nl) : 1;
-  for (int l = 0; l < std::min(nlev, fork); ++l) {
+  if (!on || c->perf_no_noise || d.nchains != 1 || d.cycle != 1 || d.nlevel < 4) return;
+  if ((long long)c->lv[0].g.nx * c->lv[0].g.ny < (1ll << 20)) return;
+  const int last = (d.coarse_solver == MGMC_COARSE_CHOLESKY) ? d.nlevel - 2 : d.nlevel - 1;  // last smoothed level
+  for (int l = 2; l <= last; ++l) {
     const DevLevel &L = c->lv[l];
-    if (L.r2 || (long long)L.g.nx * L.g.ny < (l == 0 ? (1ll << 22) : (1ll << 20))) break;
-    if (l > 0 && d.cycle != 1) break;  // (W-cycles visit the levels below 0 more than once per cycle)
+    if ((long long)L.g.nx * L.g.ny > 512ll * 512ll) continue;
+    if (L.r2 || L.h.st.ncolours != 4 || (c->strip.on() && l < c->strip.ndist) || (c->tail_level >= 0 && l >= c->tail_level)) continue;
     c->nza_levels.push_back(l);
   }
   if (c->nza_levels.empty()) return;
@@ -1669,10 +1651,12 @@ void plan_nza(mgmc_ctx *c) {
   try {
     for (int l : c->nza_levels) {
       c->sweep_counter[l] = 0u;
-      c->nza_dry_post = false;
-      emit_smoothing(c, l, sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true), true, d.omega, false, 0.0, true);
-      c->nza_dry_post = true;
-      emit_smoothing(c, l, sweep_list(d.smoother, MGMC_BACKWARD, d.npostsmooth, true), true, d.omega, true, d.coarse_scaling, false);
+      if (l == d.nlevel - 1) {
+        emit_smoothing(c, l, sweep_list(MGMC_SMOOTHER_SSOR, MGMC_FORWARD, d.ncoarsesmooth, true), true, d.omega, false, 0.0, false);
+      } else {
+        emit_smoothing(c, l, sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true), true, d.omega, false, 0.0, true);
+        emit_smoothing(c, l, sweep_list(d.smoother, MGMC_BACKWARD, d.npostsmooth, true), true, d.omega, true, d.coarse_scaling, false);
+      }
     }
   } catch (...) {
     c->nza_dry = false;
@@ -1690,95 +1674,67 @@ void plan_nza(mgmc_ctx *c) {
   CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   CUDA_CHECK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, lo));  // lowest priority: fills idle SMs
   CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_post, cudaEventDisableTiming));
-  CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
-  c->d_nza_tag = c->dalloc<uint32_t>((size_t)d.nlevel, false);
-  CUDA_CHECK(cudaMemsetAsync(c->d_nza_tag, 0xFF, (size_t)d.nlevel * sizeof(uint32_t), c->stream));  // (no plane is valid yet)
-  c->d_nza_ticket = c->dalloc<unsigned int>((size_t)d.nlevel);
+  CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_gen, cudaEventDisableTiming));
   c->nza_cursor.assign(d.nlevel, 0);
-  c->nza_fork_level = fork;
+  c->nza_fork_level = 1;
   c->nza_on = true;
   c->sync();
 }
 
-// generate the planes of one group of launches of a level: post = false: the pre-smoothing launches (tagged with the
-// sample index they are for), post = true: the post-smoothing launches
-void nza_launch_gen(mgmc_ctx *c, int level, bool post, uint32_t sample_off, bool only_if_stale, cudaStream_t stream) {
+// generate the planes of all launches of a level in this cycle
+void nza_launch_gen(mgmc_ctx *c, int level, cudaStream_t stream) {
   std::vector<NzJob> jobs;
   for (const auto &sl : c->nza_slots)
-    if (sl.level == level && sl.post == post)
-      for (NzJob jb : sl.jobs) {
-        jb.sample_off = sample_off;
-        jobs.push_back(jb);
-      }
+    if (sl.level == level) jobs.insert(jobs.end(), sl.jobs.begin(), sl.jobs.end());
   if (jobs.empty()) return;
   const DevLevel &L = c->lv[level];
-  const int nc = L.h.st.ncolours;
   for (size_t j0 = 0; j0 < jobs.size(); j0 += kMaxNzJobs) {
     NzGenP G;
     std::memset(&G, 0, sizeof(G));
     G.nz = noise_params(c, level, 0);
-    G.nc = nc;
     G.nx = L.g.nx;
     G.ny = L.g.ny;
     G.gp = L.g.pitch / 4;
     G.njobs = (int)std::min<size_t>(kMaxNzJobs, jobs.size() - j0);
     for (int k = 0; k < G.njobs; ++k) G.job[k] = jobs[j0 + k];
-    const bool last = j0 + kMaxNzJobs >= jobs.size();
-    if (!post) {
-      // (every launch of the group tests the tag, the last one writes it)
-      G.tag = c->d_nza_tag + level;
-      G.tag_off = sample_off;
-      G.only_if_stale = only_if_stale ? 1 : 0;
-      G.ticket = last ? c->d_nza_ticket + level : nullptr;
-    }
+    const int units = G.njobs * (L.g.ny / 2) * ((int)(G.nz.G + 31) / 32);  // (job, row, chunk of 32 groups) items, one per warp
+    const int grid = std::max(1, std::min(2 * c->num_sms, (units + 2 * (kNzGenThreads / 32) - 1) / (2 * (kNzGenThreads / 32))));
     ++c->launch_count;
-    const void *fn = (nc == 2) ? (const void *)noise_gen_kernel<2> : (const void *)noise_gen_kernel<4>;
-    if (c->func_attr_done.insert(fn).second) {
-      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kNzGenSmem));
-      CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->prof_on) {  // (timed on the stream it runs on)
       CUDA_CHECK(cudaEventCreate(&e0));
       CUDA_CHECK(cudaEventCreate(&e1));
       CUDA_CHECK(cudaEventRecord(e0, stream));
     }
-    if (nc == 2) noise_gen_kernel<2><<<c->num_sms, kNzGenThreads, kNzGenSmem, stream>>>(G);
-    else noise_gen_kernel<4><<<c->num_sms, kNzGenThreads, kNzGenSmem, stream>>>(G);
+    noise_gen_kernel<4><<<grid, kNzGenThreads, 0, stream>>>(G);
     CUDA_CHECK(cudaGetLastError());
     if (c->prof_on) {
       CUDA_CHECK(cudaEventRecord(e1, stream));
-      c->prof_events.push_back({std::string(only_if_stale ? "noise_check" : (post ? "noise_ahead_post" : "noise_ahead_pre")) + "/L" + std::to_string(level), e0, e1, 0.0});
+      c->prof_events.push_back({"noise_ahead/L" + std::to_string(level), e0, e1, 0.0});
     }
   }
 }
 
-// head of a cycle: the planes of the pre-smoothing launches must hold the normals of the current sample index -- they
-// do when the previous cycle generated them; otherwise (first cycle, sample index moved) they are generated now
-void nza_begin_cycle(mgmc_ctx *c) {
+void nza_begin(mgmc_ctx *c) {
   if (!c->nza_on) return;
   std::fill(c->nza_cursor.begin(), c->nza_cursor.end(), 0);
   c->nza_forked = c->nza_joined = false;
   c->nza_in_cycle = true;
-  for (int l : c->nza_levels) nza_launch_gen(c, l, false, 0u, true, c->stream);
 }
 
-// the branch: normals of this cycle's post-smoothing launches, then of the next cycle's pre-smoothing launches
+// the branch: the normals of this cycle's launches of the small levels, the levels visited first first
 void nza_fork(mgmc_ctx *c) {
   c->nza_forked = true;
   CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
   CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-  for (int l = (int)c->nza_levels.size() - 1; l >= 0; --l) nza_launch_gen(c, c->nza_levels[l], true, 0u, false, c->stream2);  // (coarser levels are read first)
-  CUDA_CHECK(cudaEventRecord(c->ev_post, c->stream2));
-  for (int l : c->nza_levels) nza_launch_gen(c, l, false, 1u, false, c->stream2);
-  CUDA_CHECK(cudaEventRecord(c->ev_done, c->stream2));
+  for (int l : c->nza_levels) nza_launch_gen(c, l, c->stream2);
+  CUDA_CHECK(cudaEventRecord(c->ev_gen, c->stream2));
 }
 
-void nza_end_cycle(mgmc_ctx *c) {
+void nza_end(mgmc_ctx *c) {
   if (!c->nza_on) return;
   c->nza_in_cycle = false;
-  if (c->nza_forked) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_done, 0));  // joins the branch (before the sample index moves)
+  if (c->nza_forked && !c->nza_joined) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_gen, 0));  // (a captured branch must be joined)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1868,14 +1824,14 @@ void emit_mgmc_cycle(mgmc_ctx *c) {
   lr_begin_epoch(c);
   c->strip_index = 0;
   std::fill(c->sweep_counter.begin(), c->sweep_counter.end(), 0u);
-  nza_begin_cycle(c);
+  nza_begin(c);
   try {
     mgmc_sample_level(c, 0);
   } catch (...) {
     c->nza_in_cycle = false;
     throw;
   }
-  nza_end_cycle(c);
+  nza_end(c);
 }
 
 void emit_end_of_cycle(mgmc_ctx *c, bool merged = false) {
@@ -1952,7 +1908,14 @@ void emit_merge_prologue(mgmc_ctx *c) {
   lr_begin_epoch(c);
   std::fill(c->sweep_counter.begin(), c->sweep_counter.end(), 0u);
   emit_smoothing(c, 0, sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true), true, d.omega, false, 0.0, true);
-  mgmc_sample_level(c, 1);
+  nza_begin(c);
+  try {
+    mgmc_sample_level(c, 1);
+  } catch (...) {
+    c->nza_in_cycle = false;
+    throw;
+  }
+  nza_end(c);
   // (the merged launch that follows reuses the packet slots of the pre-smoothing: new epoch)
   if (c->d_lr_epoch) c->launch("lr_epoch", 0, [&] { bump_kernel<<<1, 1, 0, c->stream>>>(c->d_lr_epoch); });
 }
@@ -1964,12 +1927,15 @@ void emit_merge_unit(mgmc_ctx *c) {
   emit_merged_level0(c);
   emit_end_of_cycle(c, true);
   c->next_x_zero = true;  // the merged launch does not zero the iterate of level 1
+  nza_begin(c);
   try {
     mgmc_sample_level(c, 1);
   } catch (...) {
     c->next_x_zero = false;
+    c->nza_in_cycle = false;
     throw;
   }
+  nza_end(c);
   if (c->next_x_zero) {
     c->next_x_zero = false;
     fail(MGMC_ERR_INVALID, "internal: level 1 did not start with a fused launch");
@@ -2332,7 +2298,7 @@ void mgmc_destroy(mgmc_ctx *c) {
     cudaStreamSynchronize(c->stream2);
     cudaStreamDestroy(c->stream2);
   }
-  for (cudaEvent_t e : {c->ev_fork, c->ev_post, c->ev_done})
+  for (cudaEvent_t e : {c->ev_fork, c->ev_gen})
     if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;

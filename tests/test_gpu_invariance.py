@@ -49,9 +49,9 @@ def test_chain_independent_of_tiling_and_dead_pass_skipping(tmp_path, n, nlevel,
     assert np.all(np.isfinite(ref))
     variants = {
         "all_passes": {"MGMC_NO_DEAD_PASS": "1"},
-        "low_tiles": {"MGMC_TILE_ROWS": "32,32,16,8,32"},
-        "tall_tiles": {"MGMC_TILE_ROWS": "24,40,32,16,36"},
-        "no_fold": {"MGMC_NO_RES_FOLD": "1", "MGMC_TILE_ROWS": "16,16,8,8,16"},
+        "low_tiles": {"MGMC_TILE_ROWS": "32,32,16,8,32,32,16"},
+        "tall_tiles": {"MGMC_TILE_ROWS": "24,40,32,16,36,24,24"},
+        "no_fold": {"MGMC_NO_RES_FOLD": "1", "MGMC_TILE_ROWS": "16,16,8,8,16,16,8"},
         # the small levels and the coarse solve as phases of ONE persistent cooperative kernel (tail.cuh) instead of a
         # launch per level visit
         "tail": {"MGMC_TAIL": "1"},
@@ -88,10 +88,10 @@ ctx.set_rhs(f)
 ctx.set_state(rng.standard_normal(nd))
 ctx.set_qoi([nd // 3], [1.0])
 ctx.set_philox_position(0)
-z1 = ctx.sample(3)                      # graph replays: planes of cycle k + 1 generated during cycle k
+z1 = ctx.sample(3)                      # graph replays
 x = ctx.mgmc_apply(f, ctx.get_state())  # one cycle outside the graph, host vectors
 ctx.set_state(x)
-ctx.set_philox_position(100)            # the sample index jumps: the planes in memory are stale
+ctx.set_philox_position(100)            # the sample index jumps
 z2 = ctx.sample(2)
 np.save(out, np.concatenate([ctx.get_state(), x, np.asarray(z1).ravel(), np.asarray(z2).ravel()]))
 '''
@@ -100,9 +100,9 @@ np.save(out, np.concatenate([ctx.get_state(), x, np.asarray(z1).ravel(), np.asar
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,nlevel,nmeas,omega", [(2048, 6, 0, 1.0), (2048, 6, 8, 1.0), (2048, 6, 8, 1.3)])
 def test_chain_independent_of_noise_generated_ahead(tmp_path, n, nlevel, nmeas, omega):
-    """Normals of the level-0 launches generated ahead of the launch by a second branch of the cycle graph
-    (noise_ahead.cuh) vs generated in registers by the launch itself: the same chain bit for bit -- through graph
-    replays, a cycle outside the graph and a jump of the sample index (stale planes must be regenerated)."""
+    """Normals of the small levels generated ahead of their launches by a second branch of the cycle graph
+    (noise_ahead.cuh) vs generated in registers by the launches themselves: the same chain bit for bit -- through graph
+    replays, a cycle outside the graph and a jump of the sample index."""
     kw = dict(n=n, nlevel=nlevel, nmeas=nmeas, omega=omega)
 
     def run(tag, env):
@@ -112,9 +112,10 @@ def test_chain_independent_of_noise_generated_ahead(tmp_path, n, nlevel, nmeas, 
         subprocess.check_call([sys.executable, "-c", SNIPPET_AHEAD % dict(root=ROOT, out=out, **kw)], env=e)
         return np.load(out)
 
-    ref = run("in_register", {"MGMC_NO_NOISE_AHEAD": "1"})
+    ref = run("in_register", {})
     assert np.all(np.isfinite(ref))
-    for tag, env in {"ahead": {}, "ahead_two_levels": {"MGMC_NOISE_AHEAD_LEVELS": "2"}, "ahead_no_graph": {"MGMC_NO_GRAPH": "1"}}.items():
+    on = {"MGMC_NOISE_AHEAD": "1"}  # (opt-in: measured, no gain -- profiles/r02_noise_ahead.md)
+    for tag, env in {"ahead": on, "ahead_no_merge": dict(on, MGMC_NO_MERGE="1"), "ahead_no_graph": dict(on, MGMC_NO_GRAPH="1")}.items():
         x = run(tag, env)
         assert np.array_equal(x, ref), f"{tag}: max abs diff {np.max(np.abs(x - ref)):.3e}"
 

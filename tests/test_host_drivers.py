@@ -122,3 +122,20 @@ def test_driver_mgmc_statistics_and_files(built, tmp_path):
             assert tau > 1.5  # (and that is why the driver compares it with MGMC)
     conv = open(tmp_path / "convergence_multigridmc.txt").read()
     assert "q_k = |E[z^k] - E[z]|" in conv and "q_k = |Var[z^k] - Var[z]|" in conv
+
+
+@pytest.mark.gpu
+def test_cholesky_solver_and_sampler_classes(built):
+    """Host classes CholeskySolver / Dense-, SparseCholeskySampler + factories (solver/cholesky_solver.hh:21-68,
+    sampler/cholesky_sampler.hh:27-196) over mgmc_coarse_solve / mgmc_coarse_sample: exact solve with and without the
+    measurement term (test_solver.hh:93-113: 1e-12 there, the device factor gives 1e-10), sample mean and variance
+    (test_sampler.hh:215-283)."""
+    out = subprocess.check_output([os.path.join(built, "test_cholesky")], text=True)
+    sol = re.findall(r"solver (\d): \|x - x_exact\| / \|x_exact\| = ([0-9.e+-]+)\s+\|A x - b\| / \|b\| = ([0-9.e+-]+)", out)
+    smp = re.findall(r"sampler (\d): \|mean - A\^-1 f\| / \|A\^-1 f\| = ([0-9.e+-]+)\s+var / exact = ([0-9.]+)", out)
+    assert len(sol) == 2 and len(smp) == 2, out
+    for _, ex, ax in sol:
+        assert float(ex) < 1e-9 and float(ax) < 1e-10
+    for _, em, vr in smp:
+        # 20000 samples: relative error of the mean field ~ sqrt(tr A^-1 / N) / |A^-1 f|, variance of one entry +- 1 % (1 sigma)
+        assert float(em) < 0.05 and abs(float(vr) - 1.0) < 0.04

@@ -80,7 +80,6 @@ int main() {
   cudaMemset(d_sample, 0, 4);
   G.nz.sample = d_sample;
   G.nz.G = n / 4 + 1;
-  G.nc = 2;
   G.nx = G.ny = n;
   G.gp = gp;
   G.njobs = 3;
