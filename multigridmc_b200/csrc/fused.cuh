@@ -60,6 +60,8 @@ struct Stage {
   int mode;
   uint32_t soff;  // added to the sample index (1: the pass belongs to the pre-smoothing of the NEXT cycle, merged level-0 launch)
 };
+constexpr int kMaxStages = 16;  // colour passes per launch (8 on the big levels; the latency-bound small 4-colour levels take the 16
+                                // passes of a V(2,2) smoothing step in one launch instead of two)
 constexpr int kMaxFix = 4;   // low-rank fix-ups per launch (merged level-0 launch: 2 sweeps of cycle k + 2 of cycle k + 1)
 constexpr int kMaxQoi = 8;   // observed sites a merged level-0 launch can record (more: the launches are not merged)
 
@@ -153,7 +155,7 @@ struct FusedP {
   double *xc_zero;      // RESTRICT: coarse iterate, set to zero (multigridmc_sampler.cc:122)
   int nstages;
   int res_stage;  // RESTRICT, omega = 1: index of the last pass (its sites get their residual for free), else -1
-  Stage st[8];
+  Stage st[kMaxStages];
   double winv, noise_scale;  // omega / a_ii, sqrt(a_ii (2 - omega) / omega)
   NoiseP nz;
   int HXL, TX, TY, RY, hl;  // region geometry (host-computed, identical for all tiles)

@@ -175,6 +175,7 @@ struct mgmc_ctx {
   long long *d_tail_stamps = nullptr;  // MGMC_TAIL_STAMPS=1: per-phase time stamps of the last tail launch
   std::vector<int> tail_stamp_kinds;
   double *dAinv = nullptr;         // A^{-1} of the coarsest level (one-pass coarse phase)
+  double *d_coarse_xi = nullptr;   // ensembles: normals of the coarse sampler for all chains (coarse_xi_kernel)
   std::set<const void *> func_attr_done;  // kernels whose dynamic shared memory limit has been raised on this device
   // noise of the small levels generated ahead of their launches (noise_ahead.cuh): a second branch of the cycle graph
   // generates the normals of the latency-bound levels while the big levels run
@@ -304,7 +305,7 @@ Coef9 to_coef9(const StencilSet &s) {
   return a;
 }
 
-inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool merged = false);
+inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool merged = false, int nchains = 1);
 
 StripPlan make_strip_plan(const mgmc_desc &d, const std::vector<HostLevel> &H) {
   StripPlan p;
@@ -629,7 +630,7 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
 // ---- fused tile kernel dispatch ----
 // tile height: 32 rows on the big (bandwidth / issue bound) levels; the small levels are latency bound,
 // there short tiles give every warp at most one row per colour pass and spread over more SMs
-inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool merged) {
+inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool merged, int nchains) {
   if (strips) return ny > 1024 ? 32 : (ny > 256 ? 16 : 8);  // strips must start on tile boundaries: powers of two only
   static const char *ov = std::getenv("MGMC_TILE_ROWS");    // perf experiments: "rb_big,4c_big,4c_mid,small,rb_big_prolong,rb_big_merged"
   static int t[7] = {36, 46, 24, 8, 40, 40, 36};  // (... ,rb_big_merged,4c_1024)
@@ -642,6 +643,15 @@ inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool mer
   //  the tallest tile that leaves two CTAs per SM; also on mid-size lattices -- the 16-row tiles of their two-sweep
   //  launches would nearly double the rows a merged launch stages)
   if (ny > 256 && nc == 2 && merged) return t[5];
+  // Many chains per launch (ensembles: BASELINE config 5): every level has thousands of tiles, nothing is latency bound --
+  // tall tiles everywhere (the 8 / 16 / 24-row tiles of a single chain's small levels stage twice the rows they own),
+  // the rows of the level dealt out evenly
+  static const bool tall_off = std::getenv("MGMC_NO_TALL_ENSEMBLE_TILES") != nullptr;
+  if (nchains >= 8 && ny >= 32 && !tall_off) {
+    const int cap = (nc == 2) ? (restrict_ ? t[0] : t[4]) : t[1];
+    const int parts = (ny - 1 + cap - 1) / cap;
+    return std::min(cap, ((ny - 1 + parts - 1) / parts + 1) / 2 * 2);
+  }
   // The rows of a colour pass are dealt out to 16 warps, so the tile heights are chosen to make the passes come out
   // at whole rounds (plan_stages: a red-black launch with restriction updates TY + 7 / 5 / 3 rows, without TY + 4 / 2 / 0;
   // a 4-colour launch every other row of TY + 7 ... TY + 3).
@@ -847,7 +857,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   DevLevel &L = c->lv[level];
   const int nc = L.h.st.ncolours;
   const int S = (int)stages.size();
-  if (S > 8) fail(MGMC_ERR_INVALID, "internal: more than 8 stages in one fused launch");
+  if (S > kMaxStages || (S > 8 && c->tail_rec)) fail(MGMC_ERR_INVALID, "internal: too many stages in one fused launch");
   if (S == 0 && !prolong && !restrict_) return;
   FusedP P;
   std::memset(&P, 0, sizeof(P));
@@ -911,7 +921,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   P.HXL = up4(halo.v[0]);
   const int HXR = up4(halo.v[1]);
   P.TX = 128 - P.HXL - HXR;
-  P.TY = fused_tile_rows(L.g.ny, nc, c->strip.on() && !c->tail_rec, restrict_, prolong && restrict_);
+  P.TY = fused_tile_rows(L.g.ny, nc, c->strip.on() && !c->tail_rec, restrict_, prolong && restrict_, c->d.nchains);
   // persistent kernel of the small levels / interacting measurements: all tiles of a chain must be resident at once
   // (one CTA per SM)
   bool lr_coupled = false;
@@ -940,7 +950,7 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   if (smem > (size_t)kFusedSmemMax) fail(MGMC_ERR_INVALID, "internal: fused tile does not fit in shared memory");
   // ---- normals generated ahead of the launch (noise_ahead.cuh) ----
   bool nzg = false;
-  if (gibbs && nc == 4 && !c->tail_rec && (c->nza_dry || (c->nza_on && c->nza_in_cycle)) && std::find(c->nza_levels.begin(), c->nza_levels.end(), level) != c->nza_levels.end()) {
+  if (gibbs && nc == 4 && S <= 8 && !c->tail_rec && (c->nza_dry || (c->nza_on && c->nza_in_cycle)) && std::find(c->nza_levels.begin(), c->nza_levels.end(), level) != c->nza_levels.end()) {
     const bool fits = ((P.RY + 1) / 2 + kFusedWarps - 1) / kFusedWarps <= kNzgRows;  // rows of a warp per pass held in registers
     if (c->nza_dry) {
       // planning run: record the launch (one plane of normals per full colour pass) instead of emitting it
@@ -1231,7 +1241,11 @@ void emit_smoothing(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps
   // colour passes per launch: 2 sweeps (tile + halo of x and f stay below ~100 KB, 2 CTAs / SM, and a launch carries at
   // most two low-rank fix-ups); red-black levels without a low-rank term take 4 sweeps -- V(2,2): with omega = 1 only
   // 5 of the 8 passes are live (plan_stages), one launch instead of two per smoothing step
-  const int max_stages = (nc == 2 && (lowrank || omega != 1.0)) ? 4 : 8;
+  // Small 4-colour levels (latency bound: a launch costs its in-order latency, not its passes) take up to 16 passes --
+  // the 4 sweeps of a V(2,2) smoothing step, at most 4 fix-ups -- in one launch
+  static const bool no16 = std::getenv("MGMC_NO_LONG_LAUNCHES") != nullptr;
+  const bool small_level = nc == 4 && !c->tail_rec && !no16 && c->d.nchains < 8 && (long long)L.g.nx * L.g.ny <= 512ll * 512ll && !(c->strip.on() && level < c->strip.ndist);
+  const int max_stages = (nc == 2 && (lowrank || omega != 1.0)) ? 4 : (small_level ? kMaxStages : 8);
   bool fusedlr = false;
   if (lowrank) {
     fusedlr = lr_fusable(c, get_lowrank(c, level, omega), level);
@@ -1441,6 +1455,7 @@ void ensure_coarse(mgmc_ctx *c) {
     c->dAinv = c->dupload(Ainv);
   }
   if (!c->d_tail_bar) c->d_tail_bar = c->dalloc<unsigned long long>(1);
+  if (c->d.nchains > kCoarseBatch) c->d_coarse_xi = c->dalloc<double>((size_t)c->d.nchains * cf.Np);
   c->sync();
 }
 
@@ -1456,13 +1471,22 @@ void dev_coarse(mgmc_ctx *c, bool sample, const double *f, double *x) {
   c->next_x_zero = false;  // (the coarse solve overwrites x: nothing to zero)
   const uint32_t c1 = next_c1(c, lc, sample);
   const bool standalone = !c->tail_rec;
+  if (sample && !c->perf_no_noise && c->d.nchains > kCoarseBatch) {
+    // ensembles: the normals of all chains once, ahead of the phase (a launch of its own also in front of the
+    // persistent kernel: they only depend on the counters)
+    if (!c->d_coarse_xi) fail(MGMC_ERR_INVALID, "internal: coarse noise buffer missing");
+    const int pairs = c->d.nchains * (c->Ncp / 2);
+    c->launch("coarse_xi", lc, [&] {
+      coarse_xi_kernel<<<std::min((pairs + 255) / 256, 4 * c->num_sms), 256, 0, c->stream>>>(noise_params(c, lc, 0), c1, c->Nc, c->Ncp, c->d.nchains, c->d_coarse_xi);
+    });
+  }
   TailPhase ph;
   std::memset(&ph, 0, sizeof(ph));
   ph.kind = TAIL_COARSE;
   ph.nc = sample ? 1 : 0;
   ph.c1 = (int)c1;
   c->tail_ph.push_back(ph);
-  c->tail_smem = std::max(c->tail_smem, coarse_phase_smem(c->Ncp, c->Nc, c->num_sms, c->d.nchains));
+  c->tail_smem = std::max(c->tail_smem, coarse_phase_smem(c->Ncp, c->Nc, c->num_sms, c->d.nchains, coarse_phase_stage(c->Ncp, c->Nc, c->num_sms, c->d.nchains, kTailSmemMax)));
   c->tail_bytes += 8.0 * c->Nc * c->Nc * c->d.nchains;
   if (standalone) tail_flush(c, sample, lc);
 }
@@ -1563,6 +1587,8 @@ void tail_flush(mgmc_ctx *c, bool gibbs, int level) {
       T.coarse.stride = LC.g.stride;
       T.coarse.f = LC.f;
       T.coarse.x = LC.x;
+      T.coarse.xi_pre = c->d_coarse_xi;  // (nullptr for up to kCoarseBatch chains)
+      T.coarse.stage = coarse_phase_stage(c->Ncp, c->Nc, c->num_sms, c->d.nchains, kTailSmemMax) ? 1 : 0;
     }
     if (p0 == 0) c->tail_stamp_kinds.clear();
     for (int k = 0; k < T.nphase; ++k) {
@@ -2738,7 +2764,7 @@ int mgmc_strip_partition(const mgmc_desc *desc, int level, int rank, int *row_lo
 int mgmc_plan_passes(int ncolours, int npass, const int *colours, int nfix, const int *fix_after, int omega_is_one, int restrict_behind, int lr_mx,
                      int lr_my, int *mode, int *margins, int *halo) {
   API_BEGIN
-  if ((ncolours != 2 && ncolours != 4) || npass < 0 || npass > 8 || !colours || !mode || !margins || !halo || nfix < 0 || (nfix > 0 && !fix_after))
+  if ((ncolours != 2 && ncolours != 4) || npass < 0 || npass > kMaxStages || !colours || !mode || !margins || !halo || nfix < 0 || (nfix > 0 && !fix_after))
     fail(MGMC_ERR_INVALID, "invalid argument");
   std::vector<Stage> st(npass);
   for (int s = 0; s < npass; ++s) {

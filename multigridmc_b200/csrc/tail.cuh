@@ -31,6 +31,9 @@ struct CoarseP {
   long long stride;
   const double *f;  // padded lattice layout
   double *x;
+  int stage;        // ensembles: the matrix rows of a CTA are staged in shared memory once and reused for every chain
+  const double *xi_pre;  // ensembles: the normals of all chains, generated once by coarse_xi_kernel ([chain][Np]); nullptr:
+                         // every CTA generates the normals of the chains of a batch itself (one chain: cheaper than a launch)
 };
 
 struct TailPhase {
@@ -42,7 +45,7 @@ struct TailPhase {
   FusedP P;    // TAIL_FUSED: the launch; TAIL_COPY / TAIL_ZERO: P.g, P.x_in (source), P.x_out (destination)
 };
 
-constexpr int kMaxTailPhases = 22;
+constexpr int kMaxTailPhases = 18;
 
 struct TailP {
   int nphase, nchains;
@@ -81,9 +84,16 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned l
 // x = A^{-1} f (+ L^{-T} xi): rows dealt out to the CTAs, one warp per (row, matrix) pair, vectors in shared memory.
 // Chains are processed in batches of kCoarseBatch: a matrix element is loaded once and used for every chain of the batch.
 constexpr int kCoarseBatch = 4;
-inline size_t coarse_phase_smem(int Np, int N, int ncta, int nchains) {
+inline size_t coarse_phase_smem(int Np, int N, int ncta, int nchains, bool stage = false) {
   const int nb = nchains < kCoarseBatch ? nchains : kCoarseBatch;
-  return ((size_t)2 * nb * Np + (size_t)2 * nb * ((N + ncta - 1) / ncta) + 2) * sizeof(double);
+  const size_t rows = (size_t)((N + ncta - 1) / ncta);
+  return ((size_t)2 * nb * Np + (size_t)2 * nb * rows + 2 + (stage ? 2 * rows * Np : 0)) * sizeof(double);
+}
+// Many chains per launch: streaming the two dense matrices from L2 once per batch of chains is what the phase costs
+// (256 chains: 64 x 15 MB).  The 7 rows per matrix a CTA works on are 108 KB: staged in shared memory once, every chain
+// of the ensemble reuses them -- same products, same summation order, bit-identical chains.
+inline bool coarse_phase_stage(int Np, int N, int ncta, int nchains, size_t smem_max) {
+  return nchains > kCoarseBatch && coarse_phase_smem(Np, N, ncta, nchains, true) <= smem_max;
 }
 
 template <bool GIBBS>
@@ -98,13 +108,25 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
   double *fv = sm, *xi = sm + (size_t)nbmax * Np, *part = xi + (size_t)nbmax * Np;  // [nb][Np], [nb][Np], [tasks][nb]
   const int nseg = sample ? 2 : 1;
   const int ntask = (r1 - r0) * nseg;
+  double *Mst = part + (size_t)2 * nbmax * rpc + 2;  // [row - r0][seg][Np] (C.stage)
+  if (C.stage) {
+    for (int task = warp; task < ntask; task += kFusedWarps) {
+      const int row = r0 + task / nseg, seg = task % nseg;
+      const double *__restrict__ M = (seg ? C.TT : C.Ainv) + (long long)row * Np;
+      double *dst = Mst + (size_t)task * Np;
+      for (int c = lane; c < Np; c += 32) dst[c] = M[c];
+    }
+    // (published by the barrier behind the vector loads of the first batch)
+  }
   for (int ch0 = 0; ch0 < nchains; ch0 += kCoarseBatch) {
     const int nb = min(kCoarseBatch, nchains - ch0);
     for (int idx = threadIdx.x; idx < nb * Np; idx += kFusedThreads) {
       const int b = idx / Np, e = idx - b * Np;
       fv[idx] = (e < C.N) ? C.f[(long long)(ch0 + b) * C.stride + (long long)(e / C.w + 1) * C.pitch + (e % C.w + 1)] : 0.0;
     }
-    if (sample) {
+    if (sample && C.xi_pre) {
+      for (int idx = threadIdx.x; idx < nb * Np; idx += kFusedThreads) xi[idx] = C.xi_pre[(size_t)ch0 * Np + idx];
+    } else if (sample) {
       // xi_row: Philox counter 0x40000000 | row / 2 (philox.cuh), normal = (row & 1) ? z1 : z0
       const int hp = Np / 2;
       for (int idx = threadIdx.x; idx < nb * hp; idx += kFusedThreads) {
@@ -121,7 +143,7 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
 #endif
     for (int task = warp; task < ntask; task += kFusedWarps) {
       const int row = r0 + task / nseg, seg = task % nseg;
-      const double *__restrict__ M = (seg ? C.TT : C.Ainv) + (long long)row * Np;
+      const double *__restrict__ M = C.stage ? (Mst + (size_t)task * Np) : ((seg ? C.TT : C.Ainv) + (long long)row * Np);
       const double *v = seg ? xi : fv;
       int c = (seg ? (row & ~31) : 0) + lane;  // L^{-T} is upper triangular: row `row` starts at column `row`
       // (the summation order of a chain must not depend on the batch: chains are compared bit for bit with the same
@@ -162,6 +184,22 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
       C.x[(long long)(ch0 + b) * C.stride + (long long)(row / C.w + 1) * C.pitch + (row % C.w + 1)] = v;
     }
     __syncthreads();
+  }
+}
+
+// Ensembles: the normals of the coarse sampler for all chains, once (inside the coarse phase every CTA would generate
+// the normals of all chains again: 148-fold).  Same counters and pairing as in coarse_phase.
+__global__ void __launch_bounds__(256) coarse_xi_kernel(NoiseP nz, uint32_t c1, int N, int Np, int nchains, double *__restrict__ xi) {
+  __shared__ __align__(16) double ntab[128];
+  if (threadIdx.x < 128) ntab[threadIdx.x] = kNormalTabDev[threadIdx.x];
+  __syncthreads();
+  const int hp = Np / 2;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nchains * hp; idx += gridDim.x * blockDim.x) {
+    const int b = idx / hp, p = idx - b * hp;
+    double z0 = 0.0, z1 = 0.0;
+    if (2 * p < N) normal_pair(nz.keys, 0x40000000u | (uint32_t)p, c1, *nz.sample, nz.chain0 + b, nz.mc, ntab, z0, z1);
+    xi[(size_t)b * Np + 2 * p] = z0;
+    xi[(size_t)b * Np + 2 * p + 1] = (2 * p + 1 < N) ? z1 : 0.0;
   }
 }
 

@@ -30,7 +30,8 @@ def sweep_pass(x, f, nc, colour, omega, w, rect, rng_noise):
 
 
 @pytest.mark.parametrize("nc,seq", [(2, [0, 1, 1, 0]), (2, [0, 1]), (2, [0, 1, 1, 0, 0, 1, 1, 0]), (4, [0, 1, 2, 3, 3, 2, 1, 0]),
-                                    (4, [3, 2, 1, 0]), (4, [0, 1, 2, 3, 0, 1, 2, 3])])
+                                    (4, [3, 2, 1, 0]), (4, [0, 1, 2, 3, 0, 1, 2, 3]),
+                                    (4, [0, 1, 2, 3, 3, 2, 1, 0, 0, 1, 2, 3, 3, 2, 1, 0])])  # (16 passes: a V(2,2) smoothing step of a small level in one launch)
 @pytest.mark.parametrize("omega", [1.0, 1.3])
 @pytest.mark.parametrize("restrict_behind", [False, True])
 def test_planned_tile_reproduces_global_sweep(nc, seq, omega, restrict_behind):
