@@ -84,8 +84,10 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned l
 // x = A^{-1} f (+ L^{-T} xi): rows dealt out to the CTAs, one warp per (row, matrix) pair, vectors in shared memory.
 // Chains are processed in batches of kCoarseBatch: a matrix element is loaded once and used for every chain of the batch.
 constexpr int kCoarseBatch = 4;
+constexpr int kCoarseBatchEnsemble = 8;  // chains per matrix pass when there are at least that many (64 accumulator registers)
+inline int coarse_batch(int nchains) { return nchains >= kCoarseBatchEnsemble ? kCoarseBatchEnsemble : (nchains < kCoarseBatch ? nchains : kCoarseBatch); }
 inline size_t coarse_phase_smem(int Np, int N, int ncta, int nchains, bool stage = false) {
-  const int nb = nchains < kCoarseBatch ? nchains : kCoarseBatch;
+  const int nb = coarse_batch(nchains);
   const size_t rows = (size_t)((N + ncta - 1) / ncta);
   return ((size_t)2 * nb * Np + (size_t)2 * nb * rows + 2 + (stage ? 2 * rows * Np : 0)) * sizeof(double);
 }
@@ -96,7 +98,7 @@ inline bool coarse_phase_stage(int Np, int N, int ncta, int nchains, size_t smem
   return nchains > kCoarseBatch && coarse_phase_smem(Np, N, ncta, nchains, true) <= smem_max;
 }
 
-template <bool GIBBS>
+template <bool GIBBS, int NB>
 __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz, bool with_noise, uint32_t c1, int nchains, double *sm, const double *ntab,
                                              long long *dbg = nullptr) {
   const int G = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -104,7 +106,7 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
   const int r0 = blockIdx.x * rpc, r1 = min(r0 + rpc, C.N);
   if (r0 >= r1) return;  // (uniform over the CTA; the grid barrier is outside)
   const bool sample = GIBBS && with_noise;
-  const int Np = C.Np, nbmax = min(nchains, kCoarseBatch);
+  const int Np = C.Np, nbmax = min(nchains, NB);
   double *fv = sm, *xi = sm + (size_t)nbmax * Np, *part = xi + (size_t)nbmax * Np;  // [nb][Np], [nb][Np], [tasks][nb]
   const int nseg = sample ? 2 : 1;
   const int ntask = (r1 - r0) * nseg;
@@ -118,8 +120,8 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
     }
     // (published by the barrier behind the vector loads of the first batch)
   }
-  for (int ch0 = 0; ch0 < nchains; ch0 += kCoarseBatch) {
-    const int nb = min(kCoarseBatch, nchains - ch0);
+  for (int ch0 = 0; ch0 < nchains; ch0 += NB) {
+    const int nb = min(NB, nchains - ch0);
     for (int idx = threadIdx.x; idx < nb * Np; idx += kFusedThreads) {
       const int b = idx / Np, e = idx - b * Np;
       fv[idx] = (e < C.N) ? C.f[(long long)(ch0 + b) * C.stride + (long long)(e / C.w + 1) * C.pitch + (e % C.w + 1)] : 0.0;
@@ -148,15 +150,15 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
       int c = (seg ? (row & ~31) : 0) + lane;  // L^{-T} is upper triangular: row `row` starts at column `row`
       // (the summation order of a chain must not depend on the batch: chains are compared bit for bit with the same
       //  chain run on its own -- four partial sums per chain, element c + 32 k into partial sum k mod 4)
-      double acc[kCoarseBatch][4];
+      double acc[NB][4];
 #pragma unroll
-      for (int b = 0; b < kCoarseBatch; ++b) acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.0;
+      for (int b = 0; b < NB; ++b) acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.0;
       for (; c + 224 < Np; c += 256) {  // 8 independent loads in flight per lane
         double t[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) t[k] = M[c + 32 * k];
 #pragma unroll
-        for (int b = 0; b < kCoarseBatch; ++b)
+        for (int b = 0; b < NB; ++b)
           if (b < nb) {
             const double *vb = v + b * Np + c;
 #pragma unroll
@@ -166,11 +168,11 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
       for (; c < Np; c += 32) {
         const double t0 = M[c];
 #pragma unroll
-        for (int b = 0; b < kCoarseBatch; ++b)
+        for (int b = 0; b < NB; ++b)
           if (b < nb) acc[b][0] = fma(t0, v[b * Np + c], acc[b][0]);
       }
 #pragma unroll
-      for (int b = 0; b < kCoarseBatch; ++b) {
+      for (int b = 0; b < NB; ++b) {
         double a = (acc[b][0] + acc[b][1]) + (acc[b][2] + acc[b][3]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -259,9 +261,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tail_kernel(const __grid_con
       }
     } else if (ph.kind == TAIL_COARSE) {
 #ifdef MGMC_TILE_TIMING
-      coarse_phase<GIBBS>(T.coarse, T.nz, ph.nc != 0, (uint32_t)ph.c1, T.nchains, sm, ntab, T.cta_stamps ? T.cta_stamps + ((long long)p * G + blockIdx.x) * 4 + 3 : nullptr);
+      coarse_phase<GIBBS, kCoarseBatch>(T.coarse, T.nz, ph.nc != 0, (uint32_t)ph.c1, T.nchains, sm, ntab, T.cta_stamps ? T.cta_stamps + ((long long)p * G + blockIdx.x) * 4 + 3 : nullptr);
 #else
-      coarse_phase<GIBBS>(T.coarse, T.nz, ph.nc != 0, (uint32_t)ph.c1, T.nchains, sm, ntab);
+      if (T.nchains >= kCoarseBatchEnsemble) coarse_phase<GIBBS, kCoarseBatchEnsemble>(T.coarse, T.nz, ph.nc != 0, (uint32_t)ph.c1, T.nchains, sm, ntab);
+      else coarse_phase<GIBBS, kCoarseBatch>(T.coarse, T.nz, ph.nc != 0, (uint32_t)ph.c1, T.nchains, sm, ntab);
 #endif
     } else {
       // x_out = x_in (TAIL_COPY) or x_out = 0 (TAIL_ZERO) on the interior
