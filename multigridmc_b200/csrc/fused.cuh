@@ -434,10 +434,10 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
 #define MGMC_LR_PTRS                                                                                                  \
   const int lrm = P.lr.m;                                                                                             \
   double *darr = sm + 2 * P.RY * 128, *tarr = darr + lrm, *sarr = tarr + lrm;                                         \
-  double *spre = sarr + lrm;    /* [kMaxFix][m] noise of fix-up q for owned k */                                      \
-  double *cms = spre + kMaxFix * lrm; /* [kMaxFix][m] Ms_kk per fix-up (owned k) */                                   \
-  double *cmn = cms + kMaxFix * lrm;  /* [kMaxFix][m] Mneg_kk */                                                      \
-  double *uarr = cmn + kMaxFix * lrm; /* u_k = s_k - d_k of the last fix-up (low-rank part of the residual) */         \
+  double *spre = sarr + lrm;    /* [nfix][m] noise of fix-up q for owned k (sized by the fix-ups of THIS launch: */   \
+  double *cms = spre + P.nfix * lrm; /* [nfix][m] Ms_kk per fix-up (owned k)     1.5 KB more per CTA push the two-sweep */ \
+  double *cmn = cms + P.nfix * lrm;  /* [nfix][m] Mneg_kk                        launches of level 0 over a carve-out step) */ \
+  double *uarr = cmn + P.nfix * lrm; /* u_k = s_k - d_k of the last fix-up (low-rank part of the residual) */          \
   int *own_list = reinterpret_cast<int *>(uarr + lrm), *need_list = own_list + lrm; /* need_list: [3][m] */           \
   int *is_own = need_list + 3 * lrm;                                                                                  \
   const int lr_epoch = *P.lr.epoch;                                                                                   \
@@ -671,9 +671,8 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
       own_list[atomicAdd(&lr_cnt[0], 1)] = k;
       is_own[k] = 1;
     }
-#pragma unroll
-    for (int q = 0; q < kMaxFix; ++q) {
-      if (q >= P.nfix) break;
+#pragma unroll 1  // (not unrolled: every copy carries a normal_pair, and the code size of the kernel costs instruction-cache misses in the pass loops)
+    for (int q = 0; q < P.nfix; ++q) {
       const int dir = P.fix_dir[q];
       if (owner) {
         cms[q * lrm + k] = R.Ms[dir][(size_t)k * lrm + k];
@@ -749,19 +748,25 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
       // (an observed site inside supp(B_k) of an owned measurement is updated by that box: the boxes of one tile must
       //  not update a site twice in a pass -- a second update would draw the same normal and give the same value, but
       //  two warps would write it concurrently; same value, benign, and excluded here for the observed sites)
+      // (one loop and one call site for both kinds of boxes: every copy of the pass code carries a normal_pair)
+      int n_own = 0;
+      const int *own = nullptr;
       if (LOWRANK && lr_own) {
         MGMC_LR_PTRS
-        for (int o = warp; o < lr_cnt[0]; o += kFusedWarps) {
-          const int4 bb = reinterpret_cast<const int4 *>(P.lr.bbox)[own_list[o]];  // i0, i1, j0, j1
-          sparse_box(bb.x, bb.y, bb.z, bb.w);
-        }
+        n_own = lr_cnt[0];
+        own = own_list;
       }
-      if (tile_qoi) {
-        for (int e = warp; e < P.nqoi; e += kFusedWarps) {
-          const int qi = P.qoi_i[e], qj = P.qoi_j[e];
-          if (!(qi >= i_t0 && qi < i_t0 + TX && qj >= j_t0 && qj < j_t0 + TY)) continue;
-          sparse_box(qi, qi, qj, qj);
+      for (int o = warp; o < n_own + (tile_qoi ? P.nqoi : 0); o += kFusedWarps) {
+        int bi0, bi1, bj0, bj1;
+        if (o < n_own) {
+          const int4 bb = reinterpret_cast<const int4 *>(P.lr.bbox)[own[o]];  // i0, i1, j0, j1
+          bi0 = bb.x, bi1 = bb.y, bj0 = bb.z, bj1 = bb.w;
+        } else {
+          bi0 = bi1 = P.qoi_i[o - n_own];
+          bj0 = bj1 = P.qoi_j[o - n_own];
+          if (!(bi0 >= i_t0 && bi0 < i_t0 + TX && bj0 >= j_t0 && bj0 < j_t0 + TY)) continue;
         }
+        sparse_box(bi0, bi1, bj0, bj1);
       }
       __syncthreads();
       continue;

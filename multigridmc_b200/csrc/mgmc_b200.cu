@@ -684,9 +684,12 @@ void launch_fused_t(mgmc_ctx *c, const FusedP &P, dim3 grid, size_t smem, bool c
   const void *fn = (const void *)fused_smooth_kernel<NC, G, PR, RS, LR, NZ>;
   if (c->func_attr_done.insert(fn).second) {
     CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
-    // (always the largest shared-memory carve-out: an SM that has to change its L1 / shared split for a new CTA first
-    //  drains -- a small-level launch would wait for the co-resident noise_gen_kernel CTA to finish, noise_ahead.cuh)
-    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // (with the noise branch in use, always the largest shared-memory carve-out: an SM that has to change its L1 / shared
+    //  split for a new CTA first drains -- a small-level launch would wait for a co-resident noise_gen_kernel CTA to finish.
+    //  Not otherwise: the prolongation gathers reuse the coarse iterate through L1, and the smaller L1 costs the launches
+    //  that do not fill the shared memory anyway 4-12 %)
+    static const bool nza_env = std::getenv("MGMC_NOISE_AHEAD") != nullptr;
+    if (nza_env) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
   if (coop) {
     cudaLaunchConfig_t cfg;
@@ -720,7 +723,7 @@ void lr_begin_epoch(mgmc_ctx *c) {
 }
 
 // shared memory the low-rank bookkeeping of a tile needs behind the tile itself
-inline size_t lr_tile_smem(int m) { return (size_t)(4 + 3 * kMaxFix) * m * sizeof(double) + (size_t)6 * m * sizeof(int); }
+inline size_t lr_tile_smem(int m, int nfix) { return (size_t)(4 + 3 * nfix) * m * sizeof(double) + (size_t)6 * m * sizeof(int); }
 
 // Can the fix-ups of this level run inside the fused launch?  Always when the measurements do not interact;
 // otherwise every tile that needs a fix-up waits for ALL owner tiles of its chain, so all tiles of a chain must be
@@ -940,11 +943,11 @@ void dev_fused(mgmc_ctx *c, int level, const std::vector<Stage> &stages, const s
   P.hl = halo.v[2];
   const int hh = halo.v[3];
   P.RY = P.TY + P.hl + hh;
-  size_t smem = (size_t)2 * P.RY * 128 * sizeof(double) + (use_lr ? lr_tile_smem(c->d.m_lowrank) : 0);
+  size_t smem = (size_t)2 * P.RY * 128 * sizeof(double) + (use_lr ? lr_tile_smem(c->d.m_lowrank, (int)fixes.size()) : 0);
   while (smem > (size_t)kFusedSmemMax && P.TY > 8) {  // (many measurements: a lower tile makes room for their bookkeeping)
     P.TY -= 8;
     P.RY = P.TY + P.hl + hh;
-    smem = (size_t)2 * P.RY * 128 * sizeof(double) + (use_lr ? lr_tile_smem(c->d.m_lowrank) : 0);
+    smem = (size_t)2 * P.RY * 128 * sizeof(double) + (use_lr ? lr_tile_smem(c->d.m_lowrank, (int)fixes.size()) : 0);
   }
   if (c->strip.on() && !c->tail_rec && P.TY != fused_tile_rows(L.g.ny, nc, true, restrict_)) fail(MGMC_ERR_UNSUPPORTED, "row strips: too many measurements for the tile geometry");
   if (smem > (size_t)kFusedSmemMax) fail(MGMC_ERR_INVALID, "internal: fused tile does not fit in shared memory");
@@ -1537,10 +1540,7 @@ void plan_tail(mgmc_ctx *c) {
 template <bool G_, bool LR_>
 void launch_tail_t(mgmc_ctx *c, const TailP &T, size_t smem) {
   const void *fn = (const void *)tail_kernel<G_, LR_>;
-  if (c->func_attr_done.insert(fn).second) {
-    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemMax));
-    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  }
+  if (c->func_attr_done.insert(fn).second) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemMax));
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(c->num_sms, 1, 1);  // one CTA per SM: the cooperative launch guarantees that all of them are resident
