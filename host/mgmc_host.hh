@@ -160,6 +160,7 @@ struct OperatorData {
   int pde_model = MGMC_PDE_SHIFTEDLAPLACE_FD;
   double Lambda = 1.0;
   bool constant_kappa = true;
+  std::vector<double> kappa_sq;  // variable correlation length: kappa^2 at every interior vertex (lexicographic)
   std::vector<int64_t> B_rows;
   std::vector<int32_t> B_cols;
   std::vector<double> B_vals, Sigma;
@@ -168,12 +169,9 @@ struct OperatorData {
 class DeviceHierarchy {
  public:
   DeviceHierarchy(const OperatorData &d, const MultigridParameters &p, uint64_t seed) : data(d), params(p) {
-    if (!d.constant_kappa) {
-      std::cout << "ERROR: the device path supports the constant correlation length model only" << std::endl;
-      exit(-1);
-    }
     mgmc_desc desc;
     std::memset(&desc, 0, sizeof(desc));
+    desc.kappa_sq = d.constant_kappa ? nullptr : d.kappa_sq.data();
     desc.dim = 2;
     desc.nx = (int)d.nx;
     desc.ny = (int)d.ny;
@@ -276,6 +274,11 @@ class ShiftedLaplaceFDOperator : public LinearOperator {
     data->ny = s[1];
     data->pde_model = MGMC_PDE_SHIFTEDLAPLACE_FD;
     data->constant_kappa = clm->is_constant(data->Lambda);
+    if (!data->constant_kappa) {
+      // kappa^2 at every interior vertex, evaluated as the reference's assembly loop does (shiftedlaplace_fd_operator.cc:33-36)
+      data->kappa_sq.resize(lattice->Nvertex);
+      for (unsigned int ell = 0; ell < lattice->Nvertex; ++ell) data->kappa_sq[ell] = clm->kappa_sq(lattice->vertex_coordinates(ell));
+    }
   }
 };
 

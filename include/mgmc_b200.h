@@ -65,6 +65,12 @@ typedef struct {
    * rank strip_rank of strip_nranks owns a contiguous block of rows of every distributed level; the
    * coarse levels are replicated.  0 / 1 ranks = off.  See mgmc_strip_* below. */
   int strip_rank, strip_nranks;
+  /* Correlation length that varies in space (CorrelationLengthModel::kappa_sq, linear_operator/
+   * correlationlength_model.hh:45-113; PeriodicCorrelationLengthModel :83-113): kappa^2 at every interior vertex of the
+   * finest lattice, lexicographic, (nx-1)*(ny-1) entries, as ShiftedLaplaceFDOperator evaluates it
+   * (shiftedlaplace_fd_operator.cc:35-36).  NULL: constant, 1 / Lambda^2.  shiftedlaplace_fd only; the operators of all
+   * levels then carry per-vertex coefficients (Galerkin products R A R^T on the host, csrc/varcoef.cuh on the device). */
+  const double *kappa_sq;
 } mgmc_desc;
 
 const char *mgmc_last_error(void);
@@ -83,6 +89,11 @@ int mgmc_level_info(const mgmc_ctx *, int level, int *nx, int *ny, int64_t *ndof
 int mgmc_get_stencil(const mgmc_ctx *, int level, double *out225);
 /* same algebra run on the host only (needs no CUDA device; desc->B_* may be empty) */
 int mgmc_host_stencil(const mgmc_desc *desc, int level, double *out225, int *ncolours);
+/* Operators with per-vertex coefficients (desc->kappa_sq != NULL): the matrix of `level` as nine planes, entry
+ * A[(i, j), (i + di, j + dj)] at out[((dj + 1) * 3 + (di + 1)) * (nx_l + 1) * (ny_l + 1) + j * (nx_l + 1) + i] with (i, j)
+ * the Euclidean vertex index of that level (zero on the boundary).  Host only; lets the CPU tests compare with the
+ * oracle's R A R^T (linear_operator.cc:12-15). */
+int mgmc_host_coefficients(const mgmc_desc *desc, int level, double *out, int *ncolours);
 
 /* ---- single-level operations on HOST vectors (lexicographic, length ndof(level) * nchains) ---- */
 /* LinearOperator::apply (linear_operator.hh:66-76): y = A_0 x + B Sigma^{-1} B^T x */

@@ -5,6 +5,8 @@ The product is the CUDA library ``csrc/libmgmc_b200.so`` behind the C ABI of
 The reference-compatible C++ host layer lives in ``host/``.  There is no CPU fallback: importing
 works without a GPU, every compute call needs one.
 """
-from .capi import Context, Desc, MgmcError, lib, build, host_stencil, strip_partition  # noqa: F401
+from .capi import (Context, Desc, MgmcError, lib, build, host_stencil, strip_partition,  # noqa: F401
+                   host_coefficients, periodic_kappa_sq)
 
-__all__ = ["Context", "Desc", "MgmcError", "lib", "build", "host_stencil", "strip_partition"]
+__all__ = ["Context", "Desc", "MgmcError", "lib", "build", "host_stencil", "strip_partition",
+           "host_coefficients", "periodic_kappa_sq"]

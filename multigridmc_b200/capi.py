@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
 ]
 SOURCES = ["mgmc_b200.cu"]
-HEADERS = ["fused.cuh", "tail.cuh", "noise_ahead.cuh", "kernels.cuh", "philox.cuh", "normal_tables.inc", "setup.hh", "../../include/mgmc_b200.h"]
+HEADERS = ["fused.cuh", "tail.cuh", "noise_ahead.cuh", "varcoef.cuh", "kernels.cuh", "philox.cuh", "normal_tables.inc", "setup.hh", "../../include/mgmc_b200.h"]
 
 
 def build(force=False, verbose=False):
@@ -49,6 +49,7 @@ class Desc(C.Structure):
         ("cycle", C.c_int), ("coarse_scaling", C.c_double), ("omega", C.c_double),
         ("seed", C.c_uint64), ("device", C.c_int), ("nchains", C.c_int), ("first_chain", C.c_int),
         ("strip_rank", C.c_int), ("strip_nranks", C.c_int),
+        ("kappa_sq", C.POINTER(C.c_double)),
     ]
 
 
@@ -73,6 +74,7 @@ def lib():
         "mgmc_level_info": (i, [vp, i, ip, ip, C.POINTER(i64), ip]),
         "mgmc_get_stencil": (i, [vp, i, c_dp]),
         "mgmc_host_stencil": (i, [C.POINTER(Desc), i, c_dp, ip]),
+        "mgmc_host_coefficients": (i, [C.POINTER(Desc), i, c_dp, ip]),
         "mgmc_op_apply": (i, [vp, i, c_dp, c_dp]),
         "mgmc_restrict": (i, [vp, i, c_dp, c_dp]),
         "mgmc_prolongate_add": (i, [vp, i, dbl, c_dp, c_dp]),
@@ -118,7 +120,7 @@ EXPORTS = [
     "mgmc_loop_solve", "mgmc_set_philox_position", "mgmc_set_rhs", "mgmc_set_state", "mgmc_get_state", "mgmc_set_qoi",
     "mgmc_sample", "mgmc_sample_moments", "mgmc_sample_timed", "mgmc_launch_count", "mgmc_profile_cycle",
     "mgmc_cycle_model", "mgmc_strip_partition", "mgmc_strip_handle_bytes", "mgmc_strip_export", "mgmc_strip_connect",
-    "mgmc_strip_error", "mgmc_plan_passes", "mgmc_tail_stamps",
+    "mgmc_strip_error", "mgmc_plan_passes", "mgmc_tail_stamps", "mgmc_host_coefficients",
 ]
 
 
@@ -140,23 +142,31 @@ FORWARD, BACKWARD = 1, 2
 
 def make_desc(nx, ny, nlevel, pde="shiftedlaplace_fd", Lambda=0.2, B=None, smoother="SSOR", coarse_solver="Cholesky",
               npresmooth=1, npostsmooth=1, ncoarsesmooth=1, cycle=1, coarse_scaling=1.0, omega=1.0, seed=5418513,
-              device=0, nchains=1, first_chain=0, strip_rank=0, strip_nranks=0):
-    """B = (rows, cols, vals, sigma) COO triplets of the measurement matrix (lexicographic rows)."""
+              device=0, nchains=1, first_chain=0, strip_rank=0, strip_nranks=0, kappa_sq=None):
+    """B = (rows, cols, vals, sigma) COO triplets of the measurement matrix (lexicographic rows).
+    kappa_sq = kappa^2 at every interior vertex (lexicographic, (nx-1)*(ny-1) values) for a correlation length
+    that varies in space (`periodic_kappa_sq`); None: constant, 1 / Lambda^2."""
     d = Desc()
     d.dim, d.nx, d.ny, d.nz = 2, nx, ny, 1
     d.pde_model, d.Lambda = PDE[pde], Lambda
     keep = []
+    if kappa_sq is not None:
+        ks = np.ascontiguousarray(kappa_sq, dtype=np.float64).ravel()
+        if ks.size != (nx - 1) * (ny - 1):
+            raise ValueError("kappa_sq needs (nx-1)*(ny-1) entries")
+        keep.append(ks)
+        d.kappa_sq = ks.ctypes.data_as(c_dp)
     if B is not None:
         rows = np.ascontiguousarray(B[0], dtype=np.int64)
         cols = np.ascontiguousarray(B[1], dtype=np.int32)
         vals = np.ascontiguousarray(B[2], dtype=np.float64)
         sigma = np.ascontiguousarray(B[3], dtype=np.float64)
-        keep = [rows, cols, vals, sigma]
         d.m_lowrank, d.B_nnz = len(sigma), len(vals)
         d.B_rows = rows.ctypes.data_as(C.POINTER(C.c_int64))
         d.B_cols = cols.ctypes.data_as(C.POINTER(C.c_int32))
         d.B_vals = vals.ctypes.data_as(c_dp)
         d.Sigma = sigma.ctypes.data_as(c_dp)
+        keep += [rows, cols, vals, sigma]
     d.nlevel, d.smoother, d.coarse_solver = nlevel, SMOOTHER[smoother], COARSE[coarse_solver]
     d.npresmooth, d.npostsmooth, d.ncoarsesmooth = npresmooth, npostsmooth, ncoarsesmooth
     d.cycle, d.coarse_scaling, d.omega = cycle, coarse_scaling, omega
@@ -183,6 +193,26 @@ def strip_partition(desc, level, rank):
     lo, hi, dist = C.c_int(), C.c_int(), C.c_int()
     _chk(lib().mgmc_strip_partition(C.byref(desc), level, rank, C.byref(lo), C.byref(hi), C.byref(dist)))
     return lo.value, hi.value, bool(dist.value)
+
+
+def periodic_kappa_sq(nx, ny, Lambda_min, Lambda_max):
+    """kappa^2 of PeriodicCorrelationLengthModel (correlationlength_model.hh:83-113) at the interior vertices of an
+    nx x ny lattice, lexicographic: Lambda(x) = Lambda_1 + Lambda_2 cos(pi x_1) cos(pi x_2)."""
+    L1, L2 = 0.5 * (Lambda_max + Lambda_min), 0.5 * (Lambda_max - Lambda_min)
+    cx = np.cos(np.pi * (np.arange(1, nx) / nx))
+    cy = np.cos(np.pi * (np.arange(1, ny) / ny))
+    lam = (L2 * cx)[None, :] * cy[:, None] + L1
+    out = 1.0 / (lam * lam)
+    return out.ravel()
+
+
+def host_coefficients(desc, level):
+    """Per-vertex operator of `level` (desc.kappa_sq given) as (9, ny_l + 1, nx_l + 1) planes, host-only."""
+    nx, ny = desc.nx >> level, desc.ny >> level
+    out = np.zeros((9, ny + 1, nx + 1))
+    nc = C.c_int()
+    _chk(lib().mgmc_host_coefficients(C.byref(desc), level, out.ctypes.data_as(c_dp), C.byref(nc)))
+    return out, nc.value
 
 
 def host_stencil(desc, level):

@@ -17,6 +17,7 @@
 #include "setup.hh"
 #include "tail.cuh"
 #include "noise_ahead.cuh"
+#include "varcoef.cuh"
 
 #include <set>
 
@@ -66,6 +67,9 @@ struct DevLevel {
   bool nine = false;
   bool r2 = false;             // radius-2 stencil with position classes: generic kernels, 9 colours
   double *d_st = nullptr;      // [9][25] stencil classes (radius-2 levels)
+  bool vc = false;             // per-vertex coefficients (variable kappa): generic kernels of varcoef.cuh, 2 / 4 colours
+  VarCoef dvc{nullptr, 0};     // nine coefficient planes in the layout of the level vectors
+  bool generic() const { return r2 || vc; }  // colour-by-colour launches instead of the fused tile kernel
   DevSparse B;
   std::map<double, LowRankDev> lowrank;  // keyed by omega
 };
@@ -358,6 +362,14 @@ std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
   L[0].nx = d.nx;
   L[0].ny = d.ny;
   L[0].st = fine_stencil(d.pde_model, d.nx, d.ny, d.Lambda);
+  if (d.kappa_sq) {
+    // correlation length that varies in space: kappa^2 per interior vertex instead of 1 / Lambda^2
+    if (d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FD) fail(MGMC_ERR_UNSUPPORTED, "a variable correlation length is implemented for shiftedlaplace_fd only");
+    if (std::max(d.strip_nranks, 1) > 1) fail(MGMC_ERR_UNSUPPORTED, "row strips of an operator with per-vertex coefficients are not implemented");
+    for (long long k = 0; k < (long long)(d.nx - 1) * (d.ny - 1); ++k)
+      if (!(d.kappa_sq[k] >= 0.0)) fail(MGMC_ERR_INVALID, "kappa_sq entries must be non-negative");
+    fine_varcoef(L[0], d.kappa_sq);
+  }
   const int w = d.nx - 1;
   for (int64_t e = 0; e < d.B_nnz; ++e) {
     const int64_t row = d.B_rows[e];
@@ -371,7 +383,8 @@ std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
     if (!(f.nx / 2 > 1 && f.ny / 2 > 1)) fail(MGMC_ERR_INVALID, "cannot coarsen lattice [resulting lattice would have no interior vertices]");
     L[l].nx = f.nx / 2;
     L[l].ny = f.ny / 2;
-    L[l].st = coarsen_stencil(f.st, f.nx, f.ny);
+    if (f.varcoef()) coarsen_varcoef(f, L[l]);
+    else L[l].st = coarsen_stencil(f.st, f.nx, f.ny);
     L[l].B = coarsen_B(f.B, f.nx, f.ny);
   }
   return L;
@@ -618,6 +631,8 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
   const DevLevel &L = c->lv[level];
   c->launch("apply", level, [&] {
     if (L.r2) apply25_kernel<false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.d_st, x, nullptr, y, RowRange{1, L.g.ny - 1});
+    else if (L.vc && L.nine) apply9v_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.dvc, x, nullptr, y);
+    else if (L.vc) apply9v_kernel<false, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.dvc, x, nullptr, y);
     else if (L.nine) apply_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
     else apply_kernel<false, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
   });
@@ -1238,7 +1253,7 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
 
 void emit_smoothing(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps, bool gibbs, double omega, bool prolong, double alpha, bool restrict_) {
   DevLevel &L = c->lv[level];
-  if (L.r2) return emit_smoothing_r2(c, level, sweeps, gibbs, omega, prolong, alpha, restrict_);
+  if (L.generic()) return emit_smoothing_r2(c, level, sweeps, gibbs, omega, prolong, alpha, restrict_);
   const int nc = L.h.st.ncolours;
   const bool lowrank = c->d.m_lowrank > 0;
   // colour passes per launch: 2 sweeps (tile + halo of x and f stay below ~100 KB, 2 CTAs / SM, and a launch carries at
@@ -1307,6 +1322,8 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
   const int halo = strip_level ? sp.halo[level] : 0;
   const bool has_dn = strip_level && sp.rank > 0, has_up = strip_level && sp.rank + 1 < sp.nranks;
   if (strip_level && lowrank) fail(MGMC_ERR_UNSUPPORTED, "row strips of a radius-2 operator with a low-rank term are not implemented");
+  if (strip_level && L.vc) fail(MGMC_ERR_UNSUPPORTED, "row strips of an operator with per-vertex coefficients are not implemented");
+  const int ncol = L.h.st.ncolours;  // 9: radius 2; 2 / 4: per-vertex coefficients (varcoef.cuh)
   const double n = (double)(hi - lo + 1) * (L.g.nx - 1) * nch;
   auto rows_grid = [&](int j0, int j1) { return dim3((L.g.nx - 1 + 63) / 64, (std::max(j1 - j0 + 1, 1) + 3) / 4, nch); };
   int *ctl = c->d_strip_ctl;
@@ -1336,11 +1353,27 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
     const SweepSpec &sw = sweeps[si];
     const uint32_t c1 = next_c1(c, level, gibbs);
     NoiseP nz = noise_params(c, level, c1);
-    for (int cc = 0; cc < 9; ++cc) {
-      const int colour = sw.fwd ? cc : 8 - cc;
+    for (int cc = 0; cc < ncol; ++cc) {
+      const int colour = sw.fwd ? cc : ncol - 1 - cc;
       // omega = 1: an update does not read the site's own value, so the last colour of this sweep is dead if the next
       // sweep starts with the same colour and nothing reads x in between (see plan_stages for the tile kernel)
-      if (cc == 8 && omega == 1.0 && !noskip && si + 1 < sweeps.size() && sweeps[si + 1].fwd != sw.fwd && !(lowrank && sw.fix_after)) continue;
+      if (cc == ncol - 1 && omega == 1.0 && !noskip && si + 1 < sweeps.size() && sweeps[si + 1].fwd != sw.fwd && !(lowrank && sw.fix_after)) continue;
+      if (L.vc) {
+        // per-vertex coefficients: red-black (every row) or 4 colours (every other row), whole lattice
+        const int j0 = L.nine ? ((colour >> 1) ? 1 : 2) : 1, jstep = L.nine ? 2 : 1;
+        const int nrows = (L.g.ny - 1 - j0) / jstep + 1;
+        dim3 gridv((L.g.nx / 2 + 1 + 63) / 64, std::max((nrows + 3) / 4, 1), nch);
+        c->launch(gibbs ? (L.nine ? "gibbs_4c1v" : "gibbs_rb1v") : (L.nine ? "sor_4c1v" : "sor_rb1v"), level, [&] {
+          if (L.nine) {
+            if (gibbs) sweep_colour9v_kernel<true, true><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, omega, nz, j0, jstep);
+            else sweep_colour9v_kernel<true, false><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, omega, nz, j0, jstep);
+          } else {
+            if (gibbs) sweep_colour9v_kernel<false, true><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, omega, nz, j0, jstep);
+            else sweep_colour9v_kernel<false, false><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, omega, nz, j0, jstep);
+          }
+        }, 24.0 * n / ncol);
+        continue;
+      }
       const int cj = colour / 3;
       // first row of this colour at or above lo: rows j = cj (mod 3), j >= 1 (row 0 is the boundary)
       int jfirst = (cj == 0) ? 3 : cj;
@@ -1392,7 +1425,11 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
     // the restriction to the own coarse rows reads the residual one fine row beyond the own rows
     const RowRange rr{lo, std::min(L.g.ny - 1, hi + (has_up ? 1 : 0))};
     strip_sync();
-    c->launch("residual", level, [&] { apply25_kernel<true><<<rows_grid(rr.j0, rr.j1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, L.r, rr); }, 16.0 * n);
+    c->launch("residual", level, [&] {
+      if (L.vc && L.nine) apply9v_kernel<true, true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, L.r);
+      else if (L.vc) apply9v_kernel<false, true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, L.r);
+      else apply25_kernel<true><<<rows_grid(rr.j0, rr.j1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, L.r, rr);
+    }, 16.0 * n);
     if (lowrank)
       c->launch("lowrank_residual", level, [&] {
         lowrank_apply_kernel<<<nch, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, L.B.rows, c->d_sigma_inv_neg, L.g.stride, L.x, L.r);
@@ -1514,7 +1551,7 @@ void plan_tail(mgmc_ctx *c) {
   const long long max_sites = ms ? std::atoll(ms) : 512ll * 512ll;
   for (int l = nl - 1; l >= 0; --l) {
     const DevLevel &L = c->lv[l];
-    if (L.r2 || (c->strip.on() && l < c->strip.ndist)) break;
+    if (L.generic() || (c->strip.on() && l < c->strip.ndist)) break;
     const bool smoothed = (l < nl - 1) || c->d.coarse_solver != MGMC_COARSE_CHOLESKY;
     if (l == nl - 1 && !smoothed && L.h.ndof() > 4096) break;
     if (smoothed) {
@@ -1663,7 +1700,7 @@ void plan_nza(mgmc_ctx *c) {
   for (int l = 2; l <= last; ++l) {
     const DevLevel &L = c->lv[l];
     if ((long long)L.g.nx * L.g.ny > 512ll * 512ll) continue;
-    if (L.r2 || L.h.st.ncolours != 4 || (c->strip.on() && l < c->strip.ndist) || (c->tail_level >= 0 && l >= c->tail_level)) continue;
+    if (L.generic() || L.h.st.ncolours != 4 || (c->strip.on() && l < c->strip.ndist) || (c->tail_level >= 0 && l >= c->tail_level)) continue;
     c->nza_levels.push_back(l);
   }
   if (c->nza_levels.empty()) return;
@@ -1881,7 +1918,7 @@ void plan_merge(mgmc_ctx *c) {
   c->merge_on = false;
   if (off || c->strip.on() || d.nlevel < 2 || c->tail_level == 0 || c->perf_no_noise) return;
   const DevLevel &L = c->lv[0];
-  if (L.r2 || L.h.st.ncolours != 2 || d.omega != 1.0) return;
+  if (L.generic() || L.h.st.ncolours != 2 || d.omega != 1.0) return;
   const size_t npre = sweep_list(d.smoother, MGMC_FORWARD, d.npresmooth, true).size(), npost = sweep_list(d.smoother, MGMC_BACKWARD, d.npostsmooth, true).size();
   if (npre == 0 || npost == 0 || 2 * (npre + npost) > 8) return;
   if (d.m_lowrank > 0 && ((int)(npre + npost) > kMaxFix || !lr_fusable(c, get_lowrank(c, 0, d.omega), 0))) return;
@@ -2208,6 +2245,7 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
     c->d.B_cols = nullptr;
     c->d.B_vals = nullptr;
     c->d.Sigma = nullptr;
+    c->d.kappa_sq = nullptr;
     c->Sigma.assign(desc->Sigma, desc->Sigma + desc->m_lowrank);
     for (double s : c->Sigma)
       if (!(s > 0.0)) fail(MGMC_ERR_INVALID, "Sigma entries must be positive");
@@ -2277,6 +2315,17 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
       if (L.r2) {
         std::vector<double> st(&L.h.st.a[0][0], &L.h.st.a[0][0] + 225);
         L.d_st = c->dupload(st);
+      }
+      L.vc = L.h.varcoef();
+      if (L.vc) {
+        // nine coefficient planes in the padded layout of the vectors (zeros on the boundary / ghost lines)
+        std::vector<double> planes((size_t)9 * L.g.stride, 0.0);
+        const size_t np = (size_t)(L.h.nx + 1) * (L.h.ny + 1);
+        for (int k = 0; k < 9; ++k)
+          for (int j = 0; j <= L.h.ny; ++j)
+            std::memcpy(&planes[(size_t)k * L.g.stride + origin + (size_t)j * L.g.pitch], &L.h.vc[(size_t)k * np + (size_t)j * (L.h.nx + 1)], sizeof(double) * (L.h.nx + 1));
+        L.dvc.a = c->dupload(planes) + origin;
+        L.dvc.plane = L.g.stride;
       }
       if (desc->m_lowrank > 0) L.B = upload_sparse(c, L.h.B, desc->m_lowrank, L.g.pitch);
     }
@@ -2355,6 +2404,17 @@ int mgmc_host_stencil(const mgmc_desc *desc, int level, double *out225, int *nco
   std::vector<HostLevel> H = build_host_levels(*desc);
   if (level < 0 || level >= (int)H.size()) fail(MGMC_ERR_INVALID, "level out of range");
   std::memcpy(out225, H[level].st.a, sizeof(double) * 225);
+  if (ncolours) *ncolours = H[level].st.ncolours;
+  API_END
+}
+
+int mgmc_host_coefficients(const mgmc_desc *desc, int level, double *out, int *ncolours) {
+  API_BEGIN
+  if (!desc || !out) fail(MGMC_ERR_INVALID, "null argument");
+  if (!desc->kappa_sq) fail(MGMC_ERR_INVALID, "mgmc_host_coefficients needs desc->kappa_sq (constant coefficients: mgmc_host_stencil)");
+  std::vector<HostLevel> H = build_host_levels(*desc);
+  if (level < 0 || level >= (int)H.size()) fail(MGMC_ERR_INVALID, "level out of range");
+  std::memcpy(out, H[level].vc.data(), sizeof(double) * H[level].vc.size());
   if (ncolours) *ncolours = H[level].st.ncolours;
   API_END
 }
@@ -2540,6 +2600,8 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
   auto emit_residual = [&] {
     c->launch("residual_norm", 0, [&] {
       if (L.r2) residual_norm25_kernel<<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, c->sol_x, c->sol_b, L.f, c->d_partial);
+      else if (L.vc && L.nine) residual_norm9v_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.dvc, c->sol_x, c->sol_b, L.f, c->d_partial);
+      else if (L.vc) residual_norm9v_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.dvc, c->sol_x, c->sol_b, L.f, c->d_partial);
       else if (L.nine) residual_norm_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
       else residual_norm_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
     }, 24.0 * (double)L.h.ndof());

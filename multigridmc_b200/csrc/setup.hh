@@ -180,8 +180,94 @@ struct HostLevel {
   int nx = 0, ny = 0;
   StencilSet st;
   std::vector<SEntry> B;  // sorted by column
+  // Variable coefficients (a correlation length that depends on x: PeriodicCorrelationLengthModel,
+  // correlationlength_model.hh:83-113): one radius-1 stencil PER VERTEX, vc[k * np + j * (nx + 1) + i] with
+  // k = (dj + 1) * 3 + (di + 1), np = (nx + 1) * (ny + 1).  Entries of boundary vertices and entries that point to a
+  // boundary vertex are zero (the reference's matrices hold interior vertices only).  Empty: `st` is the operator.
+  std::vector<double> vc;
+  bool varcoef() const { return !vc.empty(); }
   long long ndof() const { return (long long)(nx - 1) * (ny - 1); }
+  // matrix entry A[(i, j), (i + di, j + dj)] of an interior vertex (i, j)
+  double coef(int i, int j, int di, int dj) const {
+    if (vc.empty()) return st.at(pos_class(i, nx) + 3 * pos_class(j, ny), di, dj);
+    if (di < -1 || di > 1 || dj < -1 || dj > 1) return 0.0;
+    return vc[(size_t)((dj + 1) * 3 + (di + 1)) * (size_t)(nx + 1) * (ny + 1) + (size_t)j * (nx + 1) + i];
+  }
 };
+
+// radius / number of colours of a per-vertex operator, as the oracle's scan of the matrix rows: which offsets occur at all
+// (`st` of such a level only carries this classification)
+inline void classify_varcoef(HostLevel &L) {
+  const size_t np = (size_t)(L.nx + 1) * (L.ny + 1);
+  std::memset(L.st.a, 0, sizeof(L.st.a));
+  for (int k = 0; k < 9; ++k) {
+    double big = 0.0;
+    for (size_t v = 0; v < np; ++v) big = std::max(big, std::fabs(L.vc[(size_t)k * np + v]));
+    for (int cls = 0; cls < 9; ++cls) L.st.a[cls][(k / 3 + 1) * 5 + (k % 3 + 1)] = big;
+  }
+  classify(L.st);
+}
+
+// ShiftedLaplaceFDOperator with kappa^2 given per interior vertex (lexicographic, shiftedlaplace_fd_operator.cc:33-56:
+// diagonal h^d kappa^2(x) + sum_d 2 h^d / h_d^2 accumulated in the reference's order, off-diagonals -h^d / h_d^2 towards
+// interior neighbours only)
+inline void fine_varcoef(HostLevel &L, const double *kappa_sq) {
+  const int nx = L.nx, ny = L.ny;
+  const size_t np = (size_t)(nx + 1) * (ny + 1);
+  L.vc.assign(9 * np, 0.0);
+  const double hx = 1.0 / double(nx), hy = 1.0 / double(ny);
+  const double hinv2x = 1.0 / (hx * hx), hinv2y = 1.0 / (hy * hy);
+  const double vol = hx * hy;
+  auto A = [&](int i, int j, int di, int dj) -> double & { return L.vc[(size_t)((dj + 1) * 3 + (di + 1)) * np + (size_t)j * (nx + 1) + i]; };
+  for (int j = 1; j < ny; ++j)
+    for (int i = 1; i < nx; ++i) {
+      double diagonal = vol * kappa_sq[(size_t)(j - 1) * (nx - 1) + (i - 1)];
+      diagonal += 2. * vol * hinv2x;
+      diagonal += 2. * vol * hinv2y;
+      A(i, j, 0, 0) = diagonal;
+      if (i > 1) A(i, j, -1, 0) = -vol * hinv2x;
+      if (i < nx - 1) A(i, j, +1, 0) = -vol * hinv2x;
+      if (j > 1) A(i, j, 0, -1) = -vol * hinv2y;
+      if (j < ny - 1) A(i, j, 0, +1) = -vol * hinv2y;
+    }
+  classify_varcoef(L);
+}
+
+// Galerkin product A_c = R A R^T (LinearOperator::coarsen, linear_operator.cc:12-15) of a per-vertex radius-1 operator
+// with the un-normalised full-weighting R = {1/2, 1, 1/2} x {1/2, 1, 1/2}: again a per-vertex radius-1 (9-point) operator
+inline void coarsen_varcoef(const HostLevel &f, HostLevel &c) {
+  const int nxc = c.nx, nyc = c.ny;
+  const size_t npc = (size_t)(nxc + 1) * (nyc + 1);
+  c.vc.assign(9 * npc, 0.0);
+  const double w1[3] = {0.5, 1.0, 0.5};
+  for (int J = 1; J < nyc; ++J)
+    for (int I = 1; I < nxc; ++I) {
+      // t = (row (I, J) of R) A on the 5 x 5 fine window around (2 I, 2 J)
+      double t[5][5];
+      for (int a = 0; a < 5; ++a)
+        for (int b = 0; b < 5; ++b) t[a][b] = 0.0;
+      for (int py = -1; py <= 1; ++py)
+        for (int px = -1; px <= 1; ++px) {
+          const int pi = 2 * I + px, pj = 2 * J + py;  // always an interior fine vertex
+          const double w = w1[px + 1] * w1[py + 1];
+          for (int dj = -1; dj <= 1; ++dj)
+            for (int di = -1; di <= 1; ++di) t[py + dj + 2][px + di + 2] += w * f.coef(pi, pj, di, dj);
+        }
+      for (int Dy = -1; Dy <= 1; ++Dy)
+        for (int Dx = -1; Dx <= 1; ++Dx) {
+          if (I + Dx < 1 || I + Dx > nxc - 1 || J + Dy < 1 || J + Dy > nyc - 1) continue;
+          double acc = 0.0;
+          for (int qy = -1; qy <= 1; ++qy)
+            for (int qx = -1; qx <= 1; ++qx) {
+              const int oy = 2 * Dy + qy, ox = 2 * Dx + qx;
+              if (ox < -2 || ox > 2 || oy < -2 || oy > 2) continue;
+              acc += w1[qx + 1] * w1[qy + 1] * t[oy + 2][ox + 2];
+            }
+          c.vc[(size_t)((Dy + 1) * 3 + (Dx + 1)) * npc + (size_t)J * (nxc + 1) + I] = acc;
+        }
+    }
+  classify_varcoef(c);
+}
 
 // general m x m inverse (Gauss-Jordan, partial pivoting); replaces Eigen's .inverse() (sor_smoother.cc:29,35)
 inline std::vector<double> invert_dense(std::vector<double> A, int n) {
@@ -255,16 +341,15 @@ inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &S
       for (int j = jlo; j <= jhi; ++j)
         for (int i = ilo; i <= ihi; ++i) {
           if (site_colour(nc, i, j) != colour) continue;
-          const int cls = pos_class(i, L.nx) + 3 * pos_class(j, L.ny);
           double s = 0.0;
           for (int dj = -rad; dj <= rad; ++dj)
             for (int di = -rad; di <= rad; ++di) {
               const int ii = i + di, jj = j + dj;
               if (ii < ilo || ii > ihi || jj < jlo || jj > jhi) continue;
-              s += L.st.at(cls, di, dj) * xw[(size_t)(jj - jlo) * wx + (ii - ilo)];
+              s += L.coef(i, j, di, dj) * xw[(size_t)(jj - jlo) * wx + (ii - ilo)];
             }
           double &xc = xw[(size_t)(j - jlo) * wx + (i - ilo)];
-          xc += omega * (bw[(size_t)(j - jlo) * wx + (i - ilo)] - s) / L.st.at(cls, 0, 0);
+          xc += omega * (bw[(size_t)(j - jlo) * wx + (i - ilo)] - s) / L.coef(i, j, 0, 0);
         }
     }
     for (int j = jlo; j <= jhi; ++j)
@@ -348,12 +433,11 @@ inline CoarseFactor coarse_factor(const HostLevel &Lv, const std::vector<double>
   for (int j = 1; j <= h; ++j)
     for (int i = 1; i <= w; ++i) {
       const int row = (j - 1) * w + (i - 1);
-      const int cls = pos_class(i, Lv.nx) + 3 * pos_class(j, Lv.ny);
       for (int dj = -2; dj <= 2; ++dj)
         for (int di = -2; di <= 2; ++di) {
           const int ii = i + di, jj = j + dj;
           if (ii < 1 || ii > w || jj < 1 || jj > h) continue;
-          const double v = Lv.st.at(cls, di, dj);
+          const double v = Lv.coef(i, j, di, dj);
           if (v != 0.0) A[(size_t)row * Np + (jj - 1) * w + (ii - 1)] = v;
         }
     }

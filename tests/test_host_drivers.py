@@ -87,6 +87,27 @@ def test_driver_mg_residual_history_matches_oracle(built, oracle, tmp_path):
 
 
 @pytest.mark.gpu
+def test_driver_mg_periodic_correlation_length(built, oracle, tmp_path):
+    """driver_mg with `correlationlengthmodel = "periodic"` (parameters.cc:225-243, correlationlength_model.hh:83-113; the
+    model of the reference's own solver tests, test_solver.hh:41): the host classes evaluate kappa^2 at the vertices, the
+    device runs per-vertex coefficients; printed ||r_k|| == oracle LoopSolver on the same operator."""
+    n, nlevel = 128, 4
+    _write_cfg(tmp_path / "mg.cfg", "c2_mg_1024.cfg", nx=n, ny=n, nlevel=nlevel, maxiter=12, filename=f'"{CONFIGS}/measurements_8.cfg"',
+               correlationlengthmodel='"periodic"', Lambda_min=0.15, Lambda_max=0.45)
+    out = subprocess.check_output([os.path.join(built, "driver_mg"), "mg.cfg"], cwd=tmp_path, text=True)
+    assert "correlation length model = periodic" in out
+    hist = np.array([float(l.split()[1]) for l in out.splitlines() if re.match(r"^\s*\d+\s+\d\.\d+e[+-]\d+\s", l)])
+    op = oracle.Operator.prior((n, n), "shiftedlaplace_fd", Lambda_min=0.15, Lambda_max=0.45)
+    H = oracle.Hierarchy(op, nlevel, oracle.COLOUR)
+    b = oracle.StdRng(1482817).normal(op.ndof)
+    prec = H.preconditioner(npresmooth=2, npostsmooth=2)
+    _, h_ref, _, _ = oracle.loop_solve(op, prec, b, rtol=1e-12, atol=1e-15, maxiter=12)
+    assert len(hist) == len(h_ref) == 12
+    big = h_ref > 1e-11 * h_ref[0]
+    assert big.sum() >= 8 and np.abs(hist[big] / h_ref[big] - 1).max() < 2e-3
+
+
+@pytest.mark.gpu
 def test_driver_mgmc_statistics_and_files(built, tmp_path):
     """driver_mgmc on a 128^2 posterior: sampled mean / variance of the observation agree with the exact
     values the driver prints (computed by device MG solves, linear_operator.hh:153-174) within error bars."""

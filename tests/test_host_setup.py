@@ -78,3 +78,65 @@ def test_create_rejects_what_the_reference_rejects():
         with pytest.raises(m.MgmcError) as e:
             m.host_stencil(desc, 0)
         assert e.value.code == -1
+
+
+def _planes_matrix(P, nx, ny):
+    """Dense matrix of a per-vertex radius-1 operator given as (9, ny + 1, nx + 1) planes."""
+    w, h = nx - 1, ny - 1
+    A = np.zeros((w * h, w * h))
+    for j in range(1, ny):
+        for i in range(1, nx):
+            for dj in range(-1, 2):
+                for di in range(-1, 2):
+                    ii, jj = i + di, j + dj
+                    v = P[(dj + 1) * 3 + di + 1, j, i]
+                    if 1 <= ii < nx and 1 <= jj < ny:
+                        A[(j - 1) * w + i - 1, (jj - 1) * w + ii - 1] = v
+                    else:
+                        assert v == 0.0  # nothing points at the boundary
+    return A
+
+
+@pytest.mark.parametrize("n,nlevel", [((32, 32), 4), ((48, 16), 3), ((16, 64), 4)])
+def test_periodic_kappa_operators_match_oracle_triple_product(oracle, n, nlevel):
+    """PeriodicCorrelationLengthModel (correlationlength_model.hh:83-113) in ShiftedLaplaceFDOperator
+    (shiftedlaplace_fd_operator.cc:33-56) and LinearOperator::coarsen (linear_operator.cc:10-23): the per-vertex
+    coefficient planes of every level reproduce the oracle's matrices entry by entry (1e-12 relative), with the same
+    number of sweep colours."""
+    Lmin, Lmax = 0.12, 0.37
+    op = oracle.Operator.prior(n, "shiftedlaplace_fd", Lambda_min=Lmin, Lambda_max=Lmax)
+    H = oracle.Hierarchy(op, nlevel)
+    desc = capi.make_desc(n[0], n[1], nlevel, kappa_sq=m.periodic_kappa_sq(n[0], n[1], Lmin, Lmax))
+    nx, ny = n
+    for level in range(nlevel):
+        P, nc = m.host_coefficients(desc, level)
+        A_ref = H.level_op(level).csr().toarray()
+        A = _planes_matrix(P, nx, ny)
+        assert np.abs(A - A_ref).max() <= 1e-12 * np.abs(A_ref).max(), f"level {level}"
+        assert np.abs(A - A.T).max() <= 1e-13 * np.abs(A).max()
+        assert nc == H.ncolours(level)
+        nx, ny = nx // 2, ny // 2
+    # the constant model through the same path reproduces the stencil algebra
+    desc_c = capi.make_desc(32, 32, 3, kappa_sq=np.full(31 * 31, 1.0 / 0.2 ** 2))
+    desc_s = capi.make_desc(32, 32, 3, Lambda=0.2)
+    for level in range(3):
+        P, nc = m.host_coefficients(desc_c, level)
+        st, nc_s = m.host_stencil(desc_s, level)
+        nl = 32 >> level
+        assert nc == nc_s
+        assert np.abs(_planes_matrix(P, nl, nl) - _stencil_matrix(st, nl, nl)).max() <= 1e-12 * np.abs(st).max()
+
+
+def test_variable_kappa_rejections():
+    ks = m.periodic_kappa_sq(16, 16, 0.1, 0.3)
+    with pytest.raises(m.MgmcError) as e:  # only the shifted Laplacian carries a variable correlation length on the device
+        m.host_coefficients(capi.make_desc(16, 16, 2, pde="squared_shiftedlaplace_fd", kappa_sq=ks), 0)
+    assert e.value.code == -2
+    with pytest.raises(m.MgmcError) as e:
+        m.host_coefficients(capi.make_desc(16, 16, 2), 0)  # constant coefficients: mgmc_host_stencil
+    assert e.value.code == -1
+    bad = ks.copy()
+    bad[3] = -1.0
+    with pytest.raises(m.MgmcError) as e:
+        m.host_coefficients(capi.make_desc(16, 16, 2, kappa_sq=bad), 0)
+    assert e.value.code == -1
