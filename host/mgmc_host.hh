@@ -317,7 +317,7 @@ class MeasuredOperator : public LinearOperator {
         data->B_vals.push_back(e.second);
       }
     }
-    if (params.measure_global) {  // measured_operator.cc:31-46 (dense column: the device path rejects it)
+    if (params.measure_global) {  // measured_operator.cc:31-46 (a dense column of B: the device runs its chip-wide low-rank kernels)
       const double cv = lattice->cell_volume();
       for (unsigned int ell = 0; ell < lattice->Nvertex; ++ell) {
         data->B_rows.push_back(ell);

@@ -495,6 +495,79 @@ __global__ void __launch_bounds__(256) lowrank_fix_kernel(LowRankFix F, long lon
 }
 
 // ------------------------------------------------------------------------------------------------
+// Wide supports: a GLOBAL measurement (MeasurementParameters::measure_global, measured_operator.cc:31-46) is a dense
+// column of B, and then W = M_0^{-1} B has a dense column as well.  The padded one-CTA kernels above do not scale to
+// that (they stage m x max-column-length products in shared memory); these three do the same algebra over the whole
+// chip, deterministically (fixed reduction trees, no atomics):
+//   1. lowrank_bt_partial_kernel   partial[chain][k][b] = sum of B_ek x_e over chunk b of column k
+//   2. lowrank_d_kernel            t = sum_b partial;  MODE 0: d = scale * t  (apply / residual / restriction)
+//                                  MODE 1 / 2: d = -K t (+ (I - K G) Sigma^{-1/2} xi)  (Woodbury fix-up, as lowrank_fix_kernel)
+//   3. lowrank_scatter_kernel      y_u += sign * sum_k R_uk d_k  over the unique sites of R (B, the coarse B, or W)
+// ------------------------------------------------------------------------------------------------
+constexpr int kLrWideBlocks = 64;
+
+__global__ void __launch_bounds__(256) lowrank_bt_partial_kernel(SparseCols B, long long stride, const double *__restrict__ x, double *__restrict__ partial) {
+  const int k = blockIdx.y;
+  const double *xc = x + (long long)blockIdx.z * stride;
+  const int e0 = B.colptr[k], e1 = B.colptr[k + 1];
+  const int chunk = (e1 - e0 + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int lo = e0 + (int)blockIdx.x * chunk, hi = min(lo + chunk, e1);
+  double v = 0.0;
+  for (int e = lo + (int)threadIdx.x; e < hi; e += 256) v = fma(B.val[e], xc[B.site[e]], v);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  __shared__ double ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += ws[w];
+    partial[((long long)blockIdx.z * B.m + k) * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) lowrank_d_kernel(int m, int nblk, const double *__restrict__ partial, const double *__restrict__ scale,
+                                                       const double *__restrict__ Mneg, const double *__restrict__ Ms, const double *__restrict__ sigma_inv_sqrt, NoiseP nz,
+                                                       double *__restrict__ d_out) {
+  extern __shared__ double sh[];
+  double *t = sh, *s = sh + m;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < m; k += 256) {
+    double acc = 0.0;
+    for (int b = 0; b < nblk; ++b) acc += partial[((long long)blockIdx.x * m + k) * nblk + b];
+    t[k] = acc;
+    if (MODE == 0) d_out[(long long)blockIdx.x * m + k] = scale[k] * acc;
+    if (MODE == 2) {
+      double z0, z1;
+      normal_pair(nz.keys, 0x80000000u | ((uint32_t)k >> 1), nz.c1, *nz.sample, nz.chain0 + blockIdx.x, nz.mc, kNormalTabDev, z0, z1);
+      s[k] = sigma_inv_sqrt[k] * ((k & 1) ? z1 : z0);
+    }
+  }
+  if (MODE == 0) return;
+  __syncthreads();
+  for (int k = warp; k < m; k += 8) {
+    double acc = 0.0;
+    for (int c = lane; c < m; c += 32) {
+      acc = fma(Mneg[k * m + c], t[c], acc);
+      if (MODE == 2) acc = fma(Ms[k * m + c], s[c], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) d_out[(long long)blockIdx.x * m + k] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) lowrank_scatter_kernel(SparseRows R, int m, const double *__restrict__ d, long long stride, double *__restrict__ y, double sign) {
+  const int u = blockIdx.x * 256 + threadIdx.x;
+  if (u >= R.nu) return;
+  const double *dc = d + (long long)blockIdx.y * m;
+  double acc = 0.0;
+  for (int e = R.uptr[u]; e < R.uptr[u + 1]; ++e) acc = fma(R.uval[e], dc[R.ucol[e]], acc);
+  y[(long long)blockIdx.y * stride + R.usite[u]] += sign * acc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row-strip domain decomposition over several GPUs (one process per GPU, peer memory mapped with CUDA
 // IPC).  After a fused launch a rank stores the boundary rows of its output straight into the
 // neighbours' arrays over NVLink and raises their flag; before a fused launch it waits (on the device,

@@ -56,6 +56,9 @@ struct LowRankDev {
   int bw = 0, bh = 0;             // largest extent of supp(B_k)
   int wreach = 0;                 // largest distance of a site of supp(W_k) from the bounding box of supp(B_k)
   bool diag[2] = {false, false};  // capacitance matrix diagonal (measurements do not interact on this level)
+  // wide supports (a global measurement = a dense column of B): chip-wide kernels instead of the padded one-CTA ones
+  bool wide = false;
+  DevSparse W[2];                 // W = M_0^{-1} B per sweep direction (row grouping used)
 };
 
 struct DevLevel {
@@ -71,6 +74,7 @@ struct DevLevel {
   VarCoef dvc{nullptr, 0};     // nine coefficient planes in the layout of the level vectors
   bool generic() const { return r2 || vc; }  // colour-by-colour launches instead of the fused tile kernel
   DevSparse B;
+  bool lr_wide = false;        // some column of B has more entries than the padded low-rank kernels stage (kernels.cuh "Wide supports")
   std::map<double, LowRankDev> lowrank;  // keyed by omega
 };
 
@@ -179,6 +183,7 @@ struct mgmc_ctx {
   long long *d_tail_stamps = nullptr;  // MGMC_TAIL_STAMPS=1: per-phase time stamps of the last tail launch
   std::vector<int> tail_stamp_kinds;
   double *dAinv = nullptr;         // A^{-1} of the coarsest level (one-pass coarse phase)
+  double *d_lr_partial = nullptr, *d_lr_d = nullptr;  // wide low-rank supports: partial sums of B^T x, coefficients d
   double *d_coarse_xi = nullptr;   // ensembles: normals of the coarse sampler for all chains (coarse_xi_kernel)
   std::set<const void *> func_attr_done;  // kernels whose dynamic shared memory limit has been raised on this device
   // noise of the small levels generated ahead of their launches (noise_ahead.cuh): a second branch of the cycle graph
@@ -396,6 +401,21 @@ const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega) {
   if (it != L.lowrank.end()) return it->second;
   LowRankDev dev;
   const int m = c->d.m_lowrank;
+  if (L.lr_wide) {
+    // a dense column of B (global measurement): W and the m x m matrices only, for the chip-wide kernels
+    dev.wide = true;
+    dev.bw = dev.bh = 1 << 20;  // (never fusable into the tile kernel)
+    for (int dir = 0; dir < 2; ++dir) {
+      LowRankDir h = lowrank_setup(L.h, c->Sigma, omega, dir == 0);
+      dev.W[dir] = upload_sparse(c, h.W, m, L.g.pitch);
+      std::memset(&dev.fix[dir], 0, sizeof(dev.fix[dir]));
+      dev.fix[dir].m = m;
+      dev.fix[dir].Mneg = c->dupload(h.Mneg);
+      dev.fix[dir].Ms = c->dupload(h.Ms);
+      dev.fix[dir].sigma_inv_sqrt = c->d_sigma_inv_sqrt;
+    }
+    return L.lowrank.emplace(omega, dev).first->second;
+  }
   // B padded to EB entries per column
   std::vector<std::vector<SEntry>> cols(m);
   for (const SEntry &e : L.h.B) cols[e.col].push_back(e);
@@ -626,6 +646,27 @@ void normalize_x(mgmc_ctx *c, int level) {
   std::swap(L.x, L.x_alt);
 }
 
+// ---- wide low-rank supports (kernels.cuh "Wide supports") ----
+// partial sums of B^T x (B of `level`) for every chain of x
+void dev_lowrank_wide_partial(mgmc_ctx *c, int level, const double *x, int nch) {
+  const DevLevel &L = c->lv[level];
+  const int m = c->d.m_lowrank;
+  if (!c->d_lr_partial) {
+    c->d_lr_partial = c->dalloc<double>((size_t)c->d.nchains * m * kLrWideBlocks);
+    c->d_lr_d = c->dalloc<double>((size_t)c->d.nchains * m);
+  }
+  c->launch("lowrank_bt", level, [&] { lowrank_bt_partial_kernel<<<dim3(kLrWideBlocks, m, nch), 256, 0, c->stream>>>(L.B.cols, L.g.stride, x, c->d_lr_partial); });
+}
+// y += sign * R diag(scale) B^T x with R = the row grouping of B on this level or of the coarse B (restriction)
+void dev_lowrank_wide_apply(mgmc_ctx *c, int level, const double *x, const SparseRows &R, long long stride_y, double *y, const double *scale, double sign, int nch) {
+  const int m = c->d.m_lowrank;
+  dev_lowrank_wide_partial(c, level, x, nch);
+  c->launch("lowrank_d", level, [&] {
+    lowrank_d_kernel<0><<<nch, 256, 2 * m * sizeof(double), c->stream>>>(m, kLrWideBlocks, c->d_lr_partial, scale, nullptr, nullptr, nullptr, NoiseP{}, c->d_lr_d);
+  });
+  c->launch("lowrank_scatter", level, [&] { lowrank_scatter_kernel<<<dim3((R.nu + 255) / 256, nch), 256, 0, c->stream>>>(R, m, c->d_lr_d, stride_y, y, sign); });
+}
+
 // y = A x (incl. low-rank term)
 void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
   const DevLevel &L = c->lv[level];
@@ -636,7 +677,9 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
     else if (L.nine) apply_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
     else apply_kernel<false, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
   });
-  if (c->d.m_lowrank > 0)
+  if (c->d.m_lowrank > 0 && L.lr_wide) {
+    dev_lowrank_wide_apply(c, level, x, L.B.rows, L.g.stride, y, c->d_sigma_inv, 1.0, c->d.nchains);
+  } else if (c->d.m_lowrank > 0)
     c->launch("lowrank_apply", level, [&] {
       lowrank_apply_kernel<<<c->d.nchains, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, L.B.rows, c->d_sigma_inv, L.g.stride, x, y);
     });
@@ -1213,6 +1256,17 @@ void dev_lowrank_fix(mgmc_ctx *c, int level, bool fwd, bool gibbs, double omega,
   const LowRankDev &lr = get_lowrank(c, level, omega);
   const LowRankFix &F = lr.fix[fwd ? 0 : 1];
   NoiseP nz = noise_params(c, level, c1);
+  if (lr.wide) {
+    const int m = c->d.m_lowrank, nch = c->d.nchains;
+    const SparseRows &R = lr.W[fwd ? 0 : 1].rows;
+    dev_lowrank_wide_partial(c, level, L.x, nch);
+    c->launch("lowrank_d", level, [&] {
+      if (gibbs) lowrank_d_kernel<2><<<nch, 256, 2 * m * sizeof(double), c->stream>>>(m, kLrWideBlocks, c->d_lr_partial, nullptr, F.Mneg, F.Ms, F.sigma_inv_sqrt, nz, c->d_lr_d);
+      else lowrank_d_kernel<1><<<nch, 256, 2 * m * sizeof(double), c->stream>>>(m, kLrWideBlocks, c->d_lr_partial, nullptr, F.Mneg, F.Ms, F.sigma_inv_sqrt, nz, c->d_lr_d);
+    });
+    c->launch("lowrank_scatter", level, [&] { lowrank_scatter_kernel<<<dim3((R.nu + 255) / 256, nch), 256, 0, c->stream>>>(R, m, c->d_lr_d, L.g.stride, L.x, 1.0); });
+    return;
+  }
   c->launch("lowrank_fix", level, [&] {
     if (gibbs) lowrank_fix_kernel<true><<<c->d.nchains, 256, lr.smem, c->stream>>>(F, L.g.stride, L.x, nz);
     else lowrank_fix_kernel<false><<<c->d.nchains, 256, lr.smem, c->stream>>>(F, L.g.stride, L.x, nz);
@@ -1298,9 +1352,11 @@ void emit_smoothing(mgmc_ctx *c, int level, const std::vector<SweepSpec> &sweeps
     if (restrict_) {
       flush(true);
       DevLevel &C = c->lv[level + 1];
-      c->launch("lowrank_restrict", level, [&] {
-        lowrank_restrict_kernel<<<c->d.nchains, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, C.B.rows, c->d_sigma_inv, L.g.stride, C.g.stride, L.x, C.f);
-      });
+      if (L.lr_wide) dev_lowrank_wide_apply(c, level, L.x, C.B.rows, C.g.stride, C.f, c->d_sigma_inv, -1.0, c->d.nchains);
+      else
+        c->launch("lowrank_restrict", level, [&] {
+          lowrank_restrict_kernel<<<c->d.nchains, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, C.B.rows, c->d_sigma_inv, L.g.stride, C.g.stride, L.x, C.f);
+        });
     }
   }
 }
@@ -1430,7 +1486,8 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
       else if (L.vc) apply9v_kernel<false, true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, L.r);
       else apply25_kernel<true><<<rows_grid(rr.j0, rr.j1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, L.r, rr);
     }, 16.0 * n);
-    if (lowrank)
+    if (lowrank && L.lr_wide) dev_lowrank_wide_apply(c, level, L.x, L.B.rows, L.g.stride, L.r, c->d_sigma_inv, -1.0, nch);
+    else if (lowrank)
       c->launch("lowrank_residual", level, [&] {
         lowrank_apply_kernel<<<nch, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, L.B.rows, c->d_sigma_inv_neg, L.g.stride, L.x, L.r);
       });
@@ -2327,7 +2384,15 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
         L.dvc.a = c->dupload(planes) + origin;
         L.dvc.plane = L.g.stride;
       }
-      if (desc->m_lowrank > 0) L.B = upload_sparse(c, L.h.B, desc->m_lowrank, L.g.pitch);
+      if (desc->m_lowrank > 0) {
+        L.B = upload_sparse(c, L.h.B, desc->m_lowrank, L.g.pitch);
+        // the padded one-CTA kernels stage m x (longest column) products in shared memory (lowrank_fix_kernel)
+        std::vector<int> cnt(desc->m_lowrank, 0);
+        int longest = 0;
+        for (const SEntry &e : L.h.B) longest = std::max(longest, ++cnt[e.col]);
+        const size_t mm = (size_t)desc->m_lowrank;
+        L.lr_wide = (mm * longest + 3 * mm + (mm <= 48 ? 2 * mm * mm : 0)) * sizeof(double) > 40 * 1024;
+      }
     }
     if (desc->m_lowrank > 0) {
       std::vector<double> si(desc->m_lowrank), sis(desc->m_lowrank);
@@ -2607,9 +2672,11 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
     }, 24.0 * (double)L.h.ndof());
     if (c->d.m_lowrank > 0) {
       // low-rank part of A x is added to r, then the norm is recomputed from r
-      c->launch("lowrank_apply", 0, [&] {
-        lowrank_apply_kernel<<<1, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, L.B.rows, c->d_sigma_inv, L.g.stride, c->sol_x, L.f);
-      });
+      if (L.lr_wide) dev_lowrank_wide_apply(c, 0, c->sol_x, L.B.rows, L.g.stride, L.f, c->d_sigma_inv, 1.0, 1);
+      else
+        c->launch("lowrank_apply", 0, [&] {
+          lowrank_apply_kernel<<<1, 256, c->d.m_lowrank * sizeof(double), c->stream>>>(L.B.cols, L.B.rows, c->d_sigma_inv, L.g.stride, c->sol_x, L.f);
+        });
       c->launch("norm", 0, [&] {
         residual_norm_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, Coef9{0, 0, 0, 0, 0, 0, 0, 0, 0}, c->sol_x, L.f, L.r, c->d_partial);
       });

@@ -319,7 +319,16 @@ inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &S
   const int nc = L.st.ncolours, reach = (nc - 1) * L.st.radius, rad = L.st.radius;
   std::vector<std::vector<SEntry>> cols(m);
   for (const SEntry &e : L.B) cols[e.col].push_back(e);
-  std::vector<std::map<long long, double>> Wmap(m);
+  // W_k on its window (dense: a global measurement has the whole lattice as window)
+  struct Win {
+    int ilo = 0, jlo = 0, wx = 0, wy = 0;
+    std::vector<double> v;
+    double at(int i, int j) const {
+      if (i < ilo || i >= ilo + wx || j < jlo || j >= jlo + wy) return 0.0;
+      return v[(size_t)(j - jlo) * wx + (i - ilo)];
+    }
+  };
+  std::vector<Win> Wwin(m);
   for (int k = 0; k < m; ++k) {
     if (cols[k].empty()) continue;
     int ilo = 1 << 30, ihi = -1, jlo = 1 << 30, jhi = -1;
@@ -355,20 +364,23 @@ inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &S
     for (int j = jlo; j <= jhi; ++j)
       for (int i = ilo; i <= ihi; ++i) {
         const double v = xw[(size_t)(j - jlo) * wx + (i - ilo)];
-        if (v != 0.0) {
-          out.W.push_back({i, j, k, v});
-          Wmap[k][(long long)j * (1ll << 20) + i] = v;
-        }
+        if (v != 0.0) out.W.push_back({i, j, k, v});
       }
+    Wwin[k].ilo = ilo;
+    Wwin[k].jlo = jlo;
+    Wwin[k].wx = wx;
+    Wwin[k].wy = wy;
+    Wwin[k].v.swap(xw);
   }
   std::vector<double> S((size_t)m * m, 0.0);
   for (int a = 0; a < m; ++a)
     for (int b = 0; b < m; ++b) {
       double g = 0.0;
-      for (const SEntry &e : cols[a]) {
-        auto it = Wmap[b].find((long long)e.j * (1ll << 20) + e.i);
-        if (it != Wmap[b].end()) g += e.val * it->second;
-      }
+      if (!Wwin[b].v.empty())
+        for (const SEntry &e : cols[a]) {
+          const double w = Wwin[b].at(e.i, e.j);
+          if (w != 0.0) g += e.val * w;
+        }
       out.G[(size_t)a * m + b] = g;
       S[(size_t)a * m + b] = g + ((a == b) ? Sigma[a] : 0.0);
     }

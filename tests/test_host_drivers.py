@@ -146,6 +146,25 @@ def test_driver_mgmc_statistics_and_files(built, tmp_path):
 
 
 @pytest.mark.gpu
+def test_driver_mgmc_global_measurement(built, tmp_path):
+    """driver_mgmc with `measure_global = true` (measured_operator.cc:31-46: the average of the field over the domain is
+    observed as well -- a dense column of B): the MultigridMC mean / variance of the observation agree with the exact
+    values within error bars, as for point measurements."""
+    _write_cfg(tmp_path / "mgmc.cfg", "small_posterior_128.cfg", filename=f'"{CONFIGS}/measurements_8.cfg"', measure_global="true", do_ssor="false")
+    out = subprocess.check_output([os.path.join(built, "driver_mgmc"), "mgmc.cfg"], cwd=tmp_path, text=True)
+    blk = out[out.index("**** Multigrid MC ****"):]
+    mean, err = map(float, re.search(r"MultigridMC mean\s+=\s+(\S+) \+/-\s+(\S+)", blk).groups())
+    mean_exact = float(re.search(r"exact mean\s+=\s+(\S+)", blk).group(1))
+    var = float(re.search(r"MultigridMC variance =\s+(\S+)", blk).group(1))
+    var_exact = float(re.search(r"exact variance =\s+(\S+)", blk).group(1))
+    tau = float(re.search(r"MultigridMC tau_int\s+=\s+(\S+)", blk).group(1))
+    nsamp = len(np.loadtxt(tmp_path / "timeseries_multigridmc.txt"))
+    assert nsamp == 4000 and tau < 2.0
+    assert abs(mean - mean_exact) < 4.5 * err * np.sqrt(max(tau, 1.0))
+    assert abs(var / var_exact - 1) < 4.5 * np.sqrt(2.0 * max(tau, 1.0) / nsamp)
+
+
+@pytest.mark.gpu
 def test_cholesky_solver_and_sampler_classes(built):
     """Host classes CholeskySolver / Dense-, SparseCholeskySampler + factories (solver/cholesky_solver.hh:21-68,
     sampler/cholesky_sampler.hh:27-196) over mgmc_coarse_solve / mgmc_coarse_sample: exact solve with and without the
