@@ -226,9 +226,9 @@ def other_configs(m, peak):
     the C ABI, device-timed -- sub-records of the bench line, not bench lines of their own."""
     out = []
 
-    def mgmc(name, n, nlevel, nchains=1, pde="shiftedlaplace_fd", steps=100, target=None):
+    def mgmc(name, n, nlevel, nchains=1, pde="shiftedlaplace_fd", steps=100, target=None, kappa_sq=None):
         try:
-            ctx = m.Context(n, n, nlevel, Lambda=0.2, pde=pde, nchains=nchains)
+            ctx = m.Context(n, n, nlevel, Lambda=0.2, pde=pde, nchains=nchains, kappa_sq=kappa_sq)
             nd = ctx.ndof()
             xs = np.arange(1, n) / n
             u = np.outer(np.sin(np.pi * xs), np.sin(np.pi * xs)).ravel()
@@ -267,6 +267,10 @@ def other_configs(m, peak):
     mgmc("C4 squared_shiftedlaplace_fd 2048x2048, 7 levels, prior, V(1,1) SSOR, one GPU", 2048, 7, pde="squared_shiftedlaplace_fd", steps=20,
          target="<= 0.193 ms / cycle at 60 % of the model")
     mgmc("C5 256 chains x 512x512, 5 levels, prior, one GPU", 512, 5, nchains=256, steps=20, target=">= 8.4e4 chain-samples/s per GPU at 60 % of the model")
+    # not a BASELINE configuration: the correlation length model of the reference's own sampler / solver tests
+    # (PeriodicCorrelationLengthModel), per-vertex coefficients on every level, one launch per colour (csrc/varcoef.cuh)
+    mgmc("periodic correlation length (Lambda 0.1 .. 0.4), 2048x2048, 7 levels, prior, V(1,1) SSOR, one GPU (per-vertex coefficients: first correct path)",
+         2048, 7, steps=20, kappa_sq=m.periodic_kappa_sq(2048, 2048, 0.1, 0.4))
     return out
 
 

@@ -71,7 +71,8 @@ struct DevLevel {
   bool r2 = false;             // radius-2 stencil with position classes: generic kernels, 9 colours
   double *d_st = nullptr;      // [9][25] stencil classes (radius-2 levels)
   bool vc = false;             // per-vertex coefficients (variable kappa): generic kernels of varcoef.cuh, 2 / 4 colours
-  VarCoef dvc{nullptr, 0};     // nine coefficient planes in the layout of the level vectors
+  VarCoef dvc{nullptr, 0, 0, 0, 0, 0};  // coefficient planes in the layout of the level vectors
+  bool vc_full = false;        // ... all nine planes (the Galerkin operators); false: the 5-point fine operator, diagonal plane only
   bool generic() const { return r2 || vc; }  // colour-by-colour launches instead of the fused tile kernel
   DevSparse B;
   bool lr_wide = false;        // some column of B has more entries than the padded low-rank kernels stage (kernels.cuh "Wide supports")
@@ -672,7 +673,7 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
   const DevLevel &L = c->lv[level];
   c->launch("apply", level, [&] {
     if (L.r2) apply25_kernel<false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.d_st, x, nullptr, y, RowRange{1, L.g.ny - 1});
-    else if (L.vc && L.nine) apply9v_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.dvc, x, nullptr, y);
+    else if (L.vc && L.vc_full) apply9v_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.dvc, x, nullptr, y);
     else if (L.vc) apply9v_kernel<false, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.dvc, x, nullptr, y);
     else if (L.nine) apply_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
     else apply_kernel<false, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
@@ -1416,16 +1417,17 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
       if (cc == ncol - 1 && omega == 1.0 && !noskip && si + 1 < sweeps.size() && sweeps[si + 1].fwd != sw.fwd && !(lowrank && sw.fix_after)) continue;
       if (L.vc) {
         // per-vertex coefficients: red-black (every row) or 4 colours (every other row), whole lattice
-        const int j0 = L.nine ? ((colour >> 1) ? 1 : 2) : 1, jstep = L.nine ? 2 : 1;
+        const bool four = (ncol == 4);
+        const int j0 = four ? ((colour >> 1) ? 1 : 2) : 1, jstep = four ? 2 : 1;
         const int nrows = (L.g.ny - 1 - j0) / jstep + 1;
         dim3 gridv((L.g.nx / 2 + 1 + 63) / 64, std::max((nrows + 3) / 4, 1), nch);
-        c->launch(gibbs ? (L.nine ? "gibbs_4c1v" : "gibbs_rb1v") : (L.nine ? "sor_4c1v" : "sor_rb1v"), level, [&] {
-          if (L.nine) {
-            if (gibbs) sweep_colour9v_kernel<true, true><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, omega, nz, j0, jstep);
-            else sweep_colour9v_kernel<true, false><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, omega, nz, j0, jstep);
+        c->launch(gibbs ? (four ? "gibbs_4c1v" : "gibbs_rb1v") : (four ? "sor_4c1v" : "sor_rb1v"), level, [&] {
+          if (L.vc_full) {
+            if (gibbs) sweep_colour9v_kernel<true, true><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, ncol, omega, nz, j0, jstep);
+            else sweep_colour9v_kernel<true, false><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, ncol, omega, nz, j0, jstep);
           } else {
-            if (gibbs) sweep_colour9v_kernel<false, true><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, omega, nz, j0, jstep);
-            else sweep_colour9v_kernel<false, false><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, omega, nz, j0, jstep);
+            if (gibbs) sweep_colour9v_kernel<false, true><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, ncol, omega, nz, j0, jstep);
+            else sweep_colour9v_kernel<false, false><<<gridv, kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, colour, ncol, omega, nz, j0, jstep);
           }
         }, 24.0 * n / ncol);
         continue;
@@ -1482,7 +1484,7 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
     const RowRange rr{lo, std::min(L.g.ny - 1, hi + (has_up ? 1 : 0))};
     strip_sync();
     c->launch("residual", level, [&] {
-      if (L.vc && L.nine) apply9v_kernel<true, true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, L.r);
+      if (L.vc && L.vc_full) apply9v_kernel<true, true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, L.r);
       else if (L.vc) apply9v_kernel<false, true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, L.r);
       else apply25_kernel<true><<<rows_grid(rr.j0, rr.j1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, L.r, rr);
     }, 16.0 * n);
@@ -2375,14 +2377,23 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
       }
       L.vc = L.h.varcoef();
       if (L.vc) {
-        // nine coefficient planes in the padded layout of the vectors (zeros on the boundary / ghost lines)
-        std::vector<double> planes((size_t)9 * L.g.stride, 0.0);
+        // coefficient planes in the padded layout of the vectors (zeros on the boundary / ghost lines): all nine for the
+        // 9-point Galerkin operators, the diagonal alone for the 5-point fine operator (varcoef.cuh)
         const size_t np = (size_t)(L.h.nx + 1) * (L.h.ny + 1);
-        for (int k = 0; k < 9; ++k)
+        L.vc_full = (l > 0);
+        const int k0 = L.vc_full ? 0 : 4, k1 = L.vc_full ? 9 : 5;
+        std::vector<double> planes((size_t)(k1 - k0) * L.g.stride, 0.0);
+        for (int k = k0; k < k1; ++k)
           for (int j = 0; j <= L.h.ny; ++j)
-            std::memcpy(&planes[(size_t)k * L.g.stride + origin + (size_t)j * L.g.pitch], &L.h.vc[(size_t)k * np + (size_t)j * (L.h.nx + 1)], sizeof(double) * (L.h.nx + 1));
+            std::memcpy(&planes[(size_t)(k - k0) * L.g.stride + origin + (size_t)j * L.g.pitch], &L.h.vc[(size_t)k * np + (size_t)j * (L.h.nx + 1)], sizeof(double) * (L.h.nx + 1));
         L.dvc.a = c->dupload(planes) + origin;
         L.dvc.plane = L.g.stride;
+        // (5-point: the neighbour coefficients of a vertex in the interior -- constant, shiftedlaplace_fd_operator.cc:46)
+        const int im = std::min(2, L.h.nx - 1), jm = std::min(2, L.h.ny - 1);
+        L.dvc.w = L.h.coef(im, jm, -1, 0);
+        L.dvc.e = L.h.coef(std::max(L.h.nx - 2, 1), jm, +1, 0);
+        L.dvc.s = L.h.coef(im, jm, 0, -1);
+        L.dvc.n = L.h.coef(im, std::max(L.h.ny - 2, 1), 0, +1);
       }
       if (desc->m_lowrank > 0) {
         L.B = upload_sparse(c, L.h.B, desc->m_lowrank, L.g.pitch);
@@ -2665,7 +2676,7 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
   auto emit_residual = [&] {
     c->launch("residual_norm", 0, [&] {
       if (L.r2) residual_norm25_kernel<<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, c->sol_x, c->sol_b, L.f, c->d_partial);
-      else if (L.vc && L.nine) residual_norm9v_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.dvc, c->sol_x, c->sol_b, L.f, c->d_partial);
+      else if (L.vc && L.vc_full) residual_norm9v_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.dvc, c->sol_x, c->sol_b, L.f, c->d_partial);
       else if (L.vc) residual_norm9v_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.dvc, c->sol_x, c->sol_b, L.f, c->d_partial);
       else if (L.nine) residual_norm_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
       else residual_norm_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
