@@ -652,10 +652,7 @@ void normalize_x(mgmc_ctx *c, int level) {
 void dev_lowrank_wide_partial(mgmc_ctx *c, int level, const double *x, int nch) {
   const DevLevel &L = c->lv[level];
   const int m = c->d.m_lowrank;
-  if (!c->d_lr_partial) {
-    c->d_lr_partial = c->dalloc<double>((size_t)c->d.nchains * m * kLrWideBlocks);
-    c->d_lr_d = c->dalloc<double>((size_t)c->d.nchains * m);
-  }
+  if (!c->d_lr_partial) fail(MGMC_ERR_INVALID, "internal: buffers of the wide low-rank kernels missing");
   c->launch("lowrank_bt", level, [&] { lowrank_bt_partial_kernel<<<dim3(kLrWideBlocks, m, nch), 256, 0, c->stream>>>(L.B.cols, L.g.stride, x, c->d_lr_partial); });
 }
 // y += sign * R diag(scale) B^T x with R = the row grouping of B on this level or of the coarse B (restriction)
@@ -2403,6 +2400,10 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
         for (const SEntry &e : L.h.B) longest = std::max(longest, ++cnt[e.col]);
         const size_t mm = (size_t)desc->m_lowrank;
         L.lr_wide = (mm * longest + 3 * mm + (mm <= 48 ? 2 * mm * mm : 0)) * sizeof(double) > 40 * 1024;
+        if (L.lr_wide && !c->d_lr_partial) {  // (allocated here: the first use may be inside a stream capture)
+          c->d_lr_partial = c->dalloc<double>((size_t)desc->nchains * mm * kLrWideBlocks);
+          c->d_lr_d = c->dalloc<double>((size_t)desc->nchains * mm);
+        }
       }
     }
     if (desc->m_lowrank > 0) {
