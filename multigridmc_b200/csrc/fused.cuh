@@ -41,6 +41,9 @@ constexpr int kGY = 2;   // allocated rows below j = 0 / above j = ny
 #ifndef MGMC_PASS_ILP
 #define MGMC_PASS_ILP 1
 #endif
+#ifndef MGMC_FUSED_MINBLOCKS
+#define MGMC_FUSED_MINBLOCKS 2  // CTAs per SM the tile kernel is compiled for (register cap); 1 with -DMGMC_FUSED_THREADS=1024
+#endif
 constexpr int kFusedThreads = MGMC_FUSED_THREADS;
 constexpr int kFusedWarps = kFusedThreads / 32;
 
@@ -1194,7 +1197,7 @@ __device__ __forceinline__ void fused_tile(const FusedP &P, const int tile_id, c
 }
 
 template <int NC, bool GIBBS, bool PROLONG, bool RESTRICT, bool LOWRANK, bool NZG = false>
-__global__ void __launch_bounds__(kFusedThreads, NZG ? 1 : 2) fused_smooth_kernel(const __grid_constant__ FusedP P) {  // (NZG: small levels, at most one CTA per SM -- no register cap)
+__global__ void __launch_bounds__(kFusedThreads, NZG ? 1 : MGMC_FUSED_MINBLOCKS) fused_smooth_kernel(const __grid_constant__ FusedP P) {  // (NZG: small levels, at most one CTA per SM -- no register cap)
   extern __shared__ double sm[];
   __shared__ int lr_cnt[4];
   __shared__ __align__(16) double ntab[128];

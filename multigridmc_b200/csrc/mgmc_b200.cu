@@ -718,7 +718,10 @@ inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool mer
   if (ny > 256) return nc == 2 ? 16 : t[2];
   return t[3];
 }
-constexpr int kFusedSmemMax = 112 * 1024;  // 2 CTAs per SM: 2 x (112 + 1 KB reserved) <= 227 KB
+#ifndef MGMC_FUSED_SMEM_KB
+#define MGMC_FUSED_SMEM_KB 112  // 2 CTAs per SM: 2 x (112 + 1 KB reserved) <= 227 KB  (experiment: 224 with one 1024-thread CTA per SM)
+#endif
+constexpr int kFusedSmemMax = MGMC_FUSED_SMEM_KB * 1024;
 constexpr int kTailTileRowsMax = 40;
 constexpr int kTailSmemMax = 200 * 1024;  // the persistent kernel runs one CTA per SM
 
