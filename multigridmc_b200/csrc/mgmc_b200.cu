@@ -689,11 +689,11 @@ void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
 inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool merged, int nchains) {
   if (strips) return ny > 1024 ? 32 : (ny > 256 ? 16 : 8);  // strips must start on tile boundaries: powers of two only
   static const char *ov = std::getenv("MGMC_TILE_ROWS");    // perf experiments: "rb_big,4c_big,4c_mid,small,rb_big_prolong,rb_big_merged"
-  static int t[7] = {36, 46, 24, 8, 40, 40, 36};  // (... ,rb_big_merged,4c_1024)
+  static int t[8] = {36, 46, 24, 8, 40, 40, 36, 38};  // (... ,rb_big_merged,4c_1024,4c_big_restrict)
   static bool parsed = false;
   if (!parsed) {
     parsed = true;
-    if (ov) std::sscanf(ov, "%d,%d,%d,%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3], &t[4], &t[5], &t[6]);
+    if (ov) std::sscanf(ov, "%d,%d,%d,%d,%d,%d,%d,%d", &t[0], &t[1], &t[2], &t[3], &t[4], &t[5], &t[6], &t[7]);
   }
   // (merged level-0 launch, restrict_ and prolongation: 40 rows + the 13 halo rows of its 5 live passes + residual is
   //  the tallest tile that leaves two CTAs per SM; also on mid-size lattices -- the 16-row tiles of their two-sweep
@@ -712,7 +712,8 @@ inline int fused_tile_rows(int ny, int nc, bool strips, bool restrict_, bool mer
   // at whole rounds (plan_stages: a red-black launch with restriction updates TY + 7 / 5 / 3 rows, without TY + 4 / 2 / 0;
   // a 4-colour launch every other row of TY + 7 ... TY + 3).
   if (ny > 2048 && nc == 2) return restrict_ ? t[0] : t[4];
-  if (ny > 1024) return nc == 2 ? 32 : t[1];
+  // (a 2048 x 2048 4-colour level with restriction behind stages TY + 15 rows: 38 is the tallest tile that fits)
+  if (ny > 1024) return nc == 2 ? 32 : (restrict_ ? t[7] : t[1]);
   // (a 1024 x 1024 4-colour level in 36-row tiles is 290 tiles: one wave of 2 CTAs per SM instead of 1.45 with 24 rows)
   if (ny > 512) return nc == 2 ? 16 : t[6];
   if (ny > 256) return nc == 2 ? 16 : t[2];

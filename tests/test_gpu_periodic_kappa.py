@@ -172,3 +172,46 @@ def test_many_chains_and_large_lattice_properties(m):
         assert np.array_equal(single.get_state(), xb[ch]), ch
         single.close()
     assert rel(xb[0], xb[1]) > 1e-3
+
+
+def test_statistics_agree_with_reference_chain_periodic_and_global(oracle, m):
+    """North-star check (SURVEY.md section 8c procedure) on the operator family of the reference's own sampler tests
+    (test_sampler.hh:286: periodic correlation length) with point measurements AND the global measurement: the coloured /
+    Philox GPU chains and the reference's lexicographic / std::mt19937_64 chain (oracle in reference ordering and RNG call
+    order) sample the same law -- QoI mean, variance, integrated autocorrelation time within Monte-Carlo error bars -- and both
+    agree with the exact posterior mean / variance of the observation (linear_operator.hh:153-174, dense solve in the oracle)."""
+    n, nlevel, nchains, nsamples, nref = (32, 32), 3, 16, 3000, 12000
+    prior = oracle.Operator.prior(n, "shiftedlaplace_fd", Lambda_min=LMIN, Lambda_max=LMAX)
+    rng = np.random.default_rng(12)
+    locs, var, y = 0.15 + 0.7 * rng.random((5, 2)), 1.0 + rng.random(5), 1.0 + 3.0 * rng.random(6)
+    op = prior.measured(locs, var, variance_scaling=1e-2, measure_global=True, variance_global=1e-2)
+    assert op.m_lowrank == 6
+    xbar = op.mean(np.zeros(op.ndof), y)
+    f = op.apply(xbar)
+    b_obs = op.measurement_vector([0.4, 0.6], 0.0)
+    # reference chain on the CPU
+    H = oracle.Hierarchy(op, nlevel, oracle.LEX)
+    s = H.mgmc(rng=oracle.StdRng(5418513))
+    x, _ = s.run(f, np.zeros(op.ndof), b_obs, 200)
+    _, z_ref = s.run(f, x, b_obs, nref)
+    tau_ref = oracle.tau_int(z_ref, 20)
+    se_mean_ref = np.sqrt(z_ref.var(ddof=1) * max(tau_ref, 1.0) / nref)
+    se_var_ref = z_ref.var(ddof=1) * np.sqrt(2.0 * max(tau_ref, 1.0) / nref)
+    # GPU chains
+    ctx = m.Context(n[0], n[1], nlevel, B=op.B(), kappa_sq=m.periodic_kappa_sq(n[0], n[1], LMIN, LMAX), nchains=nchains, seed=777)
+    idx = np.nonzero(b_obs)[0]
+    ctx.set_qoi(idx, b_obs[idx])
+    ctx.set_rhs(np.tile(f, nchains))
+    ctx.set_state(np.zeros(op.ndof * nchains))
+    ctx.sample(200, series=False)
+    z = ctx.sample(nsamples)
+    means, variances = z.mean(axis=0), z.var(axis=0, ddof=1)
+    se_mean = means.std(ddof=1) / np.sqrt(nchains)
+    se_var = variances.std(ddof=1) / np.sqrt(nchains)
+    tau = np.array([oracle.tau_int(z[:, c], 20) for c in range(nchains)])
+    assert abs(means.mean() - z_ref.mean()) < 4 * np.hypot(se_mean, se_mean_ref)
+    assert abs(variances.mean() - z_ref.var(ddof=1)) < 4 * np.hypot(se_var, se_var_ref)
+    assert tau.mean() <= tau_ref + 3 * (tau.std(ddof=1) / np.sqrt(nchains) + 0.15)
+    assert tau.mean() < 2.0 and tau_ref < 2.0
+    # exact posterior mean of the observation: b^T xbar
+    assert abs(means.mean() - b_obs.dot(xbar)) < 4 * se_mean
