@@ -29,8 +29,13 @@ namespace mgmc {
 
 constexpr int kGX = 16;  // allocated doubles left of i = 0
 constexpr int kGY = 2;   // allocated rows below j = 0 / above j = ny
+// 256 threads (8 warps) per CTA, 2 CTAs per SM, up to 128 registers per thread, two rows of a warp per pass iteration
+// (MGMC_PASS_ILP 2): measured 1307 samples/s on C3 against 1267 with 512 threads / 64 registers / one row per iteration --
+// a warp runs twice as many rows per colour pass, so the per-pass set-up (rectangle geometry, generator constants) is
+// amortised over twice the work, and the two independent Philox / Box-Muller chains hide the fp64 latency that the
+// second half of the warps used to hide (profiles/r02_summary.md)
 #ifndef MGMC_FUSED_THREADS
-#define MGMC_FUSED_THREADS 512
+#define MGMC_FUSED_THREADS 256
 #endif
 #ifndef MGMC_LOAD_ROWS
 #define MGMC_LOAD_ROWS 2
@@ -39,7 +44,7 @@ constexpr int kGY = 2;   // allocated rows below j = 0 / above j = ny
 #define MGMC_PASS_PIPELINE 0
 #endif
 #ifndef MGMC_PASS_ILP
-#define MGMC_PASS_ILP 1
+#define MGMC_PASS_ILP 2
 #endif
 #ifndef MGMC_FUSED_MINBLOCKS
 #define MGMC_FUSED_MINBLOCKS 2  // CTAs per SM the tile kernel is compiled for (register cap); 1 with -DMGMC_FUSED_THREADS=1024

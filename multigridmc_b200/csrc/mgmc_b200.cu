@@ -1641,7 +1641,10 @@ void launch_tail_t(mgmc_ctx *c, const TailP &T, size_t smem) {
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(c->num_sms, 1, 1);  // one CTA per SM: the cooperative launch guarantees that all of them are resident
-  cfg.blockDim = dim3(kFusedThreads, 1, 1);
+  // (tile phases need the block size of the tile code; the coarse solve on its own takes the full kTailThreads)
+  bool tiles = false;
+  for (int k = 0; k < T.nphase; ++k) tiles = tiles || (T.ph[k].kind == TAIL_FUSED);
+  cfg.blockDim = dim3(tiles ? kFusedThreads : kTailThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = c->stream;
   cudaLaunchAttribute at[1];

@@ -98,6 +98,10 @@ inline bool coarse_phase_stage(int Np, int N, int ncta, int nchains, size_t smem
   return nchains > kCoarseBatch && coarse_phase_smem(Np, N, ncta, nchains, true) <= smem_max;
 }
 
+// Threads of a tail CTA.  The coarse phase (and the copy / zero phases) work with whatever the launch gives them; launches
+// that run tile phases (fused_tile) use kFusedThreads, the block size the tile code is written for.
+constexpr int kTailThreads = (kFusedThreads > 512) ? kFusedThreads : 512;
+
 template <bool GIBBS, int NB>
 __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz, bool with_noise, uint32_t c1, int nchains, double *sm, const double *ntab,
                                              long long *dbg = nullptr) {
@@ -112,7 +116,7 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
   const int ntask = (r1 - r0) * nseg;
   double *Mst = part + (size_t)2 * nbmax * rpc + 2;  // [row - r0][seg][Np] (C.stage)
   if (C.stage) {
-    for (int task = warp; task < ntask; task += kFusedWarps) {
+    for (int task = warp; task < ntask; task += (int)(blockDim.x >> 5)) {
       const int row = r0 + task / nseg, seg = task % nseg;
       const double *__restrict__ M = (seg ? C.TT : C.Ainv) + (long long)row * Np;
       double *dst = Mst + (size_t)task * Np;
@@ -122,16 +126,16 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
   }
   for (int ch0 = 0; ch0 < nchains; ch0 += NB) {
     const int nb = min(NB, nchains - ch0);
-    for (int idx = threadIdx.x; idx < nb * Np; idx += kFusedThreads) {
+    for (int idx = threadIdx.x; idx < nb * Np; idx += (int)blockDim.x) {
       const int b = idx / Np, e = idx - b * Np;
       fv[idx] = (e < C.N) ? C.f[(long long)(ch0 + b) * C.stride + (long long)(e / C.w + 1) * C.pitch + (e % C.w + 1)] : 0.0;
     }
     if (sample && C.xi_pre) {
-      for (int idx = threadIdx.x; idx < nb * Np; idx += kFusedThreads) xi[idx] = C.xi_pre[(size_t)ch0 * Np + idx];
+      for (int idx = threadIdx.x; idx < nb * Np; idx += (int)blockDim.x) xi[idx] = C.xi_pre[(size_t)ch0 * Np + idx];
     } else if (sample) {
       // xi_row: Philox counter 0x40000000 | row / 2 (philox.cuh), normal = (row & 1) ? z1 : z0
       const int hp = Np / 2;
-      for (int idx = threadIdx.x; idx < nb * hp; idx += kFusedThreads) {
+      for (int idx = threadIdx.x; idx < nb * hp; idx += (int)blockDim.x) {
         const int b = idx / hp, p = idx - b * hp;
         double z0 = 0.0, z1 = 0.0;
         if (2 * p < C.N) normal_pair(nz.keys, 0x40000000u | (uint32_t)p, c1, *nz.sample, nz.chain0 + ch0 + b, nz.mc, ntab, z0, z1);
@@ -143,7 +147,7 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
 #ifdef MGMC_TILE_TIMING
     if (dbg && threadIdx.x == 0) dbg[0] = gtimer();
 #endif
-    for (int task = warp; task < ntask; task += kFusedWarps) {
+    for (int task = warp; task < ntask; task += (int)(blockDim.x >> 5)) {
       const int row = r0 + task / nseg, seg = task % nseg;
       const double *__restrict__ M = C.stage ? (Mst + (size_t)task * Np) : ((seg ? C.TT : C.Ainv) + (long long)row * Np);
       const double *v = seg ? xi : fv;
@@ -180,7 +184,7 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
       }
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < (r1 - r0) * nb; idx += kFusedThreads) {
+    for (int idx = threadIdx.x; idx < (r1 - r0) * nb; idx += (int)blockDim.x) {
       const int r = idx / nb, b = idx - r * nb, row = r0 + r;
       const double v = part[(r * nseg) * nb + b] + (sample ? part[(r * nseg + 1) * nb + b] : 0.0);
       C.x[(long long)(ch0 + b) * C.stride + (long long)(row / C.w + 1) * C.pitch + (row % C.w + 1)] = v;
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(256) coarse_xi_kernel(NoiseP nz, uint32_t c1, 
 }
 
 template <bool GIBBS, bool LOWRANK>
-__global__ void __launch_bounds__(kFusedThreads, 1) tail_kernel(const __grid_constant__ TailP T) {
+__global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const __grid_constant__ TailP T) {
   extern __shared__ double sm[];
   __shared__ int lr_cnt[4];
   __shared__ __align__(16) double ntab[128];
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tail_kernel(const __grid_con
     const int rpc = (C.N + G - 1) / G;
     const int r0 = blockIdx.x * rpc, r1 = min(r0 + rpc, C.N);
     const int lines = (C.Np * 8 + 127) / 128;
-    for (int k = threadIdx.x; k < (r1 - r0) * lines * 2; k += kFusedThreads) {
+    for (int k = threadIdx.x; k < (r1 - r0) * lines * 2; k += (int)blockDim.x) {
       const int mat = k / ((r1 - r0) * lines), rem = k - mat * (r1 - r0) * lines;
       const int row = r0 + rem / lines, ln = rem % lines;
       if (mat == 1 && (ln + 1) * 16 <= (row & ~31)) continue;  // (zero part of the upper triangle)
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tail_kernel(const __grid_con
     if (ph.kind == TAIL_FUSED) {
       {
         const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&ph.P);
-        for (int k = threadIdx.x; k < (int)(sizeof(FusedP) / 8); k += kFusedThreads) Pbuf[k] = src[k];
+        for (int k = threadIdx.x; k < (int)(sizeof(FusedP) / 8); k += (int)blockDim.x) Pbuf[k] = src[k];
         __syncthreads();
       }
       // whole chains per wave: the owner / consumer exchange of the low-rank fix-ups needs every tile of a chain resident
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tail_kernel(const __grid_con
       // x_out = x_in (TAIL_COPY) or x_out = 0 (TAIL_ZERO) on the interior
       const GridP &g = ph.P.g;
       const long long nrow = (long long)(g.ny - 1) * T.nchains;
-      for (long long r = (long long)blockIdx.x * kFusedWarps + (threadIdx.x >> 5); r < nrow; r += (long long)G * kFusedWarps) {
+      for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrow; r += (long long)G * (blockDim.x >> 5)) {
         const long long o = (r / (g.ny - 1)) * g.stride + (r % (g.ny - 1) + 1) * g.pitch;
         for (int i = 1 + (threadIdx.x & 31); i < g.nx; i += 32) ph.P.x_out[o + i] = (ph.kind == TAIL_COPY) ? ph.P.x_in[o + i] : 0.0;
       }
