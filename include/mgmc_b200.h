@@ -37,8 +37,10 @@ enum { MGMC_VEC_X = 0, MGMC_VEC_F = 1, MGMC_VEC_R = 2 };
  * ConstantCorrelationLengthModelParameters, MultigridParameters (auxilliary/parameters.hh:94-277)
  * and the host-assembled low-rank part of MeasuredOperator (linear_operator/measured_operator.cc:9-49). */
 typedef struct {
-  int dim;                /* 2 (1 and 3 are reported as MGMC_ERR_UNSUPPORTED) */
-  int nx, ny, nz;         /* cells per direction */
+  int dim;                /* 2 (Lattice2d, lattice/lattice2d.hh) or 3 (Lattice3d, lattice/lattice3d.hh: shiftedlaplace_fd with a
+                           * constant correlation length and no measurements; host vectors in the reference's order
+                           * ell = (k-1)(nx-1)(ny-1) + (j-1)(nx-1) + (i-1), lattice3d.hh:122-135); 1 is MGMC_ERR_UNSUPPORTED */
+  int nx, ny, nz;         /* cells per direction (nz: dim = 3 only) */
   int pde_model;          /* MGMC_PDE_* */
   double Lambda;          /* constant correlation length: kappa^2 = 1/Lambda^2 */
   /* low-rank term B Sigma^{-1} B^T: B as COO triplets (row = lexicographic vertex index) */
@@ -83,12 +85,19 @@ void mgmc_destroy(mgmc_ctx *);
 
 /* level geometry: cells, unknowns, colours used by the sweeps (2: red-black, 4, 9) */
 int mgmc_level_info(const mgmc_ctx *, int level, int *nx, int *ny, int64_t *ndof, int *ncolours);
+/* cells in z of a level of a 3d hierarchy (Lattice3d::get_coarse_lattice, lattice3d.hh:242-257); 0 on 2d lattices.
+ * 3d levels sweep in 2 colours ((i + j + k) & 1, 7-point fine operator) or 8 ((i & 1) + 2 (j & 1) + 4 (k & 1), 27-point). */
+int mgmc_level_nz(const mgmc_ctx *, int level, int *nz);
 /* Galerkin stencil of a level: 9 position classes x 25 coefficients, class = cx + 3*cy with
  * cx,cy in {0: first interior line, 1: interior, 2: last interior line}; coefficient (di,dj) at
  * [(dj+2)*5 + (di+2)].  Lets tests compare against the oracle's R A R^T (linear_operator.cc:12-15). */
 int mgmc_get_stencil(const mgmc_ctx *, int level, double *out225);
 /* same algebra run on the host only (needs no CUDA device; desc->B_* may be empty) */
 int mgmc_host_stencil(const mgmc_desc *desc, int level, double *out225, int *ncolours);
+/* 3d twin: the uniform radius-1 stencil of `level` (7-point fine operator, shiftedlaplace_fd_operator.cc:33-56; 27-point
+ * Galerkin products R A R^T with the trilinear full weighting, linear_operator.cc:12-15), coefficient (di, dj, dk) at
+ * [(dk+1)*9 + (dj+1)*3 + (di+1)].  Host only. */
+int mgmc_host_stencil3(const mgmc_desc *desc, int level, double *out27, int *ncolours);
 /* Operators with per-vertex coefficients (desc->kappa_sq != NULL): the matrix of `level` as nine planes, entry
  * A[(i, j), (i + di, j + dj)] at out[((dj + 1) * 3 + (di + 1)) * (nx_l + 1) * (ny_l + 1) + j * (nx_l + 1) + i] with (i, j)
  * the Euclidean vertex index of that level (zero on the boundary).  Host only; lets the CPU tests compare with the

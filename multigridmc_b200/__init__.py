@@ -6,7 +6,7 @@ The reference-compatible C++ host layer lives in ``host/``.  There is no CPU fal
 works without a GPU, every compute call needs one.
 """
 from .capi import (Context, Desc, MgmcError, lib, build, host_stencil, strip_partition,  # noqa: F401
-                   host_coefficients, periodic_kappa_sq)
+                   host_coefficients, periodic_kappa_sq, host_stencil3, make_desc)
 
 __all__ = ["Context", "Desc", "MgmcError", "lib", "build", "host_stencil", "strip_partition",
-           "host_coefficients", "periodic_kappa_sq"]
+           "host_coefficients", "periodic_kappa_sq", "host_stencil3", "make_desc"]

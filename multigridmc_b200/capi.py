@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
 ]
 SOURCES = ["mgmc_b200.cu"]
-HEADERS = ["fused.cuh", "tail.cuh", "noise_ahead.cuh", "varcoef.cuh", "kernels.cuh", "philox.cuh", "normal_tables.inc", "setup.hh", "../../include/mgmc_b200.h"]
+HEADERS = ["fused.cuh", "tail.cuh", "noise_ahead.cuh", "varcoef.cuh", "lattice3d.cuh", "kernels.cuh", "philox.cuh", "normal_tables.inc", "setup.hh", "../../include/mgmc_b200.h"]
 
 
 def build(force=False, verbose=False):
@@ -72,6 +72,8 @@ def lib():
         "mgmc_create": (i, [C.POINTER(Desc), C.POINTER(vp)]),
         "mgmc_destroy": (None, [vp]),
         "mgmc_level_info": (i, [vp, i, ip, ip, C.POINTER(i64), ip]),
+        "mgmc_level_nz": (i, [vp, i, ip]),
+        "mgmc_host_stencil3": (i, [C.POINTER(Desc), i, c_dp, ip]),
         "mgmc_get_stencil": (i, [vp, i, c_dp]),
         "mgmc_host_stencil": (i, [C.POINTER(Desc), i, c_dp, ip]),
         "mgmc_host_coefficients": (i, [C.POINTER(Desc), i, c_dp, ip]),
@@ -120,7 +122,7 @@ EXPORTS = [
     "mgmc_loop_solve", "mgmc_set_philox_position", "mgmc_set_rhs", "mgmc_set_state", "mgmc_get_state", "mgmc_set_qoi",
     "mgmc_sample", "mgmc_sample_moments", "mgmc_sample_timed", "mgmc_launch_count", "mgmc_profile_cycle",
     "mgmc_cycle_model", "mgmc_strip_partition", "mgmc_strip_handle_bytes", "mgmc_strip_export", "mgmc_strip_connect",
-    "mgmc_strip_error", "mgmc_plan_passes", "mgmc_tail_stamps", "mgmc_host_coefficients",
+    "mgmc_strip_error", "mgmc_plan_passes", "mgmc_tail_stamps", "mgmc_host_coefficients", "mgmc_level_nz", "mgmc_host_stencil3",
 ]
 
 
@@ -142,12 +144,13 @@ FORWARD, BACKWARD = 1, 2
 
 def make_desc(nx, ny, nlevel, pde="shiftedlaplace_fd", Lambda=0.2, B=None, smoother="SSOR", coarse_solver="Cholesky",
               npresmooth=1, npostsmooth=1, ncoarsesmooth=1, cycle=1, coarse_scaling=1.0, omega=1.0, seed=5418513,
-              device=0, nchains=1, first_chain=0, strip_rank=0, strip_nranks=0, kappa_sq=None):
+              device=0, nchains=1, first_chain=0, strip_rank=0, strip_nranks=0, kappa_sq=None, nz=None):
     """B = (rows, cols, vals, sigma) COO triplets of the measurement matrix (lexicographic rows).
     kappa_sq = kappa^2 at every interior vertex (lexicographic, (nx-1)*(ny-1) values) for a correlation length
-    that varies in space (`periodic_kappa_sq`); None: constant, 1 / Lambda^2."""
+    that varies in space (`periodic_kappa_sq`); None: constant, 1 / Lambda^2.
+    nz = cells in z of a 3d lattice (Lattice3d; host vectors lexicographic with x fastest, z slowest); None: 2d."""
     d = Desc()
-    d.dim, d.nx, d.ny, d.nz = 2, nx, ny, 1
+    d.dim, d.nx, d.ny, d.nz = (2, nx, ny, 1) if nz is None else (3, nx, ny, nz)
     d.pde_model, d.Lambda = PDE[pde], Lambda
     keep = []
     if kappa_sq is not None:
@@ -212,6 +215,14 @@ def host_coefficients(desc, level):
     out = np.zeros((9, ny + 1, nx + 1))
     nc = C.c_int()
     _chk(lib().mgmc_host_coefficients(C.byref(desc), level, out.ctypes.data_as(c_dp), C.byref(nc)))
+    return out, nc.value
+
+
+def host_stencil3(desc, level):
+    """Uniform radius-1 stencil of `level` of a 3d hierarchy as a (3, 3, 3) array [dk + 1, dj + 1, di + 1], host-only."""
+    out = np.zeros((3, 3, 3))
+    nc = C.c_int()
+    _chk(lib().mgmc_host_stencil3(C.byref(desc), level, out.ctypes.data_as(c_dp), C.byref(nc)))
     return out, nc.value
 
 

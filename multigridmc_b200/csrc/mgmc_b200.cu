@@ -18,6 +18,8 @@
 #include "tail.cuh"
 #include "noise_ahead.cuh"
 #include "varcoef.cuh"
+#include "lattice3d.cuh"
+#include <climits>
 
 #include <set>
 
@@ -73,7 +75,11 @@ struct DevLevel {
   bool vc = false;             // per-vertex coefficients (variable kappa): generic kernels of varcoef.cuh, 2 / 4 colours
   VarCoef dvc{nullptr, 0, 0, 0, 0, 0};  // coefficient planes in the layout of the level vectors
   bool vc_full = false;        // ... all nine planes (the Galerkin operators); false: the 5-point fine operator, diagonal plane only
-  bool generic() const { return r2 || vc; }  // colour-by-colour launches instead of the fused tile kernel
+  bool d3 = false;             // 3d lattice: planes stacked in the row direction (lattice3d.cuh), generic kernels, 2 / 8 colours
+  Grid3 q{0, 0};
+  Coef27 c27;
+  bool full27 = false;         // 27-point (Galerkin) operator; false: the 7-point fine operator
+  bool generic() const { return r2 || vc || d3; }  // colour-by-colour launches instead of the fused tile kernel
   DevSparse B;
   bool lr_wide = false;        // some column of B has more entries than the padded low-rank kernels stage (kernels.cuh "Wide supports")
   std::map<double, LowRankDev> lowrank;  // keyed by omega
@@ -354,8 +360,8 @@ StripPlan make_strip_plan(const mgmc_desc &d, const std::vector<HostLevel> &H) {
 }
 
 std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
-  if (d.dim != 2) fail(MGMC_ERR_UNSUPPORTED, "only dim = 2 lattices are implemented on the device path");
-  if (d.nx < 2 || d.ny < 2) fail(MGMC_ERR_INVALID, "invalid lattice size");
+  if (d.dim != 2 && d.dim != 3) fail(MGMC_ERR_UNSUPPORTED, "only dim = 2 and dim = 3 lattices are implemented on the device path");
+  if (d.nx < 2 || d.ny < 2 || (d.dim == 3 && d.nz < 2)) fail(MGMC_ERR_INVALID, "invalid lattice size");
   if (d.nlevel < 1) fail(MGMC_ERR_INVALID, "nlevel must be >= 1");
   if (d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FD && d.pde_model != MGMC_PDE_SQUARED_SHIFTEDLAPLACE_FD) fail(MGMC_ERR_INVALID, "invalid pde_model");
   if (!(d.Lambda > 0.0)) fail(MGMC_ERR_INVALID, "Lambda must be positive");
@@ -365,6 +371,40 @@ std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
   // coarse-sampler / low-rank streams (philox.cuh): the site counters must stay below 2^30
   if (2ll * ((long long)d.ny + 1) * ((long long)d.nx / 4 + 1) >= (1ll << 30)) fail(MGMC_ERR_UNSUPPORTED, "lattice too large for the 32-bit site counter of the noise streams (about 46000 x 46000)");
   std::vector<HostLevel> L(d.nlevel);
+  if (d.dim == 3) {
+    // Lattice3d (lattice/lattice3d.hh): shiftedlaplace_fd with a constant correlation length, no measurements yet
+    if (d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FD) fail(MGMC_ERR_UNSUPPORTED, "3d lattices are implemented for shiftedlaplace_fd only");
+    if (d.kappa_sq) fail(MGMC_ERR_UNSUPPORTED, "3d lattices: a variable correlation length is not implemented");
+    if (d.m_lowrank > 0 || d.B_nnz > 0) fail(MGMC_ERR_UNSUPPORTED, "3d lattices: the low-rank (measurement) term is not implemented");
+    if (std::max(d.strip_nranks, 1) > 1) fail(MGMC_ERR_UNSUPPORTED, "3d lattices: row strips are not implemented");
+    if (d.nz >= (1 << 20)) fail(MGMC_ERR_INVALID, "lattice too large");
+    // (the stacked planes are the y dimension of the launch grids: 4 rows per CTA, at most 65535 CTAs)
+    if (((long long)d.nz + 1) * ((long long)d.ny + 1) > 4ll * 65535) fail(MGMC_ERR_UNSUPPORTED, "3d lattice too large for the launch geometry of the first 3d path ((ny + 1)(nz + 1) <= 262140)");
+    if (2ll * ((long long)d.nz + 1) * ((long long)d.ny + 1) * ((long long)d.nx / 4 + 1) >= (1ll << 30)) fail(MGMC_ERR_UNSUPPORTED, "lattice too large for the 32-bit site counter of the noise streams");
+    for (int l = 0; l < d.nlevel; ++l) {
+      HostLevel &h = L[l];
+      std::memset(h.st.a, 0, sizeof(h.st.a));
+      if (l == 0) {
+        h.nx = d.nx;
+        h.ny = d.ny;
+        h.nz = d.nz;
+        fine_stencil3(d.nx, d.ny, d.nz, d.Lambda, h.st3);
+      } else {
+        const HostLevel &f = L[l - 1];
+        // Lattice3d::get_coarse_lattice (lattice3d.hh:242-257)
+        if ((f.nx % 2) || (f.ny % 2) || (f.nz % 2)) fail(MGMC_ERR_INVALID, "cannot coarsen lattice of size " + std::to_string(f.nx) + " x " + std::to_string(f.ny) + " x " + std::to_string(f.nz) + " [one of the extents is odd]");
+        if (!(f.nx / 2 > 1 && f.ny / 2 > 1 && f.nz / 2 > 1)) fail(MGMC_ERR_INVALID, "cannot coarsen lattice [resulting lattice would have no interior vertices]");
+        h.nx = f.nx / 2;
+        h.ny = f.ny / 2;
+        h.nz = f.nz / 2;
+        coarsen_stencil3(f.st3, h.st3);
+      }
+      h.st.radius = 1;
+      h.st.uniform = true;
+      h.st.ncolours = colours_stencil3(h.st3);
+    }
+    return L;
+  }
   L[0].nx = d.nx;
   L[0].ny = d.ny;
   L[0].st = fine_stencil(d.pde_model, d.nx, d.ny, d.Lambda);
@@ -585,6 +625,14 @@ const LowRankDev &get_lowrank(mgmc_ctx *c, int level, double omega) {
 // ---------------------------------------------------------------------------------------------
 void upload_vec(mgmc_ctx *c, int level, double *dev, const double *host) {
   const DevLevel &L = c->lv[level];
+  if (L.d3) {  // plane by plane (lexicographic: lattice3d.hh:122-135)
+    const size_t w = L.g.nx - 1, h = L.q.ny - 1, d = L.q.nz - 1;
+    for (int ch = 0; ch < c->d.nchains; ++ch)
+      for (size_t k = 1; k <= d; ++k)
+        CUDA_CHECK(cudaMemcpy2DAsync(dev + (size_t)ch * L.g.stride + (k * (L.q.ny + 1) + 1) * L.g.pitch + 1, L.g.pitch * sizeof(double),
+                                     host + ((size_t)ch * d + (k - 1)) * w * h, w * sizeof(double), w * sizeof(double), h, cudaMemcpyHostToDevice, c->stream));
+    return;
+  }
   const size_t w = L.g.nx - 1, h = L.g.ny - 1;
   for (int ch = 0; ch < c->d.nchains; ++ch)
     CUDA_CHECK(cudaMemcpy2DAsync(dev + (size_t)ch * L.g.stride + L.g.pitch + 1, L.g.pitch * sizeof(double), host + (size_t)ch * w * h, w * sizeof(double),
@@ -592,6 +640,15 @@ void upload_vec(mgmc_ctx *c, int level, double *dev, const double *host) {
 }
 void download_vec(mgmc_ctx *c, int level, const double *dev, double *host) {
   const DevLevel &L = c->lv[level];
+  if (L.d3) {
+    const size_t w = L.g.nx - 1, h = L.q.ny - 1, d = L.q.nz - 1;
+    for (int ch = 0; ch < c->d.nchains; ++ch)
+      for (size_t k = 1; k <= d; ++k)
+        CUDA_CHECK(cudaMemcpy2DAsync(host + ((size_t)ch * d + (k - 1)) * w * h, w * sizeof(double),
+                                     dev + (size_t)ch * L.g.stride + (k * (L.q.ny + 1) + 1) * L.g.pitch + 1, L.g.pitch * sizeof(double), w * sizeof(double), h,
+                                     cudaMemcpyDeviceToHost, c->stream));
+    return;
+  }
   const size_t w = L.g.nx - 1, h = L.g.ny - 1;
   for (int ch = 0; ch < c->d.nchains; ++ch)
     CUDA_CHECK(cudaMemcpy2DAsync(host + (size_t)ch * w * h, w * sizeof(double), dev + (size_t)ch * L.g.stride + L.g.pitch + 1, L.g.pitch * sizeof(double),
@@ -669,7 +726,9 @@ void dev_lowrank_wide_apply(mgmc_ctx *c, int level, const double *x, const Spars
 void dev_apply(mgmc_ctx *c, int level, const double *x, double *y) {
   const DevLevel &L = c->lv[level];
   c->launch("apply", level, [&] {
-    if (L.r2) apply25_kernel<false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.d_st, x, nullptr, y, RowRange{1, L.g.ny - 1});
+    if (L.d3 && L.full27) apply27_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.q, L.c27, x, nullptr, y);
+    else if (L.d3) apply27_kernel<false, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.q, L.c27, x, nullptr, y);
+    else if (L.r2) apply25_kernel<false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.d_st, x, nullptr, y, RowRange{1, L.g.ny - 1});
     else if (L.vc && L.vc_full) apply9v_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.dvc, x, nullptr, y);
     else if (L.vc) apply9v_kernel<false, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.dvc, x, nullptr, y);
     else if (L.nine) apply_kernel<true, false><<<grid_sites(L.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.coef, x, nullptr, y);
@@ -1382,7 +1441,7 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
   if (strip_level && lowrank) fail(MGMC_ERR_UNSUPPORTED, "row strips of a radius-2 operator with a low-rank term are not implemented");
   if (strip_level && L.vc) fail(MGMC_ERR_UNSUPPORTED, "row strips of an operator with per-vertex coefficients are not implemented");
   const int ncol = L.h.st.ncolours;  // 9: radius 2; 2 / 4: per-vertex coefficients (varcoef.cuh)
-  const double n = (double)(hi - lo + 1) * (L.g.nx - 1) * nch;
+  const double n = L.d3 ? (double)L.h.ndof() * nch : (double)(hi - lo + 1) * (L.g.nx - 1) * nch;
   auto rows_grid = [&](int j0, int j1) { return dim3((L.g.nx - 1 + 63) / 64, (std::max(j1 - j0 + 1, 1) + 3) / 4, nch); };
   int *ctl = c->d_strip_ctl;
   auto strip_sync = [&] {  // wait until the neighbours have finished every distributed launch emitted so far
@@ -1394,7 +1453,10 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
     DevLevel &C = c->lv[level + 1];
     const RowRange rr{std::max(1, lo - (has_dn ? halo : 0)), std::min(L.g.ny - 1, hi + (has_up ? halo : 0))};
     strip_sync();
-    c->launch("prolongate_add", level, [&] { prolongate_add_kernel<<<rows_grid(rr.j0, rr.j1), kBlockSites, 0, c->stream>>>(L.g, C.g, alpha, C.x, L.x, rr); }, 18.0 * n);
+    c->launch("prolongate_add", level, [&] {
+      if (L.d3) prolongate_add27_kernel<<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.q, C.g, C.q, alpha, C.x, L.x);
+      else prolongate_add_kernel<<<rows_grid(rr.j0, rr.j1), kBlockSites, 0, c->stream>>>(L.g, C.g, alpha, C.x, L.x, rr);
+    }, (L.d3 ? 17.0 : 18.0) * n);
     if (strip_level) {  // counts as a distributed launch: the neighbours' next colour launch waits for it
       c->strip_index++;
       c->launch("strip_raise", level, [&] {
@@ -1416,6 +1478,20 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
       // omega = 1: an update does not read the site's own value, so the last colour of this sweep is dead if the next
       // sweep starts with the same colour and nothing reads x in between (see plan_stages for the tile kernel)
       if (cc == ncol - 1 && omega == 1.0 && !noskip && si + 1 < sweeps.size() && sweeps[si + 1].fwd != sw.fwd && !(lowrank && sw.fix_after)) continue;
+      if (L.d3) {
+        // 3d lattice: red-black (7-point) or 8 colours (27-point), whole lattice, rows = stacked planes (lattice3d.cuh)
+        dim3 grid3((L.g.nx / 2 + 1 + 63) / 64, (L.g.ny - 1 + 3) / 4, nch);
+        c->launch(gibbs ? (L.full27 ? "gibbs_8c1" : "gibbs_rb1/3d") : (L.full27 ? "sor_8c1" : "sor_rb1/3d"), level, [&] {
+          if (L.full27) {
+            if (gibbs) sweep_colour27_kernel<true, true><<<grid3, kBlockSites, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, colour, omega, nz);
+            else sweep_colour27_kernel<true, false><<<grid3, kBlockSites, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, colour, omega, nz);
+          } else {
+            if (gibbs) sweep_colour27_kernel<false, true><<<grid3, kBlockSites, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, colour, omega, nz);
+            else sweep_colour27_kernel<false, false><<<grid3, kBlockSites, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, colour, omega, nz);
+          }
+        }, 24.0 * n / ncol);
+        continue;
+      }
       if (L.vc) {
         // per-vertex coefficients: red-black (every row) or 4 colours (every other row), whole lattice
         const bool four = (ncol == 4);
@@ -1485,7 +1561,9 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
     const RowRange rr{lo, std::min(L.g.ny - 1, hi + (has_up ? 1 : 0))};
     strip_sync();
     c->launch("residual", level, [&] {
-      if (L.vc && L.vc_full) apply9v_kernel<true, true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, L.r);
+      if (L.d3 && L.full27) apply27_kernel<true, true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, L.r);
+      else if (L.d3) apply27_kernel<false, true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, L.r);
+      else if (L.vc && L.vc_full) apply9v_kernel<true, true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, L.r);
       else if (L.vc) apply9v_kernel<false, true><<<grid_sites(L.g, nch), kBlockSites, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, L.r);
       else apply25_kernel<true><<<rows_grid(rr.j0, rr.j1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, L.r, rr);
     }, 16.0 * n);
@@ -1521,7 +1599,8 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
 void dev_restrict_plain(mgmc_ctx *c, int level, const double *r, double *fc) {
   const DevLevel &L = c->lv[level], &C = c->lv[level + 1];
   c->launch("restrict", level, [&] {
-    restrict_kernel<<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, r, fc, RowRange{1, C.g.ny - 1});
+    if (L.d3) restrict27_kernel<<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, L.q, C.g, C.q, r, fc);
+    else restrict_kernel<<<grid_sites(C.g, c->d.nchains), kBlockSites, 0, c->stream>>>(L.g, C.g, r, fc, RowRange{1, C.g.ny - 1});
   });
 }
 
@@ -1683,6 +1762,8 @@ void tail_flush(mgmc_ctx *c, bool gibbs, int level) {
       T.coarse.N = c->Nc;
       T.coarse.Np = c->Ncp;
       T.coarse.w = LC.g.nx - 1;
+      T.coarse.h = LC.h.d3() ? LC.h.ny - 1 : INT_MAX;
+      T.coarse.prow = LC.h.d3() ? LC.h.ny + 1 : 0;
       T.coarse.pitch = LC.g.pitch;
       T.coarse.stride = LC.g.stride;
       T.coarse.f = LC.f;
@@ -2362,8 +2443,16 @@ int mgmc_create(const mgmc_desc *desc, mgmc_ctx **out) {
       L.h = H[l];
       L.g.nx = L.h.nx;
       L.g.ny = L.h.ny;
+      if (L.h.d3()) {
+        // planes k = 0 .. nz stacked in the row direction: the last row (k = nz, j = ny) is a boundary row, like row 0
+        L.d3 = true;
+        L.q = Grid3{L.h.ny, L.h.nz};
+        L.g.ny = (L.h.nz + 1) * (L.h.ny + 1) - 1;
+        std::memcpy(L.c27.a, L.h.st3, sizeof(L.c27.a));
+        L.full27 = (L.h.st.ncolours == 8);
+      }
       L.g.pitch = ((GX + L.h.nx + 1 + 2 + 15) / 16) * 16;
-      const size_t rows = (size_t)L.h.ny + 1 + 2 * GY;
+      const size_t rows = (size_t)L.g.ny + 1 + 2 * GY;
       L.g.stride = (long long)rows * L.g.pitch;
       const size_t total = (size_t)L.g.stride * desc->nchains;
       const size_t origin = (size_t)GY * L.g.pitch + GX;
@@ -2474,9 +2563,28 @@ int mgmc_level_info(const mgmc_ctx *c, int level, int *nx, int *ny, int64_t *ndo
   API_END
 }
 
+int mgmc_level_nz(const mgmc_ctx *c, int level, int *nz) {
+  API_BEGIN
+  check_level(c, level);
+  if (nz) *nz = c->lv[level].h.nz;
+  API_END
+}
+
+int mgmc_host_stencil3(const mgmc_desc *desc, int level, double *out27, int *ncolours) {
+  API_BEGIN
+  if (!desc || !out27) fail(MGMC_ERR_INVALID, "null argument");
+  if (desc->dim != 3) fail(MGMC_ERR_INVALID, "mgmc_host_stencil3 needs a 3d lattice (2d: mgmc_host_stencil)");
+  std::vector<HostLevel> H = build_host_levels(*desc);
+  if (level < 0 || level >= (int)H.size()) fail(MGMC_ERR_INVALID, "level out of range");
+  std::memcpy(out27, H[level].st3, sizeof(double) * 27);
+  if (ncolours) *ncolours = H[level].st.ncolours;
+  API_END
+}
+
 int mgmc_get_stencil(const mgmc_ctx *c, int level, double *out225) {
   API_BEGIN
   check_level(c, level);
+  if (c->lv[level].d3) fail(MGMC_ERR_INVALID, "mgmc_get_stencil: 2d lattices only (3d: mgmc_host_stencil3)");
   std::memcpy(out225, c->lv[level].h.st.a, sizeof(double) * 225);
   API_END
 }
@@ -2485,6 +2593,7 @@ int mgmc_get_stencil(const mgmc_ctx *c, int level, double *out225) {
  * CPU test-suite to check the Galerkin stencils against the oracle's sparse triple product) */
 int mgmc_host_stencil(const mgmc_desc *desc, int level, double *out225, int *ncolours) {
   API_BEGIN
+  if (desc && desc->dim == 3) fail(MGMC_ERR_INVALID, "mgmc_host_stencil: 2d lattices only (3d: mgmc_host_stencil3)");
   std::vector<HostLevel> H = build_host_levels(*desc);
   if (level < 0 || level >= (int)H.size()) fail(MGMC_ERR_INVALID, "level out of range");
   std::memcpy(out225, H[level].st.a, sizeof(double) * 225);
@@ -2683,7 +2792,9 @@ int mgmc_loop_solve(mgmc_ctx *c, const double *b, double *x, double rtol, double
   // r = A x - b (into f_ell[0], the preconditioner's input), ||r|| into the device-side history + convergence test
   auto emit_residual = [&] {
     c->launch("residual_norm", 0, [&] {
-      if (L.r2) residual_norm25_kernel<<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, c->sol_x, c->sol_b, L.f, c->d_partial);
+      if (L.d3 && L.full27) residual_norm27_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.q, L.c27, c->sol_x, c->sol_b, L.f, c->d_partial);
+      else if (L.d3) residual_norm27_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.q, L.c27, c->sol_x, c->sol_b, L.f, c->d_partial);
+      else if (L.r2) residual_norm25_kernel<<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.d_st, c->sol_x, c->sol_b, L.f, c->d_partial);
       else if (L.vc && L.vc_full) residual_norm9v_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.dvc, c->sol_x, c->sol_b, L.f, c->d_partial);
       else if (L.vc) residual_norm9v_kernel<false><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.dvc, c->sol_x, c->sol_b, L.f, c->d_partial);
       else if (L.nine) residual_norm_kernel<true><<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.coef, c->sol_x, c->sol_b, L.f, c->d_partial);
@@ -2809,7 +2920,11 @@ int mgmc_set_qoi(mgmc_ctx *c, int64_t nnz, const int64_t *idx, const double *val
   std::vector<double> v(val, val + nnz);
   for (int64_t e = 0; e < nnz; ++e) {
     if (idx[e] < 0 || idx[e] >= L.h.ndof()) fail(MGMC_ERR_INVALID, "QoI index out of range");
-    const int j = (int)(idx[e] / w) + 1;
+    int j = (int)(idx[e] / w) + 1;
+    if (L.d3) {  // lexicographic 3d index (lattice3d.hh:122-135) -> row of the stacked planes
+      const int r = (int)(idx[e] / w), h = L.q.ny - 1;
+      j = (r / h + 1) * (L.q.ny + 1) + (r % h) + 1;
+    }
     site[e] = (long long)j * L.g.pitch + (idx[e] % w + 1);
     // row strips: every rank sums the entries it owns; the caller adds the partial series of all ranks
     if (c->strip.on() && (j < c->strip.lo[0] || j > c->strip.hi[0])) v[e] = 0.0;
@@ -2882,7 +2997,11 @@ int mgmc_sample_moments(mgmc_ctx *c, int64_t nsamples, double *mean_field, doubl
     run_cycles(c, 1);
     c->launch("moments", 0, [&] { moments_kernel<<<grid_sites(L.g, 1), kBlockSites, 0, c->stream>>>(L.g, L.x, c->d_mean, c->d_second, 1.0 / (k + 1.0)); });
   }
-  {
+  if (L.d3) {
+    if (c->d.nchains != 1) fail(MGMC_ERR_UNSUPPORTED, "3d lattices: moment fields need nchains = 1");
+    download_vec(c, 0, c->d_mean, mean_field);
+    download_vec(c, 0, c->d_second, second_moment_field);
+  } else {
     const size_t w = L.g.nx - 1, h = L.g.ny - 1;
     CUDA_CHECK(cudaMemcpy2DAsync(mean_field, w * sizeof(double), c->d_mean + L.g.pitch + 1, L.g.pitch * sizeof(double), w * sizeof(double), h,
                                  cudaMemcpyDeviceToHost, c->stream));
@@ -3046,7 +3165,7 @@ int mgmc_cycle_model(const mgmc_ctx *c, double *bytes, double *site_updates) {
     if (l > 0) visits *= d.cycle;  // multigridmc_sampler.cc:112
     const double n = (double)c->lv[l].h.ndof();
     const double sweeps = per_smooth * (d.npresmooth + d.npostsmooth);
-    B += visits * n * (24.0 * sweeps + 38.0);
+    B += visits * n * (24.0 * sweeps + (c->lv[l].d3 ? 35.0 : 38.0));  // (3d: the coarse lattice has 1/8 of the sites)
     U += visits * n * sweeps;
   }
   const double nc = (double)c->lv[d.nlevel - 1].h.ndof();

@@ -146,6 +146,61 @@ inline StencilSet coarsen_stencil(const StencilSet &f, int nxf, int nyf) {
   return c;
 }
 
+// ---- 3d lattices (Lattice3d, lattice/lattice3d.hh:43-270): shiftedlaplace_fd with a constant correlation length ----
+// 7-point fine operator (shiftedlaplace_fd_operator.cc:33-56 with dim = 3: diagonal h^3 kappa^2 + sum_d 2 h^3 / h_d^2 accumulated
+// in the reference's order, off-diagonals -h^3 / h_d^2).  Entries that point to a boundary vertex multiply the zero
+// boundary planes of the device layout, so one stencil serves every vertex.
+inline void fine_stencil3(int nx, int ny, int nz, double Lambda, double *a27) {
+  std::memset(a27, 0, sizeof(double) * 27);
+  const int n[3] = {nx, ny, nz};
+  double hinv2[3], vol = 1.0;
+  for (int d = 0; d < 3; ++d) {
+    const double h = 1. / double(n[d]);
+    hinv2[d] = 1. / (h * h);
+    vol *= h;
+  }
+  double diagonal = vol * (1.0 / std::pow(Lambda, 2));
+  const int step[3] = {1, 3, 9};
+  for (int d = 0; d < 3; ++d) {
+    a27[13 - step[d]] = a27[13 + step[d]] = -vol * hinv2[d];
+    diagonal += 2. * vol * hinv2[d];
+  }
+  a27[13] = diagonal;
+}
+
+// Galerkin product R A R^T (linear_operator.cc:12-15) of a uniform radius-1 stencil with the trilinear full weighting
+// {1/2, 1, 1/2}^(x)3 (intergrid_operator_linear.cc:8-30): again a uniform radius-1 (27-point) stencil,
+//   A_c(D) = sum_{p, q in {-1,0,1}^3} w(p) w(q) a(2 D + q - p)
+// (every fine vertex 2 I + p of an interior coarse vertex I is interior, so no position classes arise).
+inline void coarsen_stencil3(const double *f27, double *c27) {
+  const double w1[3] = {0.5, 1.0, 0.5};
+  for (int Dz = -1; Dz <= 1; ++Dz)
+    for (int Dy = -1; Dy <= 1; ++Dy)
+      for (int Dx = -1; Dx <= 1; ++Dx) {
+        double acc = 0.0;
+        for (int pz = -1; pz <= 1; ++pz)
+          for (int py = -1; py <= 1; ++py)
+            for (int px = -1; px <= 1; ++px)
+              for (int qz = -1; qz <= 1; ++qz)
+                for (int qy = -1; qy <= 1; ++qy)
+                  for (int qx = -1; qx <= 1; ++qx) {
+                    const int ox = 2 * Dx + qx - px, oy = 2 * Dy + qy - py, oz = 2 * Dz + qz - pz;
+                    if (std::abs(ox) > 1 || std::abs(oy) > 1 || std::abs(oz) > 1) continue;
+                    acc += w1[px + 1] * w1[py + 1] * w1[pz + 1] * w1[qx + 1] * w1[qy + 1] * w1[qz + 1] * f27[(oz + 1) * 9 + (oy + 1) * 3 + (ox + 1)];
+                  }
+        c27[(Dz + 1) * 9 + (Dy + 1) * 3 + (Dx + 1)] = acc;
+      }
+}
+
+// colours of a 3d radius-1 stencil: 2 (7-point: (i + j + k) & 1) or 8 ((i & 1) + 2 (j & 1) + 4 (k & 1))
+inline int colours_stencil3(const double *a27) {
+  for (int dk = -1; dk <= 1; ++dk)
+    for (int dj = -1; dj <= 1; ++dj)
+      for (int di = -1; di <= 1; ++di)
+        if (std::abs(di) + std::abs(dj) + std::abs(dk) > 1 && a27[(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)] != 0.0) return 8;
+  return 2;
+}
+
 // one entry of the sparse n x m matrix B (or W): Euclidean vertex (i, j), column, value
 struct SEntry {
   int i, j, col;
@@ -178,6 +233,9 @@ inline int site_colour(int nc, int i, int j) {
 
 struct HostLevel {
   int nx = 0, ny = 0;
+  int nz = 0;             // > 0: 3d lattice (Lattice3d, lattice/lattice3d.hh); the operator is st3, `st` only carries radius / ncolours
+  double st3[27] = {0};   // 3d: uniform radius-1 stencil, entry (di, dj, dk) at [(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)]
+  bool d3() const { return nz > 0; }
   StencilSet st;
   std::vector<SEntry> B;  // sorted by column
   // Variable coefficients (a correlation length that depends on x: PeriodicCorrelationLengthModel,
@@ -186,7 +244,7 @@ struct HostLevel {
   // boundary vertex are zero (the reference's matrices hold interior vertices only).  Empty: `st` is the operator.
   std::vector<double> vc;
   bool varcoef() const { return !vc.empty(); }
-  long long ndof() const { return (long long)(nx - 1) * (ny - 1); }
+  long long ndof() const { return (long long)(nx - 1) * (ny - 1) * (nz > 0 ? nz - 1 : 1); }
   // matrix entry A[(i, j), (i + di, j + dj)] of an interior vertex (i, j)
   double coef(int i, int j, int di, int dj) const {
     if (vc.empty()) return st.at(pos_class(i, nx) + 3 * pos_class(j, ny), di, dj);
@@ -437,12 +495,28 @@ struct CoarseFactor {
 inline CoarseFactor coarse_factor(const HostLevel &Lv, const std::vector<double> &Sigma) {
   CoarseFactor cf;
   const int w = Lv.nx - 1, h = Lv.ny - 1;
-  const int N = w * h, Np = ((N + 31) / 32) * 32;
+  const int N = (int)Lv.ndof(), Np = ((N + 31) / 32) * 32;
   cf.N = N;
   cf.Np = Np;
   std::vector<double> &A = cf.L;
   A.assign((size_t)Np * Np, 0.0);
-  for (int j = 1; j <= h; ++j)
+  if (Lv.d3()) {
+    const int d = Lv.nz - 1;
+    for (int k = 1; k <= d; ++k)
+      for (int j = 1; j <= h; ++j)
+        for (int i = 1; i <= w; ++i) {
+          const int row = ((k - 1) * h + (j - 1)) * w + (i - 1);
+          for (int dk = -1; dk <= 1; ++dk)
+            for (int dj = -1; dj <= 1; ++dj)
+              for (int di = -1; di <= 1; ++di) {
+                const int ii = i + di, jj = j + dj, kk = k + dk;
+                if (ii < 1 || ii > w || jj < 1 || jj > h || kk < 1 || kk > d) continue;
+                const double v = Lv.st3[(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)];
+                if (v != 0.0) A[(size_t)row * Np + ((kk - 1) * h + (jj - 1)) * w + (ii - 1)] = v;
+              }
+        }
+  }
+  for (int j = 1; j <= h && !Lv.d3(); ++j)
     for (int i = 1; i <= w; ++i) {
       const int row = (j - 1) * w + (i - 1);
       for (int dj = -2; dj <= 2; ++dj)

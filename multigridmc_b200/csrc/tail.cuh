@@ -28,6 +28,7 @@ struct CoarseP {
   const double *TT;    // L^{-T}, Np x Np row-major (upper triangular)
   int N, Np, w;        // unknowns, padded row length, interior vertices per lattice row
   int pitch;
+  int h, prow;         // 3d lattices (planes stacked in the row direction): interior rows per plane, rows between planes; 2d: INT_MAX, 0
   long long stride;
   const double *f;  // padded lattice layout
   double *x;
@@ -35,6 +36,12 @@ struct CoarseP {
   const double *xi_pre;  // ensembles: the normals of all chains, generated once by coarse_xi_kernel ([chain][Np]); nullptr:
                          // every CTA generates the normals of the chains of a batch itself (one chain: cheaper than a launch)
 };
+
+// padded-layout offset of unknown e of the coarsest level (lexicographic: lattice2d.hh:96-103, lattice3d.hh:122-135)
+__device__ __forceinline__ long long coarse_site(const CoarseP &C, int e) {
+  const int r = e / C.w;
+  return (long long)((r / C.h) * C.prow + (r % C.h) + 1 + C.prow) * C.pitch + (e % C.w + 1);
+}
 
 struct TailPhase {
   int kind;
@@ -128,7 +135,7 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
     const int nb = min(NB, nchains - ch0);
     for (int idx = threadIdx.x; idx < nb * Np; idx += (int)blockDim.x) {
       const int b = idx / Np, e = idx - b * Np;
-      fv[idx] = (e < C.N) ? C.f[(long long)(ch0 + b) * C.stride + (long long)(e / C.w + 1) * C.pitch + (e % C.w + 1)] : 0.0;
+      fv[idx] = (e < C.N) ? C.f[(long long)(ch0 + b) * C.stride + coarse_site(C, e)] : 0.0;
     }
     if (sample && C.xi_pre) {
       for (int idx = threadIdx.x; idx < nb * Np; idx += (int)blockDim.x) xi[idx] = C.xi_pre[(size_t)ch0 * Np + idx];
@@ -187,7 +194,7 @@ __device__ __forceinline__ void coarse_phase(const CoarseP &C, const NoiseP &nz,
     for (int idx = threadIdx.x; idx < (r1 - r0) * nb; idx += (int)blockDim.x) {
       const int r = idx / nb, b = idx - r * nb, row = r0 + r;
       const double v = part[(r * nseg) * nb + b] + (sample ? part[(r * nseg + 1) * nb + b] : 0.0);
-      C.x[(long long)(ch0 + b) * C.stride + (long long)(row / C.w + 1) * C.pitch + (row % C.w + 1)] = v;
+      C.x[(long long)(ch0 + b) * C.stride + coarse_site(C, row)] = v;
     }
     __syncthreads();
   }

@@ -328,8 +328,26 @@ LinearOperator make_measured_operator(const LinearOperator &base, int n_meas, co
 // ---------------------------------------------------------------------------------------------
 // orderings
 // ---------------------------------------------------------------------------------------------
+// 3d (radius-1 operators only): 2 colours for the 7-point operator, 8 for operators that couple diagonal neighbours
+static int colour_count_3d(const Lattice &lat, const CSR &A) {
+  const long w = lat.n[0] - 1, h = lat.n[1] - 1;
+  bool diag_coupling = false;
+  for (long r = 0; r < A.rows; ++r) {
+    const long i = r % w, j = (r / w) % h, k = r / (w * h);
+    for (long q = A.rowptr[r]; q < A.rowptr[r + 1]; ++q) {
+      if (A.val[q] == 0.0) continue;
+      const long c = A.col[q];
+      const int di = (int)std::labs(c % w - i), dj = (int)std::labs((c / w) % h - j), dk = (int)std::labs(c / (w * h) - k);
+      if (std::max(di, std::max(dj, dk)) > 1) throw std::runtime_error("colour ordering in 3d: radius-1 operators only");
+      if ((di > 0) + (dj > 0) + (dk > 0) > 1) diag_coupling = true;
+    }
+  }
+  return diag_coupling ? 8 : 2;
+}
+
 int colour_count_2d(const Lattice &lat, const CSR &A) {
-  if (lat.dim != 2) throw std::runtime_error("colour ordering implemented for 2d lattices only");
+  if (lat.dim == 3) return colour_count_3d(lat, A);
+  if (lat.dim != 2) throw std::runtime_error("colour ordering implemented for 2d and 3d lattices only");
   const long w = lat.n[0] - 1;
   int radius = 0;
   bool diag_coupling = false;
@@ -358,7 +376,9 @@ std::vector<long> make_order(const Lattice &lat, const CSR &A, int ordering) {
     int idx[3];
     lat.vertex_l2e(ell, idx);
     const int i = idx[0], j = idx[1];
-    if (nc == 2)
+    if (lat.dim == 3)  // the B200 path's 3d colourings (csrc/lattice3d.cuh)
+      colour[ell] = (nc == 2) ? ((i + j + idx[2]) & 1) : ((i & 1) + 2 * (j & 1) + 4 * (idx[2] & 1));
+    else if (nc == 2)
       colour[ell] = (i + j) & 1;
     else if (nc == 4)
       colour[ell] = (i & 1) + 2 * (j & 1);
@@ -483,12 +503,16 @@ void SORSampler::apply(const double *f, double *x) const {
         for (int q = 0; q < m; ++q) xi[q] = noise.dist(*noise.engine);
     } else {
       PhiloxCtx &px = *noise.px;
-      if (op->lattice.dim != 2) throw std::runtime_error("philox noise implemented for 2d lattices only");
+      if (op->lattice.dim != 2 && op->lattice.dim != 3) throw std::runtime_error("philox noise implemented for 2d and 3d lattices only");
       const uint32_t c1 = ((uint32_t)level << 24) | (px.sweep_counter[level]++ & 0xFFFFFFu);
       const int w = op->lattice.n[0] - 1;
       const uint32_t G = (uint32_t)(op->lattice.n[0] / 4 + 1);
+      // 3d: the B200 path stacks the planes k = 0 .. nz in the row direction, row = k (ny + 1) + j (csrc/lattice3d.cuh)
+      const bool d3 = (op->lattice.dim == 3);
+      const long h = d3 ? op->lattice.n[1] - 1 : 0;
       for (long ell = 0; ell < n; ++ell) {
-        const uint32_t i = (uint32_t)(ell % w) + 1, j = (uint32_t)(ell / w) + 1;
+        const uint32_t i = (uint32_t)(ell % w) + 1;
+        const uint32_t j = d3 ? (uint32_t)(((ell / w) / h + 1) * (op->lattice.n[1] + 1) + (ell / w) % h + 1) : (uint32_t)(ell / w) + 1;
         double z0, z1;
         Philox::normal_pair(px.seed, ((j * G + (i >> 2)) << 1) | (i & 1u), c1, px.sample, px.chain, z0, z1);
         c_rhs[ell] = sqrt_precision_diag[ell] * ((i & 2u) ? z1 : z0) + f[ell];
