@@ -226,12 +226,14 @@ def other_configs(m, peak):
     the C ABI, device-timed -- sub-records of the bench line, not bench lines of their own."""
     out = []
 
-    def mgmc(name, n, nlevel, nchains=1, pde="shiftedlaplace_fd", steps=100, target=None, kappa_sq=None):
+    def mgmc(name, n, nlevel, nchains=1, pde="shiftedlaplace_fd", steps=100, target=None, kappa_sq=None, nz=None):
         try:
-            ctx = m.Context(n, n, nlevel, Lambda=0.2, pde=pde, nchains=nchains, kappa_sq=kappa_sq)
+            ctx = m.Context(n, n, nlevel, Lambda=0.2, pde=pde, nchains=nchains, kappa_sq=kappa_sq, nz=nz)
             nd = ctx.ndof()
             xs = np.arange(1, n) / n
             u = np.outer(np.sin(np.pi * xs), np.sin(np.pi * xs)).ravel()
+            if nz is not None:
+                u = np.outer(np.sin(np.pi * np.arange(1, nz) / nz), u).ravel()
             ctx.set_rhs(ctx.op_apply(0, np.tile(u, nchains)))
             ctx.set_state(np.zeros(nd * nchains))
             ctx.set_qoi([nd // 2], [1.0])
@@ -271,6 +273,9 @@ def other_configs(m, peak):
     # (PeriodicCorrelationLengthModel), per-vertex coefficients on every level, one launch per colour (csrc/varcoef.cuh)
     mgmc("periodic correlation length (Lambda 0.1 .. 0.4), 2048x2048, 7 levels, prior, V(1,1) SSOR, one GPU (per-vertex coefficients: first correct path)",
          2048, 7, steps=20, kappa_sq=m.periodic_kappa_sq(2048, 2048, 0.1, 0.4))
+    # not a BASELINE configuration either: a 3d lattice (Lattice3d; 7-point fine / 27-point Galerkin operators, red-black / 8-colour
+    # sweeps, one launch per colour, csrc/lattice3d.cuh)
+    mgmc("3d lattice 128x128x128, 5 levels, prior, V(1,1) SSOR, one GPU (first correct path)", 128, 5, steps=20, nz=128)
     return out
 
 

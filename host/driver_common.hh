@@ -45,7 +45,7 @@ inline ProblemSetup setup_problem(const std::string &filename, bool need_samplin
   std::cout << "B200 device path: matrix-free stencils, multicolour sweeps, Philox noise (libmgmc_b200)." << std::endl << std::endl;
 
   if (s.general.dim == 2) s.lattice = std::make_shared<Lattice2d>(s.lattice_p.nx, s.lattice_p.ny);
-  else if (s.general.dim == 3) die("ERROR: dim = 3 is not on the device path yet");
+  else if (s.general.dim == 3) s.lattice = std::make_shared<Lattice3d>(s.lattice_p.nx, s.lattice_p.ny, s.lattice_p.nz);
   else die("ERROR: Invalid dimension : " + std::to_string(s.general.dim));
 
   std::shared_ptr<CorrelationLengthModel> clm;

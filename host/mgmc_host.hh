@@ -115,6 +115,61 @@ class Lattice2d : public Lattice {
   const double hx, hy;
 };
 
+/** Lattice3d (lattice/lattice3d.hh:43-270): interior vertices in the order ell = (k-1)(nx-1)(ny-1) + (j-1)(nx-1) + (i-1) */
+class Lattice3d : public Lattice {
+ public:
+  Lattice3d(const unsigned int nx_, const unsigned int ny_, const unsigned int nz_)
+      : Lattice(nx_ * ny_ * nz_, (nx_ - 1) * (ny_ - 1) * (nz_ - 1)), nx(nx_), ny(ny_), nz(nz_), hx(1. / double(nx_)), hy(1. / double(ny_)), hz(1. / double(nz_)) {}
+  Eigen::VectorXi shape() const override { return Eigen::VectorXi({(int)nx, (int)ny, (int)nz}); }
+  Eigen::VectorXi cellidx_linear2euclidean(const unsigned int ell) const override {
+    return Eigen::VectorXi({(int)((ell % (nx * ny)) % nx), (int)((ell % (nx * ny)) / nx), (int)(ell / (nx * ny))});
+  }
+  unsigned int cellidx_euclidean2linear(const Eigen::VectorXi idx) const override { return idx[2] * nx * ny + idx[1] * nx + idx[0]; }
+  Eigen::VectorXi vertexidx_linear2euclidean(const unsigned int ell) const override {
+    const unsigned int w = nx - 1, h = ny - 1;
+    return Eigen::VectorXi({(int)((ell % (w * h)) % w) + 1, (int)((ell % (w * h)) / w) + 1, (int)(ell / (w * h)) + 1});
+  }
+  unsigned int vertexidx_euclidean2linear(const Eigen::VectorXi idx) const override {
+    return (idx[2] - 1) * (nx - 1) * (ny - 1) + (idx[1] - 1) * (nx - 1) + (idx[0] - 1);
+  }
+  unsigned int shift_vertexidx(const unsigned int ell, const Eigen::VectorXi shift) const override {
+    const Eigen::VectorXi p = vertexidx_linear2euclidean(ell);
+    return (p[2] + shift[2] - 1) * (nx - 1) * (ny - 1) + (p[1] + shift[1] - 1) * (nx - 1) + (p[0] + shift[0] - 1);
+  }
+  bool shifted_vertex_is_internal_vertex(const unsigned int ell, const Eigen::VectorXi shift, unsigned int &idx_vertex) const override {
+    const Eigen::VectorXi p = vertexidx_linear2euclidean(ell);
+    const int i = p[0] + shift[0], j = p[1] + shift[1], k = p[2] + shift[2];
+    idx_vertex = (k - 1) * (nx - 1) * (ny - 1) + (j - 1) * (nx - 1) + (i - 1);
+    return (i > 0) && (i < (int)nx) && (j > 0) && (j < (int)ny) && (k > 0) && (k < (int)nz);
+  }
+  unsigned int fine_vertex_idx(const unsigned int ell) const override {  // lattice3d.hh:217-225
+    const Eigen::VectorXi p = vertexidx_linear2euclidean(ell);
+    return (2 * p[2] - 1) * (2 * nx - 1) * (2 * ny - 1) + (2 * p[1] - 1) * (2 * nx - 1) + 2 * p[0] - 1;
+  }
+  Eigen::VectorXd vertex_coordinates(const unsigned int ell) const override {
+    const Eigen::VectorXi p = vertexidx_linear2euclidean(ell);
+    return Eigen::VectorXd({p[0] * hx, p[1] * hy, p[2] * hz});
+  }
+  std::shared_ptr<Lattice> get_coarse_lattice() const override {  // lattice3d.hh:242-257
+    if (!((nx % 2 == 0) && (ny % 2 == 0) && (nz % 2 == 0))) {
+      std::cout << "ERROR: cannot coarsen lattice of size " << nx << " x " << ny << " x " << nz << " [one of the extents is odd]" << std::endl;
+      exit(-1);
+    }
+    if (!((nx / 2 > 1) && (ny / 2 > 1) && (nz / 2 > 1))) {
+      std::cout << "ERROR: cannot coarsen lattice of size " << nx << " x " << ny << " x " << nz << " [resulting lattice would have no interior vertices]" << std::endl;
+      exit(-1);
+    }
+    return std::make_shared<Lattice3d>(nx / 2, ny / 2, nz / 2);
+  }
+  std::string get_info() const override {  // lattice3d.cc:8-14
+    char b[128];
+    std::snprintf(b, 128, "3d lattice, %4d x %4d x %4d points, %4d unknowns", nx, ny, nz, Nvertex);
+    return std::string(b);
+  }
+  const unsigned int nx, ny, nz;
+  const double hx, hy, hz;
+};
+
 // ------------------------------------------------------------------------------------------------
 // Correlation length models (linear_operator/correlationlength_model.hh:45-113)
 // ------------------------------------------------------------------------------------------------
@@ -157,6 +212,7 @@ class PeriodicCorrelationLengthModel : public CorrelationLengthModel {
 // ------------------------------------------------------------------------------------------------
 struct OperatorData {
   unsigned int nx = 0, ny = 0;
+  unsigned int nz = 0;  // > 0: Lattice3d
   int pde_model = MGMC_PDE_SHIFTEDLAPLACE_FD;
   double Lambda = 1.0;
   bool constant_kappa = true;
@@ -172,10 +228,10 @@ class DeviceHierarchy {
     mgmc_desc desc;
     std::memset(&desc, 0, sizeof(desc));
     desc.kappa_sq = d.constant_kappa ? nullptr : d.kappa_sq.data();
-    desc.dim = 2;
+    desc.dim = d.nz ? 3 : 2;
     desc.nx = (int)d.nx;
     desc.ny = (int)d.ny;
-    desc.nz = 1;
+    desc.nz = d.nz ? (int)d.nz : 1;
     desc.pde_model = d.pde_model;
     desc.Lambda = d.Lambda;
     desc.m_lowrank = (int)d.Sigma.size();
@@ -266,12 +322,13 @@ class ShiftedLaplaceFDOperator : public LinearOperator {
   ShiftedLaplaceFDOperator(const std::shared_ptr<Lattice> lattice_, const std::shared_ptr<CorrelationLengthModel> clm, const int verbose = 0) : LinearOperator(lattice_) {
     (void)verbose;
     Eigen::VectorXi s = lattice->shape();
-    if (lattice->dim() != 2) {
-      std::cout << "ERROR: the device path supports dim = 2 only" << std::endl;
+    if (lattice->dim() != 2 && lattice->dim() != 3) {
+      std::cout << "ERROR: the device path supports dim = 2 and dim = 3 only" << std::endl;
       exit(-1);
     }
     data->nx = s[0];
     data->ny = s[1];
+    data->nz = (lattice->dim() == 3) ? s[2] : 0;
     data->pde_model = MGMC_PDE_SHIFTEDLAPLACE_FD;
     data->constant_kappa = clm->is_constant(data->Lambda);
     if (!data->constant_kappa) {
@@ -289,6 +346,10 @@ class SquaredShiftedLaplaceFDOperator : public LinearOperator {
   SquaredShiftedLaplaceFDOperator(const std::shared_ptr<Lattice> lattice_, const std::shared_ptr<CorrelationLengthModel> clm, const int verbose = 0) : LinearOperator(lattice_) {
     (void)verbose;
     Eigen::VectorXi s = lattice->shape();
+    if (lattice->dim() != 2) {  // (the reference's assembly is 2d only as well: squared_shiftedlaplace_fd_operator.cc:16-20)
+      std::cout << "ERROR: the squared shifted Laplace operator is implemented for dim = 2 only" << std::endl;
+      exit(-1);
+    }
     data->nx = s[0];
     data->ny = s[1];
     data->pde_model = MGMC_PDE_SQUARED_SHIFTEDLAPLACE_FD;
@@ -332,6 +393,7 @@ class MeasuredOperator : public LinearOperator {
   Eigen::SparseVector<double> measurement_vector(const Eigen::VectorXd x0, const double radius) const {
     Eigen::SparseVector<double> r(lattice->Nvertex);
     const Eigen::VectorXi shape = lattice->shape();
+    if (lattice->dim() == 3) return measurement_vector3(x0, radius);
     const int nx = shape[0], ny = shape[1];
     const double hx = 1. / nx, hy = 1. / ny;
     if (radius < 1.E-12) {
@@ -386,6 +448,80 @@ class MeasuredOperator : public LinearOperator {
             r.coeffRef((j - 1) * (nx - 1) + (i - 1)) += local;
           }
       }
+    return r;
+  }
+
+  /** measurement functional on a Lattice3d (measured_operator.cc:69-170 with dim = 3): closest vertex for radius ~ 0 (first
+   *  minimum in lexicographic order; only the 2 x 2 x 2 candidates around x0 can win), else the average over a ball of the
+   *  given radius against the trilinear hat functions, 2-point Gauss rule per direction, normalised by 4/3 pi r^3 */
+  Eigen::SparseVector<double> measurement_vector3(const Eigen::VectorXd x0, const double radius) const {
+    Eigen::SparseVector<double> r(lattice->Nvertex);
+    const Eigen::VectorXi shape = lattice->shape();
+    const int n[3] = {shape[0], shape[1], shape[2]};
+    const double h[3] = {1. / n[0], 1. / n[1], 1. / n[2]};
+    auto lin = [&](int i, int j, int k) { return (unsigned int)(((k - 1) * (n[1] - 1) + (j - 1)) * (n[0] - 1) + (i - 1)); };
+    if (radius < 1.E-12) {
+      double d_min = 3.0;
+      unsigned int ell_min = 0;
+      int lo[3], hi[3];
+      for (int d = 0; d < 3; ++d) {
+        const int c = (int)std::floor(x0[d] * n[d]);
+        lo[d] = std::min(std::max(c, 1), n[d] - 1);
+        hi[d] = std::min(std::max(c + 1, 1), n[d] - 1);
+      }
+      for (int k = lo[2]; k <= hi[2]; ++k)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+          for (int i = lo[0]; i <= hi[0]; ++i) {
+            const double dx = i * h[0] - x0[0], dy = j * h[1] - x0[1], dz = k * h[2] - x0[2];
+            const double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+            if (dist < d_min) {
+              d_min = dist;
+              ell_min = lin(i, j, k);
+            }
+          }
+      r.coeffRef(ell_min) = 1.0;
+      return r;
+    }
+    const double cell_volume = lattice->cell_volume();
+    const double normalisation = 1. / (4. / 3. * M_PI * radius * radius * radius);
+    const double gp[2] = {0.5 * (1.0 - 1.0 / std::sqrt(3.0)), 0.5 * (1.0 + 1.0 / std::sqrt(3.0))};
+    int c_lo[3], c_hi[3];
+    for (int d = 0; d < 3; ++d) {
+      c_lo[d] = std::max(0, (int)std::floor((x0[d] - radius) * n[d]) - 1);
+      c_hi[d] = std::min(n[d] - 1, (int)std::floor((x0[d] + radius) * n[d]) + 1);
+    }
+    for (int ck = c_lo[2]; ck <= c_hi[2]; ++ck)
+      for (int cj = c_lo[1]; cj <= c_hi[1]; ++cj)
+        for (int ci = c_lo[0]; ci <= c_hi[0]; ++ci) {
+          const int cc[3] = {ci, cj, ck};
+          bool overlap = false, centre_in_cell = true;
+          for (int o = 0; o < 8; ++o) {
+            double d2 = 0.0;
+            for (int d = 0; d < 3; ++d) {
+              const double dx = h[d] * (cc[d] + ((o >> d) & 1)) - x0[d];
+              d2 += dx * dx;
+            }
+            overlap = overlap || (std::sqrt(d2) < radius);
+          }
+          for (int d = 0; d < 3; ++d) centre_in_cell = centre_in_cell && (h[d] * cc[d] <= x0[d]) && (x0[d] <= h[d] * (cc[d] + 1));
+          if (!(overlap || centre_in_cell)) continue;
+          for (int a = 0; a < 8; ++a) {
+            const int v[3] = {ci + (a & 1), cj + ((a >> 1) & 1), ck + ((a >> 2) & 1)};
+            if (!(v[0] > 0 && v[0] < n[0] && v[1] > 0 && v[1] < n[1] && v[2] > 0 && v[2] < n[2])) continue;
+            double local = 0.0;
+            for (int q = 0; q < 8; ++q) {
+              double d2 = 0.0, phi = 1.0;
+              for (int d = 0; d < 3; ++d) {
+                const double xh = gp[(q >> d) & 1];
+                const double dx = h[d] * (xh + cc[d]) - x0[d];
+                d2 += dx * dx;
+                phi *= ((a >> d) & 1) ? xh : (1.0 - xh);
+              }
+              if (std::sqrt(d2) / radius < 1.0) local += phi * 0.125 * cell_volume * normalisation;
+            }
+            r.coeffRef(lin(v[0], v[1], v[2])) += local;
+          }
+        }
     return r;
   }
 
@@ -819,8 +955,17 @@ inline std::vector<Eigen::VectorXd> LinearOperator::prior_solve_columns(const st
   prior.Sigma.clear();
   MultigridParameters p;
   unsigned int n = std::min(data->nx, data->ny), nl = 1;
-  unsigned int nx = data->nx, ny = data->ny;
-  while (nx % 2 == 0 && ny % 2 == 0 && std::min(nx, ny) / 2 >= 16 && n > 32) {
+  unsigned int nx = data->nx, ny = data->ny, nz = data->nz;
+  if (nz) {
+    // Lattice3d: coarsen until the dense coarse factor fits (at most 4096 unknowns: 16^3 cells)
+    while (nx % 2 == 0 && ny % 2 == 0 && nz % 2 == 0 && std::min(std::min(nx, ny), nz) / 2 >= 2 && (unsigned long long)(nx - 1) * (ny - 1) * (nz - 1) > 4096ull) {
+      nx /= 2;
+      ny /= 2;
+      nz /= 2;
+      ++nl;
+    }
+  }
+  while (!nz && nx % 2 == 0 && ny % 2 == 0 && std::min(nx, ny) / 2 >= 16 && n > 32) {
     nx /= 2;
     ny /= 2;
     n /= 2;
@@ -977,6 +1122,7 @@ class VTKWriter2d {
   void add_state(const Eigen::VectorXd &phi, const std::string label) { states.push_back({label, phi}); }
   void write() const {
     const Eigen::VectorXi s = lattice->shape();
+    if (lattice->dim() == 3) return write3d();
     const int nx = s[0], ny = s[1];
     std::ofstream out(filename);
     out << "# vtk DataFile Version 2.0\nSample state\nASCII\nDATASET STRUCTURED_POINTS\n";
@@ -988,9 +1134,34 @@ class VTKWriter2d {
     }
   }
 
- private:
+ protected:
+  /** VTKWriter3d::write (auxilliary/vtk_writer3d.cc:8-58): same header, origin and |data| < 1e-20 -> 0 clamp */
+  void write3d() const {
+    const Eigen::VectorXi s = lattice->shape();
+    const int nx = s[0], ny = s[1], nz = s[2];
+    std::ofstream out(filename);
+    out << "# vtk DataFile Version 2.0\nSample state\nASCII\nDATASET STRUCTURED_POINTS\n";
+    out << "DIMENSIONS " << nx + 1 << " " << ny + 1 << " " << nz + 1 << "\nORIGIN -0.5 -0.5 -5.0\nSPACING " << 1. / nx << " " << 1. / ny << " " << 1. / nz << "\n\nPOINT_DATA "
+        << (nx + 1) * (ny + 1) * (nz + 1) << "\n";
+    for (auto &st : states) {
+      out << "SCALARS " << st.first << " double 1\nLOOKUP_TABLE default\n";
+      for (int k = 0; k <= nz; ++k)
+        for (int j = 0; j <= ny; ++j)
+          for (int i = 0; i <= nx; ++i) {
+            double data = 0.0;
+            if (i > 0 && i < nx && j > 0 && j < ny && k > 0 && k < nz) data = st.second[((k - 1) * (ny - 1) + (j - 1)) * (nx - 1) + (i - 1)];
+            if (std::fabs(data) < 1.0E-20) data = 0.0;
+            out << data << "\n";
+          }
+    }
+  }
   const std::string filename;
   const std::shared_ptr<Lattice> lattice;
   std::vector<std::pair<std::string, Eigen::VectorXd>> states;
+};
+/** VTKWriter3d (auxilliary/vtk_writer3d.hh): the writer above picks the format from the lattice */
+class VTKWriter3d : public VTKWriter2d {
+ public:
+  using VTKWriter2d::VTKWriter2d;
 };
 #endif

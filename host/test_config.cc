@@ -41,5 +41,19 @@ int main(int argc, char *argv[]) {
   // lattice known answers (test_lattice.hh)
   Lattice2d lat(4, 5);
   printf("lattice2d Nvertex=%u Ncell=%u fine_vertex_idx(7)=%u\n", lat.Nvertex, lat.Ncell, lat.fine_vertex_idx(7));
+  // test_lattice.hh:171-242 (3d lattice 4 x 5 x 6)
+  Lattice3d lat3(4, 5, 6);
+  const Eigen::VectorXi c53 = lat3.cellidx_linear2euclidean(53), v23 = lat3.vertexidx_linear2euclidean(23);
+  printf("lattice3d Nvertex=%u Ncell=%u cell53=%d,%d,%d cell(1,3,2)=%u vertex23=%d,%d,%d vertex(3,4,2)=%u\n", lat3.Nvertex, lat3.Ncell, c53[0], c53[1], c53[2],
+         lat3.cellidx_euclidean2linear(Eigen::VectorXi({1, 3, 2})), v23[0], v23[1], v23[2], lat3.vertexidx_euclidean2linear(Eigen::VectorXi({3, 4, 2})));
+  printf("lattice3d shifts(23)=%u,%u,%u,%u,%u,%u fine_vertex_idx(23)=%u\n", lat3.shift_vertexidx(23, Eigen::VectorXi({0, 1, 0})),
+         lat3.shift_vertexidx(23, Eigen::VectorXi({0, -1, 0})), lat3.shift_vertexidx(23, Eigen::VectorXi({1, 0, 0})), lat3.shift_vertexidx(23, Eigen::VectorXi({-1, 0, 0})),
+         lat3.shift_vertexidx(23, Eigen::VectorXi({0, 0, 1})), lat3.shift_vertexidx(23, Eigen::VectorXi({0, 0, -1})), lat3.fine_vertex_idx(23));
+  {
+    const Eigen::VectorXd xc = lat3.vertex_coordinates(23);
+    const std::shared_ptr<Lattice> coarse = Lattice3d(8, 4, 6).get_coarse_lattice();
+    const Eigen::VectorXi cs = coarse->shape();
+    printf("lattice3d coords(23)=%.4f,%.4f,%.4f coarse(8,4,6)=%d,%d,%d info='%s'\n", xc[0], xc[1], xc[2], cs[0], cs[1], cs[2], lat3.get_info().c_str());
+  }
   return 0;
 }

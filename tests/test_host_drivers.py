@@ -48,6 +48,10 @@ def test_config_reader_reads_reference_format(built):
     assert (float(m.group(1)), float(m.group(2))) == (float(sample[0]), float(sample[1]))
     # test_lattice.hh:166 (2d lattice 4 x 5): fine_vertex_idx(7) == 38
     assert "lattice2d Nvertex=12 Ncell=20 fine_vertex_idx(7)=38" in out
+    # test_lattice.hh:171-242 (3d lattice 4 x 5 x 6)
+    assert "lattice3d Nvertex=60 Ncell=120 cell53=1,3,2 cell(1,3,2)=53 vertex23=3,4,2 vertex(3,4,2)=23" in out
+    assert "lattice3d shifts(23)=26,20,24,22,35,11 fine_vertex_idx(23)=243" in out
+    assert "lattice3d coords(23)=0.7500,0.8000,0.3333 coarse(8,4,6)=4,2,3 info='3d lattice,    4 x    5 x    6 points,   60 unknowns'" in out
 
 
 def test_config_reader_errors_like_the_reference(built, tmp_path):
@@ -179,3 +183,59 @@ def test_cholesky_solver_and_sampler_classes(built):
     for _, em, vr in smp:
         # 20000 samples: relative error of the mean field ~ sqrt(tr A^-1 / N) / |A^-1 f|, variance of one entry +- 1 % (1 sigma)
         assert float(em) < 0.05 and abs(float(vr) - 1.0) < 0.04
+
+
+MEAS_3D = """// four point measurements in the unit cube (format of measurements_template.cfg with dim = 3)
+dim = 3;
+n = 4;
+measurement_locations = [0.25, 0.25, 0.25, 0.75, 0.25, 0.5, 0.25, 0.75, 0.75, 0.6, 0.6, 0.4];
+mean = [1.0, 2.0, 3.0, 4.0];
+variance = [1.0, 1.5, 1.2, 1.8];
+"""
+
+
+@pytest.mark.gpu
+def test_driver_mg_3d_residual_history_matches_oracle(built, oracle, tmp_path):
+    """driver_mg with `dim = 3` (Lattice3d, driver_mg.cc:383-392): 32^3, 3 levels, V(2,2) SSOR; printed ||r_k|| == oracle
+    LoopSolver in the same (red-black / 8-colour) ordering; solution.vtk in the 3d writer's format (vtk_writer3d.cc:8-58)."""
+    n, nlevel = 32, 3
+    (tmp_path / "meas3d.cfg").write_text(MEAS_3D)
+    _write_cfg(tmp_path / "mg.cfg", "c2_mg_1024.cfg", dim=3, nx=n, ny=n, nz=n, nlevel=nlevel, maxiter=12, filename='"meas3d.cfg"',
+               sample_location="[0.5, 0.5, 0.5]")
+    out = subprocess.check_output([os.path.join(built, "driver_mg"), "mg.cfg"], cwd=tmp_path, text=True)
+    hist = np.array([float(l.split()[1]) for l in out.splitlines() if re.match(r"^\s*\d+\s+\d\.\d+e[+-]\d+\s", l)])
+    op = oracle.Operator.prior((n, n, n), "shiftedlaplace_fd", Lambda=0.2)
+    H = oracle.Hierarchy(op, nlevel, oracle.COLOUR)
+    b = oracle.StdRng(1482817).normal(op.ndof)
+    prec = H.preconditioner(npresmooth=2, npostsmooth=2)
+    _, h_ref, _, _ = oracle.loop_solve(op, prec, b, rtol=1e-12, atol=1e-15, maxiter=12)
+    assert len(hist) == len(h_ref) == 12
+    big = h_ref > 1e-11 * h_ref[0]
+    assert big.sum() >= 8 and np.abs(hist[big] / h_ref[big] - 1).max() < 2e-3
+    vtk = open(tmp_path / "solution.vtk").read().splitlines()
+    assert vtk[4] == f"DIMENSIONS {n + 1} {n + 1} {n + 1}" and vtk[5] == "ORIGIN -0.5 -0.5 -5.0"
+    assert f"POINT_DATA {(n + 1) ** 3}" in vtk[:10]
+
+
+@pytest.mark.gpu
+def test_driver_mgmc_3d_prior_statistics(built, tmp_path):
+    """driver_mgmc with `dim = 3`, operator = "prior" (32^3, 3 levels): the sampled variance of the observation at the vertex
+    nearest (0.5, 0.5, 0.5) agrees with the exact b^T A^-1 b the driver prints (device MG solves), the mean with 0."""
+    # (the driver's "exact" values are those of the MEASURED operator whatever `operator` says, driver_mgmc.cc:56-58,90-94:
+    #  measurement variances of 1e12 make it the prior to 12 digits)
+    (tmp_path / "meas3d.cfg").write_text(MEAS_3D.replace("variance = [1.0, 1.5, 1.2, 1.8]", "variance = [1.0e+12, 1.5e+12, 1.2e+12, 1.8e+12]"))
+    _write_cfg(tmp_path / "mgmc.cfg", "c1_mgmc_64.cfg", dim=3, nx=32, ny=32, nz=32, nlevel=3, do_ssor="false", measure_convergence="false",
+               nsamples=4000, nwarmup=100, filename='"meas3d.cfg"', sample_location="[0.5, 0.5, 0.5]")
+    out = subprocess.check_output([os.path.join(built, "driver_mgmc"), "mgmc.cfg"], cwd=tmp_path, text=True)
+    assert "3d lattice,   32 x   32 x   32 points" in out
+    blk = out[out.index("**** Multigrid MC ****"):]
+    mean, err = map(float, re.search(r"MultigridMC mean\s+=\s+(\S+) \+/-\s+(\S+)", blk).groups())
+    mean_exact = float(re.search(r"exact mean\s+=\s+(\S+)", blk).group(1))
+    var = float(re.search(r"MultigridMC variance =\s+(\S+)", blk).group(1))
+    var_exact = float(re.search(r"exact variance =\s+(\S+)", blk).group(1))
+    tau = float(re.search(r"MultigridMC tau_int\s+=\s+(\S+)", blk).group(1))
+    series = np.loadtxt(tmp_path / "timeseries_multigridmc.txt")
+    assert len(series) == 4000
+    assert tau < 2.0 and abs(mean_exact) < 1e-8
+    assert abs(mean - mean_exact) < 4.5 * err * np.sqrt(max(tau, 1.0))
+    assert abs(var / var_exact - 1) < 4.5 * np.sqrt(2.0 * max(tau, 1.0) / len(series))
