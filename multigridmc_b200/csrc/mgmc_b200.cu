@@ -375,7 +375,6 @@ std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
     // Lattice3d (lattice/lattice3d.hh): shiftedlaplace_fd with a constant correlation length, no measurements yet
     if (d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FD) fail(MGMC_ERR_UNSUPPORTED, "3d lattices are implemented for shiftedlaplace_fd only");
     if (d.kappa_sq) fail(MGMC_ERR_UNSUPPORTED, "3d lattices: a variable correlation length is not implemented");
-    if (d.m_lowrank > 0 || d.B_nnz > 0) fail(MGMC_ERR_UNSUPPORTED, "3d lattices: the low-rank (measurement) term is not implemented");
     if (std::max(d.strip_nranks, 1) > 1) fail(MGMC_ERR_UNSUPPORTED, "3d lattices: row strips are not implemented");
     if (d.nz >= (1 << 20)) fail(MGMC_ERR_INVALID, "lattice too large");
     // (the stacked planes are the y dimension of the launch grids: 4 rows per CTA, at most 65535 CTAs)
@@ -389,6 +388,13 @@ std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
         h.ny = d.ny;
         h.nz = d.nz;
         fine_stencil3(d.nx, d.ny, d.nz, d.Lambda, h.st3);
+        const long long w3 = d.nx - 1, h3 = d.ny - 1;
+        for (int64_t e = 0; e < d.B_nnz; ++e) {
+          const int64_t row = d.B_rows[e];
+          if (row < 0 || row >= w3 * h3 * (d.nz - 1) || d.B_cols[e] < 0 || d.B_cols[e] >= d.m_lowrank) fail(MGMC_ERR_INVALID, "B entry out of range");
+          // (entries of B / W on a 3d lattice: (i, row of the stacked planes), setup.hh coarsen_B3)
+          h.B.push_back({int(row % w3) + 1, int(row / (w3 * h3) + 1) * (d.ny + 1) + int((row / w3) % h3) + 1, d.B_cols[e], d.B_vals[e]});
+        }
       } else {
         const HostLevel &f = L[l - 1];
         // Lattice3d::get_coarse_lattice (lattice3d.hh:242-257)
@@ -398,6 +404,7 @@ std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
         h.ny = f.ny / 2;
         h.nz = f.nz / 2;
         coarsen_stencil3(f.st3, h.st3);
+        h.B = coarsen_B3(f.B, f.nx, f.ny, f.nz);
       }
       h.st.radius = 1;
       h.st.uniform = true;

@@ -225,6 +225,29 @@ inline std::vector<SEntry> coarsen_B(const std::vector<SEntry> &B, int nxf, int 
   return out;
 }
 
+// 3d lattices: an entry of B / W stores the vertex (i, j, k) as (i, J) with J = k (ny + 1) + j, the row of the stacked planes
+// (csrc/lattice3d.cuh).  B_c = R B with the trilinear full weighting (linear_operator.cc:19, intergrid_operator_linear.cc:8-30)
+inline std::vector<SEntry> coarsen_B3(const std::vector<SEntry> &B, int nxf, int nyf, int nzf) {
+  const int nxc = nxf / 2, nyc = nyf / 2, nzc = nzf / 2;
+  std::map<std::pair<int, long long>, double> acc;  // (col, (K (nyc + 1) + J) * 2^20 + I)
+  for (const SEntry &e : B) {
+    const int ek = e.j / (nyf + 1), ej = e.j % (nyf + 1);
+    for (int K = (ek - 1 + 1) / 2; K <= (ek + 1) / 2; ++K)
+      for (int J = (ej - 1 + 1) / 2; J <= (ej + 1) / 2; ++J)
+        for (int I = (e.i - 1 + 1) / 2; I <= (e.i + 1) / 2; ++I) {
+          if (I < 1 || I > nxc - 1 || J < 1 || J > nyc - 1 || K < 1 || K > nzc - 1) continue;
+          const int di = std::abs(e.i - 2 * I), dj = std::abs(ej - 2 * J), dk = std::abs(ek - 2 * K);
+          if (di > 1 || dj > 1 || dk > 1) continue;
+          acc[{e.col, (long long)(K * (nyc + 1) + J) * (1ll << 20) + I}] += (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * (dk ? 0.5 : 1.0) * e.val;
+        }
+  }
+  std::vector<SEntry> out;
+  for (auto &kv : acc) out.push_back({int(kv.first.second % (1ll << 20)), int(kv.first.second >> 20), kv.first.first, kv.second});
+  return out;
+}
+
+inline int site_colour3(int nc, int i, int j, int k) { return (nc == 2) ? ((i + j + k) & 1) : ((i & 1) + 2 * (j & 1) + 4 * (k & 1)); }
+
 inline int site_colour(int nc, int i, int j) {
   if (nc == 2) return (i + j) & 1;
   if (nc == 4) return (i & 1) + 2 * (j & 1);
@@ -370,7 +393,11 @@ struct LowRankDir {
   std::vector<double> Mneg, Ms;  // -K and I - K G: d = Ms s + Mneg (B^T x)
 };
 
+inline void lowrank_finish(LowRankDir &out, const std::vector<double> &Sigma);
+inline LowRankDir lowrank_setup3(const HostLevel &L, const std::vector<double> &Sigma, double omega, bool forward);
+
 inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &Sigma, double omega, bool forward) {
+  if (L.d3()) return lowrank_setup3(L, Sigma, omega, forward);
   const int m = (int)Sigma.size();
   LowRankDir out;
   out.G.assign((size_t)m * m, 0.0);
@@ -430,7 +457,6 @@ inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &S
     Wwin[k].wy = wy;
     Wwin[k].v.swap(xw);
   }
-  std::vector<double> S((size_t)m * m, 0.0);
   for (int a = 0; a < m; ++a)
     for (int b = 0; b < m; ++b) {
       double g = 0.0;
@@ -440,8 +466,17 @@ inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &S
           if (w != 0.0) g += e.val * w;
         }
       out.G[(size_t)a * m + b] = g;
-      S[(size_t)a * m + b] = g + ((a == b) ? Sigma[a] : 0.0);
     }
+  lowrank_finish(out, Sigma);
+  return out;
+}
+
+// K = (Sigma + G)^{-1} and the two m x m matrices of the fix-up, from G = B^T W
+inline void lowrank_finish(LowRankDir &out, const std::vector<double> &Sigma) {
+  const int m = (int)Sigma.size();
+  std::vector<double> S((size_t)m * m, 0.0);
+  for (int a = 0; a < m; ++a)
+    for (int b = 0; b < m; ++b) S[(size_t)a * m + b] = out.G[(size_t)a * m + b] + ((a == b) ? Sigma[a] : 0.0);
   out.K = invert_dense(S, m);
   out.Mneg.assign((size_t)m * m, 0.0);
   out.Ms.assign((size_t)m * m, 0.0);
@@ -452,6 +487,83 @@ inline LowRankDir lowrank_setup(const HostLevel &L, const std::vector<double> &S
       out.Mneg[(size_t)a * m + b] = -out.K[(size_t)a * m + b];
       out.Ms[(size_t)a * m + b] = ((a == b) ? 1.0 : 0.0) - kg;
     }
+}
+
+// 3d twin of lowrank_setup (uniform radius-1 stencil st3, 2 / 8 colours): W_k by one colour sweep from x = 0 on a 3d window
+inline LowRankDir lowrank_setup3(const HostLevel &L, const std::vector<double> &Sigma, double omega, bool forward) {
+  const int m = (int)Sigma.size();
+  LowRankDir out;
+  out.G.assign((size_t)m * m, 0.0);
+  const int nc = L.st.ncolours, reach = nc - 1, pr = L.ny + 1;
+  std::vector<std::vector<SEntry>> cols(m);
+  for (const SEntry &e : L.B) cols[e.col].push_back(e);
+  struct Win {
+    int lo[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+    std::vector<double> v;
+    double at(int i, int j, int k) const {
+      if (i < lo[0] || i >= lo[0] + w[0] || j < lo[1] || j >= lo[1] + w[1] || k < lo[2] || k >= lo[2] + w[2]) return 0.0;
+      return v[((size_t)(k - lo[2]) * w[1] + (j - lo[1])) * w[0] + (i - lo[0])];
+    }
+  };
+  std::vector<Win> Wwin(m);
+  const int n[3] = {L.nx, L.ny, L.nz};
+  for (int q = 0; q < m; ++q) {
+    if (cols[q].empty()) continue;
+    int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
+    for (const SEntry &e : cols[q]) {
+      const int p[3] = {e.i, e.j % pr, e.j / pr};
+      for (int d = 0; d < 3; ++d) {
+        lo[d] = std::min(lo[d], p[d]);
+        hi[d] = std::max(hi[d], p[d]);
+      }
+    }
+    Win &W = Wwin[q];
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = std::max(1, lo[d] - reach);
+      hi[d] = std::min(n[d] - 1, hi[d] + reach);
+      W.lo[d] = lo[d];
+      W.w[d] = hi[d] - lo[d] + 1;
+    }
+    const size_t nw = (size_t)W.w[0] * W.w[1] * W.w[2];
+    std::vector<double> xw(nw, 0.0), bw(nw, 0.0);
+    auto idx = [&](int i, int j, int k) { return ((size_t)(k - lo[2]) * W.w[1] + (j - lo[1])) * W.w[0] + (i - lo[0]); };
+    for (const SEntry &e : cols[q]) bw[idx(e.i, e.j % pr, e.j / pr)] += e.val;
+    for (int cc = 0; cc < nc; ++cc) {
+      const int colour = forward ? cc : nc - 1 - cc;
+      for (int k = lo[2]; k <= hi[2]; ++k)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+          for (int i = lo[0]; i <= hi[0]; ++i) {
+            if (site_colour3(nc, i, j, k) != colour) continue;
+            double s = 0.0;
+            for (int dk = -1; dk <= 1; ++dk)
+              for (int dj = -1; dj <= 1; ++dj)
+                for (int di = -1; di <= 1; ++di) {
+                  const int ii = i + di, jj = j + dj, kk = k + dk;
+                  if (ii < lo[0] || ii > hi[0] || jj < lo[1] || jj > hi[1] || kk < lo[2] || kk > hi[2]) continue;
+                  s += L.st3[(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)] * xw[idx(ii, jj, kk)];
+                }
+            xw[idx(i, j, k)] += omega * (bw[idx(i, j, k)] - s) / L.st3[13];
+          }
+    }
+    for (int k = lo[2]; k <= hi[2]; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) {
+          const double v = xw[idx(i, j, k)];
+          if (v != 0.0) out.W.push_back({i, k * pr + j, q, v});
+        }
+    W.v.swap(xw);
+  }
+  for (int a = 0; a < m; ++a)
+    for (int b = 0; b < m; ++b) {
+      double g = 0.0;
+      if (!Wwin[b].v.empty())
+        for (const SEntry &e : cols[a]) {
+          const double w = Wwin[b].at(e.i, e.j % pr, e.j / pr);
+          if (w != 0.0) g += e.val * w;
+        }
+      out.G[(size_t)a * m + b] = g;
+    }
+  lowrank_finish(out, Sigma);
   return out;
 }
 
@@ -532,7 +644,13 @@ inline CoarseFactor coarse_factor(const HostLevel &Lv, const std::vector<double>
   for (const SEntry &e : Lv.B) cols[e.col].push_back(e);
   for (int k = 0; k < m; ++k)
     for (const SEntry &p : cols[k])
-      for (const SEntry &q : cols[k]) A[(size_t)((p.j - 1) * w + (p.i - 1)) * Np + (q.j - 1) * w + (q.i - 1)] += p.val * q.val / Sigma[k];
+      for (const SEntry &q : cols[k]) {
+        // (3d: j is the row of the stacked planes, k_z (ny + 1) + j)
+        const int pr = Lv.ny + 1;
+        const int rp = Lv.d3() ? ((p.j / pr - 1) * h + (p.j % pr - 1)) * w + (p.i - 1) : (p.j - 1) * w + (p.i - 1);
+        const int rq = Lv.d3() ? ((q.j / pr - 1) * h + (q.j % pr - 1)) * w + (q.i - 1) : (q.j - 1) * w + (q.i - 1);
+        A[(size_t)rp * Np + rq] += p.val * q.val / Sigma[k];
+      }
   for (int r = N; r < Np; ++r) A[(size_t)r * Np + r] = 1.0;
   // in-place lower Cholesky
   for (int j = 0; j < Np; ++j) {

@@ -239,3 +239,25 @@ def test_driver_mgmc_3d_prior_statistics(built, tmp_path):
     assert tau < 2.0 and abs(mean_exact) < 1e-8
     assert abs(mean - mean_exact) < 4.5 * err * np.sqrt(max(tau, 1.0))
     assert abs(var / var_exact - 1) < 4.5 * np.sqrt(2.0 * max(tau, 1.0) / len(series))
+
+
+@pytest.mark.gpu
+def test_driver_mgmc_3d_posterior_statistics(built, tmp_path):
+    """driver_mgmc with `dim = 3`, operator = "posterior" (32^3, 3 levels, four point measurements; MeasuredOperator on a Lattice3d,
+    measured_operator.cc:9-49): sampled mean / variance of the observation at (0.45, 0.55, 0.5) agree with the exact posterior values
+    the driver prints (Woodbury with device MG solves, linear_operator.hh:153-174) within Monte-Carlo error bars."""
+    (tmp_path / "meas3d.cfg").write_text(MEAS_3D)
+    _write_cfg(tmp_path / "mgmc.cfg", "small_posterior_128.cfg", dim=3, nx=32, ny=32, nz=32, nlevel=3, do_ssor="false", filename='"meas3d.cfg"',
+               sample_location="[0.45, 0.55, 0.5]", variance_scaling="1.E-3")
+    out = subprocess.check_output([os.path.join(built, "driver_mgmc"), "mgmc.cfg"], cwd=tmp_path, text=True)
+    blk = out[out.index("**** Multigrid MC ****"):]
+    mean, err = map(float, re.search(r"MultigridMC mean\s+=\s+(\S+) \+/-\s+(\S+)", blk).groups())
+    mean_exact = float(re.search(r"exact mean\s+=\s+(\S+)", blk).group(1))
+    var = float(re.search(r"MultigridMC variance =\s+(\S+)", blk).group(1))
+    var_exact = float(re.search(r"exact variance =\s+(\S+)", blk).group(1))
+    tau = float(re.search(r"MultigridMC tau_int\s+=\s+(\S+)", blk).group(1))
+    series = np.loadtxt(tmp_path / "timeseries_multigridmc.txt")
+    assert len(series) == 4000 and tau < 2.0
+    assert abs(mean_exact) > 1e-3  # (the measurements pull the mean away from zero)
+    assert abs(mean - mean_exact) < 4.5 * err * np.sqrt(max(tau, 1.0))
+    assert abs(var / var_exact - 1) < 4.5 * np.sqrt(2.0 * max(tau, 1.0) / len(series))

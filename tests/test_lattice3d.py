@@ -67,21 +67,29 @@ def test_create_3d_rejects_what_the_reference_rejects():
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU parity
 # ---------------------------------------------------------------------------------------------------------------------
-def _setup(oracle, n, nlevel, **kw):
+def _setup(oracle, n, nlevel, n_meas=0, radius=0.0, measure_global=False, **kw):
     op = oracle.Operator.prior(n, "shiftedlaplace_fd", Lambda=0.2)
+    if n_meas:
+        # MeasuredOperator on a 3d lattice (measured_operator.cc:9-49, :69-170 with dim = 3): point / ball measurements,
+        # optionally the global average (a dense column of B)
+        rng = np.random.default_rng(7)
+        locs = 0.15 + 0.7 * rng.random((n_meas, 3))
+        op = op.measured(locs, 1.0 + rng.random(n_meas), variance_scaling=1e-4, radius=radius, measure_global=measure_global, variance_global=1e-3)
     H = oracle.Hierarchy(op, nlevel, oracle.COLOUR)
-    ctx = m.Context(n[0], n[1], nlevel, nz=n[2], Lambda=0.2, **kw)
+    ctx = m.Context(n[0], n[1], nlevel, nz=n[2], Lambda=0.2, B=op.B() if n_meas else None, **kw)
     return op, H, ctx
 
 
-CASES = [((16, 16, 16), 3), ((24, 8, 16), 2), ((32, 16, 8), 2), ((12, 20, 28), 2)]
+# (n, nlevel, measurements, radius, global measurement)
+CASES = [((16, 16, 16), 3, 0, 0.0, False), ((24, 8, 16), 2, 0, 0.0, False), ((32, 16, 8), 2, 0, 0.0, False), ((12, 20, 28), 2, 0, 0.0, False),
+         ((16, 16, 16), 3, 4, 0.0, False), ((32, 16, 16), 2, 3, 0.12, False), ((16, 16, 16), 2, 2, 0.0, True)]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,nlevel", CASES)
-def test_single_level_operations_3d(oracle, n, nlevel):
+@pytest.mark.parametrize("n,nlevel,n_meas,radius,glob", CASES)
+def test_single_level_operations_3d(oracle, n, nlevel, n_meas, radius, glob):
     seed = 4711
-    op, H, ctx = _setup(oracle, n, nlevel, seed=seed)
+    op, H, ctx = _setup(oracle, n, nlevel, n_meas, radius, glob, seed=seed)
     rng = np.random.default_rng(1)
     for level in range(nlevel):
         lop = H.level_op(level)
@@ -106,7 +114,7 @@ def test_single_level_operations_3d(oracle, n, nlevel):
             assert rel(ctx.prolongate_add(level, 0.7, xc, x), H.prolongate_add(level, 0.7, xc, x)) < TOL
     # SSOR leaves the exact solution invariant (test_smoother.hh:90-114)
     x_exact = rng.standard_normal(op.ndof)
-    assert rel(ctx.smoother_apply(0, "SSOR", op.apply(x_exact), x_exact, omega=0.8), x_exact) < TOL
+    assert rel(ctx.smoother_apply(0, "SSOR", op.apply(x_exact), x_exact, omega=0.8), x_exact) < (1e-9 if n_meas else TOL)
     # intergrid adjointness <R x, y> = <x, R^T y> (test_intergrid.hh:87-120) on the device transfers
     if nlevel > 1:
         xf, yc = rng.standard_normal(op.ndof), rng.standard_normal(H.level_op(1).ndof)
@@ -125,17 +133,20 @@ def test_single_level_operations_3d(oracle, n, nlevel):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,nlevel,kw", [
-    ((16, 16, 16), 3, {}),
-    ((32, 32, 32), 3, dict(npresmooth=2, npostsmooth=2)),
-    ((16, 32, 16), 3, dict(smoother="SOR", cycle=2, npresmooth=2, omega=0.9)),
-    ((32, 16, 16), 2, dict(coarse_solver="SSOR", ncoarsesmooth=2)),
+@pytest.mark.parametrize("n,nlevel,n_meas,kw", [
+    ((16, 16, 16), 3, 0, {}),
+    ((32, 32, 32), 3, 0, dict(npresmooth=2, npostsmooth=2)),
+    ((16, 32, 16), 3, 0, dict(smoother="SOR", cycle=2, npresmooth=2, omega=0.9)),
+    ((32, 16, 16), 2, 0, dict(coarse_solver="SSOR", ncoarsesmooth=2)),
+    ((32, 32, 32), 3, 5, {}),
+    ((16, 16, 32), 3, 3, dict(npresmooth=2, omega=0.9, measure_global=True)),
 ])
-def test_multigrid_solver_and_mgmc_chain_3d(oracle, n, nlevel, kw):
+def test_multigrid_solver_and_mgmc_chain_3d(oracle, n, nlevel, n_meas, kw):
     """MultigridPreconditioner + LoopSolver (multigrid_preconditioner.cc:74-101, loop_solver.cc:9-53) and three MGMC samples
     (multigridmc_sampler.cc:103-138) + the graph-replayed device loop against the oracle chain on the same Philox stream."""
     seed = 5418513
-    op, H, ctx = _setup(oracle, n, nlevel, seed=seed, **kw)
+    glob = kw.pop("measure_global", False)
+    op, H, ctx = _setup(oracle, n, nlevel, n_meas, 0.0, glob, seed=seed, **kw)
     b = oracle.StdRng(1482817).normal(op.ndof)
     prec = H.preconditioner(**kw)
     assert rel(ctx.mgprec_apply(b), prec.apply(b, np.zeros_like(b))) < 1e-11
