@@ -55,7 +55,7 @@ inline ProblemSetup setup_problem(const std::string &filename, bool need_samplin
 
   if (s.prior.pde_model == "shiftedlaplace_fd") s.prior_operator = std::make_shared<ShiftedLaplaceFDOperator>(s.lattice, clm, 1);
   else if (s.prior.pde_model == "squared_shiftedlaplace_fd") s.prior_operator = std::make_shared<SquaredShiftedLaplaceFDOperator>(s.lattice, clm, 1);
-  else if (s.prior.pde_model == "shiftedlaplace_fem") die("ERROR: pdemodel 'shiftedlaplace_fem' is not on the device path (use shiftedlaplace_fd)");
+  else if (s.prior.pde_model == "shiftedlaplace_fem") s.prior_operator = std::make_shared<ShiftedLaplaceFEMOperator>(s.lattice, clm, 1);
   else die("Error: invalid prior '" + s.prior.pde_model + "'");
 
   s.posterior_operator = std::make_shared<MeasuredOperator>(s.prior_operator, s.measurements);

@@ -339,6 +339,29 @@ class ShiftedLaplaceFDOperator : public LinearOperator {
   }
 };
 
+/** ShiftedLaplaceFEMOperator (linear_operator/shiftedlaplace_fem_operator.hh:31-75): multilinear elements; on the device with a constant
+ *  correlation length (a uniform 9-point / 27-point stencil), dim = 2 and 3 */
+class ShiftedLaplaceFEMOperator : public LinearOperator {
+ public:
+  ShiftedLaplaceFEMOperator(const std::shared_ptr<Lattice> lattice_, const std::shared_ptr<CorrelationLengthModel> clm, const int verbose = 0) : LinearOperator(lattice_) {
+    (void)verbose;
+    Eigen::VectorXi s = lattice->shape();
+    if (lattice->dim() != 2 && lattice->dim() != 3) {
+      std::cout << "ERROR: the device path supports dim = 2 and dim = 3 only" << std::endl;
+      exit(-1);
+    }
+    data->nx = s[0];
+    data->ny = s[1];
+    data->nz = (lattice->dim() == 3) ? s[2] : 0;
+    data->pde_model = MGMC_PDE_SHIFTEDLAPLACE_FEM;
+    data->constant_kappa = clm->is_constant(data->Lambda);
+    if (!data->constant_kappa) {
+      std::cout << "ERROR: pdemodel 'shiftedlaplace_fem' is on the device path with a constant correlation length only" << std::endl;
+      exit(-1);
+    }
+  }
+};
+
 /** SquaredShiftedLaplaceFDOperator (squared_shiftedlaplace_fd_operator.hh): 13 / 21-point stencils with
  *  boundary-ring classes, 9-colour sweeps on the device */
 class SquaredShiftedLaplaceFDOperator : public LinearOperator {

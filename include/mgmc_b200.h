@@ -27,7 +27,9 @@ enum {
   MGMC_ERR_NOTCONVERGED = -4
 };
 
-enum { MGMC_PDE_SHIFTEDLAPLACE_FD = 0, MGMC_PDE_SQUARED_SHIFTEDLAPLACE_FD = 1 };
+/* shiftedlaplace_fd_operator.cc, squared_shiftedlaplace_fd_operator.cc, shiftedlaplace_fem_operator.cc (the FEM operator with a constant
+ * correlation length: a uniform 9-point (2d) / 27-point (3d) stencil on the fine level as well) */
+enum { MGMC_PDE_SHIFTEDLAPLACE_FD = 0, MGMC_PDE_SQUARED_SHIFTEDLAPLACE_FD = 1, MGMC_PDE_SHIFTEDLAPLACE_FEM = 2 };
 enum { MGMC_SMOOTHER_SOR = 0, MGMC_SMOOTHER_SSOR = 1 };
 enum { MGMC_COARSE_SSOR = 0, MGMC_COARSE_CHOLESKY = 1 };
 enum { MGMC_FORWARD = 1, MGMC_BACKWARD = 2 }; /* smoother/sor_smoother.hh:50-54 */

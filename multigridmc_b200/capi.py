@@ -136,7 +136,7 @@ def _d(a):
     return a, a.ctypes.data_as(c_dp)
 
 
-PDE = {"shiftedlaplace_fd": 0, "squared_shiftedlaplace_fd": 1}
+PDE = {"shiftedlaplace_fd": 0, "squared_shiftedlaplace_fd": 1, "shiftedlaplace_fem": 2}
 SMOOTHER = {"SOR": 0, "SSOR": 1}
 COARSE = {"SSOR": 0, "Cholesky": 1}
 FORWARD, BACKWARD = 1, 2

@@ -363,7 +363,8 @@ std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
   if (d.dim != 2 && d.dim != 3) fail(MGMC_ERR_UNSUPPORTED, "only dim = 2 and dim = 3 lattices are implemented on the device path");
   if (d.nx < 2 || d.ny < 2 || (d.dim == 3 && d.nz < 2)) fail(MGMC_ERR_INVALID, "invalid lattice size");
   if (d.nlevel < 1) fail(MGMC_ERR_INVALID, "nlevel must be >= 1");
-  if (d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FD && d.pde_model != MGMC_PDE_SQUARED_SHIFTEDLAPLACE_FD) fail(MGMC_ERR_INVALID, "invalid pde_model");
+  if (d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FD && d.pde_model != MGMC_PDE_SQUARED_SHIFTEDLAPLACE_FD && d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FEM)
+    fail(MGMC_ERR_INVALID, "invalid pde_model");
   if (!(d.Lambda > 0.0)) fail(MGMC_ERR_INVALID, "Lambda must be positive");
   if (!(d.omega > 0.0 && d.omega < 2.0)) fail(MGMC_ERR_INVALID, "omega must be in (0,2)");
   if (d.nx >= (1 << 20) || d.ny >= (1 << 20)) fail(MGMC_ERR_INVALID, "lattice too large");
@@ -373,7 +374,8 @@ std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
   std::vector<HostLevel> L(d.nlevel);
   if (d.dim == 3) {
     // Lattice3d (lattice/lattice3d.hh): shiftedlaplace_fd with a constant correlation length, no measurements yet
-    if (d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FD) fail(MGMC_ERR_UNSUPPORTED, "3d lattices are implemented for shiftedlaplace_fd only");
+    if (d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FD && d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FEM)
+      fail(MGMC_ERR_UNSUPPORTED, "3d lattices are implemented for shiftedlaplace_fd and shiftedlaplace_fem only");
     if (d.kappa_sq) fail(MGMC_ERR_UNSUPPORTED, "3d lattices: a variable correlation length is not implemented");
     if (std::max(d.strip_nranks, 1) > 1) fail(MGMC_ERR_UNSUPPORTED, "3d lattices: row strips are not implemented");
     if (d.nz >= (1 << 20)) fail(MGMC_ERR_INVALID, "lattice too large");
@@ -387,7 +389,12 @@ std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
         h.nx = d.nx;
         h.ny = d.ny;
         h.nz = d.nz;
-        fine_stencil3(d.nx, d.ny, d.nz, d.Lambda, h.st3);
+        if (d.pde_model == MGMC_PDE_SHIFTEDLAPLACE_FEM) {
+          const int n3[3] = {d.nx, d.ny, d.nz};
+          fem_stencil(3, n3, d.Lambda, h.st3);
+        } else {
+          fine_stencil3(d.nx, d.ny, d.nz, d.Lambda, h.st3);
+        }
         const long long w3 = d.nx - 1, h3 = d.ny - 1;
         for (int64_t e = 0; e < d.B_nnz; ++e) {
           const int64_t row = d.B_rows[e];
@@ -417,7 +424,8 @@ std::vector<HostLevel> build_host_levels(const mgmc_desc &d) {
   L[0].st = fine_stencil(d.pde_model, d.nx, d.ny, d.Lambda);
   if (d.kappa_sq) {
     // correlation length that varies in space: kappa^2 per interior vertex instead of 1 / Lambda^2
-    if (d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FD) fail(MGMC_ERR_UNSUPPORTED, "a variable correlation length is implemented for shiftedlaplace_fd only");
+    if (d.pde_model != MGMC_PDE_SHIFTEDLAPLACE_FD)
+      fail(MGMC_ERR_UNSUPPORTED, "a variable correlation length is implemented for shiftedlaplace_fd only (the FEM operator evaluates kappa^2 at the quadrature points)");
     if (std::max(d.strip_nranks, 1) > 1) fail(MGMC_ERR_UNSUPPORTED, "row strips of an operator with per-vertex coefficients are not implemented");
     for (long long k = 0; k < (long long)(d.nx - 1) * (d.ny - 1); ++k)
       if (!(d.kappa_sq[k] >= 0.0)) fail(MGMC_ERR_INVALID, "kappa_sq entries must be non-negative");

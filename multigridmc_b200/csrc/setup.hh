@@ -54,9 +54,59 @@ inline void classify(StencilSet &s) {
   s.ncolours = (s.radius >= 2) ? 9 : (corners ? 4 : 2);
 }
 
+// ShiftedLaplaceFEMOperator (linear_operator/shiftedlaplace_fem_operator.cc:9-150) with a constant correlation length on a
+// dim-dimensional lattice (dim = 2, 3): multilinear elements, 2-point Gauss rule per direction.  Every interior vertex lies in 2^dim
+// cells, so the operator is one uniform 3^dim-point stencil: the cell with lower corner v + c, c in {-1, 0}^dim, has v as its corner
+// alpha = -c and couples it to the corners beta, i.e. to the vertices v + c + beta:
+//   a(c + beta) += sum_q (kappa^2 phi_alpha phi_beta + sum_d h_d^-2 d_d phi_alpha d_d phi_beta)(xhat_q) w_q * cell volume   (:127-135)
+// out[(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)] (dim = 2: the plane dk = 0)
+inline void fem_stencil(int dim, const int *n, double Lambda, double *out27) {
+  std::memset(out27, 0, sizeof(double) * 27);
+  double hinv2[3] = {0, 0, 0}, vol = 1.0;
+  for (int d = 0; d < dim; ++d) {
+    const double h = 1. / double(n[d]);
+    hinv2[d] = 1. / (h * h);
+    vol *= h;
+  }
+  const double kappa_sq = 1.0 / std::pow(Lambda, 2);
+  const double gp[2] = {0.5 * (1.0 - 1.0 / std::sqrt(3.0)), 0.5 * (1.0 + 1.0 / std::sqrt(3.0))};
+  const int ncorner = 1 << dim;
+  const double wq = 1.0 / ncorner;  // product of the 1d weights 1/2
+  for (int cell = 0; cell < ncorner; ++cell) {   // bit d set: c_d = -1, i.e. alpha_d = 1
+    for (int beta = 0; beta < ncorner; ++beta) {
+      double entry = 0.0;
+      for (int q = 0; q < ncorner; ++q) {
+        double pa = 1.0, pb = 1.0, grad = 0.0;
+        double fa[3], fb[3];
+        for (int d = 0; d < dim; ++d) {
+          const double x = gp[(q >> d) & 1];
+          fa[d] = ((cell >> d) & 1) ? x : 1.0 - x;
+          fb[d] = ((beta >> d) & 1) ? x : 1.0 - x;
+          pa *= fa[d];
+          pb *= fb[d];
+        }
+        for (int d = 0; d < dim; ++d) {
+          double ga = ((cell >> d) & 1) ? 1.0 : -1.0, gb = ((beta >> d) & 1) ? 1.0 : -1.0;
+          for (int e = 0; e < dim; ++e)
+            if (e != d) {
+              ga *= fa[e];
+              gb *= fb[e];
+            }
+          grad += hinv2[d] * ga * gb;
+        }
+        entry += (kappa_sq * pa * pb + grad) * wq;
+      }
+      int sh[3] = {0, 0, 0};
+      for (int d = 0; d < dim; ++d) sh[d] = -((cell >> d) & 1) + ((beta >> d) & 1);
+      out27[(sh[2] + 1) * 9 + (sh[1] + 1) * 3 + (sh[0] + 1)] += entry * vol;
+    }
+  }
+}
+
 // fine-level stencils
 //  pde 0: ShiftedLaplaceFDOperator (shiftedlaplace_fd_operator.cc:33-56): h^d (kappa^2 + sum 2/h_d^2), -h^d/h_d^2
 //  pde 1: SquaredShiftedLaplaceFDOperator (squared_shiftedlaplace_fd_operator.cc:40-93)
+//  pde 2: ShiftedLaplaceFEMOperator (shiftedlaplace_fem_operator.cc:9-150), constant correlation length
 inline StencilSet fine_stencil(int pde, int nx, int ny, double Lambda) {
   StencilSet s;
   std::memset(s.a, 0, sizeof(s.a));
@@ -68,7 +118,14 @@ inline StencilSet fine_stencil(int pde, int nx, int ny, double Lambda) {
     for (int cx = 0; cx < 3; ++cx) {
       double *a = s.a[cx + 3 * cy];
       auto A = [&](int di, int dj) -> double & { return a[(dj + 2) * 5 + (di + 2)]; };
-      if (pde == 0) {
+      if (pde == 2) {
+        // shiftedlaplace_fem: uniform 9-point stencil (all classes alike: entries towards the boundary multiply zeros)
+        const int n2[2] = {nx, ny};
+        double a27[27];
+        fem_stencil(2, n2, Lambda, a27);
+        for (int dj = -1; dj <= 1; ++dj)
+          for (int di = -1; di <= 1; ++di) A(di, dj) = a27[9 + (dj + 1) * 3 + (di + 1)];
+      } else if (pde == 0) {
         double diagonal = vol * kappa_sq;
         diagonal += 2. * vol * hinv2x;
         diagonal += 2. * vol * hinv2y;
