@@ -503,6 +503,8 @@ def run_b200(a):
                                                                            "device-side flags, coarse levels replicated" if strips_on else
                                                                            ("independent chains per GPU, no data-path collective" if world > 1 else "single GPU"))),
         "site_updates_per_sec": value * upd,
+        "site_updates_note": "reference-equivalent site updates (4 colour-pass equivalents per SSOR step as the reference sweeps; the kernels skip the dead pass between "
+                             "a forward and a backward sweep, exact for omega = 1)",
         "cycle_algorithmic_gbs": cycle_gbs, "cycle_roofline_frac": cycle_gbs / peak / (world if strips_on else 1),
         "e2e": ({"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": 8 * nd, "d2h_bytes_per_step": 8 * nd,
                  "call": "mgmc_sampler_mgmc_apply(ctx, NULL /*rhs fixed by fix_rhs*/, x) with pinned host x, QoI read on the host",

@@ -261,3 +261,22 @@ def test_driver_mgmc_3d_posterior_statistics(built, tmp_path):
     assert abs(mean_exact) > 1e-3  # (the measurements pull the mean away from zero)
     assert abs(mean - mean_exact) < 4.5 * err * np.sqrt(max(tau, 1.0))
     assert abs(var / var_exact - 1) < 4.5 * np.sqrt(2.0 * max(tau, 1.0) / len(series))
+
+
+@pytest.mark.gpu
+def test_driver_mg_fem_operator(built, oracle, tmp_path):
+    """driver_mg with `pdemodel = "shiftedlaplace_fem"` (driver_mg.cc:129-139; ShiftedLaplaceFEMOperator, constant correlation length):
+    9-point stencils on every level, 4-colour sweeps; printed ||r_k|| == oracle LoopSolver on the same operator."""
+    n, nlevel = 128, 4
+    _write_cfg(tmp_path / "mg.cfg", "c2_mg_1024.cfg", nx=n, ny=n, nlevel=nlevel, maxiter=12, filename=f'"{CONFIGS}/measurements_8.cfg"',
+               pdemodel='"shiftedlaplace_fem"')
+    out = subprocess.check_output([os.path.join(built, "driver_mg"), "mg.cfg"], cwd=tmp_path, text=True)
+    hist = np.array([float(l.split()[1]) for l in out.splitlines() if re.match(r"^\s*\d+\s+\d\.\d+e[+-]\d+\s", l)])
+    op = oracle.Operator.prior((n, n), "shiftedlaplace_fem", Lambda=0.2)
+    H = oracle.Hierarchy(op, nlevel, oracle.COLOUR)
+    b = oracle.StdRng(1482817).normal(op.ndof)
+    prec = H.preconditioner(npresmooth=2, npostsmooth=2)
+    _, h_ref, _, _ = oracle.loop_solve(op, prec, b, rtol=1e-12, atol=1e-15, maxiter=12)
+    assert len(hist) == len(h_ref) == 12
+    big = h_ref > 1e-11 * h_ref[0]
+    assert big.sum() >= 8 and np.abs(hist[big] / h_ref[big] - 1).max() < 2e-3
