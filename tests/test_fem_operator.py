@@ -151,3 +151,18 @@ def test_fem_mgmc_sampler_covariance_like_the_reference_test(oracle):
     assert np.all(np.abs(mu - mean[sites]) < 5 * se_mu)
     se_C = np.sqrt((Cx ** 2 + np.outer(np.diag(Cx), np.diag(Cx))) / N)
     assert np.all(np.abs(C - Cx) < 5 * se_C)
+
+
+@pytest.mark.parametrize("n", [(8, 8), (16, 12), (8, 8, 8), (8, 12, 16)])
+def test_coarsened_fem_operator_is_the_rediscretised_one(n):
+    """test_intergrid.hh:172-207 (TestCoarsenOperator2d / 3d, Lambda = 1): coarsening the FEM operator with constant coefficients
+    gives the FEM operator of the next-coarser lattice, 1e-12 -- here for the product's stencil algebra (setup.hh), no oracle."""
+    d3 = len(n) == 3
+    fine = capi.make_desc(n[0], n[1], 2, pde=PDE, Lambda=1.0, nz=n[2] if d3 else None)
+    coarse = capi.make_desc(n[0] // 2, n[1] // 2, 1, pde=PDE, Lambda=1.0, nz=n[2] // 2 if d3 else None)
+    get = m.host_stencil3 if d3 else m.host_stencil
+    a, _ = get(fine, 1)
+    b, _ = get(coarse, 0)
+    interior = a if d3 else a[4]
+    ref = b if d3 else b[4]
+    assert np.abs(interior - ref).max() < 1e-12 * np.abs(ref).max()
