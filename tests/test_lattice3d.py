@@ -210,3 +210,34 @@ def test_large_lattice_properties_and_chains_3d():
         assert np.array_equal(single.get_state(), xb[ch]), ch
         single.close()
     assert rel(xb[0], xb[1]) > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(64, 64, None), (16, 16, 16)])
+def test_moment_fields_equal_manual_accumulation(shape):
+    """mgmc_sample_moments (driver_mgmc.cc:146-151: running mean / second moment of the field over the samples) against the same
+    chain advanced sample by sample with the fields accumulated on the host -- 2d and 3d layouts."""
+    nx, ny, nz = shape
+    rng = np.random.default_rng(5)
+    out = []
+    for mode in range(2):
+        ctx = m.Context(nx, ny, 3, nz=nz, seed=77)
+        nd = ctx.ndof()
+        if mode == 0:
+            f, x0 = rng.standard_normal(nd), rng.standard_normal(nd)
+        ctx.set_rhs(f)
+        ctx.set_state(x0)
+        ctx.set_philox_position(0)
+        if mode == 0:
+            out.append(ctx.sample_moments(6))
+        else:
+            mean, second = np.zeros(nd), np.zeros(nd)
+            for k in range(6):
+                ctx.sample(1, series=False)
+                v = ctx.get_state()
+                mean += (v - mean) / (k + 1.0)
+                second += (v * v - second) / (k + 1.0)
+            out.append((mean, second))
+        ctx.close()
+    assert rel(out[0][0], out[1][0]) < 1e-13 and rel(out[0][1], out[1][1]) < 1e-13
+    assert np.all(out[0][1] - out[0][0] ** 2 > -1e-12)
