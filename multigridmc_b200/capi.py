@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
 ]
 SOURCES = ["mgmc_b200.cu"]
-HEADERS = ["fused.cuh", "tail.cuh", "noise_ahead.cuh", "varcoef.cuh", "lattice3d.cuh", "kernels.cuh", "philox.cuh", "normal_tables.inc", "setup.hh", "../../include/mgmc_b200.h"]
+HEADERS = ["fused.cuh", "tail.cuh", "noise_ahead.cuh", "varcoef.cuh", "lattice3d.cuh", "rowfuse.cuh", "kernels.cuh", "philox.cuh", "normal_tables.inc", "setup.hh", "../../include/mgmc_b200.h"]
 
 
 def build(force=False, verbose=False):

@@ -19,6 +19,7 @@
 #include "noise_ahead.cuh"
 #include "varcoef.cuh"
 #include "lattice3d.cuh"
+#include "rowfuse.cuh"
 #include <climits>
 
 #include <set>
@@ -1484,6 +1485,52 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
   const bool zero_first = strip_level && restrict_ && level + 1 < sp.ndist;
   if (zero_first) dev_zero(c, level + 1, c->lv[level + 1].x);
   static const bool noskip = std::getenv("MGMC_NO_DEAD_PASS") != nullptr;
+  // Colour passes of one row class in one launch (rowfuse.cuh): 9-colour radius-2 levels, 8-colour 3d levels, 4-colour
+  // per-vertex levels on one GPU.  (Row strips keep one launch per colour: the halo exchange is per colour.)
+  static const bool no_rowfuse = std::getenv("MGMC_NO_ROWFUSE") != nullptr;
+  const bool rowfuse = !no_rowfuse && !strip_level && ((L.r2 && ncol == 9) || (L.d3 && L.full27) || (L.vc && ncol == 4));
+  const int per_row = L.r2 ? 3 : 2;  // colours per row class
+  RowPasses grp;
+  grp.n = 0;
+  int grp_class = -1;
+  auto flush_rows = [&] {
+    if (grp.n == 0) return;
+    const RowPasses P = grp;
+    const int cls = grp_class;
+    const NoiseP nz0 = noise_params(c, level, 0);
+    const int per_colour = (L.g.nx - 1 + per_row - 1) / per_row;  // sites of a colour in a row (upper bound)
+    const int threads = std::min(256, std::max(32, (per_colour + 31) / 32 * 32));  // (up to 512 threads per row measured: slower)
+    if (L.r2) {
+      const int jfirst = (cls == 0) ? 3 : cls;
+      const int nrows = (L.g.ny - 1 >= jfirst) ? (L.g.ny - 1 - jfirst) / 3 + 1 : 0;
+      c->launch(gibbs ? "gibbs_9c_rows" : "sor_9c_rows", level, [&] {
+        if (gibbs) sweep_rows25_kernel<true><<<dim3(std::max(nrows, 1), 1, nch), threads, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, jfirst, omega, nz0, P);
+        else sweep_rows25_kernel<false><<<dim3(std::max(nrows, 1), 1, nch), threads, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, jfirst, omega, nz0, P);
+      }, 24.0 * n / ncol * P.n);
+    } else if (L.d3) {
+      const int j0 = (cls & 1) ? 1 : 2, k0 = (cls & 2) ? 1 : 2;
+      const int nj = (L.q.ny - 1 >= j0) ? (L.q.ny - 1 - j0) / 2 + 1 : 0, nk = (L.q.nz - 1 >= k0) ? (L.q.nz - 1 - k0) / 2 + 1 : 0;
+      c->launch(gibbs ? "gibbs_8c_rows" : "sor_8c_rows", level, [&] {
+        if (gibbs) sweep_rows27_kernel<true><<<dim3(std::max(nj, 1), std::max(nk, 1), nch), threads, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, j0, k0, omega, nz0, P);
+        else sweep_rows27_kernel<false><<<dim3(std::max(nj, 1), std::max(nk, 1), nch), threads, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, j0, k0, omega, nz0, P);
+      }, 24.0 * n / ncol * P.n);
+    } else {
+      const int j0 = (cls & 1) ? 1 : 2;
+      const int nrows = (L.g.ny - 1 >= j0) ? (L.g.ny - 1 - j0) / 2 + 1 : 0;
+      const dim3 gridr(std::max(nrows, 1), 1, nch);
+      c->launch(gibbs ? "gibbs_4cv_rows" : "sor_4cv_rows", level, [&] {
+        if (L.vc_full) {
+          if (gibbs) sweep_rows9v_kernel<true, true><<<gridr, threads, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, j0, omega, nz0, P);
+          else sweep_rows9v_kernel<true, false><<<gridr, threads, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, j0, omega, nz0, P);
+        } else {
+          if (gibbs) sweep_rows9v_kernel<false, true><<<gridr, threads, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, j0, omega, nz0, P);
+          else sweep_rows9v_kernel<false, false><<<gridr, threads, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, j0, omega, nz0, P);
+        }
+      }, 24.0 * n / ncol * P.n);
+    }
+    grp.n = 0;
+    grp_class = -1;
+  };
   for (size_t si = 0; si < sweeps.size(); ++si) {
     const SweepSpec &sw = sweeps[si];
     const uint32_t c1 = next_c1(c, level, gibbs);
@@ -1493,6 +1540,15 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
       // omega = 1: an update does not read the site's own value, so the last colour of this sweep is dead if the next
       // sweep starts with the same colour and nothing reads x in between (see plan_stages for the tile kernel)
       if (cc == ncol - 1 && omega == 1.0 && !noskip && si + 1 < sweeps.size() && sweeps[si + 1].fwd != sw.fwd && !(lowrank && sw.fix_after)) continue;
+      if (rowfuse) {
+        const int cls = colour / per_row;
+        if (cls != grp_class || grp.n == kRowPassMax) flush_rows();
+        grp_class = cls;
+        grp.ci[grp.n] = colour % per_row;
+        grp.c1[grp.n] = c1;
+        ++grp.n;
+        continue;
+      }
       if (L.d3) {
         // 3d lattice: red-black (7-point) or 8 colours (27-point), whole lattice, rows = stacked planes (lattice3d.cuh)
         dim3 grid3((L.g.nx / 2 + 1 + 63) / 64, (L.g.ny - 1 + 3) / 4, nch);
@@ -1568,8 +1624,12 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
         else sweep_colour25_kernel<false><<<grid, kBlockSites, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, colour, omega, nz, jfirst, K);
       }, 24.0 * n / 9.0);
     }
-    if (lowrank && sw.fix_after) dev_lowrank_fix(c, level, sw.fwd, gibbs, omega, c1);
+    if (lowrank && sw.fix_after) {
+      flush_rows();
+      dev_lowrank_fix(c, level, sw.fwd, gibbs, omega, c1);
+    }
   }
+  flush_rows();
   if (restrict_) {
     DevLevel &C = c->lv[level + 1];
     // the restriction to the own coarse rows reads the residual one fine row beyond the own rows

@@ -152,3 +152,61 @@ def test_repeated_runs_are_bit_identical(n, nlevel, nmeas, nchains):
             assert np.array_equal(out, ref), f"repetition {rep}: max abs diff {np.max(np.abs(out - ref)):.3e}"
         else:
             assert np.array_equal(z, ref_z), f"repetition {rep}: series differs"
+
+
+SNIPPET_ROWS = r'''
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+import multigridmc_b200 as m
+family, omega, nmeas, out = %(family)r, %(omega)r, %(nmeas)d, %(out)r
+rng = np.random.default_rng(3)
+B = None
+if family == "radius2":
+    n = (192, 160, None)
+    kw = dict(pde="squared_shiftedlaplace_fd")
+elif family == "3d":
+    n = (32, 24, 16)
+    kw = {}
+else:
+    n = (160, 96, None)
+    kw = dict(kappa_sq=m.periodic_kappa_sq(160, 96, 0.1, 0.4))
+nd = (n[0] - 1) * (n[1] - 1) * ((n[2] - 1) if n[2] else 1)
+if nmeas:
+    rows = rng.choice(nd, size=nmeas, replace=False)
+    B = (rows, np.arange(nmeas), np.ones(nmeas), 1e-3 * (1.0 + rng.random(nmeas)))
+ctx = m.Context(n[0], n[1], 3, nz=n[2], B=B, seed=4711, omega=omega, smoother=%(smoother)r, npresmooth=2, **kw)
+ctx.set_rhs(rng.standard_normal(nd))
+ctx.set_state(rng.standard_normal(nd))
+ctx.set_qoi([nd // 2], [1.0])
+ctx.set_philox_position(0)
+z = ctx.sample(3)
+xs = ctx.smoother_apply(0, "SSOR", rng.standard_normal(nd), rng.standard_normal(nd), omega=omega, nsmooth=2)
+np.save(out, np.concatenate([ctx.get_state(), np.asarray(z).ravel(), xs]))
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family,omega,nmeas,smoother", [("radius2", 1.0, 0, "SSOR"), ("radius2", 1.2, 3, "SOR"), ("3d", 1.0, 0, "SSOR"), ("3d", 0.9, 3, "SSOR"),
+                                                         ("periodic", 1.0, 0, "SSOR"), ("periodic", 1.1, 3, "SOR")])
+def test_chain_independent_of_row_class_launches(tmp_path, family, omega, nmeas, smoother):
+    """The colour passes of one row class in one launch (rowfuse.cuh: 9-colour radius-2, 8-colour 3d, 4-colour per-vertex levels)
+    against one launch per colour: the same chain bit for bit, with and without dead-pass skipping."""
+
+    def run(tag, env):
+        out = str(tmp_path / f"{tag}.npy")
+        e = dict(os.environ)
+        e.update(env)
+        subprocess.check_call([sys.executable, "-c", SNIPPET_ROWS % dict(root=ROOT, out=out, family=family, omega=omega, nmeas=nmeas, smoother=smoother)], env=e)
+        return np.load(out)
+
+    ref = run("rows", {})
+    assert np.all(np.isfinite(ref))
+    x = run("per_colour", {"MGMC_NO_ROWFUSE": "1"})
+    assert np.array_equal(x, ref), f"per_colour: max abs diff {np.max(np.abs(x - ref)):.3e}"
+    # Running the dead pass as well: these kernels update x_i += omega (b - (A x)_i) / a_ii with the own value inside (A x)_i, so for
+    # omega = 1 the skipped pass changes the next update of the site in the last bits only (the tile kernel's omega = 1 passes do
+    # not read the own value at all) -- the same chain to rounding; the two launch schemes stay bit-identical to each other.
+    a = run("rows_all_passes", {"MGMC_NO_DEAD_PASS": "1"})
+    b = run("per_colour_all_passes", {"MGMC_NO_ROWFUSE": "1", "MGMC_NO_DEAD_PASS": "1"})
+    assert np.array_equal(a, b), f"all passes: max abs diff {np.max(np.abs(a - b)):.3e}"
+    assert np.max(np.abs(a - ref)) <= 1e-9 * np.max(np.abs(ref))
