@@ -1500,32 +1500,45 @@ void emit_smoothing_r2(mgmc_ctx *c, int level, const std::vector<SweepSpec> &swe
     const NoiseP nz0 = noise_params(c, level, 0);
     const int per_colour = (L.g.nx - 1 + per_row - 1) / per_row;  // sites of a colour in a row (upper bound)
     const int threads = std::min(256, std::max(32, (per_colour + 31) / 32 * 32));  // (up to 512 threads per row measured: slower)
+    const bool pre = per_colour <= threads;  // one site per thread and pass: right-hand sides + noise of all passes up front
     if (L.r2) {
       const int jfirst = (cls == 0) ? 3 : cls;
       const int nrows = (L.g.ny - 1 >= jfirst) ? (L.g.ny - 1 - jfirst) / 3 + 1 : 0;
+      const dim3 gridr(std::max(nrows, 1), 1, nch);
       c->launch(gibbs ? "gibbs_9c_rows" : "sor_9c_rows", level, [&] {
-        if (gibbs) sweep_rows25_kernel<true><<<dim3(std::max(nrows, 1), 1, nch), threads, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, jfirst, omega, nz0, P);
-        else sweep_rows25_kernel<false><<<dim3(std::max(nrows, 1), 1, nch), threads, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, jfirst, omega, nz0, P);
+        if (gibbs && pre) sweep_rows25_kernel<true, true><<<gridr, threads, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, jfirst, omega, nz0, P);
+        else if (gibbs) sweep_rows25_kernel<true, false><<<gridr, threads, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, jfirst, omega, nz0, P);
+        else if (pre) sweep_rows25_kernel<false, true><<<gridr, threads, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, jfirst, omega, nz0, P);
+        else sweep_rows25_kernel<false, false><<<gridr, threads, 0, c->stream>>>(L.g, L.d_st, L.x, L.f, jfirst, omega, nz0, P);
       }, 24.0 * n / ncol * P.n);
     } else if (L.d3) {
       const int j0 = (cls & 1) ? 1 : 2, k0 = (cls & 2) ? 1 : 2;
       const int nj = (L.q.ny - 1 >= j0) ? (L.q.ny - 1 - j0) / 2 + 1 : 0, nk = (L.q.nz - 1 >= k0) ? (L.q.nz - 1 - k0) / 2 + 1 : 0;
+      const dim3 gridr(std::max(nj, 1), std::max(nk, 1), nch);
       c->launch(gibbs ? "gibbs_8c_rows" : "sor_8c_rows", level, [&] {
-        if (gibbs) sweep_rows27_kernel<true><<<dim3(std::max(nj, 1), std::max(nk, 1), nch), threads, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, j0, k0, omega, nz0, P);
-        else sweep_rows27_kernel<false><<<dim3(std::max(nj, 1), std::max(nk, 1), nch), threads, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, j0, k0, omega, nz0, P);
+        if (gibbs && pre) sweep_rows27_kernel<true, true><<<gridr, threads, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, j0, k0, omega, nz0, P);
+        else if (gibbs) sweep_rows27_kernel<true, false><<<gridr, threads, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, j0, k0, omega, nz0, P);
+        else if (pre) sweep_rows27_kernel<false, true><<<gridr, threads, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, j0, k0, omega, nz0, P);
+        else sweep_rows27_kernel<false, false><<<gridr, threads, 0, c->stream>>>(L.g, L.q, L.c27, L.x, L.f, j0, k0, omega, nz0, P);
       }, 24.0 * n / ncol * P.n);
     } else {
       const int j0 = (cls & 1) ? 1 : 2;
       const int nrows = (L.g.ny - 1 >= j0) ? (L.g.ny - 1 - j0) / 2 + 1 : 0;
       const dim3 gridr(std::max(nrows, 1), 1, nch);
       c->launch(gibbs ? "gibbs_4cv_rows" : "sor_4cv_rows", level, [&] {
+#define MGMC_ROWS9V(NINE_, GIBBS_)                                                                                                                       \
+  do {                                                                                                                                                   \
+    if (pre) sweep_rows9v_kernel<NINE_, GIBBS_, true><<<gridr, threads, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, j0, omega, nz0, P);                          \
+    else sweep_rows9v_kernel<NINE_, GIBBS_, false><<<gridr, threads, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, j0, omega, nz0, P);                             \
+  } while (0)
         if (L.vc_full) {
-          if (gibbs) sweep_rows9v_kernel<true, true><<<gridr, threads, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, j0, omega, nz0, P);
-          else sweep_rows9v_kernel<true, false><<<gridr, threads, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, j0, omega, nz0, P);
+          if (gibbs) MGMC_ROWS9V(true, true);
+          else MGMC_ROWS9V(true, false);
         } else {
-          if (gibbs) sweep_rows9v_kernel<false, true><<<gridr, threads, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, j0, omega, nz0, P);
-          else sweep_rows9v_kernel<false, false><<<gridr, threads, 0, c->stream>>>(L.g, L.dvc, L.x, L.f, j0, omega, nz0, P);
+          if (gibbs) MGMC_ROWS9V(false, true);
+          else MGMC_ROWS9V(false, false);
         }
+#undef MGMC_ROWS9V
       }, 24.0 * n / ncol * P.n);
     }
     grp.n = 0;
