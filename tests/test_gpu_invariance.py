@@ -33,6 +33,16 @@ np.save(out, np.concatenate([ctx.get_state(), np.asarray(z).ravel()]))
 '''
 
 
+def _parallel(fn, variants, workers=4):
+    """{tag: result}: every variant in its own process (the switches are read once per process), up to `workers` of them at a
+    time on the same GPU -- the results are pure functions of the inputs, so concurrency must not change a bit."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        futs = {tag: ex.submit(fn, tag, env) for tag, env in variants.items()}
+        return {tag: f.result() for tag, f in futs.items()}
+
+
 def _run(tmp_path, tag, env, **kw):
     out = str(tmp_path / f"{tag}.npy")
     e = dict(os.environ)
@@ -45,9 +55,8 @@ def _run(tmp_path, tag, env, **kw):
 @pytest.mark.parametrize("n,nlevel,nmeas,omega", [(512, 5, 0, 1.0), (512, 5, 8, 1.0), (1024, 6, 8, 1.0), (512, 5, 8, 1.3)])
 def test_chain_independent_of_tiling_and_dead_pass_skipping(tmp_path, n, nlevel, nmeas, omega):
     kw = dict(n=n, nlevel=nlevel, nmeas=nmeas, omega=omega)
-    ref = _run(tmp_path, "default", {}, **kw)
-    assert np.all(np.isfinite(ref))
     variants = {
+        "default": {},
         "all_passes": {"MGMC_NO_DEAD_PASS": "1"},
         "low_tiles": {"MGMC_TILE_ROWS": "32,32,16,8,32,32,16"},
         "tall_tiles": {"MGMC_TILE_ROWS": "24,40,32,16,36,24,24"},
@@ -61,8 +70,10 @@ def test_chain_independent_of_tiling_and_dead_pass_skipping(tmp_path, n, nlevel,
         "no_merge": {"MGMC_NO_MERGE": "1"},
         "no_merge_all_passes": {"MGMC_NO_MERGE": "1", "MGMC_NO_DEAD_PASS": "1"},
     }
-    for tag, env in variants.items():
-        x = _run(tmp_path, tag, env, **kw)
+    res = _parallel(lambda tag, env: _run(tmp_path, tag, env, **kw), variants)
+    ref = res.pop("default")
+    assert np.all(np.isfinite(ref))
+    for tag, x in res.items():
         if tag == "no_fold" and nmeas == 0 and omega == 1.0:
             # the folded residual (-noise) and the stencil residual differ in the last bits: same chain to rounding
             assert np.max(np.abs(x - ref)) <= 1e-9 * np.max(np.abs(ref)), tag
@@ -98,7 +109,7 @@ np.save(out, np.concatenate([ctx.get_state(), x, np.asarray(z1).ravel(), np.asar
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,nlevel,nmeas,omega", [(2048, 6, 0, 1.0), (2048, 6, 8, 1.0), (2048, 6, 8, 1.3)])
+@pytest.mark.parametrize("n,nlevel,nmeas,omega", [(2048, 6, 8, 1.0), (1024, 5, 8, 1.3)])  # (40 s per 2048^2 case: one of them, one smaller)
 def test_chain_independent_of_noise_generated_ahead(tmp_path, n, nlevel, nmeas, omega):
     """Normals of the small levels generated ahead of their launches by a second branch of the cycle graph
     (noise_ahead.cuh) vs generated in registers by the launches themselves: the same chain bit for bit -- through graph
@@ -112,11 +123,11 @@ def test_chain_independent_of_noise_generated_ahead(tmp_path, n, nlevel, nmeas, 
         subprocess.check_call([sys.executable, "-c", SNIPPET_AHEAD % dict(root=ROOT, out=out, **kw)], env=e)
         return np.load(out)
 
-    ref = run("in_register", {})
-    assert np.all(np.isfinite(ref))
     on = {"MGMC_NOISE_AHEAD": "1"}  # (opt-in: measured, no gain -- profiles/r02_noise_ahead.md)
-    for tag, env in {"ahead": on, "ahead_no_merge": dict(on, MGMC_NO_MERGE="1"), "ahead_no_graph": dict(on, MGMC_NO_GRAPH="1")}.items():
-        x = run(tag, env)
+    res = _parallel(run, {"in_register": {}, "ahead": on, "ahead_no_merge": dict(on, MGMC_NO_MERGE="1"), "ahead_no_graph": dict(on, MGMC_NO_GRAPH="1")})
+    ref = res.pop("in_register")
+    assert np.all(np.isfinite(ref))
+    for tag, x in res.items():
         assert np.array_equal(x, ref), f"{tag}: max abs diff {np.max(np.abs(x - ref)):.3e}"
 
 
@@ -199,14 +210,14 @@ def test_chain_independent_of_row_class_launches(tmp_path, family, omega, nmeas,
         subprocess.check_call([sys.executable, "-c", SNIPPET_ROWS % dict(root=ROOT, out=out, family=family, omega=omega, nmeas=nmeas, smoother=smoother)], env=e)
         return np.load(out)
 
-    ref = run("rows", {})
+    res = _parallel(run, {"rows": {}, "per_colour": {"MGMC_NO_ROWFUSE": "1"}, "rows_all_passes": {"MGMC_NO_DEAD_PASS": "1"},
+                          "per_colour_all_passes": {"MGMC_NO_ROWFUSE": "1", "MGMC_NO_DEAD_PASS": "1"}})
+    ref, x = res["rows"], res["per_colour"]
     assert np.all(np.isfinite(ref))
-    x = run("per_colour", {"MGMC_NO_ROWFUSE": "1"})
     assert np.array_equal(x, ref), f"per_colour: max abs diff {np.max(np.abs(x - ref)):.3e}"
     # Running the dead pass as well: these kernels update x_i += omega (b - (A x)_i) / a_ii with the own value inside (A x)_i, so for
     # omega = 1 the skipped pass changes the next update of the site in the last bits only (the tile kernel's omega = 1 passes do
     # not read the own value at all) -- the same chain to rounding; the two launch schemes stay bit-identical to each other.
-    a = run("rows_all_passes", {"MGMC_NO_DEAD_PASS": "1"})
-    b = run("per_colour_all_passes", {"MGMC_NO_ROWFUSE": "1", "MGMC_NO_DEAD_PASS": "1"})
+    a, b = res["rows_all_passes"], res["per_colour_all_passes"]
     assert np.array_equal(a, b), f"all passes: max abs diff {np.max(np.abs(a - b)):.3e}"
     assert np.max(np.abs(a - ref)) <= 1e-9 * np.max(np.abs(ref))
