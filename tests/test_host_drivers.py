@@ -280,3 +280,27 @@ def test_driver_mg_fem_operator(built, oracle, tmp_path):
     assert len(hist) == len(h_ref) == 12
     big = h_ref > 1e-11 * h_ref[0]
     assert big.sum() >= 8 and np.abs(hist[big] / h_ref[big] - 1).max() < 2e-3
+
+
+def test_host_measurement_functional_matches_oracle(built, oracle):
+    """MeasuredOperator::measurement_vector of the host layer (measured_operator.cc:69-170: closest vertex for radius ~ 0, ball average
+    against the multilinear hat functions otherwise) on 2d and 3d lattices against the oracle's restatement, entry by entry (no GPU)."""
+    out = subprocess.check_output([os.path.join(built, "test_measure")], text=True)
+    got = {}
+    for line in out.splitlines():
+        _, tag, ell, val = line.split()
+        got.setdefault(tag, {})[int(ell)] = float(val)
+    cases = {
+        "2d_point": ((16, 12), [0.37, 0.62], 0.0), "2d_ball": ((16, 12), [0.37, 0.62], 0.15), "2d_edge": ((16, 12), [0.97, 0.02], 0.1),
+        "3d_point": ((8, 12, 10), [0.37, 0.62, 0.48], 0.0), "3d_corner_point": ((8, 12, 10), [0.999, 0.001, 1.0], 0.0),
+        "3d_ball": ((8, 12, 10), [0.37, 0.62, 0.48], 0.2), "3d_edge": ((8, 12, 10), [0.95, 0.05, 0.5], 0.15),
+    }
+    assert set(got) == set(cases)
+    for tag, (n, x0, radius) in cases.items():
+        op = oracle.Operator.prior(n, "shiftedlaplace_fd", Lambda=0.2)
+        ref = op.measurement_vector(x0, radius)
+        vec = np.zeros(op.ndof)
+        for ell, v in got[tag].items():
+            vec[ell] = v
+        assert np.abs(vec - ref).max() <= 1e-14 * max(np.abs(ref).max(), 1.0), tag
+        assert np.count_nonzero(ref) > 0
