@@ -115,6 +115,45 @@ class Lattice2d : public Lattice {
   const double hx, hy;
 };
 
+/** Lattice1d (lattice/lattice1d.hh:27-190): index arithmetic only -- operators on 1d lattices are not on the device path
+ *  (mgmc_create reports dim = 1 as MGMC_ERR_UNSUPPORTED) */
+class Lattice1d : public Lattice {
+ public:
+  explicit Lattice1d(const unsigned int n_) : Lattice(n_, n_ - 1), n(n_), h(1. / double(n_)) {}
+  Eigen::VectorXi shape() const override { return Eigen::VectorXi({(int)n}); }
+  Eigen::VectorXi cellidx_linear2euclidean(const unsigned int ell) const override { return Eigen::VectorXi({(int)ell}); }
+  unsigned int cellidx_euclidean2linear(const Eigen::VectorXi idx) const override { return idx[0]; }
+  Eigen::VectorXi vertexidx_linear2euclidean(const unsigned int ell) const override { return Eigen::VectorXi({(int)ell + 1}); }
+  unsigned int vertexidx_euclidean2linear(const Eigen::VectorXi idx) const override { return idx[0] - 1; }
+  unsigned int shift_cellidx(const unsigned int ell, const Eigen::VectorXi shift) const { return ell + shift[0]; }
+  unsigned int shift_vertexidx(const unsigned int ell, const Eigen::VectorXi shift) const override { return ell + shift[0]; }
+  bool shifted_vertex_is_internal_vertex(const unsigned int ell, const Eigen::VectorXi shift, unsigned int &idx_vertex) const override {
+    const int i = (int)ell + shift[0] + 1;
+    idx_vertex = i - 1;
+    return (i > 0) && (i < (int)n);
+  }
+  unsigned int fine_vertex_idx(const unsigned int ell) const override { return 2 * ell + 1; }
+  Eigen::VectorXd vertex_coordinates(const unsigned int ell) const override { return Eigen::VectorXd({(ell + 1.) * h}); }
+  std::shared_ptr<Lattice> get_coarse_lattice() const override {  // lattice1d.hh:155-170
+    if (!(n % 2 == 0)) {
+      std::cout << "ERROR: cannot coarsen lattice of size " << n << " [extent is odd]" << std::endl;
+      exit(-1);
+    }
+    if (!(n / 2 > 1)) {
+      std::cout << "ERROR: cannot coarsen lattice of size " << n << " [resulting lattice would have no interior vertices]" << std::endl;
+      exit(-1);
+    }
+    return std::make_shared<Lattice1d>(n / 2);
+  }
+  std::string get_info() const override {  // lattice1d.cc:8-14
+    char b[128];
+    std::snprintf(b, 128, "1d lattice, %4d points, %4d unknowns", n, Nvertex);
+    return std::string(b);
+  }
+  const unsigned int n;
+  const double h;
+};
+
 /** Lattice3d (lattice/lattice3d.hh:43-270): interior vertices in the order ell = (k-1)(nx-1)(ny-1) + (j-1)(nx-1) + (i-1) */
 class Lattice3d : public Lattice {
  public:
@@ -131,6 +170,10 @@ class Lattice3d : public Lattice {
   }
   unsigned int vertexidx_euclidean2linear(const Eigen::VectorXi idx) const override {
     return (idx[2] - 1) * (nx - 1) * (ny - 1) + (idx[1] - 1) * (nx - 1) + (idx[0] - 1);
+  }
+  unsigned int shift_cellidx(const unsigned int ell, const Eigen::VectorXi shift) const {  // lattice3d.hh:138-156
+    const Eigen::VectorXi c = cellidx_linear2euclidean(ell);
+    return (c[2] + shift[2]) * nx * ny + (c[1] + shift[1]) * nx + (c[0] + shift[0]);
   }
   unsigned int shift_vertexidx(const unsigned int ell, const Eigen::VectorXi shift) const override {
     const Eigen::VectorXi p = vertexidx_linear2euclidean(ell);

@@ -41,11 +41,22 @@ int main(int argc, char *argv[]) {
   // lattice known answers (test_lattice.hh)
   Lattice2d lat(4, 5);
   printf("lattice2d Nvertex=%u Ncell=%u fine_vertex_idx(7)=%u\n", lat.Nvertex, lat.Ncell, lat.fine_vertex_idx(7));
+  // test_lattice.hh:30-101 (1d lattice, n = 6)
+  Lattice1d lat1(6);
+  printf("lattice1d Nvertex=%u Ncell=%u cell5=%d cell(3)=%u cellshifts=%u,%u,%u,%u vertex4=%d vertex(3)=%u shifts=%u,%u,%u,%u fine=%u,%u,%u info='%s'\n", lat1.Nvertex, lat1.Ncell,
+         lat1.cellidx_linear2euclidean(5)[0], lat1.cellidx_euclidean2linear(Eigen::VectorXi({3})), lat1.shift_cellidx(3, Eigen::VectorXi({1})),
+         lat1.shift_cellidx(3, Eigen::VectorXi({-1})), lat1.shift_cellidx(4, Eigen::VectorXi({1})), lat1.shift_cellidx(4, Eigen::VectorXi({-1})),
+         lat1.vertexidx_linear2euclidean(4)[0], lat1.vertexidx_euclidean2linear(Eigen::VectorXi({3})), lat1.shift_vertexidx(3, Eigen::VectorXi({1})),
+         lat1.shift_vertexidx(3, Eigen::VectorXi({-1})), lat1.shift_vertexidx(4, Eigen::VectorXi({1})), lat1.shift_vertexidx(4, Eigen::VectorXi({-1})),
+         lat1.fine_vertex_idx(3), lat1.fine_vertex_idx(0), lat1.fine_vertex_idx(2), lat1.get_info().c_str());
   // test_lattice.hh:171-242 (3d lattice 4 x 5 x 6)
   Lattice3d lat3(4, 5, 6);
   const Eigen::VectorXi c53 = lat3.cellidx_linear2euclidean(53), v23 = lat3.vertexidx_linear2euclidean(23);
   printf("lattice3d Nvertex=%u Ncell=%u cell53=%d,%d,%d cell(1,3,2)=%u vertex23=%d,%d,%d vertex(3,4,2)=%u\n", lat3.Nvertex, lat3.Ncell, c53[0], c53[1], c53[2],
          lat3.cellidx_euclidean2linear(Eigen::VectorXi({1, 3, 2})), v23[0], v23[1], v23[2], lat3.vertexidx_euclidean2linear(Eigen::VectorXi({3, 4, 2})));
+  printf("lattice3d cellshifts(59)=%u,%u,%u,%u,%u,%u\n", Lattice3d(4, 5, 6).shift_cellidx(59, Eigen::VectorXi({0, 1, 0})), Lattice3d(4, 5, 6).shift_cellidx(59, Eigen::VectorXi({0, -1, 0})),
+         Lattice3d(4, 5, 6).shift_cellidx(59, Eigen::VectorXi({1, 0, 0})), Lattice3d(4, 5, 6).shift_cellidx(59, Eigen::VectorXi({-1, 0, 0})),
+         Lattice3d(4, 5, 6).shift_cellidx(59, Eigen::VectorXi({0, 0, 1})), Lattice3d(4, 5, 6).shift_cellidx(59, Eigen::VectorXi({0, 0, -1})));
   printf("lattice3d shifts(23)=%u,%u,%u,%u,%u,%u fine_vertex_idx(23)=%u\n", lat3.shift_vertexidx(23, Eigen::VectorXi({0, 1, 0})),
          lat3.shift_vertexidx(23, Eigen::VectorXi({0, -1, 0})), lat3.shift_vertexidx(23, Eigen::VectorXi({1, 0, 0})), lat3.shift_vertexidx(23, Eigen::VectorXi({-1, 0, 0})),
          lat3.shift_vertexidx(23, Eigen::VectorXi({0, 0, 1})), lat3.shift_vertexidx(23, Eigen::VectorXi({0, 0, -1})), lat3.fine_vertex_idx(23));

@@ -48,6 +48,10 @@ def test_config_reader_reads_reference_format(built):
     assert (float(m.group(1)), float(m.group(2))) == (float(sample[0]), float(sample[1]))
     # test_lattice.hh:166 (2d lattice 4 x 5): fine_vertex_idx(7) == 38
     assert "lattice2d Nvertex=12 Ncell=20 fine_vertex_idx(7)=38" in out
+    # test_lattice.hh:30-101 (1d lattice, n = 6)
+    assert ("lattice1d Nvertex=5 Ncell=6 cell5=5 cell(3)=3 cellshifts=4,2,5,3 vertex4=5 vertex(3)=2 shifts=4,2,5,3 fine=7,1,5 "
+            "info='1d lattice,    6 points,    5 unknowns'") in out
+    assert "lattice3d cellshifts(59)=63,55,60,58,79,39" in out  # test_lattice.hh:189-204
     # test_lattice.hh:171-242 (3d lattice 4 x 5 x 6)
     assert "lattice3d Nvertex=60 Ncell=120 cell53=1,3,2 cell(1,3,2)=53 vertex23=3,4,2 vertex(3,4,2)=23" in out
     assert "lattice3d shifts(23)=26,20,24,22,35,11 fine_vertex_idx(23)=243" in out
