@@ -621,8 +621,13 @@ class IntergridOperator {
     if (!dev) {  // standalone use (test_intergrid.hh): a prior hierarchy on this lattice carries the transfer
       OperatorData d;
       Eigen::VectorXi s = lattice->shape();
+      if (lattice->dim() != 2 && lattice->dim() != 3) {
+        std::cout << "ERROR: the device path supports dim = 2 and dim = 3 only" << std::endl;
+        exit(-1);
+      }
       d.nx = s[0];
       d.ny = s[1];
+      d.nz = (lattice->dim() == 3) ? s[2] : 0;
       MultigridParameters p;
       p.nlevel = 2;
       dev = std::make_shared<DeviceHierarchy>(d, p, 0);
