@@ -127,7 +127,7 @@ __device__ __forceinline__ int ld_acquire_sys_i(const int *p) {
 __device__ __forceinline__ void strip_spin(const int *flag, int target, int *err) {
   const long long t0 = clock64();
   while (ld_acquire_sys_i(flag) < target) {
-    if (clock64() - t0 > 6000000000ll) {  // (= kWaitTimeoutClocks)
+    if (clock64() - t0 > kWaitTimeoutClocks) {
       *err = 1;
       break;
     }
@@ -226,7 +226,6 @@ __device__ __forceinline__ void pkt_store(LrPkt *p, double v, int epoch) {
 // bounded wait: a bug (or a dead peer) must not hang the GPU -- a time-out raises the context's error word (the API
 // call that finds it set fails with MGMC_ERR_CUDA instead of returning a chain built on a stale value).  The epoch
 // comparison is wrap-safe.
-constexpr long long kWaitTimeoutClocks = 6000000000ll;  // ~3 s at 1.9 GHz
 __device__ __forceinline__ double pkt_wait(const LrPkt *p, int epoch, int *err) {
   unsigned lo, hi;
   int e, pad;

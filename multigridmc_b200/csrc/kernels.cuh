@@ -26,6 +26,10 @@ struct NoiseP {
   uint32_t G;             // groups per row = nx / 4 + 1
 };
 
+// device-side waits (row-strip flags, low-rank packets) give up after this many SM clocks and raise the context's error word
+// instead of hanging the GPU (~3 s at 1.9 GHz)
+constexpr long long kWaitTimeoutClocks = 6000000000ll;
+
 struct GridP {
   int nx, ny, pitch;
   long long stride;  // doubles between chains
@@ -225,7 +229,7 @@ struct StripR2 {
 __device__ __forceinline__ void r2_spin(const int *flag, int target, int *err) {
   const long long t0 = clock64();
   while (ld_acquire_sys(flag) < target) {
-    if (clock64() - t0 > 6000000000ll) {  // a peer died: raise the error word instead of hanging the GPU
+    if (clock64() - t0 > kWaitTimeoutClocks) {  // a peer died: raise the error word instead of hanging the GPU
       *err = 1;
       break;
     }
@@ -619,7 +623,7 @@ __global__ void strip_wait_kernel(const int *flag0, const int *flag1, int per_wa
   for (int f = 0; f < 2; ++f) {
     if (!flags[f]) continue;
     while (ld_acquire_sys(flags[f]) < target[f]) {
-      if (clock64() - t0 > 6000000000ll) {  // ~3 s
+      if (clock64() - t0 > kWaitTimeoutClocks) {
         *err = 1;
         return;
       }
