@@ -57,7 +57,7 @@ def test_create_3d_rejects_what_the_reference_rejects():
         with pytest.raises(m.MgmcError) as e:
             m.host_stencil3(desc, 0)
         assert e.value.code == -1
-    # not on the device path yet: measurements / squared operator in 3d
+    # not on the device path: the squared operator in 3d (2d only in the reference as well)
     desc = capi.make_desc(8, 8, 2, nz=8, pde="squared_shiftedlaplace_fd")
     with pytest.raises(m.MgmcError) as e:
         m.host_stencil3(desc, 0)
