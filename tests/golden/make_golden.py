@@ -22,7 +22,7 @@ def case(n, nlevel, pde, n_meas, seed):
     op = orc.Operator.prior(n, pde, Lambda=0.2)
     locs = var = None
     if n_meas:
-        locs = 0.1 + 0.8 * rng.random((n_meas, 2))
+        locs = 0.1 + 0.8 * rng.random((n_meas, len(n)))
         var = 1.0 + rng.random(n_meas)
         op = op.measured(locs, var, variance_scaling=1e-3)
     nd = op.ndof
@@ -66,4 +66,9 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "laplace_32x32_l3_m0.npz"), **case((32, 32), 3, "shiftedlaplace_fd", 0, 1))
     np.savez_compressed(os.path.join(HERE, "laplace_64x32_l3_m3.npz"), **case((64, 32), 3, "shiftedlaplace_fd", 3, 2))
     np.savez_compressed(os.path.join(HERE, "squared_32x32_l2_m0.npz"), **case((32, 32), 2, "squared_shiftedlaplace_fd", 0, 3))
+    # round 2: FEM operator and 3d lattices (the CUDA path of these families is compared with the live oracle in
+    # tests/test_fem_operator.py / tests/test_lattice3d.py; these files pin the oracle's restatement of them)
+    np.savez_compressed(os.path.join(HERE, "oracle_only_fem_32x16_l2_m2.npz"), **case((32, 16), 2, "shiftedlaplace_fem", 2, 4))
+    np.savez_compressed(os.path.join(HERE, "oracle_only_laplace_16x16x16_l3_m2.npz"), **case((16, 16, 16), 3, "shiftedlaplace_fd", 2, 5))
+    np.savez_compressed(os.path.join(HERE, "oracle_only_fem_8x16x8_l2_m0.npz"), **case((8, 16, 8), 2, "shiftedlaplace_fem", 0, 6))
     print("written")

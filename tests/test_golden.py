@@ -9,7 +9,10 @@ import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FILES = sorted(f for f in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(f).startswith("c5_"))
+ALL = sorted(f for f in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(f).startswith("c5_"))
+# oracle_only_*: FEM operator / 3d lattices (round 2) -- regression pins of the oracle; the CUDA path of these families is
+# compared with the live oracle in tests/test_fem_operator.py and tests/test_lattice3d.py
+FILES = [f for f in ALL if not os.path.basename(f).startswith("oracle_only_")]
 
 
 def rel(a, b):
@@ -24,10 +27,10 @@ def _operator(orc, g):
 
 
 def test_fixtures_exist():
-    assert len(FILES) >= 3
+    assert len(FILES) >= 3 and len(ALL) >= 6
 
 
-@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p) for p in FILES])
+@pytest.mark.parametrize("path", ALL, ids=[os.path.basename(p) for p in ALL])
 def test_oracle_reproduces_golden(oracle, path):
     g = np.load(path)
     op = _operator(oracle, g)
