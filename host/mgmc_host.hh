@@ -79,6 +79,9 @@ class Lattice2d : public Lattice {
     return Eigen::VectorXi({(int)(ell % (nx - 1)) + 1, (int)(ell / (nx - 1)) + 1});
   }
   unsigned int vertexidx_euclidean2linear(const Eigen::VectorXi idx) const override { return (idx[1] - 1) * (nx - 1) + (idx[0] - 1); }
+  unsigned int shift_cellidx(const unsigned int ell, const Eigen::VectorXi shift) const {  // lattice2d.hh:106-118
+    return ((int)(ell / nx) + shift[1]) * nx + ((int)(ell % nx) + shift[0]);
+  }
   unsigned int shift_vertexidx(const unsigned int ell, const Eigen::VectorXi shift) const override {
     const int i = (int)(ell % (nx - 1)) + shift[0] + 1, j = (int)(ell / (nx - 1)) + shift[1] + 1;
     return (j - 1) * (nx - 1) + (i - 1);

@@ -59,6 +59,8 @@ class VectorX {
   friend VectorX operator*(T a, VectorX b) { return b *= a; }
   friend VectorX operator*(VectorX b, T a) { return b *= a; }
   friend VectorX operator/(VectorX b, T a) { return b *= (T(1) / a); }
+  friend bool operator==(const VectorX &a, const VectorX &b) { return a.v_ == b.v_; }
+  friend bool operator!=(const VectorX &a, const VectorX &b) { return !(a == b); }
   VectorX cwiseProduct(const VectorX &o) const {
     VectorX r(*this);
     for (size_t i = 0; i < v_.size(); ++i) r.v_[i] *= o.v_[i];
@@ -70,6 +72,11 @@ class VectorX {
 };
 typedef VectorX<double> VectorXd;
 typedef VectorX<int> VectorXi;
+// (fixed-size names used by the reference's tests: same dynamic type here)
+typedef VectorX<int> Vector2i;
+typedef VectorX<int> Vector3i;
+typedef VectorX<double> Vector2d;
+typedef VectorX<double> Vector3d;
 
 // sparse vector as (index, value) pairs -- what MeasuredOperator::measurement_vector returns
 template <typename T>
