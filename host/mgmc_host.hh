@@ -217,6 +217,46 @@ class Lattice3d : public Lattice {
 };
 
 // ------------------------------------------------------------------------------------------------
+// GaussLegendreQuadrature (auxilliary/quadrature.hh:22-47, quadrature.cc:11-59): tensor-product Gauss-Legendre rule with
+// order + 1 points per direction on the unit cube [0,1]^dim (order 0, 1, 2) -- the rule of the FEM assembly and of the
+// measurement functional (the host layer's own assembly loops use the order-1 rule inline)
+// ------------------------------------------------------------------------------------------------
+class GaussLegendreQuadrature {
+ public:
+  GaussLegendreQuadrature(const int dim_, const int order_) : dim(dim_), order(order_) {
+    static const double node[3][3] = {{0.0, 0.0, 0.0}, {-0.57735026918962576451, +0.57735026918962576451, 0.0}, {-0.77459666924148337704, 0.0, +0.77459666924148337704}};
+    static const double weight[3][3] = {{2.0, 0.0, 0.0}, {1.0, 1.0, 0.0}, {5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0}};
+    if (dim < 1 || order < 0 || order > 2) {
+      std::cout << "ERROR: GaussLegendreQuadrature needs dim > 0 and 0 <= order < 3" << std::endl;
+      exit(-1);
+    }
+    const int n1 = order + 1;
+    long total = 1;
+    for (int d = 0; d < dim; ++d) total *= n1;
+    for (long q = 0; q < total; ++q) {  // first direction slowest (the order of a cartesian product)
+      Eigen::VectorXd pt(dim);
+      double w = 1.0;
+      long rem = q;
+      for (int d = dim - 1; d >= 0; --d) {
+        const int k = (int)(rem % n1);
+        rem /= n1;
+        pt[d] = 0.5 * (node[order][k] + 1.0);  // [-1, +1] -> [0, 1]
+        w *= 0.5 * weight[order][k];
+      }
+      weights.push_back(w);
+      points.push_back(pt);
+    }
+  }
+  std::vector<double> get_weights() const { return weights; }
+  std::vector<Eigen::VectorXd> get_points() const { return points; }
+
+ protected:
+  const int dim, order;
+  std::vector<double> weights;
+  std::vector<Eigen::VectorXd> points;
+};
+
+// ------------------------------------------------------------------------------------------------
 // Correlation length models (linear_operator/correlationlength_model.hh:45-113)
 // ------------------------------------------------------------------------------------------------
 class CorrelationLengthModel {

@@ -330,3 +330,19 @@ def test_reference_lattice_tests_run_against_the_host_layer(built, tmp_path):
     out = subprocess.check_output([exe], text=True)
     assert "[  PASSED  ] 21 tests, 0 failed" in out, out
     assert out.count("[       OK ] LatticeTest.") == 21
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_SRC), reason="the reference checkout only exists in the build container")
+def test_reference_quadrature_tests_run_against_the_host_layer(built, tmp_path):
+    """The reference's own src/auxilliary/test_quadrature.hh (Gauss-Legendre rules of order 0 / 1 / 2 integrate monomials up to degree
+    1 / 3 / 5 on the unit cube exactly, 1e-12) compiled unmodified against the host layer's GaussLegendreQuadrature."""
+    import shutil
+
+    shutil.copy(os.path.join(REFERENCE_SRC, "auxilliary", "test_quadrature.hh"), tmp_path / "test_quadrature.hh")
+    compat = os.path.join(ROOT, "tests", "ref_compat")
+    libdir = os.path.join(ROOT, "multigridmc_b200", "csrc")
+    exe = str(tmp_path / "run_quadrature_tests")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", compat, "-I", HOST, "-I", str(tmp_path), os.path.join(compat, "main_quadrature.cc"), "-o", exe,
+                           "-L" + libdir, "-lmgmc_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe], text=True)
+    assert "[  PASSED  ] 3 tests, 0 failed" in out, out
