@@ -376,6 +376,71 @@ class LinearOperator {
     c.dev = dev;
     return c;
   }
+  /** the sparse part A_0 of this level as an explicit matrix (linear_operator.hh:79 get_sparse).  The device path is matrix-free: the
+   *  matrix is assembled on demand from the host-only stencil algebra of the library (mgmc_host_stencil / mgmc_host_stencil3: the
+   *  fine stencil and its Galerkin products R A R^T) -- no device needed; constant correlation length only */
+  typedef Eigen::SparseMatrix<double> SparseMatrixType;
+  const SparseMatrixType &get_sparse() const {
+    if (sparse_cache) return *sparse_cache;
+    if (!data->constant_kappa) {
+      std::cout << "ERROR: get_sparse() of the host layer needs a constant correlation length (per-vertex operators: mgmc_host_coefficients)" << std::endl;
+      exit(-1);
+    }
+    mgmc_desc desc;
+    std::memset(&desc, 0, sizeof(desc));
+    desc.dim = data->nz ? 3 : 2;
+    desc.nx = (int)data->nx;
+    desc.ny = (int)data->ny;
+    desc.nz = data->nz ? (int)data->nz : 1;
+    desc.pde_model = data->pde_model;
+    desc.Lambda = data->Lambda;
+    desc.nlevel = level + 1;
+    desc.smoother = MGMC_SMOOTHER_SSOR;
+    desc.coarse_solver = MGMC_COARSE_CHOLESKY;
+    desc.npresmooth = desc.npostsmooth = desc.ncoarsesmooth = 1;
+    desc.cycle = 1;
+    desc.coarse_scaling = 1.0;
+    desc.omega = 1.0;
+    desc.nchains = 1;
+    const Eigen::VectorXi shp = lattice->shape();
+    const long n = lattice->Nvertex;
+    auto M = std::make_shared<SparseMatrixType>(n, n);
+    int nc = 0;
+    if (data->nz) {
+      double st[27];
+      mgmc_host::check(mgmc_host_stencil3(&desc, level, st, &nc), "LinearOperator::get_sparse");
+      const int nx = shp[0], ny = shp[1], nz = shp[2];
+      for (int k = 1; k < nz; ++k)
+        for (int j = 1; j < ny; ++j)
+          for (int i = 1; i < nx; ++i)
+            for (int dk = -1; dk <= 1; ++dk)
+              for (int dj = -1; dj <= 1; ++dj)
+                for (int di = -1; di <= 1; ++di) {
+                  const int ii = i + di, jj = j + dj, kk = k + dk;
+                  const double v = st[(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)];
+                  if (v == 0.0 || ii < 1 || ii >= nx || jj < 1 || jj >= ny || kk < 1 || kk >= nz) continue;
+                  M->coeffRef(((long)(k - 1) * (ny - 1) + (j - 1)) * (nx - 1) + (i - 1), ((long)(kk - 1) * (ny - 1) + (jj - 1)) * (nx - 1) + (ii - 1)) = v;
+                }
+    } else {
+      double st[225];
+      mgmc_host::check(mgmc_host_stencil(&desc, level, st, &nc), "LinearOperator::get_sparse");
+      const int nx = shp[0], ny = shp[1];
+      auto cls = [](int i, int n_) { return i == 1 ? 0 : (i == n_ - 1 ? 2 : 1); };
+      for (int j = 1; j < ny; ++j)
+        for (int i = 1; i < nx; ++i) {
+          const double *a = st + 25 * (cls(i, nx) + 3 * cls(j, ny));
+          for (int dj = -2; dj <= 2; ++dj)
+            for (int di = -2; di <= 2; ++di) {
+              const int ii = i + di, jj = j + dj;
+              const double v = a[(dj + 2) * 5 + (di + 2)];
+              if (v == 0.0 || ii < 1 || ii >= nx || jj < 1 || jj >= ny) continue;
+              M->coeffRef((long)(j - 1) * (nx - 1) + (i - 1), (long)(jj - 1) * (nx - 1) + (ii - 1)) = v;
+            }
+        }
+    }
+    sparse_cache = M;
+    return *sparse_cache;
+  }
   /** device hierarchy with at least nlevel levels (created lazily, shared between the handles) */
   std::shared_ptr<DeviceHierarchy> hierarchy(int nlevel) const {
     if (!dev || (int)dev->params.nlevel < nlevel) {
@@ -400,6 +465,7 @@ class LinearOperator {
   std::shared_ptr<OperatorData> data;
   int level;
   mutable std::shared_ptr<DeviceHierarchy> dev;
+  mutable std::shared_ptr<SparseMatrixType> sparse_cache;
 };
 
 /** ShiftedLaplaceFDOperator (linear_operator/shiftedlaplace_fd_operator.hh:28-42) */

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstddef>
 #include <initializer_list>
+#include <map>
 #include <utility>
 #include <vector>
 
@@ -21,6 +22,7 @@ class VectorX {
  public:
   VectorX() {}
   explicit VectorX(std::ptrdiff_t n) : v_(n) {}
+  VectorX(std::ptrdiff_t rows, std::ptrdiff_t /*cols: Eigen's (rows, cols) form, used by test_solver.hh:45*/) : v_(rows) {}
   VectorX(std::initializer_list<T> l) : v_(l) {}
   std::ptrdiff_t size() const { return (std::ptrdiff_t)v_.size(); }
   void resize(std::ptrdiff_t n) { v_.resize(n); }
@@ -77,6 +79,36 @@ typedef VectorX<int> Vector2i;
 typedef VectorX<int> Vector3i;
 typedef VectorX<double> Vector2d;
 typedef VectorX<double> Vector3d;
+
+// sparse matrix as a (row, col) -> value map: what LinearOperator::get_sparse() returns in the host layer (difference and
+// Frobenius norm are all the reference's tests ask of it, test_intergrid.hh:188,206)
+template <typename T>
+class SparseMatrix {
+ public:
+  SparseMatrix(std::ptrdiff_t rows = 0, std::ptrdiff_t cols = 0) : rows_(rows), cols_(cols) {}
+  std::ptrdiff_t rows() const { return rows_; }
+  std::ptrdiff_t cols() const { return cols_; }
+  T &coeffRef(std::ptrdiff_t i, std::ptrdiff_t j) { return e_[{i, j}]; }
+  T coeff(std::ptrdiff_t i, std::ptrdiff_t j) const {
+    auto it = e_.find({i, j});
+    return it == e_.end() ? T(0) : it->second;
+  }
+  std::ptrdiff_t nonZeros() const { return (std::ptrdiff_t)e_.size(); }
+  double norm() const {
+    double s = 0;
+    for (auto &kv : e_) s += double(kv.second) * double(kv.second);
+    return std::sqrt(s);
+  }
+  friend SparseMatrix operator-(SparseMatrix a, const SparseMatrix &b) {
+    for (auto &kv : b.e_) a.e_[kv.first] -= kv.second;
+    return a;
+  }
+  const std::map<std::pair<std::ptrdiff_t, std::ptrdiff_t>, T> &entries() const { return e_; }
+
+ private:
+  std::ptrdiff_t rows_, cols_;
+  std::map<std::pair<std::ptrdiff_t, std::ptrdiff_t>, T> e_;
+};
 
 // sparse vector as (index, value) pairs -- what MeasuredOperator::measurement_vector returns
 template <typename T>

@@ -34,9 +34,12 @@ inline void report_failure(const char *file, int line, const char *what) {
   std::printf("%s:%d: Failure: %s\n", file, line, what);
   Registry::get().failures_in_current++;
 }
-inline int run_all_tests() {
-  int failed = 0;
+// filter: run only the tests whose name contains this substring (like --gtest_filter=*x*); empty = all
+inline int run_all_tests(const std::string &filter = "") {
+  int failed = 0, ran = 0;
   for (auto &t : Registry::get().tests) {
+    if (!filter.empty() && t.first.find(filter) == std::string::npos) continue;
+    ++ran;
     Registry::get().failures_in_current = 0;
     Test *obj = t.second();
     obj->SetUp();
@@ -47,7 +50,7 @@ inline int run_all_tests() {
     std::printf("[ %s ] %s\n", ok ? "      OK" : "  FAILED", t.first.c_str());
     failed += ok ? 0 : 1;
   }
-  std::printf("[  %s  ] %d tests, %d failed\n", failed ? "FAILED" : "PASSED", (int)Registry::get().tests.size(), failed);
+  std::printf("[  %s  ] %d tests, %d failed\n", failed ? "FAILED" : "PASSED", ran, failed);
   return failed ? 1 : 0;
 }
 }  // namespace testing

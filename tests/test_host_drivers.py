@@ -346,3 +346,43 @@ def test_reference_quadrature_tests_run_against_the_host_layer(built, tmp_path):
                            "-L" + libdir, "-lmgmc_b200", "-Wl,-rpath," + libdir])
     out = subprocess.check_output([exe], text=True)
     assert "[  PASSED  ] 3 tests, 0 failed" in out, out
+
+
+def _ref_compat_build(tmp_path, rel_test, main_cc, exe_name, syntax_only=False):
+    import shutil
+
+    shutil.copy(os.path.join(REFERENCE_SRC, rel_test), tmp_path / os.path.basename(rel_test))
+    compat = os.path.join(ROOT, "tests", "ref_compat")
+    libdir = os.path.join(ROOT, "multigridmc_b200", "csrc")
+    if syntax_only:
+        src = tmp_path / f"syntax_{exe_name}.cc"
+        src.write_text(f'#include "{os.path.basename(rel_test)}"\nint main() {{ return 0; }}\n')
+        subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", compat, "-I", HOST, "-I", str(tmp_path), str(src)])
+        return None
+    exe = str(tmp_path / exe_name)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", compat, "-I", HOST, "-I", str(tmp_path), os.path.join(compat, main_cc), "-o", exe,
+                           "-L" + libdir, "-lmgmc_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_SRC), reason="the reference checkout only exists in the build container")
+def test_reference_coarsen_operator_tests_run_against_the_library(built, tmp_path):
+    """The reference's own TestCoarsenOperator2d / TestCoarsenOperator3d (src/intergrid/test_intergrid.hh:172-207: the Galerkin-coarsened
+    FEM operator equals the rediscretised FEM operator of the coarse lattice, 1e-12) compiled unmodified against the host layer and run
+    on the CPU: LinearOperator::coarsen / get_sparse go through the library's host-side stencil algebra (mgmc_host_stencil / _stencil3),
+    i.e. the reference's test pins the product's own R A R^T.  (The other cases of the file need a device: the file compiles, they are
+    filtered out here.)"""
+    exe = _ref_compat_build(tmp_path, "intergrid/test_intergrid.hh", "main_intergrid.cc", "run_intergrid_tests")
+    out = subprocess.check_output([exe, "TestCoarsenOperator"], text=True)
+    assert "[  PASSED  ] 2 tests, 0 failed" in out, out
+    assert "IntergridTest.TestCoarsenOperator2d" in out and "IntergridTest.TestCoarsenOperator3d" in out
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_SRC), reason="the reference checkout only exists in the build container")
+@pytest.mark.parametrize("rel_test", ["smoother/test_smoother.hh", "solver/test_solver.hh", "linear_operator/test_linear_operator.hh", "intergrid/test_intergrid.hh"])
+def test_reference_test_files_compile_against_the_host_layer(built, tmp_path, rel_test):
+    """Source-level drop-in check of the interfaces that need a device at run time: the reference's own smoother / solver / linear-operator /
+    intergrid test files compile UNMODIFIED against host/mgmc_host.hh (class names, constructor signatures, apply / coarsen / restrict /
+    prolongate_add / measurement_vector ..., parameter structs) -- compile only; their GPU twins are tests/test_gpu_*.py.  (test_sampler.hh
+    and test_cholesky_wrapper.hh define matrix-based operators of their own on Eigen sparse matrices and stay with the oracle.)"""
+    _ref_compat_build(tmp_path, rel_test, None, os.path.basename(rel_test).replace(".hh", ""), syntax_only=True)
